@@ -1,0 +1,245 @@
+"""ctypes front-end of the CPU oracle (oracle/llama_ref.c) plus pure-Python restatements of the
+host-side string logic (synthetic byte-level tokenizer, chat templates).
+
+TEST INFRASTRUCTURE ONLY — only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` leg may import this module.  The product (opsagent_b200) never does.
+
+PARITY UNPINNED BY THE REFERENCE (see llama_ref.c header): the reference's Chat seam
+(reference pkg/llms/openai.go:69-104) carries no arithmetic; this oracle is pinned against
+HF transformers fp32 via tests/golden/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field, asdict
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class RefConfig(C.Structure):
+    _fields_ = [
+        ("hidden", C.c_int32), ("n_layers", C.c_int32), ("n_heads", C.c_int32), ("n_kv_heads", C.c_int32),
+        ("head_dim", C.c_int32), ("ffn", C.c_int32), ("vocab", C.c_int32),
+        ("tie_embeddings", C.c_int32), ("qkv_bias", C.c_int32), ("rope_scaling", C.c_int32),
+        ("norm_random", C.c_int32),
+        ("rope_theta", C.c_float), ("rms_eps", C.c_float),
+        ("rope_factor", C.c_float), ("rope_low_freq", C.c_float), ("rope_high_freq", C.c_float),
+        ("rope_orig_ctx", C.c_int32),
+        ("init_std", C.c_float),
+        ("seed", C.c_uint64),
+    ]
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so with the committed Makefile (gcc + OpenMP)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "llama_ref.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.oa_ref_create.restype = C.c_void_p
+        L.oa_ref_create.argtypes = [C.POINTER(RefConfig), C.c_int32, C.c_int32, C.c_int32]
+        L.oa_ref_destroy.argtypes = [C.c_void_p]
+        L.oa_ref_tensor.restype = C.c_void_p
+        L.oa_ref_tensor.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.oa_ref_forward.restype = C.c_int
+        L.oa_ref_forward.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p]
+        L.oa_ref_generate.restype = C.c_int32
+        L.oa_ref_generate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oa_ref_gen_bf16.restype = C.c_uint16
+        L.oa_ref_gen_bf16.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float]
+        L.oa_ref_rope_table.argtypes = [C.POINTER(RefConfig), C.c_int32, C.c_void_p, C.c_void_p]
+        L.oa_ref_rmsnorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32]
+        L.oa_ref_linear.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+        L.oa_ref_argmax.restype = C.c_int32
+        L.oa_ref_argmax.argtypes = [C.c_void_p, C.c_int32]
+        L.oa_ref_num_threads.restype = C.c_int32
+        _LIB = L
+    return _LIB
+
+
+# ------------------------------------------------------------------------------------------------
+# Model presets — public architectures.  The engine's csrc/model_config.cpp holds
+# the same table; tests/test_host_logic.py checks they agree through oa_model_info().
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class ModelSpec:
+    name: str
+    hidden: int
+    n_layers: int
+    n_heads: int
+    n_kv_heads: int
+    head_dim: int
+    ffn: int
+    vocab: int
+    tie_embeddings: int = 0
+    qkv_bias: int = 0
+    rope_scaling: int = 0
+    norm_random: int = 0
+    rope_theta: float = 500000.0
+    rms_eps: float = 1e-5
+    rope_factor: float = 32.0
+    rope_low_freq: float = 1.0
+    rope_high_freq: float = 4.0
+    rope_orig_ctx: int = 8192
+    init_std: float = 0.02
+    seed: int = 1234
+    template: str = "llama3"      # or "chatml"
+
+    def to_c(self) -> RefConfig:
+        d = asdict(self)
+        d.pop("name"); d.pop("template")
+        return RefConfig(**d)
+
+    def engine_json(self, **extra) -> dict:
+        d = asdict(self)
+        d["model"] = d.pop("name")
+        d.update(extra)
+        return d
+
+
+PRESETS = {
+    "llama-3.2-1b": ModelSpec("llama-3.2-1b", 2048, 16, 32, 8, 64, 8192, 128256, tie_embeddings=1, rope_scaling=1),
+    "llama-3-8b": ModelSpec("llama-3-8b", 4096, 32, 32, 8, 128, 14336, 128256),
+    "qwen2.5-32b": ModelSpec("qwen2.5-32b", 5120, 64, 40, 8, 128, 27648, 152064, qkv_bias=1, rope_theta=1e6,
+                             rms_eps=1e-6, template="chatml"),
+    "llama-3-70b": ModelSpec("llama-3-70b", 8192, 80, 64, 8, 128, 28672, 128256),
+    # tiny configs for parity tests (same code paths, seconds on CPU)
+    "tiny-llama": ModelSpec("tiny-llama", 256, 2, 4, 2, 64, 512, 2304, norm_random=1),
+    "tiny-llama-d128": ModelSpec("tiny-llama-d128", 512, 3, 4, 1, 128, 1024, 1024, norm_random=1, rope_scaling=1,
+                                 tie_embeddings=1),
+    "tiny-qwen": ModelSpec("tiny-qwen", 320, 2, 5, 1, 64, 768, 1280, qkv_bias=1, rope_theta=1e6, rms_eps=1e-6,
+                           norm_random=1, template="chatml"),
+}
+
+
+def _np_bf16_to_f32(a: np.ndarray) -> np.ndarray:
+    return (a.astype(np.uint32) << 16).view(np.float32)
+
+
+def f32_to_bf16_bits(a: np.ndarray) -> np.ndarray:
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    r = np.uint32(0x7FFF) + ((u >> 16) & 1)
+    return ((u + r) >> 16).astype(np.uint16)
+
+
+class Oracle:
+    """One random-init model on the CPU.  mode: 0 = fp32 activations, 1 = bf16-faithful."""
+
+    KINDS = {"wq": 0, "wk": 1, "wv": 2, "wo": 3, "wg": 4, "wu": 5, "wd": 6, "ln1": 7, "ln2": 8, "bq": 9, "bk": 10, "bv": 11}
+
+    def __init__(self, spec: ModelSpec, max_pos: int = 512, n_slots: int = 1, mode: int = 1):
+        self.spec, self.max_pos, self.n_slots, self.mode = spec, max_pos, n_slots, mode
+        self._cfg = spec.to_c()
+        self._h = lib().oa_ref_create(C.byref(self._cfg), max_pos, n_slots, mode)
+        if not self._h:
+            raise MemoryError("oa_ref_create failed")
+
+    def close(self):
+        if self._h:
+            lib().oa_ref_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def tensor(self, layer: int, kind, shape) -> np.ndarray:
+        """bf16 bits of a weight tensor as uint16 ndarray (copy). layer=-1: kind 0 embed / 1 norm / 2 lm_head."""
+        k = self.KINDS[kind] if isinstance(kind, str) else kind
+        p = lib().oa_ref_tensor(self._h, layer, k)
+        n = int(np.prod(shape))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint16)), (n,)).reshape(shape).copy()
+
+    def tensor_f32(self, layer, kind, shape) -> np.ndarray:
+        return _np_bf16_to_f32(self.tensor(layer, kind, shape))
+
+    def forward(self, tokens, pos0: int = 0, slot: int = 0, all_logits: bool = False, want_hidden: bool = False):
+        toks = np.ascontiguousarray(tokens, dtype=np.int32)
+        T = len(toks)
+        V = self.spec.vocab
+        logits = np.empty((T if all_logits else 1, V), dtype=np.float32)
+        hidden = np.empty((self.spec.hidden,), dtype=np.float32) if want_hidden else None
+        rc = lib().oa_ref_forward(self._h, slot, toks.ctypes.data, T, pos0, int(all_logits), logits.ctypes.data,
+                                  hidden.ctypes.data if want_hidden else None)
+        if rc != 0:
+            raise ValueError("oa_ref_forward: bad slot or position")
+        return (logits, hidden) if want_hidden else logits
+
+    def generate(self, prompt, max_new: int, eos=(), slot: int = 0):
+        """-> (tokens[int32], margins[float32], first_logits[float32 V])"""
+        p = np.ascontiguousarray(prompt, dtype=np.int32)
+        out = np.empty((max_new,), dtype=np.int32)
+        mar = np.empty((max_new,), dtype=np.float32)
+        fl = np.empty((self.spec.vocab,), dtype=np.float32)
+        e = np.ascontiguousarray(list(eos), dtype=np.int32)
+        n = lib().oa_ref_generate(self._h, slot, p.ctypes.data, len(p), max_new, e.ctypes.data if len(e) else None,
+                                  len(e), out.ctypes.data, mar.ctypes.data, fl.ctypes.data)
+        if n < 0:
+            raise ValueError("oa_ref_generate failed")
+        return out[:n].copy(), mar[:max(n, 1)].copy(), fl
+
+
+# ------------------------------------------------------------------------------------------------
+# Synthetic byte-level tokenizer + chat templates (restated; the product's is csrc/tokenizer.cpp).
+# No tokenizer files exist offline, so text maps to ids 0..255 (one per UTF-8
+# byte) and the chat-format control tokens keep their real ids inside the real vocab size.
+# ------------------------------------------------------------------------------------------------
+LLAMA3_SPECIALS = {"<|begin_of_text|>": 128000, "<|end_of_text|>": 128001, "<|start_header_id|>": 128006,
+                   "<|end_header_id|>": 128007, "<|eot_id|>": 128009}
+CHATML_SPECIALS = {"<|endoftext|>": 151643, "<|im_start|>": 151644, "<|im_end|>": 151645}
+
+
+def specials_for(spec: ModelSpec) -> dict:
+    """Control-token ids; tiny test vocabularies place them at the top of the vocab."""
+    base = LLAMA3_SPECIALS if spec.template == "llama3" else CHATML_SPECIALS
+    if max(base.values()) < spec.vocab:
+        return dict(base)
+    names = list(base.keys())
+    return {n: spec.vocab - len(names) + i for i, n in enumerate(names)}
+
+
+def apply_chat_template(spec: ModelSpec, messages) -> list[int]:
+    """messages: [(role, content)] -> prompt token ids ending with the assistant generation header.
+    Roles/order are those the ReAct loop produces (reference pkg/assistants/simple.go:358,496-501;
+    seeds at pkg/handlers/execute.go:190-199)."""
+    sp = specials_for(spec)
+    ids: list[int] = []
+    by = lambda s: list(s.encode("utf-8"))
+    if spec.template == "llama3":
+        ids.append(sp["<|begin_of_text|>"])
+        for role, content in messages:
+            ids += [sp["<|start_header_id|>"]] + by(role) + [sp["<|end_header_id|>"]] + by("\n\n") + by(content) + [sp["<|eot_id|>"]]
+        ids += [sp["<|start_header_id|>"]] + by("assistant") + [sp["<|end_header_id|>"]] + by("\n\n")
+    else:
+        for role, content in messages:
+            ids += [sp["<|im_start|>"]] + by(role + "\n") + by(content) + [sp["<|im_end|>"]] + by("\n")
+        ids += [sp["<|im_start|>"]] + by("assistant\n")
+    return ids
+
+
+def eos_ids(spec: ModelSpec) -> list[int]:
+    sp = specials_for(spec)
+    return [sp["<|eot_id|>"], sp["<|end_of_text|>"]] if spec.template == "llama3" else [sp["<|im_end|>"], sp["<|endoftext|>"]]
+
+
+def detokenize(ids) -> bytes:
+    """Generated ids -> bytes.  The synthetic vocabulary is many-to-one on decode: every non-control
+    id t renders as the single byte (t & 0xFF), so random-init models still produce text whose length
+    equals the completion length (encode is the identity on bytes 0..255)."""
+    return bytes(int(i) & 0xFF for i in ids)
