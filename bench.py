@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric on BASELINE.json configs[1]:
+Llama-3-8B bf16, 1xB200, batch=128 concurrent `analyze` ReAct steps over synthetic Pod YAML
+(P=1536 prompt tokens, G=256 generated tokens, mean decode context 1664).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one decode forward of the whole batch (128 sequences, one new token each) through the hot path.
+  value  : decode tokens/s, whole job (all N GPUs), inputs resident in HBM, K steps inside one CUDA-event bracket
+           on the engine's stream, max over ranks.
+  e2e    : the same metric through the public chat API (LocalCUDAClient / C ABI) with HOST buffers: 128 concurrent
+           chat completions per GPU (prompt bytes in, text out), tokenisation, H2D of ids/metadata, prefill, every
+           decode step's D2H of sampled ids and detokenisation inside the timed region.
+  roofline: dominant kernel = paged decode attention; achieved = algorithmic KV bytes per launch / mean launch time
+           (CUDA events on the engine stream) against the measured HBM copy bandwidth.
+  cpu_baseline: the CPU oracle (a port — the reference has no model arithmetic of its own) on the host cores.
+N>1 = data-parallel replicas (BASELINE configs[2]): one engine per GPU, no data-path collective, weak scaling.
+`--impl reference` times the CPU port alone (rank 0 only), same JSON line shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = "llama-3-8b"
+BATCH, PROMPT, GEN, MEAN_CTX = 128, 1536, 256, 1664
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_pod_yaml(i: int, n_bytes: int) -> str:
+    """Seeded synthetic Pod manifest text of exactly n_bytes ASCII bytes (byte-level tokenizer: 1 byte = 1 token)."""
+    import random
+    r = random.Random(42 + i)
+    parts = [f"apiVersion: v1\nkind: Pod\nmetadata:\n  name: app-{i:04d}-{r.randrange(16**6):06x}\n  namespace: ns-{r.randrange(40)}\n"
+             f"  labels:\n    app: svc-{r.randrange(200)}\n    tier: {r.choice(['web', 'db', 'cache', 'batch'])}\nspec:\n  containers:\n"]
+    while sum(map(len, parts)) < n_bytes:
+        c = r.randrange(1000)
+        parts.append(f"  - name: c{c}\n    image: registry.local/team{r.randrange(30)}/img{c}:{r.randrange(9)}.{r.randrange(20)}.{r.randrange(50)}\n"
+                     f"    resources:\n      requests: {{cpu: {r.randrange(50, 2000)}m, memory: {r.randrange(64, 4096)}Mi}}\n"
+                     f"      limits: {{cpu: {r.randrange(100, 4000)}m, memory: {r.randrange(128, 8192)}Mi}}\n"
+                     f"    env:\n    - name: VAR_{r.randrange(100)}\n      value: \"{r.randrange(10**8)}\"\n"
+                     f"    livenessProbe: {{httpGet: {{path: /healthz, port: {r.randrange(1024, 9999)}}}, periodSeconds: {r.randrange(5, 60)}}}\n"
+                     f"status:\n  phase: {r.choice(['Running', 'Pending', 'CrashLoopBackOff', 'Failed'])}\n  conditions:\n"
+                     f"  - type: Ready\n    status: \"{r.choice(['True', 'False'])}\"\n    reason: {r.choice(['ContainersNotReady', 'PodCompleted', 'Unschedulable', 'OK'])}\n")
+    return "".join(parts)[:n_bytes]
+
+
+ANALYSIS_SYSTEM = ("You are an expert Kubernetes and cloud native networking analyst. Analyze the given Kubernetes manifest for "
+                   "issues and misconfigurations, reason step by step, call the kubectl tool when needed, and answer in JSON with "
+                   "the fields question, thought, action{name,input}, observation, final_answer.")
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import numpy as np
+    from opsagent_b200 import Engine, LocalCUDAClient, ChatCompletionMessage
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    K, W = args.steps, max(args.warmup, 3)
+    eng = Engine({"model": MODEL, "device": local_rank, "kv_gb": args.kv_gb, "max_batch": BATCH, "max_seq_len": 2048,
+                  "max_step_tokens": 8192, "seed": 1234})
+    info = eng.info
+    # ------------------------------------------------------------------ value: device-resident decode steps
+    # context chosen so that the mean over the K timed steps is MEAN_CTX (=P+G/2)
+    ctx0 = max(64, MEAN_CTX - W - K // 2)
+    clocks = ClockSampler(local_rank); clocks.start()
+    barrier()
+    r = eng.bench_decode(BATCH, ctx0, K, W)
+    barrier()
+    clk = clocks.stop()
+    ms_step = allmax(r["ms_per_step"])
+    value = world * BATCH / (ms_step / 1e3)
+    # ------------------------------------------------------------------ roofline: dominant kernel (decode attention)
+    os.environ["OA_PROFILE_ATTN"] = "1"
+    rp = eng.bench_decode(BATCH, ctx0, max(4, min(K, 16)), 3)
+    os.environ["OA_PROFILE_ATTN"] = "0"
+    L = info["n_layers"]
+    kv_tok = info["kv_bytes_per_token"]
+    attn_launch_ms = rp["attn_ms_per_step"] / L                           # one decode_attention (+ split merge) per layer
+    attn_bytes = BATCH * rp["mean_ctx"] * kv_tok / L                      # K and V of every cached token, once
+    peak, peak_src = measured_peaks()
+    achieved = attn_bytes / (attn_launch_ms * 1e-3) / 1e9 if attn_launch_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "decode_attention_kernel<128>", "achieved": round(achieved, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": attn_bytes, "launch_ms": round(attn_launch_ms, 4),
+                "kernel_share_of_step": round(rp["attn_ms_per_step"] / rp["device_ms_per_step"], 3) if rp["device_ms_per_step"] else None,
+                "step": {"algorithmic_bytes": r["algorithmic_bytes_per_step"],
+                         "achieved": round(r["algorithmic_bytes_per_step"] / (ms_step * 1e-3) / 1e9, 1),
+                         "frac": round(r["algorithmic_bytes_per_step"] / (ms_step * 1e-3) / 1e9 / peak, 4)}}
+    # ------------------------------------------------------------------ e2e: public chat API, host buffers
+    cli = LocalCUDAClient(eng)
+    overhead = eng.count_tokens([("system", ANALYSIS_SYSTEM), ("user", "")])
+    prompts = [[ChatCompletionMessage("system", ANALYSIS_SYSTEM),
+                ChatCompletionMessage("user", synthetic_pod_yaml(rank * BATCH + i, PROMPT - overhead))] for i in range(BATCH)]
+
+    def one_round():
+        msgs = [[(m.Role, m.Content) for m in p] for p in prompts]
+        t0 = time.perf_counter()
+        tickets = [eng.chat_submit(MODEL, m, GEN, flags=1) for m in msgs]       # non-blocking submit, as Go would
+        outs = [eng.wait(t) for t in tickets]
+        dt = time.perf_counter() - t0
+        assert all(o.completion_tokens == GEN and o.prompt_tokens == PROMPT for o in outs)
+        return dt, outs
+
+    # one blocking Chat() through the Go-mirror client proves the seam itself (untimed)
+    txt = cli.Chat(MODEL, 4, prompts[0])
+    assert isinstance(txt, str)
+    one_round()                                                                  # warm-up round
+    s0 = eng.stats()
+    barrier()
+    dt, _ = one_round()
+    barrier()
+    s1 = eng.stats()
+    dt = allmax(dt)
+    n_fwd = (s1["prefill_steps"] - s0["prefill_steps"]) + (s1["decode_steps"] - s0["decode_steps"])
+    e2e = {"value": round(world * BATCH * GEN / dt, 1), "unit": "tokens/s", "react_steps_per_sec": round(world * BATCH / dt, 2),
+           "seconds_per_round": round(dt, 3), "requests": world * BATCH, "prompt_tokens": PROMPT, "completion_tokens": GEN,
+           "h2d_bytes_per_step": int((s1["h2d_bytes"] - s0["h2d_bytes"]) / max(1, n_fwd)),
+           "d2h_bytes_per_step": int((s1["d2h_bytes"] - s0["d2h_bytes"]) / max(1, n_fwd)), "forwards": n_fwd}
+    launches = int(round(r["launches_per_step"] * K))
+    line = {"metric": "decode_tokens_per_sec", "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic (seeded random-init weights seed=1234, synthetic Pod-YAML prompts, byte-level tokenizer)",
+            "config": {"workload": "BASELINE configs[1]: Llama-3-8B bf16, batch=128 concurrent analyze ReAct steps per GPU, "
+                                   f"P={PROMPT} G={GEN}, mean decode ctx {r['mean_ctx']:.0f}",
+                       "batch_per_gpu": BATCH, "parallelism": f"dp{world}", "l2": "inputs (15 GB weights + 28 GB KV) exceed L2",
+                       "kv_page_tokens": 64, "device_ms_per_step_excl_host_gaps": round(r["device_ms_per_step"], 4)},
+            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "prefill": {"tokens": BATCH * (ctx0 - 1), "ms": round(r["prefill_ms"], 1),
+                        "tokens_per_sec": round(BATCH * (ctx0 - 1) / (r["prefill_ms"] / 1e3), 1)}}
+    if rank == 0 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_tokens)
+    eng.close()
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def cpu_baseline(n_decode=6, n_prompt=16):
+    """The oracle (CPU port of the same decoder, same seeded 8B weights) on the host cores: B=1, short bounded sample."""
+    from oracle import oracle as O
+    import numpy as np
+    spec = O.PRESETS[MODEL]
+    t0 = time.perf_counter()
+    orc = O.Oracle(spec, max_pos=64, n_slots=1, mode=1)
+    t_init = time.perf_counter() - t0
+    prompt = (np.arange(n_prompt) * 7919 % 256).astype(np.int32)
+    t0 = time.perf_counter(); orc.forward(prompt); t_pre = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    tok = np.array([1], np.int32)
+    for i in range(n_decode):
+        lg = orc.forward(tok, pos0=n_prompt + i)
+        tok = np.array([int(lg[0].argmax())], np.int32)
+    t_dec = time.perf_counter() - t0
+    cores = O.lib().oa_ref_num_threads()
+    orc.close()
+    return {"value": round(n_decode / t_dec, 3), "unit": "tokens/s", "cores": int(cores), "kind": "port",
+            "sample": f"oracle/llama_ref.c bf16-faithful mode, Llama-3-8B seed=1234, B=1, {n_prompt}-token prefill ({t_pre:.1f}s) + "
+                      f"{n_decode} decode steps at ctx~{n_prompt + n_decode} ({t_dec:.1f}s); weight generation {t_init:.0f}s not timed",
+            "prefill_tokens_per_sec": round(n_prompt / t_pre, 2)}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own path is an HTTP client with no arithmetic (pkg/llms/openai.go:69); its
+    'CPU implementation' is whatever server it points at.  oracle/_ref cannot exist (pure Go, no Go toolchain), so
+    this times the CPU port with all host threads on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    K = max(1, min(args.steps, 16))
+    cb = cpu_baseline(n_decode=K + min(args.warmup, 2))
+    v = cb["value"]
+    line = {"impl": "reference", "metric": "decode_tokens_per_sec", "value": v, "unit": "tokens/s", "n_gpus": world, "steps": K,
+            "warmup": min(args.warmup, 2), "ms_per_step": round(1e3 / v, 2) if v else None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 weights, fp32 accumulate", "data": "synthetic (same seeded weights)",
+            "config": {"workload": "BASELINE configs[1] model (Llama-3-8B) on host cores, B=1 sequential (single-slot local server)",
+                       "parallelism": "cpu"},
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kv-gb", type=float, default=60.0, dest="kv_gb")
+    ap.add_argument("--cpu-tokens", type=int, default=6, dest="cpu_tokens")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # convenience: spawn torchrun ourselves
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,119 @@
+/*
+ * opsagent_b200.h — C ABI of the B200-native local chat-completion engine.
+ *
+ * This is the drop-in boundary behind OpsAgent's LLM seam.  The reference has no FFI for this path;
+ * its seam is the Go method
+ *     func (c *OpenAIClient) Chat(model string, maxTokens int, prompts []openai.ChatCompletionMessage) (string, error)
+ * (reference pkg/llms/openai.go:69-104), which today POSTs {model, messages, max_tokens, temperature}
+ * to a remote /chat/completions server.  The entry points below are what a `local-cuda` provider binds
+ * through cgo instead (INTEGRATION.md shows the Go side).  Plain C types only; no exceptions cross the
+ * boundary; every function is safe to call from any thread.
+ *
+ * Return codes mirror the HTTP statuses the reference's retry loop already understands
+ * (pkg/llms/openai.go:85-101): 0 ok; 400 bad request (fails fast); 429 queue/KV full (caller backs
+ * off 1,2,4,8,16 s and retries); 500 device or internal fault (retried likewise).
+ */
+#ifndef OPSAGENT_B200_H
+#define OPSAGENT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define OA_API __attribute__((visibility("default")))
+#else
+#define OA_API
+#endif
+
+#define OA_OK 0
+#define OA_ERR_BAD_REQUEST 400
+#define OA_ERR_TIMEOUT 408
+#define OA_ERR_OVERLOADED 429
+#define OA_ERR_INTERNAL 500
+
+typedef struct oa_engine oa_engine; /* opaque, process-global, thread-safe */
+
+/* replaces openai.ChatCompletionMessage{Role, Content} (go-openai v1.38.0; used at pkg/llms/openai.go:69) */
+typedef struct {
+    const char* role;    /* "system" | "user" | "assistant"; UTF-8, NUL-terminated, caller-owned */
+    const char* content; /* UTF-8, NUL-terminated, caller-owned */
+} oa_msg;
+
+/* replaces openai.ChatCompletionRequest as built at pkg/llms/openai.go:70-75 */
+typedef struct {
+    const char* model;     /* must name the loaded model (or be empty/NULL) — else 400 */
+    const oa_msg* msgs;
+    int32_t n_msgs;
+    int32_t max_tokens;    /* completion budget (8192 from pkg/handlers/execute.go:205) */
+    float temperature;     /* the reference always sends SmallestNonzeroFloat32: greedy. Values > 1e-3 -> 400 */
+    uint64_t seed;         /* unused under greedy decoding; kept for ABI stability */
+    uint32_t flags;        /* OA_FLAG_* */
+} oa_chat_req;
+
+#define OA_FLAG_IGNORE_EOS 1u /* throughput runs: always generate exactly max_tokens tokens */
+
+/* replaces resp.Choices[0].Message.Content (+ usage) at pkg/llms/openai.go:82 */
+typedef struct {
+    char* content;         /* engine-owned, NUL-terminated, may contain embedded NULs: use content_len */
+    int32_t content_len;
+    int32_t prompt_tokens, completion_tokens;
+    int32_t finish_reason; /* 0 stop (EOS), 1 length */
+    int32_t* token_ids;    /* completion token ids (engine-owned), length completion_tokens */
+} oa_chat_resp;
+
+/* config_json: {"model":"llama-3-8b"|"llama-3.2-1b"|"qwen2.5-32b"|"llama-3-70b"|custom dims..., "seed":1234,
+ *  "device":0, "kv_gb":100, "max_batch":128, "max_seq_len":4096, "max_step_tokens":8192, ...} — see DESIGN.md */
+OA_API int oa_engine_create(const char* config_json, oa_engine** out);
+OA_API void oa_engine_destroy(oa_engine*);
+
+/* blocking completion — what (*LocalCUDAClient).Chat calls; replaces CreateChatCompletion (openai.go:79) */
+OA_API int oa_chat_complete(oa_engine*, const oa_chat_req*, oa_chat_resp* out);
+/* non-blocking pair for callers that must not pin an OS thread per request (Go: submit, then wait) */
+OA_API int oa_chat_submit(oa_engine*, const oa_chat_req*, uint64_t* ticket);
+OA_API int oa_chat_wait(oa_engine*, uint64_t ticket, int32_t timeout_ms, oa_chat_resp* out);
+OA_API void oa_free_resp(oa_chat_resp*);
+
+/* same pair on raw token ids (bench + parity tests; bypasses the chat template) */
+OA_API int oa_tokens_submit(oa_engine*, const int32_t* prompt, int32_t n_prompt, int32_t max_tokens, uint32_t flags, uint64_t* ticket);
+
+/* tokenizer-accurate counting for pkg/llms/tokens.go:60 NumTokensFromMessages / :128 ConstrictPrompt */
+OA_API int oa_count_tokens(oa_engine*, const oa_msg* msgs, int32_t n_msgs, int32_t* out_tokens);
+/* chat template + tokenizer only: writes up to cap ids, returns total count in *n_out */
+OA_API int oa_apply_chat_template(oa_engine*, const oa_msg* msgs, int32_t n_msgs, int32_t* out_ids, int32_t cap, int32_t* n_out);
+
+OA_API const char* oa_last_error(void);                      /* thread-local message of the last failing call */
+OA_API int oa_engine_stats(oa_engine*, char* buf, size_t n); /* JSON: steps, tokens, pages, launches, timings */
+OA_API int oa_model_info(oa_engine*, char* buf, size_t n);   /* JSON: resolved architecture */
+
+/* ---- measurement + parity hooks (used by bench.py and tests/; not part of the Go seam) ---- */
+/* fresh single-sequence prefill of `tokens`; fp32 logits of every position -> logits_out[n, vocab] */
+OA_API int oa_debug_prefill_logits(oa_engine*, const int32_t* tokens, int32_t n, float* logits_out);
+/* Device-resident decode benchmark: builds `batch` sequences of `ctx_len` cached tokens (real chunked prefill of
+ * seeded synthetic ids), then runs warmup+steps decode forwards of the whole batch, timed with CUDA events on the
+ * engine stream.  out[0]=ms/step over ONE event bracket around all timed steps (host gaps included), out[1]=prefill ms, out[2]=kernel launches per step, out[3]=mean ctx over the
+ * timed steps, out[4]=attention-kernel ms/step (avg), out[5]=algorithmic bytes/step,
+ * out[6]=sum of per-step device durations / steps (host gaps excluded) */
+OA_API int oa_bench_decode(oa_engine*, int32_t batch, int32_t ctx_len, int32_t steps, int32_t warmup, double* out, int32_t n_out);
+
+/* kernel-level entry points on raw device pointers (tests call these with torch-allocated memory) */
+OA_API int oa_k_rmsnorm(const void* x, const void* gain, void* y, int32_t T, int32_t H, float eps, void* stream);
+OA_API int oa_k_gemm(const void* A, const void* B, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t block_n, void* out,
+              const void* bias, const void* resid, float* logits, int32_t* argmax_out, void* stream);
+OA_API int oa_k_init_weight(void* dst, uint64_t seed, uint64_t tensor_id, int64_t tensor_id_b, int64_t rows, int64_t cols, float std,
+                     float mean, void* stream);
+/* paged attention on a caller-provided cache [2(K,V)][num_pages][n_kv][64][D] (one layer): decode when q has one
+ * row per sequence (n_q_rows == n_seqs), otherwise causal prefill of `q_lens[i]` new rows per sequence */
+OA_API int oa_k_paged_attention(const void* q, void* out, const void* kv_cache, int32_t num_pages, const int32_t* block_tables,
+                         int32_t max_pages_per_seq, const int32_t* ctx_lens, const int32_t* q_lens, int32_t n_seqs,
+                         int32_t n_heads, int32_t n_kv, int32_t head_dim, int32_t force_splits, void* stream);
+OA_API uint64_t oa_kernel_launches(void);
+OA_API const char* oa_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,106 @@
+// capi_kernels.cpp — kernel-level C entry points on raw device pointers (parity tests drive these with
+// torch-allocated memory; nothing here is on the serving path).
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/opsagent_b200.h"
+#include "model.hpp"
+
+using namespace oa;
+
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    explicit DevBuf(size_t n) { if (cudaMalloc(&p, n ? n : 16) != cudaSuccess) p = nullptr; }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+int rc_of(cudaError_t e) { return e == cudaSuccess ? OA_OK : OA_ERR_INTERNAL; }
+}  // namespace
+
+extern "C" {
+
+int oa_k_rmsnorm(const void* x, const void* gain, void* y, int32_t T, int32_t H, float eps, void* stream) {
+    return rc_of(launch_rmsnorm(x, gain, y, T, H, eps, (cudaStream_t)stream));
+}
+
+int oa_k_init_weight(void* dst, uint64_t seed, uint64_t tensor_id, int64_t tensor_id_b, int64_t rows, int64_t cols, float std,
+                     float mean, void* stream) {
+    return rc_of(launch_init_weight(dst, seed, tensor_id, tensor_id_b, rows, cols, std, mean, (cudaStream_t)stream));
+}
+
+int oa_k_gemm(const void* A, const void* B, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t block_n, void* out,
+              const void* bias, const void* resid, float* logits, int32_t* argmax_out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CUtensorMap tmA, tmB;
+    if (make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, 64) != 0) return OA_ERR_INTERNAL;
+    if (make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)block_n, 64) != 0) return OA_ERR_INTERNAL;
+    GemmParams p{}; p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = epilogue == EPI_SWIGLU ? N / 2 : N;
+    p.bias = bias; p.resid = resid; p.ldr = N; p.logits = logits; p.ldl = N;
+    if (epilogue == EPI_LOGITS) {
+        const int nt = gemm_n_tiles(N, block_n);
+        DevBuf av((size_t)M * nt * 4), ai((size_t)M * nt * 4);
+        if (!av.p || !ai.p) return OA_ERR_INTERNAL;
+        p.amax_val = (float*)av.p; p.amax_idx = (int*)ai.p;
+        cudaError_t e = launch_gemm(&tmA, &tmB, p, epilogue, block_n, s);
+        if (e == cudaSuccess) e = launch_argmax_reduce(p.amax_val, p.amax_idx, M, nt, argmax_out, nullptr, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        return rc_of(e);
+    }
+    return rc_of(launch_gemm(&tmA, &tmB, p, epilogue, block_n, s));
+}
+
+int oa_k_paged_attention(const void* q, void* out, const void* kv_cache, int32_t num_pages, const int32_t* block_tables,
+                         int32_t max_pages_per_seq, const int32_t* ctx_lens, const int32_t* q_lens, int32_t n_seqs,
+                         int32_t n_heads, int32_t n_kv, int32_t head_dim, int32_t force_splits, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KvLayout kv{}; kv.base = const_cast<void*>(kv_cache); kv.page_size = 64; kv.n_kv = n_kv; kv.head_dim = head_dim; kv.num_pages = num_pages;
+    kv.kv_stride_rows = (int64_t)num_pages * n_kv * 64; kv.layer_stride_rows = 2 * kv.kv_stride_rows;
+    CUtensorMap tm;
+    if (make_tmap_bf16_2d(&tm, kv_cache, (uint64_t)kv.layer_stride_rows, (uint64_t)head_dim, (uint64_t)head_dim, 64, 64) != 0) return OA_ERR_INTERNAL;
+    const float scale_log2e = (1.0f / std::sqrt((float)head_dim)) * 1.4426950408889634f;
+    const int grp = n_heads / n_kv;
+    bool decode = true; int total_q = 0;
+    for (int i = 0; i < n_seqs; ++i) { if (q_lens && q_lens[i] != 1) decode = false; total_q += q_lens ? q_lens[i] : 1; }
+    DevBuf d_bt((size_t)n_seqs * max_pages_per_seq * 4), d_ctx((size_t)n_seqs * 4);
+    if (!d_bt.p || !d_ctx.p) return OA_ERR_INTERNAL;
+    cudaMemcpyAsync(d_bt.p, block_tables, (size_t)n_seqs * max_pages_per_seq * 4, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_ctx.p, ctx_lens, (size_t)n_seqs * 4, cudaMemcpyHostToDevice, s);
+    cudaError_t e;
+    if (decode) {
+        DecodePlan plan;
+        build_decode_plan(ctx_lens, n_seqs, n_kv, 2 * 148, force_splits, plan);
+        DevBuf d_segs(plan.segs.size() * sizeof(DecodeSeg)), d_ptr(plan.cta_ptr.size() * 4), d_merge(plan.merges.size() * sizeof(MergeItem));
+        DevBuf d_po((size_t)(plan.n_slots + 1) * grp * head_dim * 4), d_pml((size_t)(plan.n_slots + 1) * grp * 2 * 4);
+        if (!d_segs.p || !d_ptr.p || !d_merge.p || !d_po.p || !d_pml.p) return OA_ERR_INTERNAL;
+        cudaMemcpyAsync(d_segs.p, plan.segs.data(), plan.segs.size() * sizeof(DecodeSeg), cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(d_ptr.p, plan.cta_ptr.data(), plan.cta_ptr.size() * 4, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(d_merge.p, plan.merges.data(), plan.merges.size() * sizeof(MergeItem), cudaMemcpyHostToDevice, s);
+        DecodeAttnParams a{}; a.q = q; a.out = out; a.block_tables = (const int32_t*)d_bt.p; a.ctx_lens = (const int32_t*)d_ctx.p;
+        a.max_pages_per_seq = max_pages_per_seq; a.segs = (const DecodeSeg*)d_segs.p; a.cta_seg_ptr = (const int32_t*)d_ptr.p;
+        a.n_ctas = (int)plan.cta_ptr.size() - 1; a.part_o = (float*)d_po.p; a.part_ml = (float*)d_pml.p; a.layer = 0;
+        a.n_heads = n_heads; a.n_kv = n_kv; a.scale_log2e = scale_log2e;
+        e = launch_decode_attention(&tm, kv, a, s);
+        if (e == cudaSuccess) e = launch_decode_merge((const MergeItem*)d_merge.p, (int)plan.merges.size(), a.part_o, a.part_ml, out, n_heads, n_kv, head_dim, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        return rc_of(e);
+    }
+    std::vector<PrefillTile> tiles; int row = 0;
+    for (int i = 0; i < n_seqs; ++i) {
+        const int ql = q_lens[i], p0 = ctx_lens[i] - ql;
+        for (int r = 0; r < ql; r += 64) tiles.push_back(PrefillTile{i, row + r, p0 + r, std::min(64, ql - r)});
+        row += ql;
+    }
+    (void)total_q;
+    DevBuf d_tiles(tiles.size() * sizeof(PrefillTile));
+    if (!d_tiles.p) return OA_ERR_INTERNAL;
+    cudaMemcpyAsync(d_tiles.p, tiles.data(), tiles.size() * sizeof(PrefillTile), cudaMemcpyHostToDevice, s);
+    PrefillAttnParams a{}; a.q = q; a.out = out; a.block_tables = (const int32_t*)d_bt.p; a.max_pages_per_seq = max_pages_per_seq;
+    a.tiles = (const PrefillTile*)d_tiles.p; a.n_tiles = (int)tiles.size(); a.layer = 0; a.n_heads = n_heads; a.n_kv = n_kv; a.scale_log2e = scale_log2e;
+    e = launch_prefill_attention(&tm, kv, a, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    return rc_of(e);
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// config.hpp — model architecture table, engine options and a minimal JSON reader for oa_engine_create().
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace oa {
+
+// Flat JSON object reader: {"key": "str" | number | true | false | null, ...}.  Enough for engine configs.
+class JsonFlat {
+public:
+    std::map<std::string, std::string> kv;   // raw values (strings unescaped)
+    static JsonFlat parse(const std::string& s) {
+        JsonFlat j; size_t i = 0;
+        auto ws = [&]() { while (i < s.size() && (s[i] == ' ' || s[i] == '\n' || s[i] == '\t' || s[i] == '\r')) ++i; };
+        auto str = [&]() -> std::string {
+            if (s[i] != '"') throw std::runtime_error("config json: expected string");
+            ++i; std::string o;
+            while (i < s.size() && s[i] != '"') {
+                if (s[i] == '\\' && i + 1 < s.size()) { ++i; char c = s[i]; o += (c == 'n' ? '\n' : c == 't' ? '\t' : c); }
+                else o += s[i];
+                ++i;
+            }
+            if (i >= s.size()) throw std::runtime_error("config json: unterminated string");
+            ++i; return o;
+        };
+        ws(); if (i >= s.size() || s[i] != '{') throw std::runtime_error("config json: expected object");
+        ++i; ws();
+        if (i < s.size() && s[i] == '}') return j;
+        while (true) {
+            ws(); std::string k = str(); ws();
+            if (i >= s.size() || s[i] != ':') throw std::runtime_error("config json: expected ':'");
+            ++i; ws();
+            std::string v;
+            if (s[i] == '"') v = str();
+            else { size_t b = i; while (i < s.size() && s[i] != ',' && s[i] != '}' && s[i] != ' ' && s[i] != '\n') ++i; v = s.substr(b, i - b); }
+            j.kv[k] = v; ws();
+            if (i < s.size() && s[i] == ',') { ++i; continue; }
+            if (i < s.size() && s[i] == '}') break;
+            throw std::runtime_error("config json: expected ',' or '}'");
+        }
+        return j;
+    }
+    bool has(const std::string& k) const { return kv.count(k) && kv.at(k) != "null"; }
+    std::string s(const std::string& k, const std::string& d) const { return has(k) ? kv.at(k) : d; }
+    double f(const std::string& k, double d) const {
+        if (!has(k)) return d;
+        const std::string& v = kv.at(k);
+        if (v == "true") return 1; if (v == "false") return 0;
+        return std::strtod(v.c_str(), nullptr);
+    }
+    int64_t i(const std::string& k, int64_t d) const { return has(k) ? (int64_t)std::llround(f(k, (double)d)) : d; }
+};
+
+struct ModelConfig {
+    std::string name = "custom";
+    int hidden = 0, n_layers = 0, n_heads = 0, n_kv_heads = 0, head_dim = 0, ffn = 0, vocab = 0;
+    int tie_embeddings = 0, qkv_bias = 0, rope_scaling = 0, norm_random = 0;
+    float rope_theta = 500000.f, rms_eps = 1e-5f;
+    float rope_factor = 32.f, rope_low_freq = 1.f, rope_high_freq = 4.f; int rope_orig_ctx = 8192;
+    float init_std = 0.02f;
+    uint64_t seed = 1234;
+    std::string chat_template = "llama3";   // or "chatml"
+
+    int q_dim() const { return n_heads * head_dim; }
+    int kv_dim() const { return n_kv_heads * head_dim; }
+    int qkv_dim() const { return q_dim() + 2 * kv_dim(); }
+    size_t kv_bytes_per_token() const { return (size_t)2 * n_layers * kv_dim() * 2; }
+    double decode_weight_bytes() const {   // W_dec of SURVEY.md §8d: all layers + final norm + lm_head
+        double per = (double)qkv_dim() * hidden + (double)hidden * q_dim() + 3.0 * ffn * hidden + 2.0 * hidden + (qkv_bias ? qkv_dim() : 0);
+        return 2.0 * (per * n_layers + hidden + (double)vocab * hidden);
+    }
+};
+
+// public architectures; oracle/oracle.py PRESETS is the test-side copy
+inline bool preset_model(const std::string& n, ModelConfig& c) {
+    c.name = n;
+    if (n == "llama-3.2-1b") { c.hidden = 2048; c.n_layers = 16; c.n_heads = 32; c.n_kv_heads = 8; c.head_dim = 64; c.ffn = 8192; c.vocab = 128256; c.tie_embeddings = 1; c.rope_scaling = 1; return true; }
+    if (n == "llama-3-8b") { c.hidden = 4096; c.n_layers = 32; c.n_heads = 32; c.n_kv_heads = 8; c.head_dim = 128; c.ffn = 14336; c.vocab = 128256; return true; }
+    if (n == "qwen2.5-32b") { c.hidden = 5120; c.n_layers = 64; c.n_heads = 40; c.n_kv_heads = 8; c.head_dim = 128; c.ffn = 27648; c.vocab = 152064; c.qkv_bias = 1; c.rope_theta = 1e6f; c.rms_eps = 1e-6f; c.chat_template = "chatml"; return true; }
+    if (n == "llama-3-70b") { c.hidden = 8192; c.n_layers = 80; c.n_heads = 64; c.n_kv_heads = 8; c.head_dim = 128; c.ffn = 28672; c.vocab = 128256; return true; }
+    return false;
+}
+
+struct EngineOptions {
+    int device = 0;
+    double kv_gb = -1;            // < 0: use what is free after weights minus a reserve
+    int num_pages = -1;           // overrides kv_gb
+    int max_batch = 256;          // concurrently running sequences
+    int max_seq_len = 4096;       // prompt + completion
+    int max_step_tokens = 8192;   // token budget of one prefill forward
+    int max_queue = 4096;         // waiting requests beyond this -> 429
+    int bn_qkv = 0, bn_o = 0, bn_gu = 0, bn_down = 0, bn_lm = 0;   // GEMM N-tile overrides (0 = heuristic)
+    int attn_ctas = 0;            // decode attention CTA count override (0 = 2 per SM)
+    int start_thread = 1;
+};
+
+inline void parse_config(const std::string& json, ModelConfig& m, EngineOptions& o) {
+    JsonFlat j = JsonFlat::parse(json);
+    std::string name = j.s("model", "custom");
+    if (!preset_model(name, m)) m.name = name;
+    auto I = [&](const char* k, int& v) { v = (int)j.i(k, v); };
+    auto F = [&](const char* k, float& v) { v = (float)j.f(k, v); };
+    I("hidden", m.hidden); I("n_layers", m.n_layers); I("n_heads", m.n_heads); I("n_kv_heads", m.n_kv_heads);
+    I("head_dim", m.head_dim); I("ffn", m.ffn); I("vocab", m.vocab); I("tie_embeddings", m.tie_embeddings);
+    I("qkv_bias", m.qkv_bias); I("rope_scaling", m.rope_scaling); I("norm_random", m.norm_random);
+    F("rope_theta", m.rope_theta); F("rms_eps", m.rms_eps); F("rope_factor", m.rope_factor);
+    F("rope_low_freq", m.rope_low_freq); F("rope_high_freq", m.rope_high_freq); I("rope_orig_ctx", m.rope_orig_ctx);
+    F("init_std", m.init_std);
+    m.seed = (uint64_t)j.i("seed", (int64_t)m.seed);
+    m.chat_template = j.s("template", m.chat_template);
+    I("device", o.device); o.kv_gb = j.f("kv_gb", o.kv_gb); I("num_pages", o.num_pages); I("max_batch", o.max_batch);
+    I("max_seq_len", o.max_seq_len); I("max_step_tokens", o.max_step_tokens); I("max_queue", o.max_queue);
+    I("bn_qkv", o.bn_qkv); I("bn_o", o.bn_o); I("bn_gu", o.bn_gu); I("bn_down", o.bn_down); I("bn_lm", o.bn_lm);
+    I("attn_ctas", o.attn_ctas); I("start_thread", o.start_thread);
+    if (m.hidden <= 0 || m.n_layers <= 0 || m.n_heads <= 0 || m.n_kv_heads <= 0 || m.ffn <= 0 || m.vocab <= 0)
+        throw std::runtime_error("unknown model '" + name + "' and no explicit dimensions given");
+    if (m.head_dim != 64 && m.head_dim != 128) throw std::runtime_error("head_dim must be 64 or 128");
+    if (m.n_heads % m.n_kv_heads != 0 || m.n_heads / m.n_kv_heads > 8) throw std::runtime_error("GQA group must divide n_heads and be <= 8");
+    if (m.hidden % 64 || m.ffn % 64 || m.vocab % 8) throw std::runtime_error("hidden/ffn must be multiples of 64, vocab of 8");
+    if (m.chat_template != "llama3" && m.chat_template != "chatml") throw std::runtime_error("template must be llama3 or chatml");
+    if (o.max_seq_len % 64) o.max_seq_len = (o.max_seq_len + 63) / 64 * 64;
+}
+
+}  // namespace oa

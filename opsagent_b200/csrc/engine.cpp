@@ -1,0 +1,479 @@
+// engine.cpp — request scheduler (continuous batching over a paged KV pool) and the C ABI of
+// include/opsagent_b200.h.
+//
+// Concurrency shape preserved from the reference: every in-flight agent request blocks in one Chat call on
+// its own goroutine (reference pkg/handlers/execute.go:205 -> pkg/assistants/simple.go:343,515 ->
+// pkg/llms/openai.go:69).  Here those callers block in oa_chat_complete / oa_chat_wait while ONE scheduler
+// thread batches all of them data-parallel into shared prefill / decode forwards.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <unordered_map>
+
+#include "../../include/opsagent_b200.h"
+#include "model.hpp"
+#include "tokenizer.hpp"
+
+namespace oa {
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+
+enum class SeqState { WAITING, PREFILL, DECODE, DONE };
+
+struct Seq {
+    uint64_t ticket = 0;
+    std::vector<int32_t> tokens;     // prompt + generated so far
+    int n_prompt = 0, n_cached = 0, n_generated = 0, max_new = 0;
+    uint32_t flags = 0;
+    std::vector<int32_t> pages;
+    SeqState state = SeqState::WAITING;
+    int finish_reason = 1;
+    int error = 0; std::string error_msg;
+    bool done = false;
+};
+
+class Engine {
+public:
+    Engine(const ModelConfig& mc, const EngineOptions& eo) : model_(mc, eo), tok_(mc), opt_(eo) {
+        free_pages_.reserve(model_.num_pages);
+        for (int p = model_.num_pages - 1; p >= 0; --p) free_pages_.push_back(p);
+        if (eo.start_thread) worker_ = std::thread([this] { loop(); });
+    }
+    ~Engine() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_work_.notify_all();
+        if (worker_.joinable()) worker_.join();
+    }
+
+    int submit_tokens(std::vector<int32_t>&& prompt, int max_new, uint32_t flags, uint64_t* ticket) {
+        if (prompt.empty()) return fail(OA_ERR_BAD_REQUEST, "empty prompt");
+        if (max_new <= 0) return fail(OA_ERR_BAD_REQUEST, "max_tokens must be positive");
+        if ((int)prompt.size() + 1 > opt_.max_seq_len)
+            return fail(OA_ERR_BAD_REQUEST, "prompt of " + std::to_string(prompt.size()) + " tokens exceeds max_seq_len " + std::to_string(opt_.max_seq_len));
+        for (int32_t t : prompt) if (t < 0 || t >= model_.cfg.vocab) return fail(OA_ERR_BAD_REQUEST, "token id out of range");
+        auto s = std::make_shared<Seq>();
+        s->n_prompt = (int)prompt.size(); s->tokens = std::move(prompt);
+        s->max_new = std::min(max_new, opt_.max_seq_len - s->n_prompt); s->flags = flags;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (fatal_) return fail(OA_ERR_INTERNAL, "engine is in a failed state: " + fatal_msg_);
+            if ((int)waiting_.size() >= opt_.max_queue) return fail(OA_ERR_OVERLOADED, "request queue full");
+            s->ticket = next_ticket_++;
+            waiting_.push_back(s); by_ticket_[s->ticket] = s;
+            *ticket = s->ticket;
+        }
+        cv_work_.notify_one();
+        return OA_OK;
+    }
+
+    int wait(uint64_t ticket, int timeout_ms, oa_chat_resp* out) {
+        std::shared_ptr<Seq> s;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            auto it = by_ticket_.find(ticket);
+            if (it == by_ticket_.end()) return fail(OA_ERR_BAD_REQUEST, "unknown ticket");
+            s = it->second;
+            auto pred = [&] { return s->done; };
+            if (timeout_ms < 0) cv_done_.wait(lk, pred);
+            else if (!cv_done_.wait_for(lk, std::chrono::milliseconds(timeout_ms), pred)) return fail(OA_ERR_TIMEOUT, "timeout");
+            by_ticket_.erase(ticket);
+        }
+        if (s->error) return fail(s->error, s->error_msg);
+        std::vector<int32_t> gen(s->tokens.begin() + s->n_prompt, s->tokens.end());
+        std::string text = tok_.detokenize(gen);
+        out->content = (char*)std::malloc(text.size() + 1);
+        std::memcpy(out->content, text.data(), text.size()); out->content[text.size()] = 0;
+        out->content_len = (int32_t)text.size();
+        out->prompt_tokens = s->n_prompt; out->completion_tokens = (int32_t)gen.size(); out->finish_reason = s->finish_reason;
+        out->token_ids = (int32_t*)std::malloc(std::max<size_t>(1, gen.size()) * 4);
+        std::memcpy(out->token_ids, gen.data(), gen.size() * 4);
+        return OA_OK;
+    }
+
+    // ---- exclusive-use helpers (bench / parity); they hold step_mu_ so the scheduler is parked ----
+    int debug_prefill_logits(const int32_t* toks, int n, float* logits_out) {
+        if (n <= 0 || n > std::min(2048, opt_.max_step_tokens) || n + 1 > opt_.max_seq_len) return fail(OA_ERR_BAD_REQUEST, "debug prefill: 1..min(2048,max_step_tokens) tokens");
+        std::lock_guard<std::mutex> step(step_mu_);
+        try {
+            const int V = model_.cfg.vocab;
+            std::vector<int32_t> pages;
+            { std::lock_guard<std::mutex> lk(mu_); if (!alloc_pages_locked(pages, (n + 63) / 64)) return fail(OA_ERR_OVERLOADED, "no free KV pages"); }
+            float* d_logits = nullptr;
+            cuda_check(cudaMalloc(&d_logits, (size_t)n * V * 4), "cudaMalloc logits");
+            StepInput in; in.decode = false; in.n_seqs = 1;
+            in.block_tables.assign(model_.max_pages_per_seq, 0);
+            for (size_t i = 0; i < pages.size(); ++i) in.block_tables[i] = pages[i];
+            in.ctx_lens = {n};
+            for (int i = 0; i < n; ++i) { in.tokens.push_back(toks[i]); in.positions.push_back(i); in.slots.push_back(pages[i / 64] * 64 + i % 64); in.sample_rows.push_back(i); }
+            for (int r = 0; r < n; r += 64) in.tiles.push_back(PrefillTile{0, r, r, std::min(64, n - r)});
+            model_.forward(in, d_logits); model_.sync();
+            cudaError_t e = cudaMemcpy(logits_out, d_logits, (size_t)n * V * 4, cudaMemcpyDeviceToHost);
+            cudaFree(d_logits);
+            { std::lock_guard<std::mutex> lk(mu_); for (int p : pages) free_pages_.push_back(p); }
+            cuda_check(e, "logits D2H");
+        } catch (const std::exception& ex) { return fail(OA_ERR_INTERNAL, ex.what()); }
+        return OA_OK;
+    }
+
+    int bench_decode(int batch, int ctx_len, int steps, int warmup, double* out, int n_out) {
+        if (batch <= 0 || batch > opt_.max_batch || ctx_len <= 0 || ctx_len + steps + warmup + 1 > opt_.max_seq_len || n_out < 6)
+            return fail(OA_ERR_BAD_REQUEST, "bench_decode: batch <= max_batch, ctx_len+steps+warmup < max_seq_len, n_out >= 6");
+        std::lock_guard<std::mutex> step(step_mu_);
+        try {
+            const int V = model_.cfg.vocab;
+            const int total_len = ctx_len + steps + warmup;
+            const int pages_per = (total_len + 63) / 64;
+            std::vector<std::vector<int32_t>> pages(batch);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if ((long long)pages_per * batch > (long long)free_pages_.size()) return fail(OA_ERR_OVERLOADED, "bench_decode: not enough KV pages");
+                for (int b = 0; b < batch; ++b) alloc_pages_locked(pages[b], pages_per);
+            }
+            auto synth = [&](int b, int i) { uint64_t h = (uint64_t)(b + 1) * 0x9E3779B97F4A7C15ull + (uint64_t)i * 0xBF58476D1CE4E5B9ull; h ^= h >> 29; return (int32_t)(h % (uint64_t)V); };
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            // ---- prefill: ctx_len-1 tokens per sequence, chunked by the step token budget ----
+            const int P = ctx_len - 1;
+            cudaEventRecord(e0, model_.stream);
+            {
+                int b = 0, off = 0;
+                while (b < batch && P > 0) {
+                    StepInput in; in.decode = false;
+                    int budget = opt_.max_step_tokens;
+                    while (b < batch && budget > 0 && in.n_seqs < opt_.max_batch) {
+                        const int take = std::min(budget, P - off);
+                        const int sidx = in.n_seqs++;
+                        in.block_tables.resize((size_t)in.n_seqs * model_.max_pages_per_seq, 0);
+                        for (size_t i = 0; i < pages[b].size(); ++i) in.block_tables[(size_t)sidx * model_.max_pages_per_seq + i] = pages[b][i];
+                        in.ctx_lens.push_back(off + take);
+                        const int row0 = (int)in.tokens.size();
+                        for (int i = off; i < off + take; ++i) { in.tokens.push_back(synth(b, i)); in.positions.push_back(i); in.slots.push_back(pages[b][i / 64] * 64 + i % 64); }
+                        for (int r = 0; r < take; r += 64) in.tiles.push_back(PrefillTile{sidx, row0 + r, off + r, std::min(64, take - r)});
+                        budget -= take; off += take;
+                        if (off >= P) { off = 0; ++b; }
+                    }
+                    model_.forward(in, nullptr);
+                }
+            }
+            cudaEventRecord(e1, model_.stream); model_.sync();
+            float prefill_ms = 0; cudaEventElapsedTime(&prefill_ms, e0, e1);
+            // ---- decode steps ----
+            std::vector<int32_t> last(batch);
+            for (int b = 0; b < batch; ++b) last[b] = synth(b, P);
+            double ctx_sum = 0; float total_ms = 0; uint64_t launches0 = 0;
+            cudaEvent_t eb0, eb1; cudaEventCreate(&eb0); cudaEventCreate(&eb1);
+            model_.attn_ms_accum = 0;
+            for (int it = 0; it < warmup + steps; ++it) {
+                const int pos = P + it;
+                StepInput in; in.decode = true; in.n_seqs = batch;
+                in.block_tables.assign((size_t)batch * model_.max_pages_per_seq, 0);
+                for (int b = 0; b < batch; ++b) {
+                    for (size_t i = 0; i < pages[b].size(); ++i) in.block_tables[(size_t)b * model_.max_pages_per_seq + i] = pages[b][i];
+                    in.tokens.push_back(last[b]); in.positions.push_back(pos); in.slots.push_back(pages[b][pos / 64] * 64 + pos % 64);
+                    in.ctx_lens.push_back(pos + 1); in.sample_rows.push_back(b);
+                }
+                if (it == warmup) { launches0 = launches_total(); model_.attn_ms_accum = 0; cudaEventRecord(eb0, model_.stream); }
+                const bool timed = it >= warmup;
+                if (timed) { cudaEventRecord(e0, model_.stream); ctx_sum += pos + 1; }
+                model_.forward(in, nullptr);
+                if (timed) cudaEventRecord(e1, model_.stream);
+                model_.sync();
+                if (timed) { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); total_ms += ms; }
+                for (int b = 0; b < batch; ++b) last[b] = model_.h_out_ids[b];
+            }
+            cudaEventRecord(eb1, model_.stream); model_.sync();
+            float bracket_ms = 0; cudaEventElapsedTime(&bracket_ms, eb0, eb1);
+            const uint64_t launches1 = launches_total();
+            cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(eb0); cudaEventDestroy(eb1);
+            { std::lock_guard<std::mutex> lk(mu_); for (auto& pv : pages) for (int p : pv) free_pages_.push_back(p); }
+            const double mean_ctx = ctx_sum / steps;
+            out[0] = bracket_ms / steps; if (n_out > 6) out[6] = total_ms / steps; out[1] = prefill_ms; out[2] = (double)(launches1 - launches0) / steps; out[3] = mean_ctx;
+            out[4] = model_.profile_attn ? model_.attn_ms_accum / steps : 0.0;
+            // W_dec + sum ctx*KVB + B*KVB (the new token's KV write)
+            out[5] = model_.cfg.decode_weight_bytes() + (double)batch * mean_ctx * (double)model_.cfg.kv_bytes_per_token() +
+                     (double)batch * (double)model_.cfg.kv_bytes_per_token();
+        } catch (const std::exception& ex) { return fail(OA_ERR_INTERNAL, ex.what()); }
+        return OA_OK;
+    }
+
+    std::string stats_json() {
+        std::lock_guard<std::mutex> lk(mu_);
+        char b[1024];
+        std::snprintf(b, sizeof b,
+                      "{\"requests_completed\": %llu, \"prefill_tokens\": %llu, \"decode_tokens\": %llu, \"prefill_steps\": %llu, "
+                      "\"decode_steps\": %llu, \"preemptions\": %llu, \"pages_total\": %d, \"pages_free\": %zu, \"running\": %zu, "
+                      "\"waiting\": %zu, \"kernel_launches\": %llu, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"weight_bytes\": %zu, "
+                      "\"kv_pool_bytes\": %zu, \"busy_ms\": %.3f}",
+                      (unsigned long long)n_completed_, (unsigned long long)n_prefill_tokens_, (unsigned long long)n_decode_tokens_,
+                      (unsigned long long)n_prefill_steps_, (unsigned long long)n_decode_steps_, (unsigned long long)n_preempt_,
+                      model_.num_pages, free_pages_.size(), running_.size(), waiting_.size(), (unsigned long long)launches_total(),
+                      (unsigned long long)model_.h2d_bytes, (unsigned long long)model_.d2h_bytes, model_.weight_bytes, model_.kv_pool_bytes, busy_ms_);
+        return b;
+    }
+    std::string info_json() {
+        const ModelConfig& c = model_.cfg; char b[1024];
+        std::snprintf(b, sizeof b,
+                      "{\"model\": \"%s\", \"hidden\": %d, \"n_layers\": %d, \"n_heads\": %d, \"n_kv_heads\": %d, \"head_dim\": %d, \"ffn\": %d, "
+                      "\"vocab\": %d, \"tie_embeddings\": %d, \"qkv_bias\": %d, \"rope_scaling\": %d, \"rope_theta\": %.1f, \"rms_eps\": %g, "
+                      "\"template\": \"%s\", \"seed\": %llu, \"num_pages\": %d, \"page_size\": 64, \"max_seq_len\": %d, \"max_batch\": %d, "
+                      "\"sm_count\": %d, \"decode_weight_bytes\": %.0f, \"kv_bytes_per_token\": %zu}",
+                      c.name.c_str(), c.hidden, c.n_layers, c.n_heads, c.n_kv_heads, c.head_dim, c.ffn, c.vocab, c.tie_embeddings, c.qkv_bias,
+                      c.rope_scaling, c.rope_theta, c.rms_eps, c.chat_template.c_str(), (unsigned long long)c.seed, model_.num_pages,
+                      opt_.max_seq_len, opt_.max_batch, model_.sm_count, c.decode_weight_bytes(), c.kv_bytes_per_token());
+        return b;
+    }
+    const Tokenizer& tokenizer() const { return tok_; }
+    const ModelConfig& config() const { return model_.cfg; }
+    DeviceModel& model() { return model_; }
+
+private:
+    bool alloc_pages_locked(std::vector<int32_t>& dst, int n) {
+        if ((int)free_pages_.size() < n) return false;
+        for (int i = 0; i < n; ++i) { dst.push_back(free_pages_.back()); free_pages_.pop_back(); }
+        return true;
+    }
+    void finish_locked(const std::shared_ptr<Seq>& s, int reason) {
+        s->finish_reason = reason; s->state = SeqState::DONE; s->done = true;
+        for (int p : s->pages) free_pages_.push_back(p);
+        s->pages.clear(); ++n_completed_;
+    }
+    // Accept a sampled token for s (called with mu_ held). Returns true if the sequence finished.
+    bool accept_token_locked(const std::shared_ptr<Seq>& s, int32_t t) {
+        const bool eos = tok_.is_eos(t) && !(s->flags & OA_FLAG_IGNORE_EOS);
+        if (eos) { finish_locked(s, 0); return true; }
+        s->tokens.push_back(t); ++s->n_generated;
+        if (s->n_generated >= s->max_new || (int)s->tokens.size() >= opt_.max_seq_len) { finish_locked(s, 1); return true; }
+        return false;
+    }
+
+    void loop() {
+        cudaSetDevice(opt_.device);
+        while (true) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_work_.wait(lk, [&] { return stop_ || !waiting_.empty() || !running_.empty(); });
+                if (stop_) break;
+            }
+            std::lock_guard<std::mutex> step(step_mu_);
+            const auto t0 = std::chrono::steady_clock::now();
+            try { step_once(); }
+            catch (const std::exception& ex) {
+                std::lock_guard<std::mutex> lk(mu_);
+                fatal_ = true; fatal_msg_ = ex.what();
+                for (auto& s : running_) { s->error = OA_ERR_INTERNAL; s->error_msg = fatal_msg_; s->done = true; }
+                for (auto& s : waiting_) { s->error = OA_ERR_INTERNAL; s->error_msg = fatal_msg_; s->done = true; }
+                running_.clear(); waiting_.clear();
+                cv_done_.notify_all();
+            }
+            busy_ms_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
+    }
+
+    void step_once() {
+        std::vector<std::shared_ptr<Seq>> batch;      // sequences taking part in this forward
+        StepInput in;
+        std::vector<int> take_of;                       // prefill: tokens consumed per batch entry
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            // ---- admission: FIFO while pages for the whole current token list (+1) are free ----
+            while (!waiting_.empty() && (int)running_.size() < opt_.max_batch) {
+                auto& s = waiting_.front();
+                const int need = ((int)s->tokens.size() + 1 + 63) / 64;
+                if (need > model_.num_pages) { s->error = OA_ERR_BAD_REQUEST; s->error_msg = "request larger than the KV pool"; s->done = true; waiting_.pop_front(); cv_done_.notify_all(); continue; }
+                if (!alloc_pages_locked(s->pages, need)) break;
+                s->state = SeqState::PREFILL; s->n_cached = 0;
+                running_.push_back(s); waiting_.pop_front();
+            }
+            if (running_.empty()) return;
+            bool any_prefill = false;
+            for (auto& s : running_) if (s->state == SeqState::PREFILL) { any_prefill = true; break; }
+            if (any_prefill) {
+                in.decode = false;
+                int budget = opt_.max_step_tokens;
+                for (auto& s : running_) {
+                    if (s->state != SeqState::PREFILL || budget <= 0) continue;
+                    const int remaining = (int)s->tokens.size() - s->n_cached;
+                    const int take = std::min(remaining, budget);
+                    const int sidx = in.n_seqs++;
+                    in.block_tables.resize((size_t)in.n_seqs * model_.max_pages_per_seq, 0);
+                    for (size_t i = 0; i < s->pages.size(); ++i) in.block_tables[(size_t)sidx * model_.max_pages_per_seq + i] = s->pages[i];
+                    in.ctx_lens.push_back(s->n_cached + take);
+                    const int row0 = (int)in.tokens.size();
+                    for (int i = s->n_cached; i < s->n_cached + take; ++i) {
+                        in.tokens.push_back(s->tokens[i]); in.positions.push_back(i); in.slots.push_back(s->pages[i / 64] * 64 + i % 64);
+                    }
+                    for (int r = 0; r < take; r += 64) in.tiles.push_back(PrefillTile{sidx, row0 + r, s->n_cached + r, std::min(64, take - r)});
+                    if (take == remaining) in.sample_rows.push_back(row0 + take - 1);
+                    batch.push_back(s); take_of.push_back(take); budget -= take;
+                }
+            } else {
+                in.decode = true;
+                // every decoding sequence needs a slot for its newest token; preempt (recompute later) if the pool is dry
+                auto preempt = [&](const std::shared_ptr<Seq>& v) {
+                    for (int p : v->pages) free_pages_.push_back(p);
+                    v->pages.clear(); v->n_cached = 0; v->state = SeqState::WAITING;
+                    waiting_.push_front(v); ++n_preempt_;
+                };
+                for (size_t i = 0; i < running_.size();) {
+                    auto s = running_[i];
+                    const int pos = (int)s->tokens.size() - 1;
+                    if (pos / 64 >= (int)s->pages.size() && !alloc_pages_locked(s->pages, 1)) {
+                        auto victim = running_.back();          // most recently admitted
+                        running_.pop_back(); preempt(victim);
+                        continue;                                // retry slot i (or fall out if s itself was the victim)
+                    }
+                    ++i;
+                }
+                if (running_.empty()) return;
+                in.n_seqs = (int)running_.size();
+                in.block_tables.assign((size_t)in.n_seqs * model_.max_pages_per_seq, 0);
+                for (size_t b = 0; b < running_.size(); ++b) {
+                    auto& s = running_[b];
+                    const int pos = (int)s->tokens.size() - 1;
+                    for (size_t i = 0; i < s->pages.size(); ++i) in.block_tables[b * model_.max_pages_per_seq + i] = s->pages[i];
+                    in.tokens.push_back(s->tokens[pos]); in.positions.push_back(pos); in.slots.push_back(s->pages[pos / 64] * 64 + pos % 64);
+                    in.ctx_lens.push_back(pos + 1); in.sample_rows.push_back((int)b);
+                    batch.push_back(s);
+                }
+            }
+        }
+        model_.forward(in, nullptr);
+        model_.sync();
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            bool any_done = false;
+            if (in.decode) {
+                ++n_decode_steps_; n_decode_tokens_ += batch.size();
+                for (size_t b = 0; b < batch.size(); ++b) { batch[b]->n_cached = (int)batch[b]->tokens.size(); any_done |= accept_token_locked(batch[b], model_.h_out_ids[b]); }
+            } else {
+                ++n_prefill_steps_; n_prefill_tokens_ += in.tokens.size();
+                int si = 0;
+                for (size_t b = 0; b < batch.size(); ++b) {
+                    auto& s = batch[b];
+                    s->n_cached += take_of[b];
+                    if (s->n_cached == (int)s->tokens.size()) { s->state = SeqState::DECODE; any_done |= accept_token_locked(s, model_.h_out_ids[si++]); }
+                }
+            }
+            if (any_done) {
+                running_.erase(std::remove_if(running_.begin(), running_.end(), [](const std::shared_ptr<Seq>& s) { return s->done; }), running_.end());
+                cv_done_.notify_all();
+            }
+        }
+    }
+
+    DeviceModel model_; Tokenizer tok_; EngineOptions opt_;
+    std::mutex mu_, step_mu_;
+    std::condition_variable cv_work_, cv_done_;
+    std::deque<std::shared_ptr<Seq>> waiting_;
+    std::vector<std::shared_ptr<Seq>> running_;
+    std::unordered_map<uint64_t, std::shared_ptr<Seq>> by_ticket_;
+    std::vector<int32_t> free_pages_;
+    uint64_t next_ticket_ = 1;
+    bool stop_ = false, fatal_ = false; std::string fatal_msg_;
+    std::thread worker_;
+    uint64_t n_completed_ = 0, n_prefill_tokens_ = 0, n_decode_tokens_ = 0, n_prefill_steps_ = 0, n_decode_steps_ = 0, n_preempt_ = 0;
+    double busy_ms_ = 0;
+};
+
+}  // namespace oa
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace oa;
+struct oa_engine { std::unique_ptr<Engine> e; };
+
+static int build_messages(const oa_msg* msgs, int32_t n, std::vector<ChatMessage>& out) {
+    if (!msgs || n <= 0) return fail(OA_ERR_BAD_REQUEST, "prompts cannot be empty");   // simple.go:312 rejects empty prompts too
+    for (int i = 0; i < n; ++i) {
+        if (!msgs[i].role || !msgs[i].content) return fail(OA_ERR_BAD_REQUEST, "message role/content must be non-null");
+        out.push_back(ChatMessage{msgs[i].role, msgs[i].content});
+    }
+    return OA_OK;
+}
+
+extern "C" {
+
+int oa_engine_create(const char* config_json, oa_engine** out) {
+    if (!out) return fail(OA_ERR_BAD_REQUEST, "null out pointer");
+    *out = nullptr;
+    try {
+        ModelConfig mc; EngineOptions eo;
+        parse_config(config_json ? config_json : "{}", mc, eo);
+        int n_dev = 0;
+        if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0)
+            return fail(OA_ERR_INTERNAL, "no CUDA device: opsagent_b200 has no CPU fallback (the oracle under oracle/ is test-only)");
+        auto h = new oa_engine; h->e.reset(new Engine(mc, eo)); *out = h;
+    } catch (const std::exception& ex) { return fail(std::string(ex.what()).find("config json") == 0 || std::string(ex.what()).find("unknown model") == 0 ? OA_ERR_BAD_REQUEST : OA_ERR_INTERNAL, ex.what()); }
+    return OA_OK;
+}
+void oa_engine_destroy(oa_engine* h) { delete h; }
+
+static int submit_chat(oa_engine* h, const oa_chat_req* r, uint64_t* ticket) {
+    if (!h || !r || !ticket) return fail(OA_ERR_BAD_REQUEST, "null argument");
+    if (r->model && r->model[0] && h->e->config().name != r->model) return fail(OA_ERR_BAD_REQUEST, std::string("model '") + r->model + "' is not loaded (engine serves '" + h->e->config().name + "')");
+    if (r->temperature > 1e-3f) return fail(OA_ERR_BAD_REQUEST, "only greedy decoding is implemented (the reference sends temperature=SmallestNonzeroFloat32)");
+    std::vector<ChatMessage> msgs;
+    int rc = build_messages(r->msgs, r->n_msgs, msgs); if (rc) return rc;
+    return h->e->submit_tokens(h->e->tokenizer().apply_chat_template(msgs), r->max_tokens, r->flags, ticket);
+}
+int oa_chat_submit(oa_engine* h, const oa_chat_req* r, uint64_t* ticket) { return submit_chat(h, r, ticket); }
+int oa_chat_wait(oa_engine* h, uint64_t ticket, int32_t timeout_ms, oa_chat_resp* out) {
+    if (!h || !out) return fail(OA_ERR_BAD_REQUEST, "null argument");
+    std::memset(out, 0, sizeof *out);
+    return h->e->wait(ticket, timeout_ms, out);
+}
+int oa_chat_complete(oa_engine* h, const oa_chat_req* r, oa_chat_resp* out) {
+    uint64_t t = 0; int rc = submit_chat(h, r, &t); if (rc) return rc;
+    return oa_chat_wait(h, t, -1, out);
+}
+void oa_free_resp(oa_chat_resp* r) { if (!r) return; std::free(r->content); std::free(r->token_ids); std::memset(r, 0, sizeof *r); }
+
+int oa_tokens_submit(oa_engine* h, const int32_t* prompt, int32_t n, int32_t max_tokens, uint32_t flags, uint64_t* ticket) {
+    if (!h || !prompt || !ticket || n <= 0) return fail(OA_ERR_BAD_REQUEST, "null or empty prompt");
+    return h->e->submit_tokens(std::vector<int32_t>(prompt, prompt + n), max_tokens, flags, ticket);
+}
+int oa_count_tokens(oa_engine* h, const oa_msg* msgs, int32_t n, int32_t* out_tokens) {
+    if (!h || !out_tokens) return fail(OA_ERR_BAD_REQUEST, "null argument");
+    std::vector<ChatMessage> m; int rc = build_messages(msgs, n, m); if (rc) return rc;
+    *out_tokens = (int32_t)h->e->tokenizer().apply_chat_template(m).size();
+    return OA_OK;
+}
+int oa_apply_chat_template(oa_engine* h, const oa_msg* msgs, int32_t n, int32_t* out_ids, int32_t cap, int32_t* n_out) {
+    if (!h || !n_out) return fail(OA_ERR_BAD_REQUEST, "null argument");
+    std::vector<ChatMessage> m; int rc = build_messages(msgs, n, m); if (rc) return rc;
+    auto ids = h->e->tokenizer().apply_chat_template(m);
+    *n_out = (int32_t)ids.size();
+    if (out_ids) std::memcpy(out_ids, ids.data(), (size_t)std::min<int32_t>(cap, (int32_t)ids.size()) * 4);
+    return OA_OK;
+}
+const char* oa_last_error(void) { return g_last_error.c_str(); }
+static int copy_out(const std::string& s, char* buf, size_t n) {
+    if (!buf || n == 0) return fail(OA_ERR_BAD_REQUEST, "null buffer");
+    std::snprintf(buf, n, "%s", s.c_str()); return OA_OK;
+}
+int oa_engine_stats(oa_engine* h, char* buf, size_t n) { if (!h) return fail(OA_ERR_BAD_REQUEST, "null engine"); return copy_out(h->e->stats_json(), buf, n); }
+int oa_model_info(oa_engine* h, char* buf, size_t n) { if (!h) return fail(OA_ERR_BAD_REQUEST, "null engine"); return copy_out(h->e->info_json(), buf, n); }
+int oa_debug_prefill_logits(oa_engine* h, const int32_t* tokens, int32_t n, float* logits_out) {
+    if (!h || !tokens || !logits_out) return fail(OA_ERR_BAD_REQUEST, "null argument");
+    return h->e->debug_prefill_logits(tokens, n, logits_out);
+}
+int oa_bench_decode(oa_engine* h, int32_t batch, int32_t ctx_len, int32_t steps, int32_t warmup, double* out, int32_t n_out) {
+    if (!h || !out) return fail(OA_ERR_BAD_REQUEST, "null argument");
+    const char* pa = std::getenv("OA_PROFILE_ATTN");
+    h->e->model().profile_attn = pa && pa[0] == '1';
+    int rc = h->e->bench_decode(batch, ctx_len, steps, warmup, out, n_out);
+    h->e->model().profile_attn = false;
+    return rc;
+}
+uint64_t oa_kernel_launches(void) { return launches_total(); }
+const char* oa_version(void) { return "opsagent_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,276 @@
+// gemm_tcgen05.cu — C[M,N] = A[M,K] · B[N,K]^T for the QKV / O / gate-up / down / LM-head projections.
+//
+// sm_100a design (one CTA = one 128 x BLOCK_N output tile):
+//   warp 0   : TMA producer — cp.async.bulk.tensor 2D boxes {64 x 128} of A and {64 x BLOCK_N} of B into a
+//              STAGES-deep shared-memory ring (128-byte swizzle), completion on `full` mbarriers.
+//   warp 1   : allocates TMEM and issues tcgen05.mma (UMMA 128 x BLOCK_N x 16, bf16 -> fp32 in TMEM) from a
+//              single thread; tcgen05.commit releases ring slots (`empty`) and finally signals `acc_full`.
+//   warps 2-5: epilogue — tcgen05.ld the accumulator (thread = one output row, 32 columns per load), apply the
+//              fused epilogue (bias | residual add | SwiGLU | fp32 logits + row arg-max) and store.
+// Decode (M <= 128) is weight-streaming and HBM-bound: B tiles are fetched with an evict-first L2 policy, the
+// small A operand with evict-last.  K tails and M/N tails rely on TMA zero fill + predicated stores.
+//
+// The role of this file in the reference's terms: it is the arithmetic that sits behind
+// llms.OpenAIClient.Chat (reference pkg/llms/openai.go:69-104) once the `local-cuda` provider replaces the
+// remote HTTP server — see DESIGN.md §Kernels.
+#include "common.cuh"
+#include "kernels.hpp"
+
+namespace oa {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;     // 64 bf16 = 128 B = one swizzle row
+static constexpr int UMMA_K = 16;
+static constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;              // 16 KB
+    static constexpr int B_BYTES = BN * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    // fill ~200 KB / (CTAs per SM we want): small tiles keep several CTAs resident
+    static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 6 : (BN >= 64 ? 4 : 4));
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                      const __grid_constant__ CUtensorMap tmB,
+                                                                      const GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(acc_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
+                uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+                mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BLOCK_K, m_blk * BLOCK_M, kEvictLast);
+                tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BLOCK_K, n_blk * BN, kEvictFirst);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+            int s = 0; uint32_t ph = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[s], ph);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint64_t a_desc = umma_desc_sw128(a_addr);
+                const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
+                    umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);   // slot reusable once these MMAs have read it
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            umma_commit(acc_bar);             // accumulator complete
+        }
+    } else {
+        // ---------------- epilogue: warps 2..5, TMEM lane group = warp % 4 ----------------
+        const int q = warp & 3;
+        const int row = m_blk * BLOCK_M + q * 32 + lane;
+        const bool row_ok = row < p.M;
+        mbar_wait(acc_bar, 0);
+        tcgen05_fence_after();
+        float best_v = -INFINITY; int best_i = 0x7fffffff;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            tmem_ld_wait();
+            const int col0 = n_blk * BN + c;
+            if (EPI == EPI_STORE) {
+                if (row_ok) {
+                    uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + (size_t)row * p.ldo;
+                    const uint16_t* bias = reinterpret_cast<const uint16_t*>(p.bias);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        if (col0 + j < p.N) {
+                            float f[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]);
+                            if (bias) {
+                                uint4 bb = *reinterpret_cast<const uint4*>(bias + col0 + j);
+                                f[0] += bf16lo(bb.x); f[1] += bf16hi(bb.x); f[2] += bf16lo(bb.y); f[3] += bf16hi(bb.y);
+                                f[4] += bf16lo(bb.z); f[5] += bf16hi(bb.z); f[6] += bf16lo(bb.w); f[7] += bf16hi(bb.w);
+                            }
+                            uint4 o;
+                            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+                            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+                            *reinterpret_cast<uint4*>(orow + col0 + j) = o;
+                        }
+                    }
+                }
+            } else if (EPI == EPI_RESID) {
+                if (row_ok) {
+                    uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + (size_t)row * p.ldo;
+                    const uint16_t* rrow = reinterpret_cast<const uint16_t*>(p.resid) + (size_t)row * p.ldr;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        if (col0 + j < p.N) {
+                            uint4 rr = *reinterpret_cast<const uint4*>(rrow + col0 + j);
+                            uint4 o;
+                            o.x = pack_bf16x2(__uint_as_float(v[j + 0]) + bf16lo(rr.x), __uint_as_float(v[j + 1]) + bf16hi(rr.x));
+                            o.y = pack_bf16x2(__uint_as_float(v[j + 2]) + bf16lo(rr.y), __uint_as_float(v[j + 3]) + bf16hi(rr.y));
+                            o.z = pack_bf16x2(__uint_as_float(v[j + 4]) + bf16lo(rr.z), __uint_as_float(v[j + 5]) + bf16hi(rr.z));
+                            o.w = pack_bf16x2(__uint_as_float(v[j + 6]) + bf16lo(rr.w), __uint_as_float(v[j + 7]) + bf16hi(rr.w));
+                            *reinterpret_cast<uint4*>(orow + col0 + j) = o;
+                        }
+                    }
+                }
+            } else if (EPI == EPI_SWIGLU) {
+                // columns [c, c+16) = gate, [c+16, c+32) = up for output features (col0/2 .. col0/2+15)
+                if (row_ok && col0 < p.N) {
+                    uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + (size_t)row * p.ldo + (col0 >> 1);
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float g = __uint_as_float(v[i]), u = __uint_as_float(v[16 + i]);
+                        f[i] = __fdividef(g, 1.0f + __expf(-g)) * u;
+                    }
+                    uint4 o0, o1;
+                    o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]); o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
+                    o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]); o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                    *reinterpret_cast<uint4*>(orow) = o0;
+                    *reinterpret_cast<uint4*>(orow + 8) = o1;
+                }
+            } else {  // EPI_LOGITS
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float f = __uint_as_float(v[j]);
+                        if (col0 + j < p.N && f > best_v) { best_v = f; best_i = col0 + j; }
+                    }
+                    if (p.logits) {
+                        float* lrow = p.logits + (size_t)row * p.ldl;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (col0 + j < p.N)
+                                *reinterpret_cast<float4*>(lrow + col0 + j) =
+                                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        }
+                    }
+                }
+            }
+        }
+        if (EPI == EPI_LOGITS && row_ok) {
+            p.amax_val[(size_t)row * gridDim.x + n_blk] = best_v;
+            p.amax_idx[(size_t)row * gridDim.x + n_blk] = best_i;
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+int gemm_n_tiles(int N, int block_n) { return (N + block_n - 1) / block_n; }
+
+template <int BN, int EPI>
+static cudaError_t launch_one(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    auto kern = gemm_tcgen05_kernel<BN, EPI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid((p.N + BN - 1) / BN, (p.M + BLOCK_M - 1) / BLOCK_M, 1);
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*tmA, *tmB, p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int BN>
+static cudaError_t launch_bn(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int epi, cudaStream_t s) {
+    switch (epi) {
+        case EPI_STORE: return launch_one<BN, EPI_STORE>(tmA, tmB, p, s);
+        case EPI_RESID: return launch_one<BN, EPI_RESID>(tmA, tmB, p, s);
+        case EPI_SWIGLU: return launch_one<BN, EPI_SWIGLU>(tmA, tmB, p, s);
+        case EPI_LOGITS: return launch_one<BN, EPI_LOGITS>(tmA, tmB, p, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int epilogue, int block_n,
+                        cudaStream_t stream) {
+    if (p.M <= 0 || p.N <= 0 || p.K <= 0 || (p.N % 8) != 0 || (p.K % 8) != 0) return cudaErrorInvalidValue;
+    if (epilogue == EPI_SWIGLU && (p.N % 32) != 0) return cudaErrorInvalidValue;
+    switch (block_n) {
+        case 32: return launch_bn<32>(tmA, tmB, p, epilogue, stream);
+        case 64: return launch_bn<64>(tmA, tmB, p, epilogue, stream);
+        case 128: return launch_bn<128>(tmA, tmB, p, epilogue, stream);
+        case 256: return launch_bn<256>(tmA, tmB, p, epilogue, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void argmax_reduce_kernel(const float* __restrict__ val, const int* __restrict__ idx, int M, int n_tiles,
+                                     int32_t* __restrict__ out_ids, float* __restrict__ out_val) {
+    const int row = blockIdx.x;
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+        float v = val[(size_t)row * n_tiles + t]; int i = idx[(size_t)row * n_tiles + t];
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    __shared__ float sv[8]; __shared__ int si[8];
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
+        out_ids[row] = bi == 0x7fffffff ? 0 : bi;
+        if (out_val) out_val[row] = bv;
+    }
+}
+
+cudaError_t launch_argmax_reduce(const float* amax_val, const int* amax_idx, int M, int n_tiles, int32_t* out_ids,
+                                 float* out_val, cudaStream_t stream) {
+    argmax_reduce_kernel<<<M, 256, 0, stream>>>(amax_val, amax_idx, M, n_tiles, out_ids, out_val);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace oa

@@ -1,0 +1,100 @@
+// kernels.hpp — host-side launch API of the sm_100a kernels (csrc/*.cu).  Device pointers in,
+// cudaError_t out; every launcher is asynchronous on the given stream.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace oa {
+
+typedef uint16_t bf16_t;  // raw bf16 bits on the host side
+
+// ---- TMA descriptors (tma.cpp) --------------------------------------------------------------
+// 2D row-major bf16 tensor [rows, cols] with row pitch `pitch_elems`; box = {box_cols(<=64), box_rows(<=256)},
+// 128-byte swizzle.  Returns 0 on success (driver entry point resolved through the runtime, no -lcuda).
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                      uint32_t box_rows, uint32_t box_cols);
+
+// ---- GEMM (gemm_tcgen05.cu): C[M,N] = A[M,K] . B[N,K]^T, bf16 in, fp32 accumulate in TMEM -------
+enum GemmEpilogue : int {
+    EPI_STORE = 0,    // out[M,N] bf16 = acc (+ bias[N])
+    EPI_RESID = 1,    // out[M,N] bf16 = acc + resid[M,N]      (out may alias resid)
+    EPI_SWIGLU = 2,   // out[M,N/2] bf16 = silu(gate)*up, B rows interleaved 16 gate / 16 up
+    EPI_LOGITS = 3,   // per-row (max, argmax) partial per N-tile -> argmax_ws; optional fp32 logits store
+};
+struct GemmParams {
+    int M, N, K;
+    void* out; int ldo;             // bf16 output, leading dimension in elements
+    const void* bias;               // bf16 [N] or null        (EPI_STORE)
+    const void* resid; int ldr;     // bf16 [M, ldr]           (EPI_RESID)
+    float* logits; int ldl;         // optional fp32 [M, ldl]  (EPI_LOGITS)
+    float* amax_val; int* amax_idx; // [M, n_tiles]            (EPI_LOGITS)
+};
+// tmA: box {64, 128} over A[M,K]; tmB: box {64, block_n} over B[N,K].  block_n in {32,64,128,256}.
+cudaError_t launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int epilogue, int block_n,
+                        cudaStream_t stream);
+int gemm_n_tiles(int N, int block_n);
+// reduce EPI_LOGITS partials: out_ids[M] = argmax over n_tiles (ties -> lowest column index)
+cudaError_t launch_argmax_reduce(const float* amax_val, const int* amax_idx, int M, int n_tiles, int32_t* out_ids,
+                                 float* out_val, cudaStream_t stream);
+
+// ---- elementwise (elementwise.cu) -----------------------------------------------------------
+cudaError_t launch_embed_gather(const int32_t* ids, const void* table, void* out, int T, int H, int vocab, cudaStream_t s);
+cudaError_t launch_rmsnorm(const void* x, const void* gain, void* y, int T, int H, float eps, cudaStream_t s);
+// gather rows: out[i,:] = x[rows[i],:]
+cudaError_t launch_gather_rows(const void* x, const int32_t* rows, void* out, int n, int H, cudaStream_t s);
+// RoPE (HF rotate_half pairing) on q and k in `qkv` [T, (nh+2nkv)*D]; rotated q -> q_out [T, nh*D];
+// rotated k and v -> paged KV cache rows.  slot[t] = page*page_size + offset of token t.
+struct KvLayout {
+    void* base;            // bf16 rows of D elements
+    int64_t layer_stride_rows;   // rows between consecutive layers (= 2 * num_pages * nkv * page_size)
+    int64_t kv_stride_rows;      // rows between K and V planes of a layer (= num_pages * nkv * page_size)
+    int32_t page_size, n_kv, head_dim, num_pages;
+};
+cudaError_t launch_rope_kv_write(const void* qkv, const int32_t* positions, const int32_t* slots, const float* rope_cos,
+                                 const float* rope_sin, void* q_out, const KvLayout& kv, int layer, int T, int nh,
+                                 cudaStream_t s);
+
+// ---- weights (weights.cu): deterministic seeded init, bit-identical to oracle gen ----------------
+// logical tensor [rows, cols]; `interleave16_with` >= 0 means this is the fused gate/up tensor: physical
+// row r holds gate row (r/32)*16+r%16 when (r%32)<16 (tensor_id), else the same row of tensor `tensor_id_b`.
+cudaError_t launch_init_weight(void* dst, uint64_t seed, uint64_t tensor_id, int64_t tensor_id_b, int64_t rows, int64_t cols,
+                               float std, float mean, cudaStream_t s);
+
+// ---- attention (attention.cu) ----------------------------------------------------------------
+struct DecodeSeg {        // one contiguous piece of one (sequence, kv head) handled by one CTA
+    int32_t seq, kvh, chunk_begin, chunk_end;   // chunks of 64 tokens
+    int32_t partial_slot;                        // index into the partial workspace, or -1: single-piece, write final
+    int32_t pad0, pad1, pad2;
+};
+struct DecodeAttnParams {
+    const void* q;                 // bf16 [B, nh*D] (already rotated)
+    void* out;                     // bf16 [B, nh*D]
+    const int32_t* block_tables;   // [B, max_pages_per_seq]
+    const int32_t* ctx_lens;       // [B] tokens in cache including the current one
+    int32_t max_pages_per_seq;
+    const DecodeSeg* segs; const int32_t* cta_seg_ptr; int32_t n_ctas;   // CTA c runs segs[ptr[c] .. ptr[c+1])
+    float* part_o; float* part_ml; // partial workspace: [slots, group, D] fp32 and [slots, group, 2]
+    int32_t layer, n_heads, n_kv;
+    float scale_log2e;             // (1/sqrt(D)) * log2(e)
+};
+cudaError_t launch_decode_attention(const CUtensorMap* tm_kv, const KvLayout& kv, const DecodeAttnParams& p, cudaStream_t s);
+struct MergeItem { int32_t seq, kvh, slot_begin, n_slots; };
+cudaError_t launch_decode_merge(const MergeItem* items, int n_items, const float* part_o, const float* part_ml, void* out,
+                                int n_heads, int n_kv, int head_dim, cudaStream_t s);
+
+struct PrefillTile { int32_t seq, q_row0, pos0, n_rows; };  // 64 query rows max; q_row0 = row in the token batch
+struct PrefillAttnParams {
+    const void* q; void* out;      // bf16 [T, nh*D]
+    const int32_t* block_tables; int32_t max_pages_per_seq;
+    const PrefillTile* tiles; int32_t n_tiles;
+    int32_t layer, n_heads, n_kv;
+    float scale_log2e;
+};
+cudaError_t launch_prefill_attention(const CUtensorMap* tm_kv, const KvLayout& kv, const PrefillAttnParams& p, cudaStream_t s);
+
+// bookkeeping for bench.py's gpu_launches claim
+uint64_t launches_total();
+void count_launch();
+
+}  // namespace oa

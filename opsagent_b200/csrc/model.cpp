@@ -1,0 +1,333 @@
+// model.cpp — see model.hpp.
+#include "model.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+namespace oa {
+
+void cuda_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// tensor ids of the seeded generator: layer*16 + kind; globals at layer index n_layers (oracle/llama_ref.c)
+enum { T_WQ = 0, T_WK, T_WV, T_WO, T_WG, T_WU, T_WD, T_LN1, T_LN2, T_BQ, T_BK, T_BV };
+enum { TG_EMBED = 0, TG_NORM = 1, TG_LMHEAD = 2 };
+
+void* DeviceModel::dmalloc(size_t bytes) {
+    void* p = nullptr;
+    cuda_check(cudaMalloc(&p, bytes ? bytes : 16), "cudaMalloc");
+    allocs_.push_back(p);
+    return p;
+}
+
+void DeviceModel::make_weight_maps(WeightMat& w) {
+    const int bns[4] = {32, 64, 128, 256};
+    for (int i = 0; i < 4; ++i) {
+        int r = make_tmap_bf16_2d(&w.tm[i], w.ptr, (uint64_t)w.N, (uint64_t)w.K, (uint64_t)w.K, (uint32_t)bns[i], 64);
+        if (r != 0) throw std::runtime_error("cuTensorMapEncodeTiled failed for a weight matrix (code " + std::to_string(r) + ")");
+    }
+}
+void DeviceModel::alloc_weight(WeightMat& w, int N, int K) {
+    w.N = N; w.K = K; w.ptr = dmalloc((size_t)N * K * 2); weight_bytes += (size_t)N * K * 2;
+    make_weight_maps(w);
+}
+
+// Build the RoPE table exactly as oracle/llama_ref.c:oa_ref_rope_table does (double math, then cast).
+static void rope_table(const ModelConfig& c, int max_pos, std::vector<float>& cosv, std::vector<float>& sinv) {
+    const int half = c.head_dim / 2;
+    cosv.resize((size_t)max_pos * half); sinv.resize((size_t)max_pos * half);
+    for (int i = 0; i < half; ++i) {
+        double inv = std::pow((double)c.rope_theta, -2.0 * i / (double)c.head_dim);
+        if (c.rope_scaling == 1) {
+            double wavelen = 2.0 * M_PI / inv;
+            double low_wl = (double)c.rope_orig_ctx / c.rope_low_freq, high_wl = (double)c.rope_orig_ctx / c.rope_high_freq;
+            if (wavelen > low_wl) inv = inv / c.rope_factor;
+            else if (wavelen >= high_wl) {
+                double smooth = ((double)c.rope_orig_ctx / wavelen - c.rope_low_freq) / (c.rope_high_freq - c.rope_low_freq);
+                inv = (1.0 - smooth) * inv / c.rope_factor + smooth * inv;
+            }
+        }
+        for (int p = 0; p < max_pos; ++p) {
+            double a = (double)p * inv;
+            cosv[(size_t)p * half + i] = (float)std::cos(a); sinv[(size_t)p * half + i] = (float)std::sin(a);
+        }
+    }
+}
+
+DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c), opt(o) {
+    cuda_check(cudaSetDevice(opt.device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    cuda_check(cudaGetDeviceProperties(&prop, opt.device), "cudaGetDeviceProperties");
+    if (prop.major != 10) throw std::runtime_error("opsagent_b200 requires an sm_100 (Blackwell B200) device; found sm_" +
+                                                   std::to_string(prop.major) + std::to_string(prop.minor));
+    sm_count = prop.multiProcessorCount;
+    cuda_check(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    const int H = cfg.hidden, L = cfg.n_layers, F = cfg.ffn, V = cfg.vocab, D = cfg.head_dim;
+    const int qd = cfg.q_dim(), kd = cfg.kv_dim(), qkvd = cfg.qkv_dim();
+    const float nstd = cfg.norm_random ? 0.1f : 0.0f;
+
+    // ---- weights: seeded init directly in HBM, bit-identical to the oracle's generator ----
+    embed = dmalloc((size_t)V * H * 2); weight_bytes += (size_t)V * H * 2;
+    cuda_check(launch_init_weight(embed, cfg.seed, (uint64_t)L * 16 + TG_EMBED, -1, V, H, cfg.init_std, 0.f, stream), "init embed");
+    final_norm = dmalloc((size_t)H * 2);
+    cuda_check(launch_init_weight(final_norm, cfg.seed, (uint64_t)L * 16 + TG_NORM, -1, 1, H, nstd, 1.f, stream), "init norm");
+    if (cfg.tie_embeddings) { lm_head.ptr = embed; lm_head.N = V; lm_head.K = H; make_weight_maps(lm_head); }
+    else { alloc_weight(lm_head, V, H); cuda_check(launch_init_weight(lm_head.ptr, cfg.seed, (uint64_t)L * 16 + TG_LMHEAD, -1, V, H, cfg.init_std, 0.f, stream), "init lm_head"); }
+    layers.resize(L);
+    for (int l = 0; l < L; ++l) {
+        Layer& ly = layers[l]; const uint64_t b = (uint64_t)l * 16;
+        alloc_weight(ly.qkv, qkvd, H); alloc_weight(ly.o, H, qd); alloc_weight(ly.gu, 2 * F, H); alloc_weight(ly.down, H, F);
+        uint16_t* wq = reinterpret_cast<uint16_t*>(ly.qkv.ptr);
+        cuda_check(launch_init_weight(wq, cfg.seed, b + T_WQ, -1, qd, H, cfg.init_std, 0.f, stream), "init wq");
+        cuda_check(launch_init_weight(wq + (size_t)qd * H, cfg.seed, b + T_WK, -1, kd, H, cfg.init_std, 0.f, stream), "init wk");
+        cuda_check(launch_init_weight(wq + (size_t)(qd + kd) * H, cfg.seed, b + T_WV, -1, kd, H, cfg.init_std, 0.f, stream), "init wv");
+        cuda_check(launch_init_weight(ly.o.ptr, cfg.seed, b + T_WO, -1, H, qd, cfg.init_std, 0.f, stream), "init wo");
+        cuda_check(launch_init_weight(ly.gu.ptr, cfg.seed, b + T_WG, (int64_t)(b + T_WU), 2 * (int64_t)F, H, cfg.init_std, 0.f, stream), "init wgu");
+        cuda_check(launch_init_weight(ly.down.ptr, cfg.seed, b + T_WD, -1, H, F, cfg.init_std, 0.f, stream), "init wd");
+        ly.ln1 = dmalloc((size_t)H * 2); ly.ln2 = dmalloc((size_t)H * 2);
+        cuda_check(launch_init_weight(ly.ln1, cfg.seed, b + T_LN1, -1, 1, H, nstd, 1.f, stream), "init ln1");
+        cuda_check(launch_init_weight(ly.ln2, cfg.seed, b + T_LN2, -1, 1, H, nstd, 1.f, stream), "init ln2");
+        if (cfg.qkv_bias) {
+            ly.bqkv = dmalloc((size_t)qkvd * 2);
+            uint16_t* bq = reinterpret_cast<uint16_t*>(ly.bqkv);
+            cuda_check(launch_init_weight(bq, cfg.seed, b + T_BQ, -1, 1, qd, cfg.init_std, 0.f, stream), "init bq");
+            cuda_check(launch_init_weight(bq + qd, cfg.seed, b + T_BK, -1, 1, kd, cfg.init_std, 0.f, stream), "init bk");
+            cuda_check(launch_init_weight(bq + qd + kd, cfg.seed, b + T_BV, -1, 1, kd, cfg.init_std, 0.f, stream), "init bv");
+        }
+    }
+
+    // ---- RoPE table ----
+    {
+        std::vector<float> cs, sn; rope_table(cfg, opt.max_seq_len, cs, sn);
+        rope_cos = reinterpret_cast<float*>(dmalloc(cs.size() * 4)); rope_sin = reinterpret_cast<float*>(dmalloc(sn.size() * 4));
+        cuda_check(cudaMemcpyAsync(rope_cos, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice, stream), "rope cos");
+        cuda_check(cudaMemcpyAsync(rope_sin, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice, stream), "rope sin");
+        cuda_check(cudaStreamSynchronize(stream), "rope sync");
+    }
+
+    // ---- activations ----
+    max_rows_ = std::max(opt.max_step_tokens, opt.max_batch);
+    max_sample_ = std::max(opt.max_batch, std::min(max_rows_, 2048));
+    const int MR = max_rows_;
+    x_ = dmalloc((size_t)MR * H * 2); xn_ = dmalloc((size_t)MR * H * 2); qkv_ = dmalloc((size_t)MR * qkvd * 2);
+    q_ = dmalloc((size_t)MR * qd * 2); attn_ = dmalloc((size_t)MR * qd * 2); act_ = dmalloc((size_t)MR * F * 2);
+    cuda_check(cudaMemsetAsync(xn_, 0, (size_t)MR * H * 2, stream), "memset");
+    cuda_check(cudaMemsetAsync(attn_, 0, (size_t)MR * qd * 2, stream), "memset");
+    cuda_check(cudaMemsetAsync(act_, 0, (size_t)MR * F * 2, stream), "memset");
+    auto amap = [&](CUtensorMap* tm, void* p, int rows, int cols) {
+        int r = make_tmap_bf16_2d(tm, p, (uint64_t)rows, (uint64_t)cols, (uint64_t)cols, 128, 64);
+        if (r != 0) throw std::runtime_error("cuTensorMapEncodeTiled failed for an activation buffer (code " + std::to_string(r) + ")");
+    };
+    amap(&tm_xn_, xn_, MR, H); amap(&tm_attn_, attn_, MR, qd); amap(&tm_act_, act_, MR, F);
+    // sampled rows (debug logits sample every row of a short prefill: up to 2048)
+    const int MS = max_sample_;
+    xs_ = dmalloc((size_t)MS * H * 2); xsn_ = dmalloc((size_t)MS * H * 2);
+    cuda_check(cudaMemsetAsync(xsn_, 0, (size_t)MS * H * 2, stream), "memset");
+    amap(&tm_xsn_, xsn_, MS, H);
+    const int lm_tiles_max = gemm_n_tiles(V, 32);
+    amax_val_ = reinterpret_cast<float*>(dmalloc((size_t)MS * lm_tiles_max * 4));
+    amax_idx_ = reinterpret_cast<int*>(dmalloc((size_t)MS * lm_tiles_max * 4));
+    d_out_ids_ = reinterpret_cast<int32_t*>(dmalloc((size_t)MS * 4));
+    cuda_check(cudaMallocHost(&h_out_ids, (size_t)MS * 4), "cudaMallocHost");
+
+    // ---- paged KV pool ----
+    const size_t page_bytes = (size_t)2 * L * cfg.n_kv_heads * 64 * D * 2;    // all layers, K and V, of 64 tokens
+    if (opt.num_pages > 0) num_pages = opt.num_pages;
+    else {
+        size_t free_b = 0, total_b = 0;
+        cuda_check(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
+        double budget = opt.kv_gb > 0 ? opt.kv_gb * 1e9 : (double)free_b - 6e9;
+        budget = std::min(budget, (double)free_b - 2e9);
+        num_pages = (int)std::max(0.0, budget / (double)page_bytes);
+    }
+    max_pages_per_seq = opt.max_seq_len / 64;
+    if (num_pages < max_pages_per_seq) throw std::runtime_error("KV pool too small: " + std::to_string(num_pages) + " pages < one max-length sequence");
+    const int64_t plane_rows = (int64_t)num_pages * cfg.n_kv_heads * 64;
+    if ((double)plane_rows * 2 * L >= 2147483647.0) { num_pages = (int)(2147483647.0 / (2.0 * L * cfg.n_kv_heads * 64)) - 1; }
+    kv.page_size = 64; kv.n_kv = cfg.n_kv_heads; kv.head_dim = D; kv.num_pages = num_pages;
+    kv.kv_stride_rows = (int64_t)num_pages * cfg.n_kv_heads * 64; kv.layer_stride_rows = 2 * kv.kv_stride_rows;
+    kv_pool_bytes = (size_t)num_pages * page_bytes;
+    kv.base = dmalloc(kv_pool_bytes);
+    cuda_check(cudaMemsetAsync(kv.base, 0, kv_pool_bytes, stream), "kv memset");   // stale pages must hold finite values (0*NaN)
+    {
+        int r = make_tmap_bf16_2d(&tm_kv, kv.base, (uint64_t)kv.layer_stride_rows * L, (uint64_t)D, (uint64_t)D, 64, 64);
+        if (r != 0) throw std::runtime_error("cuTensorMapEncodeTiled failed for the KV pool (code " + std::to_string(r) + ")");
+    }
+
+    // ---- decode-attention partial workspace + per-step metadata arena ----
+    const int n_ctas = opt.attn_ctas > 0 ? opt.attn_ctas : 2 * sm_count;
+    max_part_slots_ = 2 * n_ctas + 2 * opt.max_batch * cfg.n_kv_heads + 16;
+    const int grp = cfg.n_heads / cfg.n_kv_heads;
+    part_o_ = reinterpret_cast<float*>(dmalloc((size_t)max_part_slots_ * grp * D * 4));
+    part_ml_ = reinterpret_cast<float*>(dmalloc((size_t)max_part_slots_ * grp * 2 * 4));
+    meta_cap_words_ = (size_t)4 * MR + (size_t)opt.max_batch * (max_pages_per_seq + 2) + (size_t)MR / 64 * 4 + 4 * opt.max_batch +
+                      (size_t)(opt.max_batch * cfg.n_kv_heads + n_ctas + 8) * 8 * 2 + (size_t)n_ctas + 4096;
+    cuda_check(cudaMallocHost(&h_meta_, meta_cap_words_ * 4), "cudaMallocHost meta");
+    d_meta_ = reinterpret_cast<int32_t*>(dmalloc(meta_cap_words_ * 4));
+    ev.resize(2 * (size_t)L);
+    for (auto& e : ev) cuda_check(cudaEventCreate(&e), "cudaEventCreate");
+    cuda_check(cudaStreamSynchronize(stream), "init sync");
+}
+
+DeviceModel::~DeviceModel() {
+    cudaSetDevice(opt.device);
+    if (stream) cudaStreamSynchronize(stream);
+    for (auto& e : ev) cudaEventDestroy(e);
+    for (void* p : allocs_) cudaFree(p);
+    if (h_out_ids) cudaFreeHost(h_out_ids);
+    if (h_meta_) cudaFreeHost(h_meta_);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+void DeviceModel::sync() { cuda_check(cudaStreamSynchronize(stream), "stream sync"); }
+
+// N-tile heuristic.  Decode (M <= 128) streams weights once: prefer the largest tile that still yields >= 1 CTA
+// per SM; prefill has M/128 row tiles as well, so the widest tile (least A re-reads) wins.
+int DeviceModel::pick_bn(int M, int N, int override_bn, bool swiglu) const {
+    if (override_bn == 32 || override_bn == 64 || override_bn == 128 || override_bn == 256) return override_bn;
+    const int m_tiles = (M + 127) / 128;
+    const int cands[4] = {256, 128, 64, 32};
+    for (int bn : cands) { if ((long long)((N + bn - 1) / bn) * m_tiles >= sm_count) return bn; }
+    (void)swiglu;
+    return 32;
+}
+
+void build_decode_plan(const int32_t* ctx_lens, int n_seqs, int n_kv, int n_ctas_target, int force_splits, DecodePlan& out) {
+    out.segs.clear(); out.cta_ptr.clear(); out.merges.clear(); out.n_slots = 0;
+    long long total = 0;
+    for (int i = 0; i < n_seqs; ++i) total += (long long)((ctx_lens[i] + 63) / 64) * n_kv;
+    if (total <= 0) { out.cta_ptr.push_back(0); return; }
+    if (force_splits > 0) {
+        // test mode: every (seq, kvh) item is cut into `force_splits` pieces, one CTA per piece
+        out.cta_ptr.push_back(0);
+        for (int s = 0; s < n_seqs; ++s) for (int h = 0; h < n_kv; ++h) {
+            const int nch = (ctx_lens[s] + 63) / 64; if (nch == 0) continue;
+            const int pieces = std::min(force_splits, nch), per = (nch + pieces - 1) / pieces;
+            const int real = (nch + per - 1) / per;
+            MergeItem mi{s, h, out.n_slots, real};
+            for (int pz = 0; pz < real; ++pz) {
+                DecodeSeg sg{s, h, pz * per, std::min(nch, (pz + 1) * per), real > 1 ? out.n_slots++ : -1, 0, 0, 0};
+                out.segs.push_back(sg); out.cta_ptr.push_back((int32_t)out.segs.size());
+            }
+            if (real > 1) out.merges.push_back(mi);
+        }
+        return;
+    }
+    long long n_ctas = std::min<long long>(n_ctas_target, std::max<long long>(1, total / 2));
+    const long long per = (total + n_ctas - 1) / n_ctas;
+    n_ctas = (total + per - 1) / per;
+    out.cta_ptr.assign((size_t)n_ctas + 1, 0);
+    long long gpos = 0;   // global chunk cursor
+    std::vector<int> cta_of_seg;
+    for (int s = 0; s < n_seqs; ++s) for (int h = 0; h < n_kv; ++h) {
+        const int nch = (ctx_lens[s] + 63) / 64; if (nch == 0) continue;
+        const long long g0 = gpos, g1 = gpos + nch;
+        const long long c_first = g0 / per, c_last = (g1 - 1) / per;
+        const int pieces = (int)(c_last - c_first + 1);
+        MergeItem mi{s, h, out.n_slots, pieces};
+        for (long long c = c_first; c <= c_last; ++c) {
+            const long long a = std::max(g0, c * per), b = std::min(g1, (c + 1) * per);
+            DecodeSeg sg{s, h, (int32_t)(a - g0), (int32_t)(b - g0), pieces > 1 ? out.n_slots++ : -1, 0, 0, 0};
+            out.segs.push_back(sg); cta_of_seg.push_back((int)c);
+        }
+        if (pieces > 1) out.merges.push_back(mi);
+        gpos = g1;
+    }
+    // segs are already ordered by CTA; build the CSR pointer
+    size_t k = 0;
+    for (long long c = 0; c < n_ctas; ++c) {
+        out.cta_ptr[(size_t)c] = (int32_t)k;
+        while (k < cta_of_seg.size() && cta_of_seg[k] == c) ++k;
+    }
+    out.cta_ptr[(size_t)n_ctas] = (int32_t)k;
+}
+
+void DeviceModel::forward(const StepInput& in, float* logits_out) {
+    const int T = (int)in.tokens.size(), S = (int)in.sample_rows.size();
+    const int H = cfg.hidden, L = cfg.n_layers, F = cfg.ffn, V = cfg.vocab, D = cfg.head_dim;
+    const int qd = cfg.q_dim(), qkvd = cfg.qkv_dim(), nh = cfg.n_heads, nkv = cfg.n_kv_heads;
+    if (T <= 0 || T > max_rows_ || S > max_sample_) throw std::runtime_error("forward: bad batch size");
+    if (in.decode && in.n_seqs != T) throw std::runtime_error("forward: decode needs one token per sequence");
+
+    // ---- pack per-step metadata into one pinned arena, one H2D copy ----
+    size_t w = 0;
+    auto put = [&](const void* src, size_t words) -> size_t {
+        size_t at = w; if (at + words > meta_cap_words_) throw std::runtime_error("forward: metadata arena overflow");
+        if (words) std::memcpy(h_meta_ + at, src, words * 4);
+        w = (at + words + 3) & ~size_t(3); return at;
+    };
+    const size_t o_tok = put(in.tokens.data(), T), o_pos = put(in.positions.data(), T), o_slot = put(in.slots.data(), T);
+    const size_t o_samp = put(in.sample_rows.data(), S);
+    const size_t o_bt = put(in.block_tables.data(), in.block_tables.size());
+    const size_t o_ctx = put(in.ctx_lens.data(), in.ctx_lens.size());
+    size_t o_segs = 0, o_ptr = 0, o_merge = 0, o_tiles = 0;
+    if (in.decode) {
+        const int n_ctas = opt.attn_ctas > 0 ? opt.attn_ctas : 2 * sm_count;
+        build_decode_plan(in.ctx_lens.data(), in.n_seqs, nkv, n_ctas, 0, plan_);
+        if (plan_.n_slots > max_part_slots_) throw std::runtime_error("forward: partial workspace overflow");
+        o_segs = put(plan_.segs.data(), plan_.segs.size() * 8);
+        o_ptr = put(plan_.cta_ptr.data(), plan_.cta_ptr.size());
+        o_merge = put(plan_.merges.data(), plan_.merges.size() * 4);
+    } else {
+        o_tiles = put(in.tiles.data(), in.tiles.size() * 4);
+    }
+    cuda_check(cudaMemcpyAsync(d_meta_, h_meta_, w * 4, cudaMemcpyHostToDevice, stream), "meta H2D");
+    h2d_bytes += w * 4;
+    const int32_t* d_tok = d_meta_ + o_tok; const int32_t* d_pos = d_meta_ + o_pos; const int32_t* d_slot = d_meta_ + o_slot;
+    const int32_t* d_samp = d_meta_ + o_samp; const int32_t* d_bt = d_meta_ + o_bt; const int32_t* d_ctx = d_meta_ + o_ctx;
+
+    const float scale_log2e = (1.0f / std::sqrt((float)D)) * 1.4426950408889634f;
+    cuda_check(launch_embed_gather(d_tok, embed, x_, T, H, V, stream), "embed");
+    const int bn_qkv = pick_bn(T, qkvd, opt.bn_qkv, false), bn_o = pick_bn(T, H, opt.bn_o, false);
+    const int bn_gu = pick_bn(T, 2 * F, opt.bn_gu, true), bn_down = pick_bn(T, H, opt.bn_down, false);
+    for (int l = 0; l < L; ++l) {
+        const Layer& ly = layers[l];
+        cuda_check(launch_rmsnorm(x_, ly.ln1, xn_, T, H, cfg.rms_eps, stream), "rmsnorm1");
+        GemmParams g{}; g.M = T; g.N = qkvd; g.K = H; g.out = qkv_; g.ldo = qkvd; g.bias = ly.bqkv;
+        cuda_check(launch_gemm(&tm_xn_, ly.qkv.map(bn_qkv), g, EPI_STORE, bn_qkv, stream), "qkv gemm");
+        cuda_check(launch_rope_kv_write(qkv_, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, T, nh, stream), "rope");
+        if (profile_attn) cudaEventRecord(ev[2 * l], stream);
+        if (in.decode) {
+            DecodeAttnParams a{}; a.q = q_; a.out = attn_; a.block_tables = d_bt; a.ctx_lens = d_ctx; a.max_pages_per_seq = max_pages_per_seq;
+            a.segs = reinterpret_cast<const DecodeSeg*>(d_meta_ + o_segs); a.cta_seg_ptr = d_meta_ + o_ptr; a.n_ctas = (int)plan_.cta_ptr.size() - 1;
+            a.part_o = part_o_; a.part_ml = part_ml_; a.layer = l; a.n_heads = nh; a.n_kv = nkv; a.scale_log2e = scale_log2e;
+            cuda_check(launch_decode_attention(&tm_kv, kv, a, stream), "decode attention");
+            cuda_check(launch_decode_merge(reinterpret_cast<const MergeItem*>(d_meta_ + o_merge), (int)plan_.merges.size(), part_o_, part_ml_,
+                                           attn_, nh, nkv, D, stream), "decode merge");
+        } else {
+            PrefillAttnParams a{}; a.q = q_; a.out = attn_; a.block_tables = d_bt; a.max_pages_per_seq = max_pages_per_seq;
+            a.tiles = reinterpret_cast<const PrefillTile*>(d_meta_ + o_tiles); a.n_tiles = (int)in.tiles.size();
+            a.layer = l; a.n_heads = nh; a.n_kv = nkv; a.scale_log2e = scale_log2e;
+            cuda_check(launch_prefill_attention(&tm_kv, kv, a, stream), "prefill attention");
+        }
+        if (profile_attn) cudaEventRecord(ev[2 * l + 1], stream);
+        GemmParams go{}; go.M = T; go.N = H; go.K = qd; go.out = x_; go.ldo = H; go.resid = x_; go.ldr = H;
+        cuda_check(launch_gemm(&tm_attn_, ly.o.map(bn_o), go, EPI_RESID, bn_o, stream), "o gemm");
+        cuda_check(launch_rmsnorm(x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "rmsnorm2");
+        GemmParams gg{}; gg.M = T; gg.N = 2 * F; gg.K = H; gg.out = act_; gg.ldo = F;
+        cuda_check(launch_gemm(&tm_xn_, ly.gu.map(bn_gu), gg, EPI_SWIGLU, bn_gu, stream), "gate_up gemm");
+        GemmParams gd{}; gd.M = T; gd.N = H; gd.K = F; gd.out = x_; gd.ldo = H; gd.resid = x_; gd.ldr = H;
+        cuda_check(launch_gemm(&tm_act_, ly.down.map(bn_down), gd, EPI_RESID, bn_down, stream), "down gemm");
+    }
+    if (S > 0) {
+        cuda_check(launch_gather_rows(x_, d_samp, xs_, S, H, stream), "gather");
+        cuda_check(launch_rmsnorm(xs_, final_norm, xsn_, S, H, cfg.rms_eps, stream), "final norm");
+        const int bn_lm = pick_bn(S, V, opt.bn_lm, false);
+        const int n_tiles = gemm_n_tiles(V, bn_lm);
+        GemmParams gl{}; gl.M = S; gl.N = V; gl.K = H; gl.logits = logits_out; gl.ldl = V; gl.amax_val = amax_val_; gl.amax_idx = amax_idx_;
+        cuda_check(launch_gemm(&tm_xsn_, lm_head.map(bn_lm), gl, EPI_LOGITS, bn_lm, stream), "lm_head gemm");
+        cuda_check(launch_argmax_reduce(amax_val_, amax_idx_, S, n_tiles, d_out_ids_, nullptr, stream), "argmax");
+        cuda_check(cudaMemcpyAsync(h_out_ids, d_out_ids_, (size_t)S * 4, cudaMemcpyDeviceToHost, stream), "ids D2H");
+        d2h_bytes += (size_t)S * 4;
+    }
+    if (profile_attn) {
+        cuda_check(cudaStreamSynchronize(stream), "profile sync");
+        for (int l = 0; l < L; ++l) { float ms = 0; cudaEventElapsedTime(&ms, ev[2 * l], ev[2 * l + 1]); attn_ms_accum += ms; }
+    }
+}
+
+}  // namespace oa

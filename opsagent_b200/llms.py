@@ -1,0 +1,86 @@
+"""llms — Python host-side mirror of the reference's LLM seam (reference pkg/llms/openai.go).
+
+``LocalCUDAClient.Chat(model, max_tokens, prompts) -> str`` has the signature, return value and error
+behaviour of ``(*OpenAIClient).Chat`` (openai.go:69-104); instead of POSTing to a remote
+/chat/completions it calls the in-process sm_100a engine through the C ABI.  The Go binding a
+maintainer would add is shown in INTEGRATION.md (Go is not available in this image).
+
+Behaviour kept from the reference:
+  * NewOpenAIClient rejects an empty apiKey with "OPENAI_API_KEY is not set"       (openai.go:40-42);
+    the local provider accepts and ignores any non-empty key.
+  * Retries = 5, Backoff = 1 s doubling after every 429/500                          (openai.go:57-60,91-94)
+  * 401 -> fail at once; 429/500 -> sleep + retry; anything else -> fail at once     (openai.go:85-101)
+  * after the last retry: "OpenAI request throttled after retrying 5 times"          (openai.go:103)
+  * temperature = math.SmallestNonzeroFloat32 (greedy)                               (openai.go:73)
+  * the result is Choices[0].Message.Content                                         (openai.go:82)
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+
+from . import _lib
+from .engine import Engine, EngineError
+
+ChatMessageRoleSystem, ChatMessageRoleUser, ChatMessageRoleAssistant = "system", "user", "assistant"
+
+
+@dataclass
+class ChatCompletionMessage:        # go-openai ChatCompletionMessage{Role, Content}
+    Role: str
+    Content: str
+
+
+class APIError(Exception):          # go-openai *APIError{HTTPStatusCode, Message}
+    def __init__(self, status: int, message: str):
+        super().__init__(f"error, status code: {status}, message: {message}")
+        self.HTTPStatusCode, self.Message = status, message
+
+
+class LocalCUDAClient:
+    """Drop-in for llms.OpenAIClient: same fields (Retries, Backoff), same Chat()."""
+
+    def __init__(self, engine: Engine, retries: int = 5, backoff: float = 1.0, sleep=time.sleep):
+        self.engine, self.Retries, self.Backoff, self._sleep = engine, retries, backoff, sleep
+
+    def _create_chat_completion(self, model: str, max_tokens: int, prompts) -> str:
+        msgs = [(m.Role, m.Content) if isinstance(m, ChatCompletionMessage) else (m["role"], m["content"]) for m in prompts]
+        try:
+            return self.engine.chat_complete(model, msgs, max_tokens).content.decode("utf-8", "replace")
+        except EngineError as e:
+            raise APIError(e.code, e.message) from None
+
+    def Chat(self, model: str, maxTokens: int, prompts) -> str:
+        backoff = self.Backoff
+        for _try in range(self.Retries):
+            try:
+                return self._create_chat_completion(model, maxTokens, prompts)
+            except APIError as e:
+                if e.HTTPStatusCode == 401:
+                    raise
+                if e.HTTPStatusCode in (429, 500):
+                    self._sleep(backoff)
+                    backoff *= 2
+                    continue
+                raise
+        raise RuntimeError(f"OpenAI request throttled after retrying {self.Retries} times")
+
+
+_ENGINES: dict = {}
+
+
+def new_client(api_key: str, base_url: str, engine: Engine | None = None, engine_config: dict | None = None) -> LocalCUDAClient:
+    """Mirror of NewOpenAIClient(apiKey, baseURL).  base_url ``cuda://<model>`` (or an explicit engine)
+    selects the local provider; the engine handle is a process singleton per base_url because the
+    reference constructs a client per request (pkg/assistants/simple.go:316)."""
+    if api_key == "":
+        raise ValueError("OPENAI_API_KEY is not set")
+    if engine is None:
+        if not base_url.startswith("cuda://"):
+            raise ValueError("only the local-cuda provider is implemented here: base_url must be cuda://<model>")
+        if base_url not in _ENGINES:
+            cfg = dict(engine_config or {})
+            cfg.setdefault("model", base_url[len("cuda://"):])
+            _ENGINES[base_url] = Engine(cfg)
+        engine = _ENGINES[base_url]
+    return LocalCUDAClient(engine)

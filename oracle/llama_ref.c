@@ -63,14 +63,15 @@ static inline uint64_t mix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 /* Irwin-Hall(4) of 16-bit uniforms: mean 131070, std 65536*sqrt(4/12)=37837.23 -> ~N(0,1) */
-static inline float gen_unit(uint64_t seed, uint64_t tensor_id, uint64_t idx) {
-    uint64_t h = mix64(mix64(seed ^ (tensor_id * 0xD6E8FEB86659FD93ull)) + idx);
+static inline uint64_t gen_key(uint64_t seed, uint64_t tensor_id) { return mix64(seed ^ (tensor_id * 0xD6E8FEB86659FD93ull)); }
+static inline float gen_unit_k(uint64_t key, uint64_t idx) {
+    uint64_t h = mix64(key + idx);
     int32_t s = (int32_t)(h & 0xffff) + (int32_t)((h >> 16) & 0xffff) +
                 (int32_t)((h >> 32) & 0xffff) + (int32_t)((h >> 48) & 0xffff) - 131070;
     return (float)s * (1.0f / 37837.227f);
 }
 REF_API uint16_t oa_ref_gen_bf16(uint64_t seed, uint64_t tensor_id, uint64_t idx, float std, float mean) {
-    return f32_to_bf16(gen_unit(seed, tensor_id, idx) * std + mean);
+    return f32_to_bf16(gen_unit_k(gen_key(seed, tensor_id), idx) * std + mean);
 }
 
 /* tensor ids: layer*16 + kind; globals use layer index = n_layers */
@@ -104,8 +105,9 @@ typedef struct {
 static uint16_t *gen_tensor(const ref_config *c, uint64_t tid, size_t n, float std, float mean) {
     uint16_t *p = (uint16_t *)malloc(n * sizeof(uint16_t));
     if (!p) { fprintf(stderr, "oracle: out of memory (%zu elems)\n", n); abort(); }
+    const uint64_t key = gen_key(c->seed, tid);
     #pragma omp parallel for schedule(static)
-    for (long long i = 0; i < (long long)n; ++i) p[i] = oa_ref_gen_bf16(c->seed, tid, (uint64_t)i, std, mean);
+    for (long long i = 0; i < (long long)n; ++i) p[i] = f32_to_bf16(gen_unit_k(key, (uint64_t)i) * std + mean);
     return p;
 }
 
