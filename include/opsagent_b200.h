@@ -110,6 +110,16 @@ OA_API int oa_k_init_weight(void* dst, uint64_t seed, uint64_t tensor_id, int64_
 OA_API int oa_k_paged_attention(const void* q, void* out, const void* kv_cache, int32_t num_pages, const int32_t* block_tables,
                          int32_t max_pages_per_seq, const int32_t* ctx_lens, const int32_t* q_lens, int32_t n_seqs,
                          int32_t n_heads, int32_t n_kv, int32_t head_dim, int32_t force_splits, void* stream);
+/* ---- host-only logic, callable without a GPU (CPU tests) ---- */
+/* chat template + tokenizer of the model described by config_json */
+OA_API int oa_host_apply_chat_template(const char* config_json, const oa_msg* msgs, int32_t n_msgs, int32_t* out_ids, int32_t cap, int32_t* n_out);
+/* decode-attention work plan: segs_out[cap_segs*5] = {seq, kvh, chunk_begin, chunk_end, partial_slot}, cta_ptr_out[n_ctas+1];
+ * returns the number of CTAs in *n_ctas_out and of segments in *n_segs_out */
+OA_API int oa_host_decode_plan(const int32_t* ctx_lens, int32_t n_seqs, int32_t n_kv, int32_t n_ctas_target, int32_t force_splits,
+                        int32_t* segs_out, int32_t cap_segs, int32_t* cta_ptr_out, int32_t cap_ctas, int32_t* n_ctas_out,
+                        int32_t* n_segs_out, int32_t* n_slots_out);
+/* resolved architecture + derived byte counts of a config, no device needed */
+OA_API int oa_host_model_info(const char* config_json, char* buf, size_t n);
 OA_API uint64_t oa_kernel_launches(void);
 OA_API const char* oa_version(void);
 

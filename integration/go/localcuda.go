@@ -1,0 +1,103 @@
+//go:build localcuda
+
+// Package llms — `local-cuda` provider: the in-process B200 engine behind the existing Chat seam.
+//
+// Drop this file into the reference at pkg/llms/localcuda.go and build with
+//     CGO_ENABLED=1 go build -tags localcuda ./cmd/kube-copilot        (the reference Dockerfile:17 uses CGO_ENABLED=0)
+// with CGO_CFLAGS=-I<repo>/include and CGO_LDFLAGS="-L<repo>/opsagent_b200/lib -lopsagent_b200".
+// It has NOT been compiled here (no Go toolchain in the build image); opsagent_b200/host/localcuda_client.hpp is the
+// compiled C++ twin with identical semantics, exercised by tests/test_host_cpp.py.
+package llms
+
+/*
+#include <stdlib.h>
+#include "opsagent_b200.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"math"
+	"sync"
+	"time"
+	"unsafe"
+
+	"github.com/sashabaranov/go-openai"
+)
+
+// LocalCUDAClient has the fields and the Chat method of OpenAIClient (openai.go:29-35,69).
+type LocalCUDAClient struct {
+	Retries int
+	Backoff time.Duration
+	engine  *C.oa_engine
+}
+
+var (
+	engineOnce sync.Once
+	engineInst *C.oa_engine
+	engineErr  error
+)
+
+// NewLocalCUDAClient mirrors NewOpenAIClient(apiKey, baseURL) (openai.go:38): it still demands a non-empty key so
+// callers (pkg/assistants/simple.go:316, pkg/handlers/execute.go:138) need no change; baseURL "cuda://llama-3-8b"
+// selects the model.  The engine is a process singleton because the reference builds a client per request.
+func NewLocalCUDAClient(apiKey string, baseURL string) (*LocalCUDAClient, error) {
+	if apiKey == "" {
+		return nil, fmt.Errorf("OPENAI_API_KEY is not set")
+	}
+	engineOnce.Do(func() {
+		model := "llama-3-8b"
+		if len(baseURL) > len("cuda://") {
+			model = baseURL[len("cuda://"):]
+		}
+		cfg := C.CString(fmt.Sprintf(`{"model": %q, "max_batch": 256, "max_seq_len": 16384}`, model))
+		defer C.free(unsafe.Pointer(cfg))
+		if rc := C.oa_engine_create(cfg, &engineInst); rc != 0 {
+			engineErr = fmt.Errorf("oa_engine_create: %d %s", int(rc), C.GoString(C.oa_last_error()))
+		}
+	})
+	if engineErr != nil {
+		return nil, engineErr
+	}
+	return &LocalCUDAClient{Retries: 5, Backoff: time.Second, engine: engineInst}, nil
+}
+
+// Chat — same signature and error behaviour as (*OpenAIClient).Chat (openai.go:69-104).  submit + wait keeps the
+// goroutine parked in one cgo call; many goroutines batch inside the engine (continuous batching).
+func (c *LocalCUDAClient) Chat(model string, maxTokens int, prompts []openai.ChatCompletionMessage) (string, error) {
+	msgs := (*[1 << 20]C.oa_msg)(C.malloc(C.size_t(len(prompts)) * C.size_t(unsafe.Sizeof(C.oa_msg{}))))[:len(prompts):len(prompts)]
+	defer C.free(unsafe.Pointer(&msgs[0]))
+	for i, p := range prompts {
+		msgs[i].role = C.CString(p.Role)
+		msgs[i].content = C.CString(p.Content)
+		defer C.free(unsafe.Pointer(msgs[i].role))
+		defer C.free(unsafe.Pointer(msgs[i].content))
+	}
+	cmodel := C.CString(model)
+	defer C.free(unsafe.Pointer(cmodel))
+	req := C.oa_chat_req{model: cmodel, msgs: &msgs[0], n_msgs: C.int32_t(len(prompts)), max_tokens: C.int32_t(maxTokens),
+		temperature: C.float(math.SmallestNonzeroFloat32)}
+
+	backoff := c.Backoff
+	for try := 0; try < c.Retries; try++ {
+		var resp C.oa_chat_resp
+		rc := int(C.oa_chat_complete(c.engine, &req, &resp))
+		if rc == 0 {
+			out := C.GoStringN(resp.content, C.int(resp.content_len))
+			C.oa_free_resp(&resp)
+			return out, nil
+		}
+		err := &openai.APIError{HTTPStatusCode: rc, Message: C.GoString(C.oa_last_error())}
+		switch rc {
+		case 401:
+			return "", err
+		case 429, 500:
+			time.Sleep(backoff)
+			backoff *= 2
+			continue
+		default:
+			return "", err
+		}
+	}
+	return "", fmt.Errorf("OpenAI request throttled after retrying %d times", c.Retries)
+}

@@ -1,12 +1,15 @@
 // capi_kernels.cpp — kernel-level C entry points on raw device pointers (parity tests drive these with
 // torch-allocated memory; nothing here is on the serving path).
+#include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/opsagent_b200.h"
 #include "model.hpp"
+#include "tokenizer.hpp"
 
 using namespace oa;
 
@@ -101,6 +104,47 @@ int oa_k_paged_attention(const void* q, void* out, const void* kv_cache, int32_t
     e = launch_prefill_attention(&tm, kv, a, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     return rc_of(e);
+}
+
+
+int oa_host_apply_chat_template(const char* config_json, const oa_msg* msgs, int32_t n_msgs, int32_t* out_ids, int32_t cap, int32_t* n_out) {
+    try {
+        ModelConfig mc; EngineOptions eo; parse_config(config_json ? config_json : "{}", mc, eo);
+        Tokenizer tok(mc);
+        std::vector<ChatMessage> m;
+        for (int i = 0; i < n_msgs; ++i) m.push_back(ChatMessage{msgs[i].role, msgs[i].content});
+        auto ids = tok.apply_chat_template(m);
+        *n_out = (int32_t)ids.size();
+        if (out_ids) std::memcpy(out_ids, ids.data(), (size_t)std::min<int32_t>(cap, (int32_t)ids.size()) * 4);
+    } catch (const std::exception&) { return OA_ERR_BAD_REQUEST; }
+    return OA_OK;
+}
+
+int oa_host_decode_plan(const int32_t* ctx_lens, int32_t n_seqs, int32_t n_kv, int32_t n_ctas_target, int32_t force_splits,
+                        int32_t* segs_out, int32_t cap_segs, int32_t* cta_ptr_out, int32_t cap_ctas, int32_t* n_ctas_out,
+                        int32_t* n_segs_out, int32_t* n_slots_out) {
+    DecodePlan plan;
+    build_decode_plan(ctx_lens, n_seqs, n_kv, n_ctas_target, force_splits, plan);
+    if ((int)plan.segs.size() > cap_segs || (int)plan.cta_ptr.size() > cap_ctas + 1) return OA_ERR_BAD_REQUEST;
+    for (size_t i = 0; i < plan.segs.size(); ++i) {
+        const DecodeSeg& g = plan.segs[i];
+        int32_t* o = segs_out + i * 5; o[0] = g.seq; o[1] = g.kvh; o[2] = g.chunk_begin; o[3] = g.chunk_end; o[4] = g.partial_slot;
+    }
+    std::memcpy(cta_ptr_out, plan.cta_ptr.data(), plan.cta_ptr.size() * 4);
+    *n_ctas_out = (int32_t)plan.cta_ptr.size() - 1; *n_segs_out = (int32_t)plan.segs.size(); *n_slots_out = plan.n_slots;
+    return OA_OK;
+}
+
+int oa_host_model_info(const char* config_json, char* buf, size_t n) {
+    try {
+        ModelConfig c; EngineOptions eo; parse_config(config_json ? config_json : "{}", c, eo);
+        std::snprintf(buf, n, "{\"model\": \"%s\", \"hidden\": %d, \"n_layers\": %d, \"n_heads\": %d, \"n_kv_heads\": %d, \"head_dim\": %d, "
+                      "\"ffn\": %d, \"vocab\": %d, \"tie_embeddings\": %d, \"qkv_bias\": %d, \"rope_scaling\": %d, \"rope_theta\": %.1f, "
+                      "\"rms_eps\": %g, \"template\": \"%s\", \"decode_weight_bytes\": %.0f, \"kv_bytes_per_token\": %zu}",
+                      c.name.c_str(), c.hidden, c.n_layers, c.n_heads, c.n_kv_heads, c.head_dim, c.ffn, c.vocab, c.tie_embeddings, c.qkv_bias,
+                      c.rope_scaling, c.rope_theta, c.rms_eps, c.chat_template.c_str(), c.decode_weight_bytes(), c.kv_bytes_per_token());
+    } catch (const std::exception&) { return OA_ERR_BAD_REQUEST; }
+    return OA_OK;
 }
 
 }  // extern "C"

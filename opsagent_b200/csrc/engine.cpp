@@ -17,6 +17,8 @@
 #include <thread>
 #include <unordered_map>
 
+#include <cuda_profiler_api.h>
+
 #include "../../include/opsagent_b200.h"
 #include "model.hpp"
 #include "tokenizer.hpp"
@@ -179,7 +181,10 @@ public:
                     in.tokens.push_back(last[b]); in.positions.push_back(pos); in.slots.push_back(pages[b][pos / 64] * 64 + pos % 64);
                     in.ctx_lens.push_back(pos + 1); in.sample_rows.push_back(b);
                 }
-                if (it == warmup) { launches0 = launches_total(); model_.attn_ms_accum = 0; cudaEventRecord(eb0, model_.stream); }
+                if (it == warmup) {
+                    if (std::getenv("OA_CUDA_PROFILER")) { model_.sync(); cudaProfilerStart(); }   // ncu --profile-from-start off
+                    launches0 = launches_total(); model_.attn_ms_accum = 0; cudaEventRecord(eb0, model_.stream);
+                }
                 const bool timed = it >= warmup;
                 if (timed) { cudaEventRecord(e0, model_.stream); ctx_sum += pos + 1; }
                 model_.forward(in, nullptr);
@@ -189,6 +194,7 @@ public:
                 for (int b = 0; b < batch; ++b) last[b] = model_.h_out_ids[b];
             }
             cudaEventRecord(eb1, model_.stream); model_.sync();
+            if (std::getenv("OA_CUDA_PROFILER")) cudaProfilerStop();
             float bracket_ms = 0; cudaEventElapsedTime(&bracket_ms, eb0, eb1);
             const uint64_t launches1 = launches_total();
             cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(eb0); cudaEventDestroy(eb1);

@@ -1,0 +1,183 @@
+"""Host-side logic on the CPU: chat template/tokenizer (C++ vs the oracle's Python restatement), decode work plan
+invariants, model presets, Chat() retry semantics of the Python mirror (reference pkg/llms/openai.go:69-104)."""
+import ctypes as C
+import json
+
+import numpy as np
+import pytest
+
+from opsagent_b200 import _lib
+from opsagent_b200.llms import LocalCUDAClient, APIError, ChatCompletionMessage, new_client
+from opsagent_b200.dp import shard_requests, replica_of
+from oracle import oracle as O
+
+
+def host_template(spec, msgs):
+    L = _lib.load()
+    arr = (_lib.OaMsg * len(msgs))()
+    keep = []
+    for i, (r, c) in enumerate(msgs):
+        rb, cb = r.encode(), c.encode(); keep += [rb, cb]
+        arr[i].role, arr[i].content = rb, cb
+    n = C.c_int32()
+    cfg = json.dumps(spec.engine_json()).encode()
+    assert L.oa_host_apply_chat_template(cfg, arr, len(msgs), None, 0, C.byref(n)) == 0
+    out = (C.c_int32 * n.value)()
+    assert L.oa_host_apply_chat_template(cfg, arr, len(msgs), out, n.value, C.byref(n)) == 0
+    return list(out)
+
+
+# the ReAct loop's message shapes: system+user seeds (pkg/handlers/execute.go:190-199), then assistant JSON +
+# user observation JSON per iteration (pkg/assistants/simple.go:358,496-501)
+CONVS = [
+    [("system", "你是Kubernetes和云原生网络的技术专家"), ("user", "how many namespace in the cluster?")],
+    [("system", "sys"), ("user", "q"), ("assistant", '{"question":"q","thought":"t","action":{"name":"kubectl","input":"get ns"}}'),
+     ("user", '{"question":"q","observation":"default\\nkube-system"}')],
+    [("user", "")],
+]
+
+
+@pytest.mark.parametrize("name", ["llama-3-8b", "llama-3.2-1b", "qwen2.5-32b", "llama-3-70b", "tiny-llama", "tiny-qwen"])
+@pytest.mark.parametrize("conv", CONVS)
+def test_chat_template_matches_restatement(name, conv):
+    spec = O.PRESETS[name]
+    ids = host_template(spec, conv)
+    assert ids == O.apply_chat_template(spec, conv)
+    assert all(0 <= t < spec.vocab for t in ids)
+
+
+def test_real_special_token_ids():
+    ids = host_template(O.PRESETS["llama-3-8b"], [("user", "hi")])
+    assert ids[0] == 128000 and ids[1] == 128006 and 128007 in ids and 128009 in ids
+    ids = host_template(O.PRESETS["qwen2.5-32b"], [("user", "hi")])
+    assert ids[0] == 151644 and 151645 in ids
+
+
+@pytest.mark.parametrize("name", ["llama-3.2-1b", "llama-3-8b", "qwen2.5-32b", "llama-3-70b"])
+def test_presets_agree_with_survey_table(name):
+    """SURVEY.md §8d model constants: W_dec GB and KV bytes/token"""
+    L = _lib.load()
+    buf = C.create_string_buffer(2048)
+    assert L.oa_host_model_info(json.dumps({"model": name}).encode(), buf, 2048) == 0
+    info = json.loads(buf.value)
+    spec = O.PRESETS[name]
+    for k in ("hidden", "n_layers", "n_heads", "n_kv_heads", "head_dim", "ffn", "vocab", "tie_embeddings", "qkv_bias", "rope_scaling"):
+        assert info[k] == getattr(spec, k), k
+    expect = {"llama-3.2-1b": (2.472, 32768), "llama-3-8b": (15.010, 131072), "qwen2.5-32b": (63.971, 262144), "llama-3-70b": (139.006, 327680)}[name]
+    assert abs(info["decode_weight_bytes"] / 1e9 - expect[0]) < 0.02
+    assert info["kv_bytes_per_token"] == expect[1]
+
+
+def test_bad_configs_are_rejected():
+    L = _lib.load()
+    buf = C.create_string_buffer(512)
+    assert L.oa_host_model_info(b'{"model": "gpt-4"}', buf, 512) == 400
+    assert L.oa_host_model_info(b'{"model": "x", "hidden": 256, "n_layers": 1, "n_heads": 4, "n_kv_heads": 4, "head_dim": 32, "ffn": 512, "vocab": 1024}', buf, 512) == 400
+    assert L.oa_host_model_info(b'not json', buf, 512) == 400
+
+
+def plan(ctx, n_kv, n_ctas, force=0):
+    L = _lib.load()
+    ctx = np.ascontiguousarray(ctx, np.int32)
+    cap = len(ctx) * n_kv * 64 + n_ctas + 64
+    segs = np.zeros((cap, 5), np.int32); ptr = np.zeros(cap + 1, np.int32)
+    nc, ns, nsl = C.c_int32(), C.c_int32(), C.c_int32()
+    assert L.oa_host_decode_plan(ctx.ctypes.data, len(ctx), n_kv, n_ctas, force, segs.ctypes.data, cap, ptr.ctypes.data, cap,
+                                 C.byref(nc), C.byref(ns), C.byref(nsl)) == 0
+    return segs[:ns.value], ptr[:nc.value + 1], nsl.value
+
+
+@pytest.mark.parametrize("ctx,n_kv,n_ctas,force", [
+    ([1664] * 128, 8, 296, 0), ([1, 63, 64, 65, 200, 1000, 129, 517], 2, 296, 0), ([5], 1, 296, 0), ([16896] * 64, 1, 296, 0),
+    ([100, 3000, 7, 64 * 40], 8, 7, 0), ([1, 63, 64, 65, 200, 1000], 2, 296, 3), (list(range(1, 300, 7)), 4, 296, 0)])
+def test_decode_plan_covers_every_page_exactly_once_and_is_balanced(ctx, n_kv, n_ctas, force):
+    segs, ptr, n_slots = plan(ctx, n_kv, n_ctas, force)
+    assert ptr[0] == 0 and ptr[-1] == len(segs) and (np.diff(ptr) >= 0).all()
+    cover = {}
+    for s, h, b, e, slot in segs:
+        assert 0 <= b < e
+        for c in range(b, e):
+            assert (s, h, c) not in cover
+            cover[(s, h, c)] = slot
+    for s, c in enumerate(ctx):
+        for h in range(n_kv):
+            for ch in range((c + 63) // 64):
+                assert (s, h, ch) in cover
+    assert len(cover) == sum((c + 63) // 64 for c in ctx) * n_kv
+    # partial slots: unique, dense, and only for items cut into several pieces
+    slots = [x for x in segs[:, 4] if x >= 0]
+    assert sorted(slots) == list(range(n_slots))
+    pieces = {}
+    for s, h, b, e, slot in segs:
+        pieces.setdefault((s, h), []).append(slot)
+    for k, v in pieces.items():
+        assert (len(v) == 1 and v[0] == -1) or (len(v) > 1 and all(x >= 0 for x in v) and sorted(v) == list(range(min(v), min(v) + len(v))))
+    if not force:
+        load = [sum(segs[i][3] - segs[i][2] for i in range(ptr[c], ptr[c + 1])) for c in range(len(ptr) - 1)]
+        assert max(load) - min(load[:-1] or load) <= 1 or max(load) <= -(-len(cover) // len(load))
+
+
+def test_empty_and_zero_length_plans():
+    segs, ptr, n_slots = plan([0, 0], 4, 296)
+    assert len(segs) == 0 and n_slots == 0
+
+
+# ---- Chat() retry semantics of the Python mirror (reference pkg/llms/openai.go:77-103) ----
+class FakeEngine:
+    def __init__(self, codes):
+        self.codes, self.calls = list(codes), 0
+
+    def chat_complete(self, model, msgs, max_tokens, flags=0):
+        from opsagent_b200.engine import EngineError
+        self.calls += 1
+        c = self.codes.pop(0)
+        if c:
+            raise EngineError(c, f"status {c}")
+
+        class R:
+            content = b'{"question":"q","thought":"t","action":{"name":"kubectl","input":"get ns"},"observation":"","final_answer":""}'
+        return R()
+
+
+def test_chat_retries_429_and_500_with_doubling_backoff():
+    sleeps = []
+    eng = FakeEngine([429, 500, 429, 0])
+    cli = LocalCUDAClient(eng, sleep=sleeps.append)
+    out = cli.Chat("m", 8192, [ChatCompletionMessage("user", "x")])
+    assert json.loads(out)["action"]["name"] == "kubectl"
+    assert sleeps == [1.0, 2.0, 4.0] and eng.calls == 4
+
+
+def test_chat_gives_up_after_five_tries():
+    sleeps = []
+    cli = LocalCUDAClient(FakeEngine([500] * 5), sleep=sleeps.append)
+    with pytest.raises(RuntimeError, match="OpenAI request throttled after retrying 5 times"):
+        cli.Chat("m", 10, [ChatCompletionMessage("user", "x")])
+    assert sleeps == [1.0, 2.0, 4.0, 8.0, 16.0]
+
+
+@pytest.mark.parametrize("code", [401, 400, 404])
+def test_chat_fails_fast_on_other_statuses(code):
+    sleeps = []
+    eng = FakeEngine([code])
+    with pytest.raises(APIError) as e:
+        LocalCUDAClient(eng, sleep=sleeps.append).Chat("m", 10, [ChatCompletionMessage("user", "x")])
+    assert e.value.HTTPStatusCode == code and sleeps == [] and eng.calls == 1
+
+
+def test_new_client_requires_api_key_like_the_reference():
+    with pytest.raises(ValueError, match="OPENAI_API_KEY is not set"):
+        new_client("", "cuda://llama-3-8b")
+    with pytest.raises(ValueError):
+        new_client("sk-x", "https://api.openai.com/v1")
+
+
+def test_request_sharding_is_a_partition():
+    for n, w in [(1024, 8), (10, 3), (5, 8), (128, 1)]:
+        seen = []
+        for r in range(w):
+            sh = shard_requests(n, r, w)
+            seen += list(sh)
+            for i in sh:
+                assert replica_of(i, n, w) == r
+        assert seen == list(range(n))
