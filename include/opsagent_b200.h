@@ -103,6 +103,8 @@ OA_API int oa_bench_decode(oa_engine*, int32_t batch, int32_t ctx_len, int32_t s
 OA_API int oa_k_rmsnorm(const void* x, const void* gain, void* y, int32_t T, int32_t H, float eps, void* stream);
 OA_API int oa_k_gemm(const void* A, const void* B, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t block_n, void* out,
               const void* bias, const void* resid, float* logits, int32_t* argmax_out, void* stream);
+/* persistent stream-K GEMM (M <= 128) followed by the fixed-order partial sum: out_f32[M,N] */
+OA_API int oa_k_gemm_streamk(const void* A, const void* B, int32_t M, int32_t N, int32_t K, int32_t block_n, int32_t n_ctas, float* out_f32, void* stream);
 OA_API int oa_k_init_weight(void* dst, uint64_t seed, uint64_t tensor_id, int64_t tensor_id_b, int64_t rows, int64_t cols, float std,
                      float mean, void* stream);
 /* paged attention on a caller-provided cache [2(K,V)][num_pages][n_kv][64][D] (one layer): decode when q has one

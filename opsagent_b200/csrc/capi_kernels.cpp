@@ -22,7 +22,34 @@ struct DevBuf {
 int rc_of(cudaError_t e) { return e == cudaSuccess ? OA_OK : OA_ERR_INTERNAL; }
 }  // namespace
 
+// test-only: materialise the deterministic fixed-order sum of stream-K partials as fp32 [M,N]
+__global__ void sk_reduce_f32_kernel(const StreamK sk, float* __restrict__ out, int M, int N) {
+    const int row = blockIdx.x;
+    for (int col = threadIdx.x; col < N; col += blockDim.x) {
+        const uint32_t tile = (uint32_t)col / (uint32_t)sk.bn, cc = (uint32_t)col - tile * (uint32_t)sk.bn;
+        const uint32_t ut0 = tile * (uint32_t)sk.kb, G = (uint32_t)sk.G, total = (uint32_t)sk.total;
+        const uint32_t c_first = ((ut0 + 1u) * G - 1u) / total, c_last = ((ut0 + (uint32_t)sk.kb) * G - 1u) / total;
+        float acc = 0.f;
+        for (uint32_t c = c_first; c <= c_last; ++c) acc += sk.ws[((size_t)(c + tile) * 128 + row) * sk.bn + cc];
+        out[(size_t)row * N + col] = acc;
+    }
+}
+
 extern "C" {
+
+int oa_k_gemm_streamk(const void* A, const void* B, int32_t M, int32_t N, int32_t K, int32_t block_n, int32_t n_ctas, float* out_f32, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CUtensorMap tmA, tmB;
+    if (make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, 64) != 0) return OA_ERR_INTERNAL;
+    if (make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)block_n, 64) != 0) return OA_ERR_INTERNAL;
+    DevBuf ws(streamk_ws_bytes(N, block_n, n_ctas));
+    if (!ws.p) return OA_ERR_INTERNAL;
+    StreamK sk = make_streamk((float*)ws.p, N, K, block_n, n_ctas);
+    cudaError_t e = launch_gemm_streamk(&tmA, &tmB, M, N, K, sk, s);
+    if (e == cudaSuccess) { sk_reduce_f32_kernel<<<M, 256, 0, s>>>(sk, out_f32, M, N); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    return rc_of(e);
+}
 
 int oa_k_rmsnorm(const void* x, const void* gain, void* y, int32_t T, int32_t H, float eps, void* stream) {
     return rc_of(launch_rmsnorm(x, gain, y, T, H, eps, (cudaStream_t)stream));

@@ -145,7 +145,8 @@ public:
             const int P = ctx_len - 1;
             cudaEventRecord(e0, model_.stream);
             {
-                int b = 0, off = 0;
+                int b = 0, off = 0, n_fwd = 0;
+                const bool prof_prefill = std::getenv("OA_CUDA_PROFILER_PREFILL") != nullptr;
                 while (b < batch && P > 0) {
                     StepInput in; in.decode = false;
                     int budget = opt_.max_step_tokens;
@@ -161,7 +162,10 @@ public:
                         budget -= take; off += take;
                         if (off >= P) { off = 0; ++b; }
                     }
+                    if (prof_prefill && n_fwd == 1) { model_.sync(); cudaProfilerStart(); }     // the 2nd prefill chunk (warm)
                     model_.forward(in, nullptr);
+                    if (prof_prefill && n_fwd == 1) { model_.sync(); cudaProfilerStop(); }
+                    ++n_fwd;
                 }
             }
             cudaEventRecord(e1, model_.stream); model_.sync();

@@ -13,6 +13,8 @@
 // The role of this file in the reference's terms: it is the arithmetic that sits behind
 // llms.OpenAIClient.Chat (reference pkg/llms/openai.go:69-104) once the `local-cuda` provider replaces the
 // remote HTTP server — see DESIGN.md §Kernels.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.hpp"
 
@@ -238,6 +240,161 @@ cudaError_t launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, const Ge
         case 128: return launch_bn<128>(tmA, tmB, p, epilogue, stream);
         case 256: return launch_bn<256>(tmA, tmB, p, epilogue, stream);
     }
+    return cudaErrorInvalidValue;
+}
+
+// =============================================================================================
+// stream-K (decode, M <= 128): persistent CTAs, balanced weight streaming, fp32 partials
+// =============================================================================================
+template <int BN>
+struct SkCfg {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BN * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;          // 4 x 48 KB (BN=256) or 6 x 32 KB (BN=128)
+    static constexpr int EPI_ROW_FLOATS = 36;                          // 32 + 4 pad: conflict-free 16-byte smem accesses
+    static constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_FLOATS * 4;     // one 32x32 fp32 chunk per epilogue warp
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * EPI_WARP_BYTES + 1024 + 256;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;                      // two accumulator stages
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                         const __grid_constant__ CUtensorMap tmB, const int M,
+                                                                         const StreamK sk) {
+    using Cfg = SkCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* epi_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + 4 * Cfg::EPI_WARP_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;      // [2]
+    uint64_t* acc_empty = acc_full + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long c = blockIdx.x, G = gridDim.x;
+    const long long u0 = c * sk.total / G, u1 = (c + 1) * sk.total / G;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (long long u = u0; u < u1; ++u) {
+                const int tile = (int)(u / sk.kb), kblk = (int)(u - (long long)tile * sk.kb);
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                tma_load_2d(a_dst, &tmA, &full_bar[s], kblk * BLOCK_K, 0, kEvictLast);
+                tma_load_2d(a_dst + Cfg::A_BYTES, &tmB, &full_bar[s], kblk * BLOCK_K, tile * BN, kEvictFirst);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+            int s = 0; uint32_t ph = 0; int seg = 0;
+            for (long long u = u0; u < u1; ++seg) {
+                const int tile = (int)(u / sk.kb);
+                const long long uend = min(u1, (long long)(tile + 1) * sk.kb);
+                const int as = seg & 1;
+                mbar_wait(&acc_empty[as], (((uint32_t)seg >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                for (long long uu = u; uu < uend; ++uu) {
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                    const uint64_t a_desc = umma_desc_sw128(a_addr), b_desc = umma_desc_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_bf16(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (uu > u || k > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&acc_full[as]);
+                u = uend;
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        int seg = 0;
+        for (long long u = u0; u < u1; ++seg) {
+            const int tile = (int)(u / sk.kb);
+            const long long uend = min(u1, (long long)(tile + 1) * sk.kb);
+            const int as = seg & 1;
+            mbar_wait(&acc_full[as], ((uint32_t)seg >> 1) & 1);
+            tcgen05_fence_after();
+            // TMEM gives each thread one row x 32 columns; transpose through padded smem so that every global store
+            // instruction writes four full 128-byte lines (8 lanes per row) instead of 32 scattered 16-byte pieces.
+            float* stage = epi_smem + (warp - 2) * (Cfg::EPI_WARP_BYTES / 4);
+            float* dst = sk.ws + ((size_t)(c + tile) * BLOCK_M + q * 32) * BN;
+            const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll 1
+            for (int cc = 0; cc < BN; cc += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cc), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stage + lane * Cfg::EPI_ROW_FLOATS + j) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + r_sub;
+                    const float4 val = *reinterpret_cast<const float4*>(stage + r * Cfg::EPI_ROW_FLOATS + c4);
+                    if (q * 32 + r < M) *reinterpret_cast<float4*>(dst + (size_t)r * BN + cc + c4) = val;
+                }
+                __syncwarp();
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+            u = uend;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) { tcgen05_fence_after(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
+}
+
+StreamK make_streamk(float* ws, int N, int K, int bn, int G) {
+    StreamK sk{}; sk.ws = ws; sk.bn = bn; sk.kb = (K + BLOCK_K - 1) / BLOCK_K; sk.n_tiles = (N + bn - 1) / bn;
+    sk.total = (long long)sk.n_tiles * sk.kb; sk.G = (int)std::min<long long>(G, sk.total);
+    return sk;
+}
+size_t streamk_ws_bytes(int N, int bn, int G) { return (size_t)(G + (N + bn - 1) / bn) * BLOCK_M * bn * sizeof(float); }
+
+template <int BN>
+static cudaError_t launch_sk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, const StreamK& sk, cudaStream_t stream) {
+    auto kern = gemm_streamk_kernel<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<BN>::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    kern<<<sk.G, GEMM_THREADS, SkCfg<BN>::SMEM_BYTES, stream>>>(*tmA, *tmB, M, sk);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_gemm_streamk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, cudaStream_t stream) {
+    if (M <= 0 || M > BLOCK_M || (N % 8) != 0 || (K % 8) != 0) return cudaErrorInvalidValue;
+    if (sk.bn == 256) return launch_sk<256>(tmA, tmB, M, sk, stream);
+    if (sk.bn == 128) return launch_sk<128>(tmA, tmB, M, sk, stream);
     return cudaErrorInvalidValue;
 }
 

@@ -34,6 +34,22 @@ struct GemmParams {
 cudaError_t launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int epilogue, int block_n,
                         cudaStream_t stream);
 int gemm_n_tiles(int N, int block_n);
+// ---- stream-K variant for decode (M <= 128): persistent, one CTA per SM; work unit = (n_tile, 64-wide k block),
+// units dealt out contiguously so every SM streams the same number of weight bytes.  Each CTA writes the fp32
+// partial of every tile segment it owns to ws[slot = cta + tile][128][BN]; consumers (sk_* kernels) add a tile's
+// partials in CTA order — a fixed order, so results are run-to-run deterministic — and apply bias / residual /
+// RMSNorm / RoPE / SwiGLU while they are at it.
+struct StreamK {
+    float* ws; int bn, kb, n_tiles, G; long long total;      // kb = k blocks per tile, total = n_tiles * kb, G = CTAs
+};
+StreamK make_streamk(float* ws, int N, int K, int bn, int G);
+size_t streamk_ws_bytes(int N, int bn, int G);
+cudaError_t launch_gemm_streamk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, cudaStream_t stream);
+// x[T,H] (bf16, in place) += sum of partials; xn = rmsnorm(x) * gain
+cudaError_t launch_sk_resid_rmsnorm(const StreamK& sk, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s);
+// act[T,F] = silu(gate) * up from the interleaved gate/up partials (N = 2F)
+cudaError_t launch_sk_swiglu(const StreamK& sk, void* act, int T, int F, cudaStream_t s);
+
 // reduce EPI_LOGITS partials: out_ids[M] = argmax over n_tiles (ties -> lowest column index)
 cudaError_t launch_argmax_reduce(const float* amax_val, const int* amax_idx, int M, int n_tiles, int32_t* out_ids,
                                  float* out_val, cudaStream_t stream);
@@ -51,6 +67,10 @@ struct KvLayout {
     int64_t kv_stride_rows;      // rows between K and V planes of a layer (= num_pages * nkv * page_size)
     int32_t page_size, n_kv, head_dim, num_pages;
 };
+// same, but q/k/v come from stream-K partials (+ bias): sum -> bf16 round -> RoPE -> bf16 round (the oracle's order)
+cudaError_t launch_sk_rope_kv_write(const StreamK& sk, const void* bias, const int32_t* positions, const int32_t* slots,
+                                    const float* rope_cos, const float* rope_sin, void* q_out, const KvLayout& kv, int layer, int T,
+                                    int nh, cudaStream_t s);
 cudaError_t launch_rope_kv_write(const void* qkv, const int32_t* positions, const int32_t* slots, const float* rope_cos,
                                  const float* rope_sin, void* q_out, const KvLayout& kv, int layer, int T, int nh,
                                  cudaStream_t s);

@@ -168,6 +168,16 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
                       (size_t)(opt.max_batch * cfg.n_kv_heads + n_ctas + 8) * 8 * 2 + (size_t)n_ctas + 4096;
     cuda_check(cudaMallocHost(&h_meta_, meta_cap_words_ * 4), "cudaMallocHost meta");
     d_meta_ = reinterpret_cast<int32_t*>(dmalloc(meta_cap_words_ * 4));
+    sk_bn_ = (opt.sk_bn == 128) ? 128 : 256;
+    sk_G_ = opt.sk_ctas > 0 ? opt.sk_ctas : sm_count;
+    {
+        size_t wsb = 0;
+        for (int n : {qkvd, H, 2 * F}) for (int bn : {128, 256}) wsb = std::max(wsb, streamk_ws_bytes(n, bn, sk_G_));
+        sk_ws_ = reinterpret_cast<float*>(dmalloc(wsb));
+        // 32-bit index arithmetic in the consumers: (units of the largest shape + kb) * G must stay below 2^32
+        const double worst = ((double)((2 * F + sk_bn_ - 1) / sk_bn_) * ((std::max(H, F) + 63) / 64) + (std::max(H, F) + 63) / 64) * sk_G_;
+        if (worst >= 4.0e9) throw std::runtime_error("stream-K index range exceeds 32 bits for this model");
+    }
     ev.resize(2 * (size_t)L);
     for (auto& e : ev) cuda_check(cudaEventCreate(&e), "cudaEventCreate");
     cuda_check(cudaStreamSynchronize(stream), "init sync");
@@ -282,14 +292,8 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
 
     const float scale_log2e = (1.0f / std::sqrt((float)D)) * 1.4426950408889634f;
     cuda_check(launch_embed_gather(d_tok, embed, x_, T, H, V, stream), "embed");
-    const int bn_qkv = pick_bn(T, qkvd, opt.bn_qkv, false), bn_o = pick_bn(T, H, opt.bn_o, false);
-    const int bn_gu = pick_bn(T, 2 * F, opt.bn_gu, true), bn_down = pick_bn(T, H, opt.bn_down, false);
-    for (int l = 0; l < L; ++l) {
-        const Layer& ly = layers[l];
-        cuda_check(launch_rmsnorm(x_, ly.ln1, xn_, T, H, cfg.rms_eps, stream), "rmsnorm1");
-        GemmParams g{}; g.M = T; g.N = qkvd; g.K = H; g.out = qkv_; g.ldo = qkvd; g.bias = ly.bqkv;
-        cuda_check(launch_gemm(&tm_xn_, ly.qkv.map(bn_qkv), g, EPI_STORE, bn_qkv, stream), "qkv gemm");
-        cuda_check(launch_rope_kv_write(qkv_, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, T, nh, stream), "rope");
+    const bool use_sk = opt.streamk && T <= 128;
+    auto attention = [&](int l) {
         if (profile_attn) cudaEventRecord(ev[2 * l], stream);
         if (in.decode) {
             DecodeAttnParams a{}; a.q = q_; a.out = attn_; a.block_tables = d_bt; a.ctx_lens = d_ctx; a.max_pages_per_seq = max_pages_per_seq;
@@ -305,17 +309,52 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
             cuda_check(launch_prefill_attention(&tm_kv, kv, a, stream), "prefill attention");
         }
         if (profile_attn) cudaEventRecord(ev[2 * l + 1], stream);
-        GemmParams go{}; go.M = T; go.N = H; go.K = qd; go.out = x_; go.ldo = H; go.resid = x_; go.ldr = H;
-        cuda_check(launch_gemm(&tm_attn_, ly.o.map(bn_o), go, EPI_RESID, bn_o, stream), "o gemm");
-        cuda_check(launch_rmsnorm(x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "rmsnorm2");
-        GemmParams gg{}; gg.M = T; gg.N = 2 * F; gg.K = H; gg.out = act_; gg.ldo = F;
-        cuda_check(launch_gemm(&tm_xn_, ly.gu.map(bn_gu), gg, EPI_SWIGLU, bn_gu, stream), "gate_up gemm");
-        GemmParams gd{}; gd.M = T; gd.N = H; gd.K = F; gd.out = x_; gd.ldo = H; gd.resid = x_; gd.ldr = H;
-        cuda_check(launch_gemm(&tm_act_, ly.down.map(bn_down), gd, EPI_RESID, bn_down, stream), "down gemm");
+    };
+    if (use_sk) {
+        // decode-sized batch: persistent stream-K projections (fp32 partials) + fused consumers
+        auto bn_of = [&](int o) { return (o == 128 || o == 256) ? o : sk_bn_; };
+        const StreamK sk_qkv = make_streamk(sk_ws_, qkvd, H, bn_of(opt.sk_bn_qkv), sk_G_), sk_o = make_streamk(sk_ws_, H, qd, bn_of(opt.sk_bn_o), sk_G_);
+        const StreamK sk_gu = make_streamk(sk_ws_, 2 * F, H, bn_of(opt.sk_bn_gu), sk_G_), sk_dn = make_streamk(sk_ws_, H, F, bn_of(opt.sk_bn_down), sk_G_);
+        cuda_check(launch_rmsnorm(x_, layers[0].ln1, xn_, T, H, cfg.rms_eps, stream), "rmsnorm1");
+        for (int l = 0; l < L; ++l) {
+            const Layer& ly = layers[l];
+            cuda_check(launch_gemm_streamk(&tm_xn_, ly.qkv.map(sk_qkv.bn), T, qkvd, H, sk_qkv, stream), "qkv gemm (stream-K)");
+            cuda_check(launch_sk_rope_kv_write(sk_qkv, ly.bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, T, nh, stream), "rope (stream-K)");
+            attention(l);
+            cuda_check(launch_gemm_streamk(&tm_attn_, ly.o.map(sk_o.bn), T, H, qd, sk_o, stream), "o gemm (stream-K)");
+            cuda_check(launch_sk_resid_rmsnorm(sk_o, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm2");
+            cuda_check(launch_gemm_streamk(&tm_xn_, ly.gu.map(sk_gu.bn), T, 2 * F, H, sk_gu, stream), "gate_up gemm (stream-K)");
+            cuda_check(launch_sk_swiglu(sk_gu, act_, T, F, stream), "swiglu");
+            cuda_check(launch_gemm_streamk(&tm_act_, ly.down.map(sk_dn.bn), T, H, F, sk_dn, stream), "down gemm (stream-K)");
+            const void* next_gain = (l + 1 < L) ? layers[l + 1].ln1 : final_norm;
+            cuda_check(launch_sk_resid_rmsnorm(sk_dn, x_, next_gain, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm1");
+        }
+    } else {
+        const int bn_qkv = pick_bn(T, qkvd, opt.bn_qkv, false), bn_o = pick_bn(T, H, opt.bn_o, false);
+        const int bn_gu = pick_bn(T, 2 * F, opt.bn_gu, true), bn_down = pick_bn(T, H, opt.bn_down, false);
+        for (int l = 0; l < L; ++l) {
+            const Layer& ly = layers[l];
+            cuda_check(launch_rmsnorm(x_, ly.ln1, xn_, T, H, cfg.rms_eps, stream), "rmsnorm1");
+            GemmParams g{}; g.M = T; g.N = qkvd; g.K = H; g.out = qkv_; g.ldo = qkvd; g.bias = ly.bqkv;
+            cuda_check(launch_gemm(&tm_xn_, ly.qkv.map(bn_qkv), g, EPI_STORE, bn_qkv, stream), "qkv gemm");
+            cuda_check(launch_rope_kv_write(qkv_, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, T, nh, stream), "rope");
+            attention(l);
+            GemmParams go{}; go.M = T; go.N = H; go.K = qd; go.out = x_; go.ldo = H; go.resid = x_; go.ldr = H;
+            cuda_check(launch_gemm(&tm_attn_, ly.o.map(bn_o), go, EPI_RESID, bn_o, stream), "o gemm");
+            cuda_check(launch_rmsnorm(x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "rmsnorm2");
+            GemmParams gg{}; gg.M = T; gg.N = 2 * F; gg.K = H; gg.out = act_; gg.ldo = F;
+            cuda_check(launch_gemm(&tm_xn_, ly.gu.map(bn_gu), gg, EPI_SWIGLU, bn_gu, stream), "gate_up gemm");
+            GemmParams gd{}; gd.M = T; gd.N = H; gd.K = F; gd.out = x_; gd.ldo = H; gd.resid = x_; gd.ldr = H;
+            cuda_check(launch_gemm(&tm_act_, ly.down.map(bn_down), gd, EPI_RESID, bn_down, stream), "down gemm");
+        }
     }
     if (S > 0) {
-        cuda_check(launch_gather_rows(x_, d_samp, xs_, S, H, stream), "gather");
-        cuda_check(launch_rmsnorm(xs_, final_norm, xsn_, S, H, cfg.rms_eps, stream), "final norm");
+        if (use_sk) {      // xn_ already holds final_norm(x): just pick the sampled rows
+            cuda_check(launch_gather_rows(xn_, d_samp, xsn_, S, H, stream), "gather");
+        } else {
+            cuda_check(launch_gather_rows(x_, d_samp, xs_, S, H, stream), "gather");
+            cuda_check(launch_rmsnorm(xs_, final_norm, xsn_, S, H, cfg.rms_eps, stream), "final norm");
+        }
         const int bn_lm = pick_bn(S, V, opt.bn_lm, false);
         const int n_tiles = gemm_n_tiles(V, bn_lm);
         GemmParams gl{}; gl.M = S; gl.N = V; gl.K = H; gl.logits = logits_out; gl.ldl = V; gl.amax_val = amax_val_; gl.amax_idx = amax_idx_;

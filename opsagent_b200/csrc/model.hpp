@@ -68,6 +68,7 @@ private:
     CUtensorMap tm_xn_, tm_attn_, tm_act_, tm_xsn_;
     float* amax_val_ = nullptr; int* amax_idx_ = nullptr; int32_t* d_out_ids_ = nullptr;
     float *part_o_ = nullptr, *part_ml_ = nullptr; int max_part_slots_ = 0;
+    float* sk_ws_ = nullptr; int sk_bn_ = 256, sk_G_ = 148;
     int32_t *h_meta_ = nullptr, *d_meta_ = nullptr; size_t meta_cap_words_ = 0;
     int max_rows_ = 0, max_sample_ = 0;
     DecodePlan plan_;

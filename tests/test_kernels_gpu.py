@@ -158,6 +158,24 @@ def test_gemm_logits_argmax(L, M, N, K, bn):
     assert (ids2 == ids).all()
 
 
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("M,N,K,G", [(128, 4096, 4096, 148), (128, 6144, 4096, 148), (77, 1024, 14336, 148), (1, 320, 320, 148),
+                                      (128, 28672, 4096, 148), (16, 2304, 256, 5), (128, 512, 512, 3), (100, 1000, 192, 148)])
+def test_gemm_streamk_partials_sum_to_the_product(L, M, N, K, G, bn):
+    g = torch.Generator(device="cpu").manual_seed(N + K + bn + G)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(dev())
+    B = (torch.randn(N, K, generator=g) * 0.5).to(torch.bfloat16).to(dev())
+    out = torch.full((M, N), float("nan"), dtype=torch.float32, device=dev())
+    assert L.oa_k_gemm_streamk(ptr(A), ptr(B), M, N, K, bn, G, ptr(out), None) == 0, _lib.last_error()
+    ref = A.float() @ B.float().T
+    assert torch.isfinite(out).all()
+    assert ((out - ref).abs() <= 2e-4 * (K ** 0.5) + 1e-5 * ref.abs()).all(), float((out - ref).abs().max())
+    # fixed summation order => bitwise reproducible run to run
+    out2 = torch.empty_like(out)
+    assert L.oa_k_gemm_streamk(ptr(A), ptr(B), M, N, K, bn, G, ptr(out2), None) == 0
+    assert torch.equal(out, out2)
+
+
 # ------------------------------------------------------------------------------------------------
 def _attn_ref(q, kcache, vcache, bt, ctx, qlens, nh, nkv, D):
     """fp32 reference of paged causal GQA attention.  q: [sum(qlens), nh, D]"""

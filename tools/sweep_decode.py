@@ -1,0 +1,16 @@
+"""Runs the BASELINE configs[1] decode step under several engine configs and prints ms/step for each (one engine per config)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from opsagent_b200 import Engine  # noqa: E402
+
+configs = [json.loads(a) for a in sys.argv[1:]] or [{}]
+for extra in configs:
+    cfg = {"model": "llama-3-8b", "kv_gb": 40, "max_batch": 128, "max_seq_len": 2048, "max_step_tokens": 8192}
+    cfg.update(extra)
+    eng = Engine(cfg)
+    r = eng.bench_decode(128, 1664 - 16 - 4, 32, 4)
+    print(json.dumps({"extra": extra, "ms_per_step": round(r["ms_per_step"], 3), "tok_s": round(128e3 / r["ms_per_step"], 1)}), flush=True)
+    eng.close()
