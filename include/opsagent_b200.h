@@ -99,6 +99,9 @@ OA_API int oa_debug_prefill_logits(oa_engine*, const int32_t* tokens, int32_t n,
  * out[6]=sum of per-step device durations / steps (host gaps excluded) */
 OA_API int oa_bench_decode(oa_engine*, int32_t batch, int32_t ctx_len, int32_t steps, int32_t warmup, double* out, int32_t n_out);
 
+/* in-situ per-kernel-class timings accumulated while OA_PROFILE_ALL=1 (JSON name -> [total ms, launches]) */
+OA_API int oa_debug_kernel_times(oa_engine*, char* buf, size_t n, int32_t reset);
+
 /* kernel-level entry points on raw device pointers (tests call these with torch-allocated memory) */
 OA_API int oa_k_rmsnorm(const void* x, const void* gain, void* y, int32_t T, int32_t H, float eps, void* stream);
 OA_API int oa_k_gemm(const void* A, const void* B, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t block_n, void* out,

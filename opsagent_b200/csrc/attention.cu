@@ -71,17 +71,25 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) decode_attention_kernel(const 
         fence_barrier_init();
     }
     __syncthreads();
+    griddep_launch();
 
+    // plan, block tables and context lengths were copied in before the first kernel of the step: safe to read now
     const int seg_begin = p.cta_seg_ptr[blockIdx.x], seg_end = p.cta_seg_ptr[blockIdx.x + 1];
 
     if (warp == 4) {
         // ------------------------------- producer -------------------------------
+        // Pages strictly before the one holding this step's token are immutable, so their K/V stream may start
+        // before the predecessor (RoPE + KV-page write) has finished; wait lazily, at the first page that may change
+        // or once the ring is full.
         if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
+            int s = 0; uint32_t ph = 0; int issued = 0; bool waited = false;
             for (int si = seg_begin; si < seg_end; ++si) {
                 const DecodeSeg sg = p.segs[si];
                 const int32_t* bt = p.block_tables + (size_t)sg.seq * p.max_pages_per_seq;
+                const int mutable_chunk = (p.ctx_lens[sg.seq] - 1) / PAGE;
                 for (int c = sg.chunk_begin; c < sg.chunk_end; ++c) {
+                    if (!waited && (issued >= STAGES || c >= mutable_chunk)) { griddep_wait(); waited = true; }
+                    ++issued;
                     const int page = bt[c];
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* kdst = smem + s * Cfg::STAGE_BYTES;
@@ -102,6 +110,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) decode_attention_kernel(const 
     }
 
     // ------------------------------- consumers -------------------------------
+    griddep_wait();       // Q comes from the predecessor; partial/out buffers may still be read by it
     const int g = lane >> 2, t = lane & 3;
     int s = 0; uint32_t ph = 0;
     for (int si = seg_begin; si < seg_end; ++si) {
@@ -234,6 +243,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) decode_attention_kernel(const 
 // out[seq, head, :] = sum_i 2^(m_i - m) o_i / sum_i 2^(m_i - m) l_i over the item's partial slots
 __global__ void decode_merge_kernel(const MergeItem* __restrict__ items, const float* __restrict__ part_o,
                                     const float* __restrict__ part_ml, uint16_t* __restrict__ out, int n_heads, int n_kv, int D) {
+    griddep_launch(); griddep_wait();
     const MergeItem it = items[blockIdx.x];
     const int grp = n_heads / n_kv;
     for (int idx = threadIdx.x; idx < grp * D; idx += blockDim.x) {
@@ -254,9 +264,7 @@ __global__ void decode_merge_kernel(const MergeItem* __restrict__ items, const f
 cudaError_t launch_decode_merge(const MergeItem* items, int n_items, const float* part_o, const float* part_ml, void* out,
                                 int n_heads, int n_kv, int head_dim, cudaStream_t s) {
     if (n_items <= 0) return cudaSuccess;
-    decode_merge_kernel<<<n_items, 128, 0, s>>>(items, part_o, part_ml, reinterpret_cast<uint16_t*>(out), n_heads, n_kv, head_dim);
-    count_launch();
-    return cudaGetLastError();
+    return launch_k(decode_merge_kernel, dim3(n_items), dim3(128), 0, s, items, part_o, part_ml, reinterpret_cast<uint16_t*>(out), n_heads, n_kv, head_dim);
 }
 
 template <int D>
@@ -268,9 +276,7 @@ static cudaError_t launch_decode_d(const CUtensorMap* tm_kv, const KvLayout& kv,
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    kern<<<p.n_ctas, ATT_THREADS, AttCfg<D>::SMEM_BYTES, s>>>(*tm_kv, p, (int64_t)p.layer * kv.layer_stride_rows, kv.kv_stride_rows);
-    count_launch();
-    return cudaGetLastError();
+    return launch_k(kern, dim3(p.n_ctas), dim3(ATT_THREADS), AttCfg<D>::SMEM_BYTES, s, *tm_kv, p, (int64_t)p.layer * kv.layer_stride_rows, kv.kv_stride_rows);
 }
 
 cudaError_t launch_decode_attention(const CUtensorMap* tm_kv, const KvLayout& kv, const DecodeAttnParams& p, cudaStream_t s) {
@@ -308,6 +314,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) prefill_attention_kernel(const
         fence_barrier_init();
     }
     __syncthreads();
+    griddep_launch();
+    griddep_wait();
 
     if (warp == 4) {
         if (lane == 0) {
@@ -456,9 +464,7 @@ static cudaError_t launch_prefill_d(const CUtensorMap* tm_kv, const KvLayout& kv
         attr_set = true;
     }
     dim3 grid(p.n_tiles, p.n_heads, 1);
-    kern<<<grid, ATT_THREADS, SMEM, s>>>(*tm_kv, p, (int64_t)p.layer * kv.layer_stride_rows, kv.kv_stride_rows);
-    count_launch();
-    return cudaGetLastError();
+    return launch_k(kern, grid, dim3(ATT_THREADS), SMEM, s, *tm_kv, p, (int64_t)p.layer * kv.layer_stride_rows, kv.kv_stride_rows);
 }
 
 cudaError_t launch_prefill_attention(const CUtensorMap* tm_kv, const KvLayout& kv, const PrefillAttnParams& p, cudaStream_t s) {

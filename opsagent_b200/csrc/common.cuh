@@ -47,6 +47,16 @@ OA_DEVINL bool elect_one_sync() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the forward chain is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization.  griddep_launch() lets the next kernel's CTAs become resident and
+// run their prologue (and, in the GEMMs, start streaming WEIGHTS, which no predecessor writes); griddep_wait() blocks
+// until every predecessor grid has completed and its memory is visible — nothing produced by a predecessor may be
+// touched, and nothing a predecessor reads may be written, before it.
+// ---------------------------------------------------------------------------------------------
+OA_DEVINL void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+OA_DEVINL void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 OA_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
@@ -96,6 +106,12 @@ OA_DEVINL void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int3
         " [%0], [%1, {%3, %4}], [%2], %5;"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
+}
+
+// L2 prefetch of one tensor-map box (no smem destination, no barrier)
+OA_DEVINL void tma_prefetch_l2_2d(const void* tmap, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

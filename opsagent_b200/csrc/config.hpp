@@ -98,7 +98,8 @@ struct EngineOptions {
     int bn_qkv = 0, bn_o = 0, bn_gu = 0, bn_down = 0, bn_lm = 0;   // GEMM N-tile overrides (0 = heuristic)
     int attn_ctas = 0;            // decode attention CTA count override (0 = 2 per SM)
     int streamk = 1;              // decode (T <= 128) projections through the persistent stream-K GEMM
-    int sk_bn = 256, sk_ctas = 0; // its N tile and CTA count (0 = one per SM)
+    int sk_bn = 128, sk_ctas = 0; // its N tile (128: half the partial traffic, measured faster than 256) and CTA count (0 = one per SM)
+    int sk_l2_prefetch_kb = 0;    // per-CTA weight KB prefetched into L2 ahead of the dependency wait (measured: hurts, 8.75 -> 9.3 ms; off)
     int sk_bn_qkv = 0, sk_bn_o = 0, sk_bn_gu = 0, sk_bn_down = 0;   // per-projection overrides (0 = sk_bn)
     int start_thread = 1;
 };
@@ -120,7 +121,7 @@ inline void parse_config(const std::string& json, ModelConfig& m, EngineOptions&
     I("device", o.device); o.kv_gb = j.f("kv_gb", o.kv_gb); I("num_pages", o.num_pages); I("max_batch", o.max_batch);
     I("max_seq_len", o.max_seq_len); I("max_step_tokens", o.max_step_tokens); I("max_queue", o.max_queue);
     I("bn_qkv", o.bn_qkv); I("bn_o", o.bn_o); I("bn_gu", o.bn_gu); I("bn_down", o.bn_down); I("bn_lm", o.bn_lm);
-    I("attn_ctas", o.attn_ctas); I("streamk", o.streamk); I("sk_bn", o.sk_bn); I("sk_ctas", o.sk_ctas); I("sk_bn_qkv", o.sk_bn_qkv); I("sk_bn_o", o.sk_bn_o); I("sk_bn_gu", o.sk_bn_gu); I("sk_bn_down", o.sk_bn_down); I("start_thread", o.start_thread);
+    I("attn_ctas", o.attn_ctas); I("streamk", o.streamk); I("sk_bn", o.sk_bn); I("sk_ctas", o.sk_ctas); I("sk_l2_prefetch_kb", o.sk_l2_prefetch_kb); I("sk_bn_qkv", o.sk_bn_qkv); I("sk_bn_o", o.sk_bn_o); I("sk_bn_gu", o.sk_bn_gu); I("sk_bn_down", o.sk_bn_down); I("start_thread", o.start_thread);
     if (m.hidden <= 0 || m.n_layers <= 0 || m.n_heads <= 0 || m.n_kv_heads <= 0 || m.ffn <= 0 || m.vocab <= 0)
         throw std::runtime_error("unknown model '" + name + "' and no explicit dimensions given");
     if (m.head_dim != 64 && m.head_dim != 128) throw std::runtime_error("head_dim must be 64 or 128");

@@ -8,6 +8,7 @@ namespace oa {
 // out[t,:] = table[ids[t],:]   (ids outside [0,vocab) read row 0, as the oracle does)
 __global__ void embed_gather_kernel(const int32_t* __restrict__ ids, const uint4* __restrict__ table, uint4* __restrict__ out,
                                     int H8, int vocab) {
+    griddep_launch(); griddep_wait();
     const int t = blockIdx.x;
     int id = ids[t];
     if (id < 0 || id >= vocab) id = 0;
@@ -17,27 +18,25 @@ __global__ void embed_gather_kernel(const int32_t* __restrict__ ids, const uint4
 }
 cudaError_t launch_embed_gather(const int32_t* ids, const void* table, void* out, int T, int H, int vocab, cudaStream_t s) {
     if (T <= 0) return cudaSuccess;
-    embed_gather_kernel<<<T, 128, 0, s>>>(ids, reinterpret_cast<const uint4*>(table), reinterpret_cast<uint4*>(out), H / 8, vocab);
-    count_launch();
-    return cudaGetLastError();
+    return launch_k(embed_gather_kernel, dim3(T), dim3(128), 0, s, ids, reinterpret_cast<const uint4*>(table), reinterpret_cast<uint4*>(out), H / 8, vocab);
 }
 
 __global__ void gather_rows_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ rows, uint4* __restrict__ out, int H8) {
+    griddep_launch(); griddep_wait();
     const uint4* src = x + (size_t)rows[blockIdx.x] * H8;
     uint4* dst = out + (size_t)blockIdx.x * H8;
     for (int i = threadIdx.x; i < H8; i += blockDim.x) dst[i] = src[i];
 }
 cudaError_t launch_gather_rows(const void* x, const int32_t* rows, void* out, int n, int H, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    gather_rows_kernel<<<n, 128, 0, s>>>(reinterpret_cast<const uint4*>(x), rows, reinterpret_cast<uint4*>(out), H / 8);
-    count_launch();
-    return cudaGetLastError();
+    return launch_k(gather_rows_kernel, dim3(n), dim3(128), 0, s, reinterpret_cast<const uint4*>(x), rows, reinterpret_cast<uint4*>(out), H / 8);
 }
 
 // y = x * rsqrt(mean(x^2) + eps) * g ; fp32 statistics, bf16 in/out.  Row cached in registers (H <= 8192).
 template <int VPT>   // uint4 vectors per thread, 256 threads
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const uint4* __restrict__ x, const uint4* __restrict__ g, uint4* __restrict__ y,
                                                       int H8, float inv_h, float eps) {
+    griddep_launch(); griddep_wait();
     const int t = blockIdx.x;
     const uint4* xr = x + (size_t)t * H8;
     uint4 v[VPT];
@@ -81,11 +80,9 @@ cudaError_t launch_rmsnorm(const void* x, const void* gain, void* y, int T, int 
     if (H % 8 != 0 || H > 8192) return cudaErrorInvalidValue;
     const int H8 = H / 8;
     auto X = reinterpret_cast<const uint4*>(x); auto G = reinterpret_cast<const uint4*>(gain); auto Y = reinterpret_cast<uint4*>(y);
-    if (H8 <= 256) rmsnorm_kernel<1><<<T, 256, 0, s>>>(X, G, Y, H8, 1.0f / H, eps);
-    else if (H8 <= 512) rmsnorm_kernel<2><<<T, 256, 0, s>>>(X, G, Y, H8, 1.0f / H, eps);
-    else rmsnorm_kernel<4><<<T, 256, 0, s>>>(X, G, Y, H8, 1.0f / H, eps);
-    count_launch();
-    return cudaGetLastError();
+    if (H8 <= 256) return launch_k(rmsnorm_kernel<1>, dim3(T), dim3(256), 0, s, X, G, Y, H8, 1.0f / H, eps);
+    if (H8 <= 512) return launch_k(rmsnorm_kernel<2>, dim3(T), dim3(256), 0, s, X, G, Y, H8, 1.0f / H, eps);
+    return launch_k(rmsnorm_kernel<4>, dim3(T), dim3(256), 0, s, X, G, Y, H8, 1.0f / H, eps);
 }
 
 // One CTA per token.  Thread i handles the rotate-half pair group (8 consecutive i in [0,D/2) and the
@@ -94,6 +91,7 @@ __global__ void rope_kv_write_kernel(const uint16_t* __restrict__ qkv, const int
                                      const int32_t* __restrict__ slots, const float* __restrict__ rope_cos,
                                      const float* __restrict__ rope_sin, uint16_t* __restrict__ q_out, uint16_t* __restrict__ kv_base,
                                      int64_t k_plane_row0, int64_t v_plane_row0, int page_size, int nh, int nkv, int D) {
+    griddep_launch(); griddep_wait();
     const int t = blockIdx.x;
     const int half = D >> 1, vec_per_head = half >> 3;        // 8 pairs per thread
     const int qkv_w = (nh + 2 * nkv) * D;
@@ -141,11 +139,8 @@ cudaError_t launch_rope_kv_write(const void* qkv, const int32_t* positions, cons
     if (T <= 0) return cudaSuccess;
     if (kv.head_dim % 16 != 0) return cudaErrorInvalidValue;
     const int64_t k0 = (int64_t)layer * kv.layer_stride_rows, v0 = k0 + kv.kv_stride_rows;
-    rope_kv_write_kernel<<<T, 256, 0, s>>>(reinterpret_cast<const uint16_t*>(qkv), positions, slots, rope_cos, rope_sin,
-                                           reinterpret_cast<uint16_t*>(q_out), reinterpret_cast<uint16_t*>(kv.base), k0, v0,
-                                           kv.page_size, nh, kv.n_kv, kv.head_dim);
-    count_launch();
-    return cudaGetLastError();
+    return launch_k(rope_kv_write_kernel, dim3(T), dim3(256), 0, s, reinterpret_cast<const uint16_t*>(qkv), positions, slots, rope_cos, rope_sin,
+                    reinterpret_cast<uint16_t*>(q_out), reinterpret_cast<uint16_t*>(kv.base), k0, v0, kv.page_size, nh, kv.n_kv, kv.head_dim);
 }
 
 
@@ -186,6 +181,7 @@ OA_DEVINL void sk_sum8(const StreamK& sk, int row, int col, float (&acc)[8]) {
 template <int VPT>
 __global__ void __launch_bounds__(256) sk_resid_rmsnorm_kernel(const StreamK sk, uint4* __restrict__ x, const uint4* __restrict__ g,
                                                                uint4* __restrict__ y, int H8, float inv_h, float eps) {
+    griddep_launch(); griddep_wait();
     const int t = blockIdx.x;
     uint4* xr = x + (size_t)t * H8;
     uint4 v[VPT];
@@ -233,17 +229,16 @@ cudaError_t launch_sk_resid_rmsnorm(const StreamK& sk, void* x, const void* gain
     if (H % 8 != 0 || H > 8192 || T > 128) return cudaErrorInvalidValue;
     const int H8 = H / 8;
     auto X = reinterpret_cast<uint4*>(x); auto G = reinterpret_cast<const uint4*>(gain); auto Y = reinterpret_cast<uint4*>(xn);
-    if (H8 <= 256) sk_resid_rmsnorm_kernel<1><<<T, 256, 0, s>>>(sk, X, G, Y, H8, 1.0f / H, eps);
-    else if (H8 <= 512) sk_resid_rmsnorm_kernel<2><<<T, 256, 0, s>>>(sk, X, G, Y, H8, 1.0f / H, eps);
-    else sk_resid_rmsnorm_kernel<4><<<T, 256, 0, s>>>(sk, X, G, Y, H8, 1.0f / H, eps);
-    count_launch();
-    return cudaGetLastError();
+    if (H8 <= 256) return launch_k(sk_resid_rmsnorm_kernel<1>, dim3(T), dim3(256), 0, s, sk, X, G, Y, H8, 1.0f / H, eps);
+    if (H8 <= 512) return launch_k(sk_resid_rmsnorm_kernel<2>, dim3(T), dim3(256), 0, s, sk, X, G, Y, H8, 1.0f / H, eps);
+    return launch_k(sk_resid_rmsnorm_kernel<4>, dim3(T), dim3(256), 0, s, sk, X, G, Y, H8, 1.0f / H, eps);
 }
 
 // physical columns of the fused gate/up GEMM: per 32-column block, 16 gate then 16 up
 __global__ void sk_swiglu_kernel(const StreamK sk, uint4* __restrict__ act, int F8) {
-    const int t = blockIdx.x;
-    for (int i = threadIdx.x; i < F8; i += blockDim.x) {
+    griddep_launch(); griddep_wait();
+    const int t = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F8; i += gridDim.x * blockDim.x) {
         const int f0 = i * 8, blk = f0 >> 4, o = f0 & 15;
         float gt[8], up[8];
         sk_sum8(sk, t, blk * 32 + o, gt);
@@ -259,9 +254,7 @@ __global__ void sk_swiglu_kernel(const StreamK sk, uint4* __restrict__ act, int 
 cudaError_t launch_sk_swiglu(const StreamK& sk, void* act, int T, int F, cudaStream_t s) {
     if (T <= 0) return cudaSuccess;
     if (F % 16 != 0 || T > 128) return cudaErrorInvalidValue;
-    sk_swiglu_kernel<<<T, 256, 0, s>>>(sk, reinterpret_cast<uint4*>(act), F / 8);
-    count_launch();
-    return cudaGetLastError();
+    return launch_k(sk_swiglu_kernel, dim3((F / 8 + 255) / 256, T), dim3(256), 0, s, sk, reinterpret_cast<uint4*>(act), F / 8);
 }
 
 OA_DEVINL void sk_load8_bf16(const StreamK& sk, const uint16_t* bias, int row, int col, float (&v)[8]) {
@@ -279,14 +272,16 @@ __global__ void sk_rope_kv_write_kernel(const StreamK sk, const uint16_t* __rest
                                         const int32_t* __restrict__ slots, const float* __restrict__ rope_cos,
                                         const float* __restrict__ rope_sin, uint16_t* __restrict__ q_out, uint16_t* __restrict__ kv_base,
                                         int64_t k_plane_row0, int64_t v_plane_row0, int page_size, int nh, int nkv, int D) {
-    const int t = blockIdx.x;
+    griddep_launch(); griddep_wait();
+    const int t = blockIdx.y;
     const int half = D >> 1, vec_per_head = half >> 3;
     const int pos = positions[t], slot = slots[t];
     const int page = slot / page_size, off = slot - page * page_size;
     const float* cr = rope_cos + (size_t)pos * half;
     const float* sr = rope_sin + (size_t)pos * half;
     const int n_rot = (nh + nkv) * vec_per_head;
-    for (int w = threadIdx.x; w < n_rot; w += blockDim.x) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+    for (int w = gtid; w < n_rot; w += gstride) {
         const int head = w / vec_per_head, i0 = (w - head * vec_per_head) * 8;
         float av[8], bv[8];
         sk_load8_bf16(sk, bias, t, head * D + i0, av);
@@ -308,7 +303,8 @@ __global__ void sk_rope_kv_write_kernel(const StreamK sk, const uint16_t* __rest
         *reinterpret_cast<uint4*>(dst + i0 + half) = ob;
     }
     const int n_v = nkv * (D >> 3);
-    for (int w = threadIdx.x; w < n_v; w += blockDim.x) {
+    for (int w = gtid - n_rot; w < n_v; w += gstride) {      // the threads after the rotary items take V
+        if (w < 0) continue;
         const int head = w / (D >> 3), i0 = (w - head * (D >> 3)) * 8;
         float vv[8];
         sk_load8_bf16(sk, bias, t, (nh + nkv + head) * D + i0, vv);
@@ -324,11 +320,10 @@ cudaError_t launch_sk_rope_kv_write(const StreamK& sk, const void* bias, const i
     if (T <= 0) return cudaSuccess;
     if (kv.head_dim % 16 != 0 || T > 128) return cudaErrorInvalidValue;
     const int64_t k0 = (int64_t)layer * kv.layer_stride_rows, v0 = k0 + kv.kv_stride_rows;
-    sk_rope_kv_write_kernel<<<T, 256, 0, s>>>(sk, reinterpret_cast<const uint16_t*>(bias), positions, slots, rope_cos, rope_sin,
-                                              reinterpret_cast<uint16_t*>(q_out), reinterpret_cast<uint16_t*>(kv.base), k0, v0,
-                                              kv.page_size, nh, kv.n_kv, kv.head_dim);
-    count_launch();
-    return cudaGetLastError();
+    const int items = (nh + kv.n_kv) * (kv.head_dim / 16) + kv.n_kv * (kv.head_dim / 8);
+    return launch_k(sk_rope_kv_write_kernel, dim3((items + 127) / 128, T), dim3(128), 0, s, sk, reinterpret_cast<const uint16_t*>(bias), positions, slots,
+                    rope_cos, rope_sin, reinterpret_cast<uint16_t*>(q_out), reinterpret_cast<uint16_t*>(kv.base), k0, v0, kv.page_size, nh, kv.n_kv,
+                    kv.head_dim);
 }
 
 }  // namespace oa

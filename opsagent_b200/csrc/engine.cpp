@@ -141,6 +141,7 @@ public:
             }
             auto synth = [&](int b, int i) { uint64_t h = (uint64_t)(b + 1) * 0x9E3779B97F4A7C15ull + (uint64_t)i * 0xBF58476D1CE4E5B9ull; h ^= h >> 29; return (int32_t)(h % (uint64_t)V); };
             cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            const bool prof_all = model_.profile_all; model_.profile_all = false;      // in-situ kernel timing covers the decode steps only
             // ---- prefill: ctx_len-1 tokens per sequence, chunked by the step token budget ----
             const int P = ctx_len - 1;
             cudaEventRecord(e0, model_.stream);
@@ -171,6 +172,7 @@ public:
             cudaEventRecord(e1, model_.stream); model_.sync();
             float prefill_ms = 0; cudaEventElapsedTime(&prefill_ms, e0, e1);
             // ---- decode steps ----
+            model_.profile_all = prof_all;
             std::vector<int32_t> last(batch);
             for (int b = 0; b < batch; ++b) last[b] = synth(b, P);
             double ctx_sum = 0; float total_ms = 0; uint64_t launches0 = 0;
@@ -479,9 +481,22 @@ int oa_bench_decode(oa_engine* h, int32_t batch, int32_t ctx_len, int32_t steps,
     if (!h || !out) return fail(OA_ERR_BAD_REQUEST, "null argument");
     const char* pa = std::getenv("OA_PROFILE_ATTN");
     h->e->model().profile_attn = pa && pa[0] == '1';
+    const char* pall = std::getenv("OA_PROFILE_ALL");
+    h->e->model().profile_all = pall && pall[0] == '1';
     int rc = h->e->bench_decode(batch, ctx_len, steps, warmup, out, n_out);
-    h->e->model().profile_attn = false;
+    h->e->model().profile_attn = false; h->e->model().profile_all = false;
     return rc;
+}
+int oa_debug_kernel_times(oa_engine* h, char* buf, size_t n, int32_t reset) {
+    if (!h || !buf) return fail(OA_ERR_BAD_REQUEST, "null argument");
+    DeviceModel& m = h->e->model();
+    std::string s = "{";
+    for (int i = 0; i < 14; ++i) {
+        char t[128]; std::snprintf(t, sizeof t, "%s\"%s\": [%.4f, %ld]", i ? ", " : "", DeviceModel::kt_name(i), m.kt_ms[i], m.kt_n[i]); s += t;
+        if (reset) { m.kt_ms[i] = 0; m.kt_n[i] = 0; }
+    }
+    s += "}";
+    return copy_out(s, buf, n);
 }
 uint64_t oa_kernel_launches(void) { return launches_total(); }
 const char* oa_version(void) { return "opsagent_b200 0.1 (sm_100a)"; }

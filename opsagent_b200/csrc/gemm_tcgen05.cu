@@ -66,11 +66,21 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tcgen05_kernel(const __grid
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch();
 
     if (warp == 0) {
         if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            // weights (B) are written by no kernel of the chain: fill the ring with them BEFORE waiting for the predecessor
+            const int pre = num_kb < STAGES ? num_kb : STAGES;
+            for (int kb = 0; kb < pre; ++kb) {
+                mbar_expect_tx(&full_bar[kb], Cfg::STAGE_BYTES);
+                tma_load_2d(smem + kb * Cfg::STAGE_BYTES + Cfg::A_BYTES, &tmB, &full_bar[kb], kb * BLOCK_K, n_blk * BN, kEvictFirst);
+            }
+            griddep_wait();
+            for (int kb = 0; kb < pre; ++kb)
+                tma_load_2d(smem + kb * Cfg::STAGE_BYTES, &tmA, &full_bar[kb], kb * BLOCK_K, m_blk * BLOCK_M, kEvictLast);
+            int s = pre == STAGES ? 0 : pre; uint32_t ph = pre == STAGES ? 1 : 0;
+            for (int kb = pre; kb < num_kb; ++kb) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
                 uint8_t* b_dst = a_dst + Cfg::A_BYTES;
@@ -105,6 +115,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tcgen05_kernel(const __grid
         const int q = warp & 3;
         const int row = m_blk * BLOCK_M + q * 32 + lane;
         const bool row_ok = row < p.M;
+        griddep_wait();                   // bias/residual reads and every store below come after the predecessor grid
         mbar_wait(acc_bar, 0);
         tcgen05_fence_after();
         float best_v = -INFINITY; int best_i = 0x7fffffff;
@@ -214,9 +225,7 @@ static cudaError_t launch_one(const CUtensorMap* tmA, const CUtensorMap* tmB, co
         attr_set = true;
     }
     dim3 grid((p.N + BN - 1) / BN, (p.M + BLOCK_M - 1) / BLOCK_M, 1);
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*tmA, *tmB, p);
-    count_launch();
-    return cudaGetLastError();
+    return launch_k(kern, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, *tmA, *tmB, p);
 }
 
 template <int BN>
@@ -288,11 +297,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_streamk_kernel(const __g
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch();
 
     if (warp == 0) {
         if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (long long u = u0; u < u1; ++u) {
+            // weights first: they depend on no predecessor, so the HBM stream starts while the previous kernel drains
+            const int pre = (u1 - u0) < STAGES ? (int)(u1 - u0) : STAGES;
+            for (int i = 0; i < pre; ++i) {
+                const long long u = u0 + i;
+                const int tile = (int)(u / sk.kb), kblk = (int)(u - (long long)tile * sk.kb);
+                mbar_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
+                tma_load_2d(smem + i * Cfg::STAGE_BYTES + Cfg::A_BYTES, &tmB, &full_bar[i], kblk * BLOCK_K, tile * BN, kEvictFirst);
+            }
+            // ... and pull the next weight tiles into L2 while the (L2-bound) predecessor still runs and HBM is idle
+            {
+                const long long pf_end = (u0 + pre + sk.l2_prefetch_units) < u1 ? (u0 + pre + sk.l2_prefetch_units) : u1;
+                for (long long u = u0 + pre; u < pf_end; ++u) {
+                    const int tile = (int)(u / sk.kb), kblk = (int)(u - (long long)tile * sk.kb);
+                    tma_prefetch_l2_2d(&tmB, kblk * BLOCK_K, tile * BN);
+                }
+            }
+            griddep_wait();
+            for (int i = 0; i < pre; ++i) {
+                const long long u = u0 + i;
+                const int tile = (int)(u / sk.kb), kblk = (int)(u - (long long)tile * sk.kb);
+                tma_load_2d(smem + i * Cfg::STAGE_BYTES, &tmA, &full_bar[i], kblk * BLOCK_K, 0, kEvictLast);
+            }
+            int s = pre == STAGES ? 0 : pre; uint32_t ph = pre == STAGES ? 1 : 0;
+            for (long long u = u0 + pre; u < u1; ++u) {
                 const int tile = (int)(u / sk.kb), kblk = (int)(u - (long long)tile * sk.kb);
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
@@ -331,6 +363,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_streamk_kernel(const __g
     } else {
         const int q = warp & 3;
         int seg = 0;
+        griddep_wait();                   // the predecessor may still be reading the partial workspace
         for (long long u = u0; u < u1; ++seg) {
             const int tile = (int)(u / sk.kb);
             const long long uend = min(u1, (long long)(tile + 1) * sk.kb);
@@ -374,6 +407,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_streamk_kernel(const __g
 StreamK make_streamk(float* ws, int N, int K, int bn, int G) {
     StreamK sk{}; sk.ws = ws; sk.bn = bn; sk.kb = (K + BLOCK_K - 1) / BLOCK_K; sk.n_tiles = (N + bn - 1) / bn;
     sk.total = (long long)sk.n_tiles * sk.kb; sk.G = (int)std::min<long long>(G, sk.total);
+    sk.l2_prefetch_units = 0;
     return sk;
 }
 size_t streamk_ws_bytes(int N, int bn, int G) { return (size_t)(G + (N + bn - 1) / bn) * BLOCK_M * bn * sizeof(float); }
@@ -387,9 +421,7 @@ static cudaError_t launch_sk(const CUtensorMap* tmA, const CUtensorMap* tmB, int
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    kern<<<sk.G, GEMM_THREADS, SkCfg<BN>::SMEM_BYTES, stream>>>(*tmA, *tmB, M, sk);
-    count_launch();
-    return cudaGetLastError();
+    return launch_k(kern, dim3(sk.G), dim3(GEMM_THREADS), SkCfg<BN>::SMEM_BYTES, stream, *tmA, *tmB, M, sk);
 }
 cudaError_t launch_gemm_streamk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, cudaStream_t stream) {
     if (M <= 0 || M > BLOCK_M || (N % 8) != 0 || (K % 8) != 0) return cudaErrorInvalidValue;
@@ -402,6 +434,7 @@ cudaError_t launch_gemm_streamk(const CUtensorMap* tmA, const CUtensorMap* tmB, 
 __global__ void argmax_reduce_kernel(const float* __restrict__ val, const int* __restrict__ idx, int M, int n_tiles,
                                      int32_t* __restrict__ out_ids, float* __restrict__ out_val) {
     const int row = blockIdx.x;
+    griddep_launch(); griddep_wait();
     float bv = -INFINITY; int bi = 0x7fffffff;
     for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
         float v = val[(size_t)row * n_tiles + t]; int i = idx[(size_t)row * n_tiles + t];
@@ -425,9 +458,7 @@ __global__ void argmax_reduce_kernel(const float* __restrict__ val, const int* _
 
 cudaError_t launch_argmax_reduce(const float* amax_val, const int* amax_idx, int M, int n_tiles, int32_t* out_ids,
                                  float* out_val, cudaStream_t stream) {
-    argmax_reduce_kernel<<<M, 256, 0, stream>>>(amax_val, amax_idx, M, n_tiles, out_ids, out_val);
-    count_launch();
-    return cudaGetLastError();
+    return launch_k(argmax_reduce_kernel, dim3(M), dim3(256), 0, stream, amax_val, amax_idx, M, n_tiles, out_ids, out_val);
 }
 
 }  // namespace oa

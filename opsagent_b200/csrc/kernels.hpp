@@ -41,6 +41,7 @@ int gemm_n_tiles(int N, int block_n);
 // RMSNorm / RoPE / SwiGLU while they are at it.
 struct StreamK {
     float* ws; int bn, kb, n_tiles, G; long long total;      // kb = k blocks per tile, total = n_tiles * kb, G = CTAs
+    int l2_prefetch_units;                                    // weight tiles each CTA prefetches into L2 before griddepcontrol.wait
 };
 StreamK make_streamk(float* ws, int N, int K, int bn, int G);
 size_t streamk_ws_bytes(int N, int bn, int G);
@@ -115,6 +116,21 @@ cudaError_t launch_prefill_attention(const CUtensorMap* tm_kv, const KvLayout& k
 
 // bookkeeping for bench.py's gpu_launches claim
 uint64_t launches_total();
+bool pdl_enabled();     // OA_PDL=0 disables programmatic dependent launch
 void count_launch();
+
+
+// Every kernel launch goes through here: counts it and (unless OA_PDL=0) marks it for programmatic dependent launch.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    count_launch();
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 }  // namespace oa

@@ -166,9 +166,13 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
     part_ml_ = reinterpret_cast<float*>(dmalloc((size_t)max_part_slots_ * grp * 2 * 4));
     meta_cap_words_ = (size_t)4 * MR + (size_t)opt.max_batch * (max_pages_per_seq + 2) + (size_t)MR / 64 * 4 + 4 * opt.max_batch +
                       (size_t)(opt.max_batch * cfg.n_kv_heads + n_ctas + 8) * 8 * 2 + (size_t)n_ctas + 4096;
-    cuda_check(cudaMallocHost(&h_meta_, meta_cap_words_ * 4), "cudaMallocHost meta");
+    for (int i = 0; i < 2; ++i) {
+        cuda_check(cudaMallocHost(&h_meta_buf_[i], meta_cap_words_ * 4), "cudaMallocHost meta");
+        cuda_check(cudaEventCreateWithFlags(&meta_ev_[i], cudaEventDisableTiming), "cudaEventCreate meta");
+    }
+    h_meta_ = h_meta_buf_[0];
     d_meta_ = reinterpret_cast<int32_t*>(dmalloc(meta_cap_words_ * 4));
-    sk_bn_ = (opt.sk_bn == 128) ? 128 : 256;
+    sk_bn_ = (opt.sk_bn == 256) ? 256 : 128;
     sk_G_ = opt.sk_ctas > 0 ? opt.sk_ctas : sm_count;
     {
         size_t wsb = 0;
@@ -189,10 +193,15 @@ DeviceModel::~DeviceModel() {
     for (auto& e : ev) cudaEventDestroy(e);
     for (void* p : allocs_) cudaFree(p);
     if (h_out_ids) cudaFreeHost(h_out_ids);
-    if (h_meta_) cudaFreeHost(h_meta_);
+    for (int i = 0; i < 2; ++i) { if (h_meta_buf_[i]) cudaFreeHost(h_meta_buf_[i]); if (meta_ev_[i]) cudaEventDestroy(meta_ev_[i]); }
     if (stream) cudaStreamDestroy(stream);
 }
 
+const char* DeviceModel::kt_name(int id) {
+    static const char* n[16] = {"h2d+embed", "rmsnorm", "qkv_gemm", "rope_kv", "attention", "attn_merge", "o_gemm", "resid_rmsnorm", "gate_up_gemm",
+                                "swiglu", "down_gemm", "gather+norm", "lm_head", "argmax+d2h", "", ""};
+    return n[id & 15];
+}
 void DeviceModel::sync() { cuda_check(cudaStreamSynchronize(stream), "stream sync"); }
 
 // N-tile heuristic.  Decode (M <= 128) streams weights once: prefer the largest tile that still yields >= 1 CTA
@@ -264,6 +273,8 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
     if (in.decode && in.n_seqs != T) throw std::runtime_error("forward: decode needs one token per sequence");
 
     // ---- pack per-step metadata into one pinned arena, one H2D copy ----
+    meta_idx_ ^= 1; h_meta_ = h_meta_buf_[meta_idx_];
+    cuda_check(cudaEventSynchronize(meta_ev_[meta_idx_]), "meta staging fence");     // its previous H2D copy has been consumed
     size_t w = 0;
     auto put = [&](const void* src, size_t words) -> size_t {
         size_t at = w; if (at + words > meta_cap_words_) throw std::runtime_error("forward: metadata arena overflow");
@@ -286,12 +297,20 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
         o_tiles = put(in.tiles.data(), in.tiles.size() * 4);
     }
     cuda_check(cudaMemcpyAsync(d_meta_, h_meta_, w * 4, cudaMemcpyHostToDevice, stream), "meta H2D");
+    cuda_check(cudaEventRecord(meta_ev_[meta_idx_], stream), "meta event");
     h2d_bytes += w * 4;
     const int32_t* d_tok = d_meta_ + o_tok; const int32_t* d_pos = d_meta_ + o_pos; const int32_t* d_slot = d_meta_ + o_slot;
     const int32_t* d_samp = d_meta_ + o_samp; const int32_t* d_bt = d_meta_ + o_bt; const int32_t* d_ctx = d_meta_ + o_ctx;
 
+    size_t ek = 0;
+    if (profile_all) {
+        if (ev_all.size() < (size_t)L * 12 + 16) { size_t o = ev_all.size(); ev_all.resize((size_t)L * 12 + 16); for (size_t i = o; i < ev_all.size(); ++i) cudaEventCreate(&ev_all[i]); }
+        ev_ids.assign(ev_all.size(), 0);
+        cudaEventRecord(ev_all[ek++], stream);
+    }
+    auto MARK = [&](int id) { if (profile_all && ek < ev_all.size()) { ev_ids[ek] = id; cudaEventRecord(ev_all[ek++], stream); } };
     const float scale_log2e = (1.0f / std::sqrt((float)D)) * 1.4426950408889634f;
-    cuda_check(launch_embed_gather(d_tok, embed, x_, T, H, V, stream), "embed");
+    cuda_check(launch_embed_gather(d_tok, embed, x_, T, H, V, stream), "embed"); MARK(0);
     const bool use_sk = opt.streamk && T <= 128;
     auto attention = [&](int l) {
         if (profile_attn) cudaEventRecord(ev[2 * l], stream);
@@ -299,53 +318,55 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
             DecodeAttnParams a{}; a.q = q_; a.out = attn_; a.block_tables = d_bt; a.ctx_lens = d_ctx; a.max_pages_per_seq = max_pages_per_seq;
             a.segs = reinterpret_cast<const DecodeSeg*>(d_meta_ + o_segs); a.cta_seg_ptr = d_meta_ + o_ptr; a.n_ctas = (int)plan_.cta_ptr.size() - 1;
             a.part_o = part_o_; a.part_ml = part_ml_; a.layer = l; a.n_heads = nh; a.n_kv = nkv; a.scale_log2e = scale_log2e;
-            cuda_check(launch_decode_attention(&tm_kv, kv, a, stream), "decode attention");
+            cuda_check(launch_decode_attention(&tm_kv, kv, a, stream), "decode attention"); MARK(4);
             cuda_check(launch_decode_merge(reinterpret_cast<const MergeItem*>(d_meta_ + o_merge), (int)plan_.merges.size(), part_o_, part_ml_,
-                                           attn_, nh, nkv, D, stream), "decode merge");
+                                           attn_, nh, nkv, D, stream), "decode merge"); MARK(5);
         } else {
             PrefillAttnParams a{}; a.q = q_; a.out = attn_; a.block_tables = d_bt; a.max_pages_per_seq = max_pages_per_seq;
             a.tiles = reinterpret_cast<const PrefillTile*>(d_meta_ + o_tiles); a.n_tiles = (int)in.tiles.size();
             a.layer = l; a.n_heads = nh; a.n_kv = nkv; a.scale_log2e = scale_log2e;
-            cuda_check(launch_prefill_attention(&tm_kv, kv, a, stream), "prefill attention");
+            cuda_check(launch_prefill_attention(&tm_kv, kv, a, stream), "prefill attention"); MARK(4);
         }
         if (profile_attn) cudaEventRecord(ev[2 * l + 1], stream);
     };
     if (use_sk) {
         // decode-sized batch: persistent stream-K projections (fp32 partials) + fused consumers
         auto bn_of = [&](int o) { return (o == 128 || o == 256) ? o : sk_bn_; };
+        auto with_pf = [&](StreamK k) { k.l2_prefetch_units = std::max(0, opt.sk_l2_prefetch_kb * 1024 / (k.bn * 128)); return k; };
         const StreamK sk_qkv = make_streamk(sk_ws_, qkvd, H, bn_of(opt.sk_bn_qkv), sk_G_), sk_o = make_streamk(sk_ws_, H, qd, bn_of(opt.sk_bn_o), sk_G_);
         const StreamK sk_gu = make_streamk(sk_ws_, 2 * F, H, bn_of(opt.sk_bn_gu), sk_G_), sk_dn = make_streamk(sk_ws_, H, F, bn_of(opt.sk_bn_down), sk_G_);
-        cuda_check(launch_rmsnorm(x_, layers[0].ln1, xn_, T, H, cfg.rms_eps, stream), "rmsnorm1");
+        cuda_check(launch_rmsnorm(x_, layers[0].ln1, xn_, T, H, cfg.rms_eps, stream), "rmsnorm1"); MARK(1);
+        const StreamK pf_qkv = with_pf(sk_qkv), pf_o = with_pf(sk_o), pf_gu = with_pf(sk_gu), pf_dn = with_pf(sk_dn);
         for (int l = 0; l < L; ++l) {
             const Layer& ly = layers[l];
-            cuda_check(launch_gemm_streamk(&tm_xn_, ly.qkv.map(sk_qkv.bn), T, qkvd, H, sk_qkv, stream), "qkv gemm (stream-K)");
-            cuda_check(launch_sk_rope_kv_write(sk_qkv, ly.bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, T, nh, stream), "rope (stream-K)");
+            cuda_check(launch_gemm_streamk(&tm_xn_, ly.qkv.map(sk_qkv.bn), T, qkvd, H, pf_qkv, stream), "qkv gemm (stream-K)"); MARK(2);
+            cuda_check(launch_sk_rope_kv_write(sk_qkv, ly.bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, T, nh, stream), "rope (stream-K)"); MARK(3);
             attention(l);
-            cuda_check(launch_gemm_streamk(&tm_attn_, ly.o.map(sk_o.bn), T, H, qd, sk_o, stream), "o gemm (stream-K)");
-            cuda_check(launch_sk_resid_rmsnorm(sk_o, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm2");
-            cuda_check(launch_gemm_streamk(&tm_xn_, ly.gu.map(sk_gu.bn), T, 2 * F, H, sk_gu, stream), "gate_up gemm (stream-K)");
-            cuda_check(launch_sk_swiglu(sk_gu, act_, T, F, stream), "swiglu");
-            cuda_check(launch_gemm_streamk(&tm_act_, ly.down.map(sk_dn.bn), T, H, F, sk_dn, stream), "down gemm (stream-K)");
+            cuda_check(launch_gemm_streamk(&tm_attn_, ly.o.map(sk_o.bn), T, H, qd, pf_o, stream), "o gemm (stream-K)"); MARK(6);
+            cuda_check(launch_sk_resid_rmsnorm(sk_o, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm2"); MARK(7);
+            cuda_check(launch_gemm_streamk(&tm_xn_, ly.gu.map(sk_gu.bn), T, 2 * F, H, pf_gu, stream), "gate_up gemm (stream-K)"); MARK(8);
+            cuda_check(launch_sk_swiglu(sk_gu, act_, T, F, stream), "swiglu"); MARK(9);
+            cuda_check(launch_gemm_streamk(&tm_act_, ly.down.map(sk_dn.bn), T, H, F, pf_dn, stream), "down gemm (stream-K)"); MARK(10);
             const void* next_gain = (l + 1 < L) ? layers[l + 1].ln1 : final_norm;
-            cuda_check(launch_sk_resid_rmsnorm(sk_dn, x_, next_gain, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm1");
+            cuda_check(launch_sk_resid_rmsnorm(sk_dn, x_, next_gain, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm1"); MARK(7);
         }
     } else {
         const int bn_qkv = pick_bn(T, qkvd, opt.bn_qkv, false), bn_o = pick_bn(T, H, opt.bn_o, false);
         const int bn_gu = pick_bn(T, 2 * F, opt.bn_gu, true), bn_down = pick_bn(T, H, opt.bn_down, false);
         for (int l = 0; l < L; ++l) {
             const Layer& ly = layers[l];
-            cuda_check(launch_rmsnorm(x_, ly.ln1, xn_, T, H, cfg.rms_eps, stream), "rmsnorm1");
+            cuda_check(launch_rmsnorm(x_, ly.ln1, xn_, T, H, cfg.rms_eps, stream), "rmsnorm1"); MARK(1);
             GemmParams g{}; g.M = T; g.N = qkvd; g.K = H; g.out = qkv_; g.ldo = qkvd; g.bias = ly.bqkv;
-            cuda_check(launch_gemm(&tm_xn_, ly.qkv.map(bn_qkv), g, EPI_STORE, bn_qkv, stream), "qkv gemm");
-            cuda_check(launch_rope_kv_write(qkv_, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, T, nh, stream), "rope");
+            cuda_check(launch_gemm(&tm_xn_, ly.qkv.map(bn_qkv), g, EPI_STORE, bn_qkv, stream), "qkv gemm"); MARK(2);
+            cuda_check(launch_rope_kv_write(qkv_, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, T, nh, stream), "rope"); MARK(3);
             attention(l);
             GemmParams go{}; go.M = T; go.N = H; go.K = qd; go.out = x_; go.ldo = H; go.resid = x_; go.ldr = H;
-            cuda_check(launch_gemm(&tm_attn_, ly.o.map(bn_o), go, EPI_RESID, bn_o, stream), "o gemm");
-            cuda_check(launch_rmsnorm(x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "rmsnorm2");
+            cuda_check(launch_gemm(&tm_attn_, ly.o.map(bn_o), go, EPI_RESID, bn_o, stream), "o gemm"); MARK(6);
+            cuda_check(launch_rmsnorm(x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "rmsnorm2"); MARK(1);
             GemmParams gg{}; gg.M = T; gg.N = 2 * F; gg.K = H; gg.out = act_; gg.ldo = F;
-            cuda_check(launch_gemm(&tm_xn_, ly.gu.map(bn_gu), gg, EPI_SWIGLU, bn_gu, stream), "gate_up gemm");
+            cuda_check(launch_gemm(&tm_xn_, ly.gu.map(bn_gu), gg, EPI_SWIGLU, bn_gu, stream), "gate_up gemm"); MARK(8);
             GemmParams gd{}; gd.M = T; gd.N = H; gd.K = F; gd.out = x_; gd.ldo = H; gd.resid = x_; gd.ldr = H;
-            cuda_check(launch_gemm(&tm_act_, ly.down.map(bn_down), gd, EPI_RESID, bn_down, stream), "down gemm");
+            cuda_check(launch_gemm(&tm_act_, ly.down.map(bn_down), gd, EPI_RESID, bn_down, stream), "down gemm"); MARK(10);
         }
     }
     if (S > 0) {
@@ -355,13 +376,18 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
             cuda_check(launch_gather_rows(x_, d_samp, xs_, S, H, stream), "gather");
             cuda_check(launch_rmsnorm(xs_, final_norm, xsn_, S, H, cfg.rms_eps, stream), "final norm");
         }
+        MARK(11);
         const int bn_lm = pick_bn(S, V, opt.bn_lm, false);
         const int n_tiles = gemm_n_tiles(V, bn_lm);
         GemmParams gl{}; gl.M = S; gl.N = V; gl.K = H; gl.logits = logits_out; gl.ldl = V; gl.amax_val = amax_val_; gl.amax_idx = amax_idx_;
-        cuda_check(launch_gemm(&tm_xsn_, lm_head.map(bn_lm), gl, EPI_LOGITS, bn_lm, stream), "lm_head gemm");
+        cuda_check(launch_gemm(&tm_xsn_, lm_head.map(bn_lm), gl, EPI_LOGITS, bn_lm, stream), "lm_head gemm"); MARK(12);
         cuda_check(launch_argmax_reduce(amax_val_, amax_idx_, S, n_tiles, d_out_ids_, nullptr, stream), "argmax");
-        cuda_check(cudaMemcpyAsync(h_out_ids, d_out_ids_, (size_t)S * 4, cudaMemcpyDeviceToHost, stream), "ids D2H");
+        cuda_check(cudaMemcpyAsync(h_out_ids, d_out_ids_, (size_t)S * 4, cudaMemcpyDeviceToHost, stream), "ids D2H"); MARK(13);
         d2h_bytes += (size_t)S * 4;
+    }
+    if (profile_all) {
+        cuda_check(cudaStreamSynchronize(stream), "profile sync");
+        for (size_t i = 1; i < ek; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev_all[i - 1], ev_all[i]); kt_ms[ev_ids[i] & 15] += ms; kt_n[ev_ids[i] & 15]++; }
     }
     if (profile_attn) {
         cuda_check(cudaStreamSynchronize(stream), "profile sync");

@@ -50,6 +50,9 @@ public:
     KvLayout kv{}; CUtensorMap tm_kv;
     // instrumentation
     bool profile_attn = false; double attn_ms_accum = 0; std::vector<cudaEvent_t> ev;
+    // in-situ per-kernel timing (events after every launch, warm caches, real launch gaps): OA_PROFILE_ALL=1
+    bool profile_all = false; std::vector<cudaEvent_t> ev_all; std::vector<int> ev_ids; double kt_ms[16] = {0}; long kt_n[16] = {0};
+    static const char* kt_name(int id);
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
 
     struct Layer { WeightMat qkv, o, gu, down; void *ln1 = nullptr, *ln2 = nullptr, *bqkv = nullptr; };
@@ -69,6 +72,8 @@ private:
     float* amax_val_ = nullptr; int* amax_idx_ = nullptr; int32_t* d_out_ids_ = nullptr;
     float *part_o_ = nullptr, *part_ml_ = nullptr; int max_part_slots_ = 0;
     float* sk_ws_ = nullptr; int sk_bn_ = 256, sk_G_ = 148;
+    // pinned staging is double-buffered and fenced by events: the host may run ahead of the stream by a whole forward
+    int32_t* h_meta_buf_[2] = {nullptr, nullptr}; cudaEvent_t meta_ev_[2] = {nullptr, nullptr}; int meta_idx_ = 0;
     int32_t *h_meta_ = nullptr, *d_meta_ = nullptr; size_t meta_cap_words_ = 0;
     int max_rows_ = 0, max_sample_ = 0;
     DecodePlan plan_;

@@ -3,6 +3,7 @@
 // GPU-less build box.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.hpp"
@@ -42,5 +43,9 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 static std::atomic<uint64_t> g_launches{0};
 uint64_t launches_total() { return g_launches.load(); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = std::getenv("OA_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 }  // namespace oa

@@ -135,6 +135,11 @@ class Engine:
         _check(self._L.oa_debug_prefill_logits(self._h, toks.ctypes.data, len(toks), out.ctypes.data))
         return out
 
+    def kernel_times(self, reset: bool = True) -> dict:
+        buf = C.create_string_buffer(4096)
+        _check(self._L.oa_debug_kernel_times(self._h, buf, 4096, int(reset)))
+        return json.loads(buf.value.decode())
+
     def bench_decode(self, batch: int, ctx_len: int, steps: int, warmup: int) -> dict:
         out = (C.c_double * 8)()
         _check(self._L.oa_bench_decode(self._h, batch, ctx_len, steps, warmup, out, 8))

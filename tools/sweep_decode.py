@@ -13,4 +13,13 @@ for extra in configs:
     eng = Engine(cfg)
     r = eng.bench_decode(128, 1664 - 16 - 4, 32, 4)
     print(json.dumps({"extra": extra, "ms_per_step": round(r["ms_per_step"], 3), "tok_s": round(128e3 / r["ms_per_step"], 1)}), flush=True)
+    if os.environ.get("OA_SWEEP_KT"):
+        os.environ["OA_PROFILE_ALL"] = "1"
+        eng.kernel_times(True)
+        eng.bench_decode(128, 1664 - 4 - 2, 8, 2)
+        os.environ["OA_PROFILE_ALL"] = "0"
+        kt = eng.kernel_times(True)
+        steps = 10
+        print("   in-situ us/launch (launches/step): " + ", ".join(f"{k}={v[0] * 1e3 / max(v[1], 1):.1f}({v[1] // steps})" for k, v in kt.items() if v[1]), flush=True)
+        print("   in-situ ms/step by class: " + ", ".join(f"{k}={v[0] / steps:.3f}" for k, v in kt.items() if v[1]), flush=True)
     eng.close()
