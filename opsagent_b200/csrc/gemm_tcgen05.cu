@@ -14,6 +14,7 @@
 // llms.OpenAIClient.Chat (reference pkg/llms/openai.go:69-104) once the `local-cuda` provider replaces the
 // remote HTTP server — see DESIGN.md §Kernels.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.hpp"
@@ -24,6 +25,7 @@ static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;     // 64 bf16 = 128 B = one swizzle row
 static constexpr int UMMA_K = 16;
 static constexpr int GEMM_THREADS = 192;
+static constexpr int RASTER_GROUP_M = 16;
 
 template <int BN>
 struct GemmCfg {
@@ -51,7 +53,17 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tcgen05_kernel(const __grid
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+    // Grouped rasterisation: CTAs walk bands of RASTER_GROUP_M row tiles, M fastest inside a band, so a band of A
+    // (16 x 128 rows) stays L2-resident while each B tile is streamed from HBM once per band instead of once per row tile.
+    int n_blk, m_blk;
+    {
+        const int n_tiles = (p.N + BN - 1) / BN, m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+        const int per_band = RASTER_GROUP_M * n_tiles;
+        const int band = (int)blockIdx.x / per_band, within = (int)blockIdx.x - band * per_band;
+        const int m0 = band * RASTER_GROUP_M;
+        const int rows = (m_tiles - m0) < RASTER_GROUP_M ? (m_tiles - m0) : RASTER_GROUP_M;
+        m_blk = m0 + within % rows; n_blk = within / rows;
+    }
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
 
     if (warp == 0 && lane == 0) {
@@ -200,8 +212,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tcgen05_kernel(const __grid
             }
         }
         if (EPI == EPI_LOGITS && row_ok) {
-            p.amax_val[(size_t)row * gridDim.x + n_blk] = best_v;
-            p.amax_idx[(size_t)row * gridDim.x + n_blk] = best_i;
+            const int n_tiles = (p.N + BN - 1) / BN;
+            p.amax_val[(size_t)row * n_tiles + n_blk] = best_v;
+            p.amax_idx[(size_t)row * n_tiles + n_blk] = best_i;
         }
         tcgen05_fence_before();
     }
@@ -224,7 +237,7 @@ static cudaError_t launch_one(const CUtensorMap* tmA, const CUtensorMap* tmB, co
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    dim3 grid((p.N + BN - 1) / BN, (p.M + BLOCK_M - 1) / BLOCK_M, 1);
+    dim3 grid(((p.N + BN - 1) / BN) * ((p.M + BLOCK_M - 1) / BLOCK_M), 1, 1);
     return launch_k(kern, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, *tmA, *tmB, p);
 }
 
@@ -239,10 +252,25 @@ static cudaError_t launch_bn(const CUtensorMap* tmA, const CUtensorMap* tmB, con
     return cudaErrorInvalidValue;
 }
 
+static bool persistent_disabled();
+static int sm_count_cached();
+static long long persistent_min_tiles();
+template <int EPI>
+static cudaError_t launch_persistent(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, cudaStream_t stream);
+
 cudaError_t launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int epilogue, int block_n,
                         cudaStream_t stream) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0 || (p.N % 8) != 0 || (p.K % 8) != 0) return cudaErrorInvalidValue;
     if (epilogue == EPI_SWIGLU && (p.N % 32) != 0) return cudaErrorInvalidValue;
+    // large-M (prefill) shapes with the widest tile go to the persistent kernel (epilogue overlapped with the next tile)
+    if (block_n == 256 && epilogue != EPI_LOGITS && !persistent_disabled() &&
+        (long long)((p.N + 255) / 256) * ((p.M + BLOCK_M - 1) / BLOCK_M) >= persistent_min_tiles()) {
+        switch (epilogue) {
+            case EPI_STORE: return launch_persistent<EPI_STORE>(tmA, tmB, p, stream);
+            case EPI_RESID: return launch_persistent<EPI_RESID>(tmA, tmB, p, stream);
+            case EPI_SWIGLU: return launch_persistent<EPI_SWIGLU>(tmA, tmB, p, stream);
+        }
+    }
     switch (block_n) {
         case 32: return launch_bn<32>(tmA, tmB, p, epilogue, stream);
         case 64: return launch_bn<64>(tmA, tmB, p, epilogue, stream);
@@ -250,6 +278,202 @@ cudaError_t launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, const Ge
         case 256: return launch_bn<256>(tmA, tmB, p, epilogue, stream);
     }
     return cudaErrorInvalidValue;
+}
+
+// =============================================================================================
+// persistent tile GEMM (prefill, M > 128): one CTA per SM loops over 128 x 256 tiles in grouped raster order; TMEM holds
+// TWO accumulators so the epilogue of tile i (tcgen05.ld -> smem transpose -> coalesced bf16 stores, fused bias /
+// residual / SwiGLU) overlaps the tcgen05.mma main loop of tile i+1.
+// =============================================================================================
+struct PersistCfg {
+    static constexpr int BN = 256;
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2, B_BYTES = BN * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = 4;
+    static constexpr int EPI_ROW_FLOATS = 36, EPI_WARP_BYTES = 32 * EPI_ROW_FLOATS * 4;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * EPI_WARP_BYTES + 1024 + 256;
+    static constexpr uint32_t TMEM_COLS = 512;
+};
+
+OA_DEVINL void raster_tile(int idx, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
+    const int per_band = RASTER_GROUP_M * n_tiles;
+    const int band = idx / per_band, within = idx - band * per_band;
+    const int m0 = band * RASTER_GROUP_M;
+    const int rows = (m_tiles - m0) < RASTER_GROUP_M ? (m_tiles - m0) : RASTER_GROUP_M;
+    m_blk = m0 + within % rows; n_blk = within / rows;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                            const __grid_constant__ CUtensorMap tmB,
+                                                                            const GemmParams p) {
+    using Cfg = PersistCfg;
+    constexpr int BN = Cfg::BN, STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* epi_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + 4 * Cfg::EPI_WARP_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = (p.N + BN - 1) / BN, m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const int total_tiles = n_tiles * m_tiles;
+    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    griddep_launch();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            griddep_wait();
+            int s = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                int m_blk, n_blk; raster_tile(t, m_tiles, n_tiles, m_blk, n_blk);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                    tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BLOCK_K, m_blk * BLOCK_M, kEvictNormal);
+                    tma_load_2d(a_dst + Cfg::A_BYTES, &tmB, &full_bar[s], kb * BLOCK_K, n_blk * BN, kEvictNormal);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+            int s = 0; uint32_t ph = 0; int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int as = it & 1;
+                mbar_wait(&acc_empty[as], (((uint32_t)it >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                    const uint64_t a_desc = umma_desc_sw128(a_addr), b_desc = umma_desc_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_bf16(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_commit(&empty_bar[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&acc_full[as]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        float* stage = epi_smem + (warp - 2) * (Cfg::EPI_WARP_BYTES / 4);
+        griddep_wait();
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            int m_blk, n_blk; raster_tile(t, m_tiles, n_tiles, m_blk, n_blk);
+            const int as = it & 1;
+            mbar_wait(&acc_full[as], ((uint32_t)it >> 1) & 1);
+            tcgen05_fence_after();
+            const int row_base = m_blk * BLOCK_M + q * 32;
+#pragma unroll 1
+            for (int cc = 0; cc < BN; cc += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cc), v);
+                tmem_ld_wait();
+                const int col0 = n_blk * BN + cc;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stage + lane * Cfg::EPI_ROW_FLOATS + j) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                __syncwarp();
+                if (EPI == EPI_SWIGLU) {
+                    // chunk = 16 gate + 16 up columns -> 16 output features; lane = (row, 8-feature half)
+                    const int h = lane & 1;
+#pragma unroll
+                    for (int i2 = 0; i2 < 2; ++i2) {
+                        const int r = i2 * 16 + (lane >> 1), row = row_base + r;
+                        const float* sp = stage + r * Cfg::EPI_ROW_FLOATS + h * 8;
+                        const float4 g0 = *reinterpret_cast<const float4*>(sp), g1 = *reinterpret_cast<const float4*>(sp + 4);
+                        const float4 u0 = *reinterpret_cast<const float4*>(sp + 16), u1 = *reinterpret_cast<const float4*>(sp + 20);
+                        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                        const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                        float f[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) f[k] = __fdividef(gg[k], 1.0f + __expf(-gg[k])) * uu[k];
+                        if (row < p.M && col0 < p.N) {
+                            uint4 o; o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + (size_t)row * p.ldo + (col0 >> 1) + h * 8) = o;
+                        }
+                    }
+                } else {
+                    // lane = (row, 8-column group): 8 rows x 64 B per store instruction
+                    const int c8 = (lane & 3) * 8, col = col0 + c8;
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const int r = i4 * 8 + (lane >> 2), row = row_base + r;
+                        const float* sp = stage + r * Cfg::EPI_ROW_FLOATS + c8;
+                        const float4 a0 = *reinterpret_cast<const float4*>(sp), a1 = *reinterpret_cast<const float4*>(sp + 4);
+                        float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                        if (row < p.M && col < p.N) {
+                            if (EPI == EPI_STORE) {
+                                if (p.bias) {
+                                    const uint4 bb = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias) + col);
+                                    f[0] += bf16lo(bb.x); f[1] += bf16hi(bb.x); f[2] += bf16lo(bb.y); f[3] += bf16hi(bb.y);
+                                    f[4] += bf16lo(bb.z); f[5] += bf16hi(bb.z); f[6] += bf16lo(bb.w); f[7] += bf16hi(bb.w);
+                                }
+                            } else {
+                                const uint4 rr = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.resid) + (size_t)row * p.ldr + col);
+                                f[0] += bf16lo(rr.x); f[1] += bf16hi(rr.x); f[2] += bf16lo(rr.y); f[3] += bf16hi(rr.y);
+                                f[4] += bf16lo(rr.z); f[5] += bf16hi(rr.z); f[6] += bf16lo(rr.w); f[7] += bf16hi(rr.w);
+                            }
+                            uint4 o; o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + (size_t)row * p.ldo + col) = o;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) { tcgen05_fence_after(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
+}
+
+static bool persistent_disabled() { static const bool off = [] { const char* e = std::getenv("OA_GEMM_PERSISTENT"); return e && e[0] == '0'; }(); return off; }
+// tests lower the threshold (OA_GEMM_PERSISTENT_MIN_TILES=1) to drive tiny shapes through the persistent kernel
+static long long persistent_min_tiles() { const char* e = std::getenv("OA_GEMM_PERSISTENT_MIN_TILES"); return e ? std::atoll(e) : 2LL * sm_count_cached(); }
+static int sm_count_cached() {
+    static int n = 0;
+    if (n == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
+template <int EPI>
+static cudaError_t launch_persistent(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, cudaStream_t stream) {
+    auto kern = gemm_persistent_kernel<EPI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int tiles = ((p.N + 255) / 256) * ((p.M + BLOCK_M - 1) / BLOCK_M);
+    const int grid = tiles < sm_count_cached() ? tiles : sm_count_cached();
+    return launch_k(kern, dim3(grid), dim3(GEMM_THREADS), PersistCfg::SMEM_BYTES, stream, *tmA, *tmB, p);
 }
 
 // =============================================================================================

@@ -50,6 +50,20 @@ def test_prefill_logits_match_oracle(pair):
         assert err < LOGIT_TOL, (n, err)
 
 
+def test_prefill_logits_through_persistent_gemm(monkeypatch):
+    """same parity with every prefill projection forced through the persistent tile GEMM (the 8B prefill path)"""
+    monkeypatch.setenv("OA_GEMM_PERSISTENT_MIN_TILES", "1")
+    for name in CASES:
+        spec, eng = make_engine(name, bn_qkv=256, bn_o=256, bn_gu=256, bn_down=256)
+        orc = O.Oracle(spec, max_pos=512, mode=1)
+        rng = np.random.default_rng(11)
+        toks = rng.integers(0, spec.vocab, size=200).astype(np.int32)      # T > 128: tile-GEMM path, not stream-K
+        got = eng.debug_prefill_logits(toks)
+        ref = orc.forward(toks, all_logits=True)
+        assert np.abs(got - ref).max() < LOGIT_TOL
+        eng.close(); orc.close()
+
+
 def test_greedy_generation_matches_oracle(pair):
     spec, eng, orc = pair
     rng = np.random.default_rng(2)

@@ -158,6 +158,36 @@ def test_gemm_logits_argmax(L, M, N, K, bn):
     assert (ids2 == ids).all()
 
 
+@pytest.mark.parametrize("M,N,K", [(5000, 2304, 320), (300, 1024, 512), (8192, 6144, 256)])
+def test_gemm_persistent_kernel_all_epilogues(L, M, N, K, monkeypatch):
+    """prefill path: persistent 128x256 tiles, double-buffered TMEM, transposed coalesced epilogue (forced for small shapes)"""
+    monkeypatch.setenv("OA_GEMM_PERSISTENT_MIN_TILES", "1")
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(dev())
+    B = (torch.randn(N, K, generator=g) * 0.5).to(torch.bfloat16).to(dev())
+    bias = torch.randn(N, generator=g).to(torch.bfloat16).to(dev())
+    ref = A.float() @ B.float().T
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev())
+    assert L.oa_k_gemm(ptr(A), ptr(B), M, N, K, EPI_STORE, 256, ptr(out), ptr(bias), None, None, None, None) == 0
+    torch.cuda.synchronize()
+    r = ref + bias.float()
+    assert torch.isfinite(out.float()).all()
+    assert ((out.float() - r).abs() <= r.abs() * 2.0 ** -8 * 1.01 + 2e-3).all()
+    x = torch.randn(M, N, generator=g).to(torch.bfloat16).to(dev())
+    refx = (ref + x.float()).to(torch.bfloat16)
+    assert L.oa_k_gemm(ptr(A), ptr(B), M, N, K, EPI_RESID, 256, ptr(x), None, ptr(x), None, None, None) == 0
+    torch.cuda.synchronize()
+    assert ((x.float() - refx.float()).abs() <= refx.float().abs() * 2.0 ** -7 + 1e-3).all()
+    F = N // 2
+    out2 = torch.full((M, F), float("nan"), dtype=torch.bfloat16, device=dev())
+    assert L.oa_k_gemm(ptr(A), ptr(B), M, N, K, EPI_SWIGLU, 256, ptr(out2), None, None, None, None, None) == 0
+    torch.cuda.synchronize()
+    acc = ref.view(M, N // 32, 2, 16)
+    rs = (torch.nn.functional.silu(acc[:, :, 0]) * acc[:, :, 1]).reshape(M, F)
+    assert torch.isfinite(out2.float()).all()
+    assert ((out2.float() - rs).abs() <= rs.abs() * 2.0 ** -7 + 3e-3).all()
+
+
 @pytest.mark.parametrize("bn", [128, 256])
 @pytest.mark.parametrize("M,N,K,G", [(128, 4096, 4096, 148), (128, 6144, 4096, 148), (77, 1024, 14336, 148), (1, 320, 320, 148),
                                       (128, 28672, 4096, 148), (16, 2304, 256, 5), (128, 512, 512, 3), (100, 1000, 192, 148)])
