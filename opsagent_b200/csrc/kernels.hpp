@@ -80,7 +80,7 @@ cudaError_t launch_rope_kv_write(const void* qkv, const int32_t* positions, cons
 // logical tensor [rows, cols]; `interleave16_with` >= 0 means this is the fused gate/up tensor: physical
 // row r holds gate row (r/32)*16+r%16 when (r%32)<16 (tensor_id), else the same row of tensor `tensor_id_b`.
 cudaError_t launch_init_weight(void* dst, uint64_t seed, uint64_t tensor_id, int64_t tensor_id_b, int64_t rows, int64_t cols,
-                               float std, float mean, cudaStream_t s);
+                               float std, float mean, cudaStream_t s, int64_t row_off = 0, int64_t col_off = 0, int64_t logical_cols = 0);
 
 // ---- attention (attention.cu) ----------------------------------------------------------------
 struct DecodeSeg {        // one contiguous piece of one (sequence, kv head) handled by one CTA

@@ -21,8 +21,10 @@ OA_DEVINL uint16_t gen_bf16(uint64_t key, uint64_t idx, float std, float mean) {
     return f32_to_bf16_bits(__fadd_rn(__fmul_rn(u, std), mean));
 }
 
+// (row_off, col_off, logical_cols) place this (possibly tensor-parallel) shard inside the logical tensor, so every rank
+// generates exactly the slice of the single-GPU tensor it owns.
 __global__ void init_weight_kernel(uint16_t* __restrict__ dst, uint64_t key_a, uint64_t key_b, int interleave, int64_t rows,
-                                   int64_t cols, float std, float mean) {
+                                   int64_t cols, float std, float mean, int64_t row_off, int64_t col_off, int64_t logical_cols) {
     const int64_t n = rows * cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i / cols, c = i - r * cols;
@@ -32,7 +34,7 @@ __global__ void init_weight_kernel(uint16_t* __restrict__ dst, uint64_t key_a, u
             lr = blk * 16 + (w & 15);
             key = (w < 16) ? key_a : key_b;
         }
-        dst[i] = gen_bf16(key, (uint64_t)(lr * cols + c), std, mean);
+        dst[i] = gen_bf16(key, (uint64_t)((lr + row_off) * logical_cols + col_off + c), std, mean);
     }
 }
 
@@ -44,13 +46,14 @@ static uint64_t host_mix64(uint64_t z) {
 }
 
 cudaError_t launch_init_weight(void* dst, uint64_t seed, uint64_t tensor_id, int64_t tensor_id_b, int64_t rows, int64_t cols,
-                               float std, float mean, cudaStream_t s) {
+                               float std, float mean, cudaStream_t s, int64_t row_off, int64_t col_off, int64_t logical_cols) {
+    if (logical_cols <= 0) logical_cols = cols;
     uint64_t key_a = host_mix64(seed ^ (tensor_id * 0xD6E8FEB86659FD93ull));
     uint64_t key_b = tensor_id_b >= 0 ? host_mix64(seed ^ ((uint64_t)tensor_id_b * 0xD6E8FEB86659FD93ull)) : 0;
     int64_t n = rows * cols;
     int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
     init_weight_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<uint16_t*>(dst), key_a, key_b, tensor_id_b >= 0 ? 1 : 0, rows, cols,
-                                              std, mean);
+                                              std, mean, row_off, col_off, logical_cols);
     count_launch();
     return cudaGetLastError();
 }

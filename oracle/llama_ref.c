@@ -352,6 +352,13 @@ REF_API int32_t oa_ref_generate(ref_model *m, int32_t slot, const int32_t *promp
 /* ---- standalone kernels' restatements, used by kernel-level parity tests ---- */
 REF_API void oa_ref_rmsnorm(const float *x, const uint16_t *g, float *y, int32_t T, int32_t H, float eps, int32_t mode) { rmsnorm(x, g, y, T, H, eps, mode); }
 REF_API void oa_ref_linear(const float *x, const uint16_t *W, const uint16_t *bias, float *y, int32_t T, int32_t K, int32_t N) { linear(x, W, bias, y, T, K, N); }
+REF_API void oa_ref_set_threads(int32_t n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 REF_API int32_t oa_ref_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

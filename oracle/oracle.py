@@ -44,9 +44,26 @@ def build(force: bool = False) -> str:
     return so
 
 
+def default_threads() -> int:
+    """Threads the oracle may use: the CPUs this process is allowed on, capped by the cgroup CPU quota and by 64
+    (beyond that the memory-bound mat-vec loops only add barrier contention: 128 threads measured 70x slower than 64)."""
+    env = os.environ.get("OA_ORACLE_THREADS")
+    if env:
+        return max(1, int(env))
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
 def lib():
     global _LIB
     if _LIB is None:
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
         L = C.CDLL(build())
         L.oa_ref_create.restype = C.c_void_p
         L.oa_ref_create.argtypes = [C.POINTER(RefConfig), C.c_int32, C.c_int32, C.c_int32]
@@ -67,6 +84,8 @@ def lib():
         L.oa_ref_argmax.restype = C.c_int32
         L.oa_ref_argmax.argtypes = [C.c_void_p, C.c_int32]
         L.oa_ref_num_threads.restype = C.c_int32
+        L.oa_ref_set_threads.argtypes = [C.c_int32]
+        L.oa_ref_set_threads(default_threads())
         _LIB = L
     return _LIB
 
