@@ -197,11 +197,12 @@ def run_ours(args, rank, world, local_rank):
                         "tokens_per_sec": round(BATCH * (ctx0 - 1) / (r["prefill_ms"] / 1e3), 1)}}
     if rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_tokens)
+    if rank == 0:
+        print(json.dumps(line), flush=True)      # before any teardown: a hard exit in NCCL/driver teardown must not eat the line
+        sys.stdout.flush()
     eng.close()
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
-    if rank == 0:
-        print(json.dumps(line))
 
 
 def cpu_baseline(n_decode=6, n_prompt=16):
@@ -244,7 +245,7 @@ def run_reference(args, rank, world):
                        "parallelism": "cpu"},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():

@@ -102,6 +102,8 @@ struct EngineOptions {
     int sk_l2_prefetch_kb = 0;    // per-CTA weight KB prefetched into L2 ahead of the dependency wait (measured: hurts, 8.75 -> 9.3 ms; off)
     int sk_bn_qkv = 0, sk_bn_o = 0, sk_bn_gu = 0, sk_bn_down = 0;   // per-projection overrides (0 = sk_bn)
     int start_thread = 1;
+    int tp = 1, tp_rank = 0;      // tensor parallel degree / this process's rank (one process per GPU)
+    std::string tp_shm = "/oa_tp"; // POSIX shm name shared by the ranks of one TP group
 };
 
 inline void parse_config(const std::string& json, ModelConfig& m, EngineOptions& o) {
@@ -121,7 +123,7 @@ inline void parse_config(const std::string& json, ModelConfig& m, EngineOptions&
     I("device", o.device); o.kv_gb = j.f("kv_gb", o.kv_gb); I("num_pages", o.num_pages); I("max_batch", o.max_batch);
     I("max_seq_len", o.max_seq_len); I("max_step_tokens", o.max_step_tokens); I("max_queue", o.max_queue);
     I("bn_qkv", o.bn_qkv); I("bn_o", o.bn_o); I("bn_gu", o.bn_gu); I("bn_down", o.bn_down); I("bn_lm", o.bn_lm);
-    I("attn_ctas", o.attn_ctas); I("streamk", o.streamk); I("sk_bn", o.sk_bn); I("sk_ctas", o.sk_ctas); I("sk_l2_prefetch_kb", o.sk_l2_prefetch_kb); I("sk_bn_qkv", o.sk_bn_qkv); I("sk_bn_o", o.sk_bn_o); I("sk_bn_gu", o.sk_bn_gu); I("sk_bn_down", o.sk_bn_down); I("start_thread", o.start_thread);
+    I("attn_ctas", o.attn_ctas); I("streamk", o.streamk); I("sk_bn", o.sk_bn); I("sk_ctas", o.sk_ctas); I("sk_l2_prefetch_kb", o.sk_l2_prefetch_kb); I("sk_bn_qkv", o.sk_bn_qkv); I("sk_bn_o", o.sk_bn_o); I("sk_bn_gu", o.sk_bn_gu); I("sk_bn_down", o.sk_bn_down); I("start_thread", o.start_thread); I("tp", o.tp); I("tp_rank", o.tp_rank); o.tp_shm = j.s("tp_shm", o.tp_shm);
     if (m.hidden <= 0 || m.n_layers <= 0 || m.n_heads <= 0 || m.n_kv_heads <= 0 || m.ffn <= 0 || m.vocab <= 0)
         throw std::runtime_error("unknown model '" + name + "' and no explicit dimensions given");
     if (m.head_dim != 64 && m.head_dim != 128) throw std::runtime_error("head_dim must be 64 or 128");
@@ -129,6 +131,9 @@ inline void parse_config(const std::string& json, ModelConfig& m, EngineOptions&
     if (m.hidden % 64 || m.ffn % 64 || m.vocab % 8) throw std::runtime_error("hidden/ffn must be multiples of 64, vocab of 8");
     if (m.chat_template != "llama3" && m.chat_template != "chatml") throw std::runtime_error("template must be llama3 or chatml");
     if (o.max_seq_len % 64) o.max_seq_len = (o.max_seq_len + 63) / 64 * 64;
+    if (o.tp < 1 || o.tp > 8 || o.tp_rank < 0 || o.tp_rank >= o.tp) throw std::runtime_error("tp must be 1..8 and 0 <= tp_rank < tp");
+    if (o.tp > 1 && (m.n_kv_heads % o.tp || m.n_heads % o.tp || (m.ffn / o.tp) % 64 || m.ffn % o.tp || (m.vocab / o.tp) % 8 || m.vocab % o.tp))
+        throw std::runtime_error("tp must divide n_heads, n_kv_heads, ffn (in multiples of 64) and vocab (in multiples of 8)");
 }
 
 }  // namespace oa

@@ -66,8 +66,12 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
                                                    std::to_string(prop.major) + std::to_string(prop.minor));
     sm_count = prop.multiProcessorCount;
     cuda_check(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
-    const int H = cfg.hidden, L = cfg.n_layers, F = cfg.ffn, V = cfg.vocab, D = cfg.head_dim;
-    const int qd = cfg.q_dim(), kd = cfg.kv_dim(), qkvd = cfg.qkv_dim();
+    tp = opt.tp; tp_rank = opt.tp_rank;
+    nh_l = cfg.n_heads / tp; nkv_l = cfg.n_kv_heads / tp; F_l = cfg.ffn / tp; V_l = cfg.vocab / tp;
+    const int H = cfg.hidden, L = cfg.n_layers, F = F_l, V = cfg.vocab, D = cfg.head_dim;
+    const int qd = nh_l * D, kd = nkv_l * D, qkvd = qd + 2 * kd;              // this rank's shard
+    const int qd_g = cfg.q_dim(), F_g = cfg.ffn;                              // logical (global) sizes for the weight generator
+    const int64_t r = tp_rank;
     const float nstd = cfg.norm_random ? 0.1f : 0.0f;
 
     // ---- weights: seeded init directly in HBM, bit-identical to the oracle's generator ----
@@ -75,28 +79,30 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
     cuda_check(launch_init_weight(embed, cfg.seed, (uint64_t)L * 16 + TG_EMBED, -1, V, H, cfg.init_std, 0.f, stream), "init embed");
     final_norm = dmalloc((size_t)H * 2);
     cuda_check(launch_init_weight(final_norm, cfg.seed, (uint64_t)L * 16 + TG_NORM, -1, 1, H, nstd, 1.f, stream), "init norm");
-    if (cfg.tie_embeddings) { lm_head.ptr = embed; lm_head.N = V; lm_head.K = H; make_weight_maps(lm_head); }
-    else { alloc_weight(lm_head, V, H); cuda_check(launch_init_weight(lm_head.ptr, cfg.seed, (uint64_t)L * 16 + TG_LMHEAD, -1, V, H, cfg.init_std, 0.f, stream), "init lm_head"); }
+    // LM head is vocab-parallel: this rank owns rows [r*V_l, (r+1)*V_l)
+    if (cfg.tie_embeddings) { lm_head.ptr = reinterpret_cast<uint16_t*>(embed) + (size_t)r * V_l * H; lm_head.N = V_l; lm_head.K = H; make_weight_maps(lm_head); }
+    else { alloc_weight(lm_head, V_l, H); cuda_check(launch_init_weight(lm_head.ptr, cfg.seed, (uint64_t)L * 16 + TG_LMHEAD, -1, V_l, H, cfg.init_std, 0.f, stream, r * V_l), "init lm_head"); }
     layers.resize(L);
     for (int l = 0; l < L; ++l) {
         Layer& ly = layers[l]; const uint64_t b = (uint64_t)l * 16;
         alloc_weight(ly.qkv, qkvd, H); alloc_weight(ly.o, H, qd); alloc_weight(ly.gu, 2 * F, H); alloc_weight(ly.down, H, F);
         uint16_t* wq = reinterpret_cast<uint16_t*>(ly.qkv.ptr);
-        cuda_check(launch_init_weight(wq, cfg.seed, b + T_WQ, -1, qd, H, cfg.init_std, 0.f, stream), "init wq");
-        cuda_check(launch_init_weight(wq + (size_t)qd * H, cfg.seed, b + T_WK, -1, kd, H, cfg.init_std, 0.f, stream), "init wk");
-        cuda_check(launch_init_weight(wq + (size_t)(qd + kd) * H, cfg.seed, b + T_WV, -1, kd, H, cfg.init_std, 0.f, stream), "init wv");
-        cuda_check(launch_init_weight(ly.o.ptr, cfg.seed, b + T_WO, -1, H, qd, cfg.init_std, 0.f, stream), "init wo");
-        cuda_check(launch_init_weight(ly.gu.ptr, cfg.seed, b + T_WG, (int64_t)(b + T_WU), 2 * (int64_t)F, H, cfg.init_std, 0.f, stream), "init wgu");
-        cuda_check(launch_init_weight(ly.down.ptr, cfg.seed, b + T_WD, -1, H, F, cfg.init_std, 0.f, stream), "init wd");
+        // column-parallel q|k|v and gate|up (row shards), row-parallel o and down (column shards of the logical tensors)
+        cuda_check(launch_init_weight(wq, cfg.seed, b + T_WQ, -1, qd, H, cfg.init_std, 0.f, stream, r * qd), "init wq");
+        cuda_check(launch_init_weight(wq + (size_t)qd * H, cfg.seed, b + T_WK, -1, kd, H, cfg.init_std, 0.f, stream, r * kd), "init wk");
+        cuda_check(launch_init_weight(wq + (size_t)(qd + kd) * H, cfg.seed, b + T_WV, -1, kd, H, cfg.init_std, 0.f, stream, r * kd), "init wv");
+        cuda_check(launch_init_weight(ly.o.ptr, cfg.seed, b + T_WO, -1, H, qd, cfg.init_std, 0.f, stream, 0, r * qd, qd_g), "init wo");
+        cuda_check(launch_init_weight(ly.gu.ptr, cfg.seed, b + T_WG, (int64_t)(b + T_WU), 2 * (int64_t)F, H, cfg.init_std, 0.f, stream, r * F), "init wgu");
+        cuda_check(launch_init_weight(ly.down.ptr, cfg.seed, b + T_WD, -1, H, F, cfg.init_std, 0.f, stream, 0, r * F, F_g), "init wd");
         ly.ln1 = dmalloc((size_t)H * 2); ly.ln2 = dmalloc((size_t)H * 2);
         cuda_check(launch_init_weight(ly.ln1, cfg.seed, b + T_LN1, -1, 1, H, nstd, 1.f, stream), "init ln1");
         cuda_check(launch_init_weight(ly.ln2, cfg.seed, b + T_LN2, -1, 1, H, nstd, 1.f, stream), "init ln2");
         if (cfg.qkv_bias) {
             ly.bqkv = dmalloc((size_t)qkvd * 2);
             uint16_t* bq = reinterpret_cast<uint16_t*>(ly.bqkv);
-            cuda_check(launch_init_weight(bq, cfg.seed, b + T_BQ, -1, 1, qd, cfg.init_std, 0.f, stream), "init bq");
-            cuda_check(launch_init_weight(bq + qd, cfg.seed, b + T_BK, -1, 1, kd, cfg.init_std, 0.f, stream), "init bk");
-            cuda_check(launch_init_weight(bq + qd + kd, cfg.seed, b + T_BV, -1, 1, kd, cfg.init_std, 0.f, stream), "init bv");
+            cuda_check(launch_init_weight(bq, cfg.seed, b + T_BQ, -1, 1, qd, cfg.init_std, 0.f, stream, 0, r * qd, qd_g), "init bq");
+            cuda_check(launch_init_weight(bq + qd, cfg.seed, b + T_BK, -1, 1, kd, cfg.init_std, 0.f, stream, 0, r * kd, cfg.kv_dim()), "init bk");
+            cuda_check(launch_init_weight(bq + qd + kd, cfg.seed, b + T_BV, -1, 1, kd, cfg.init_std, 0.f, stream, 0, r * kd, cfg.kv_dim()), "init bv");
         }
     }
 
@@ -128,14 +134,14 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
     xs_ = dmalloc((size_t)MS * H * 2); xsn_ = dmalloc((size_t)MS * H * 2);
     cuda_check(cudaMemsetAsync(xsn_, 0, (size_t)MS * H * 2, stream), "memset");
     amap(&tm_xsn_, xsn_, MS, H);
-    const int lm_tiles_max = gemm_n_tiles(V, 32);
+    const int lm_tiles_max = gemm_n_tiles(V_l, 32);
     amax_val_ = reinterpret_cast<float*>(dmalloc((size_t)MS * lm_tiles_max * 4));
     amax_idx_ = reinterpret_cast<int*>(dmalloc((size_t)MS * lm_tiles_max * 4));
     d_out_ids_ = reinterpret_cast<int32_t*>(dmalloc((size_t)MS * 4));
     cuda_check(cudaMallocHost(&h_out_ids, (size_t)MS * 4), "cudaMallocHost");
 
     // ---- paged KV pool ----
-    const size_t page_bytes = (size_t)2 * L * cfg.n_kv_heads * 64 * D * 2;    // all layers, K and V, of 64 tokens
+    const size_t page_bytes = (size_t)2 * L * nkv_l * 64 * D * 2;    // all layers, K and V, of 64 tokens (this rank's kv heads)
     if (opt.num_pages > 0) num_pages = opt.num_pages;
     else {
         size_t free_b = 0, total_b = 0;
@@ -146,10 +152,10 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
     }
     max_pages_per_seq = opt.max_seq_len / 64;
     if (num_pages < max_pages_per_seq) throw std::runtime_error("KV pool too small: " + std::to_string(num_pages) + " pages < one max-length sequence");
-    const int64_t plane_rows = (int64_t)num_pages * cfg.n_kv_heads * 64;
-    if ((double)plane_rows * 2 * L >= 2147483647.0) { num_pages = (int)(2147483647.0 / (2.0 * L * cfg.n_kv_heads * 64)) - 1; }
-    kv.page_size = 64; kv.n_kv = cfg.n_kv_heads; kv.head_dim = D; kv.num_pages = num_pages;
-    kv.kv_stride_rows = (int64_t)num_pages * cfg.n_kv_heads * 64; kv.layer_stride_rows = 2 * kv.kv_stride_rows;
+    const int64_t plane_rows = (int64_t)num_pages * nkv_l * 64;
+    if ((double)plane_rows * 2 * L >= 2147483647.0) { num_pages = (int)(2147483647.0 / (2.0 * L * nkv_l * 64)) - 1; }
+    kv.page_size = 64; kv.n_kv = nkv_l; kv.head_dim = D; kv.num_pages = num_pages;
+    kv.kv_stride_rows = (int64_t)num_pages * nkv_l * 64; kv.layer_stride_rows = 2 * kv.kv_stride_rows;
     kv_pool_bytes = (size_t)num_pages * page_bytes;
     kv.base = dmalloc(kv_pool_bytes);
     cuda_check(cudaMemsetAsync(kv.base, 0, kv_pool_bytes, stream), "kv memset");   // stale pages must hold finite values (0*NaN)
@@ -160,12 +166,12 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
 
     // ---- decode-attention partial workspace + per-step metadata arena ----
     const int n_ctas = opt.attn_ctas > 0 ? opt.attn_ctas : 2 * sm_count;
-    max_part_slots_ = 2 * n_ctas + 2 * opt.max_batch * cfg.n_kv_heads + 16;
+    max_part_slots_ = 2 * n_ctas + 2 * opt.max_batch * nkv_l + 16;
     const int grp = cfg.n_heads / cfg.n_kv_heads;
     part_o_ = reinterpret_cast<float*>(dmalloc((size_t)max_part_slots_ * grp * D * 4));
     part_ml_ = reinterpret_cast<float*>(dmalloc((size_t)max_part_slots_ * grp * 2 * 4));
     meta_cap_words_ = (size_t)4 * MR + (size_t)opt.max_batch * (max_pages_per_seq + 2) + (size_t)MR / 64 * 4 + 4 * opt.max_batch +
-                      (size_t)(opt.max_batch * cfg.n_kv_heads + n_ctas + 8) * 8 * 2 + (size_t)n_ctas + 4096;
+                      (size_t)(opt.max_batch * nkv_l + n_ctas + 8) * 8 * 2 + (size_t)n_ctas + 4096;
     for (int i = 0; i < 2; ++i) {
         cuda_check(cudaMallocHost(&h_meta_buf_[i], meta_cap_words_ * 4), "cudaMallocHost meta");
         cuda_check(cudaEventCreateWithFlags(&meta_ev_[i], cudaEventDisableTiming), "cudaEventCreate meta");
@@ -184,6 +190,11 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
     }
     ev.resize(2 * (size_t)L);
     for (auto& e : ev) cuda_check(cudaEventCreate(&e), "cudaEventCreate");
+    if (tp > 1) {
+        if (opt.num_pages <= 0) throw std::runtime_error("tensor parallel engines need an explicit num_pages (all ranks must agree on the pool size)");
+        const size_t sym_bytes = std::max((size_t)MR * H * 2, (size_t)128 * H * 4);
+        comm.reset(new TpComm(tp, tp_rank, opt.tp_shm, sym_bytes, max_sample_));
+    }
     cuda_check(cudaStreamSynchronize(stream), "init sync");
 }
 

@@ -1,11 +1,13 @@
 // model.hpp — device-resident model: weights, paged KV pool, activation buffers, TMA descriptors, and the
 // forward pass (prefill chunk or decode step) as a fixed sequence of sm_100a kernel launches on one stream.
 #pragma once
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "config.hpp"
 #include "kernels.hpp"
+#include "tp_comm.hpp"
 
 namespace oa {
 
@@ -44,6 +46,9 @@ public:
     int32_t* h_out_ids = nullptr;        // pinned, [max_batch or max_step_tokens]
 
     ModelConfig cfg; EngineOptions opt;
+    // tensor-parallel shard sizes (== the global sizes when tp == 1)
+    int tp = 1, tp_rank = 0, nh_l = 0, nkv_l = 0, F_l = 0, V_l = 0;
+    std::unique_ptr<TpComm> comm;
     cudaStream_t stream = nullptr;
     int num_pages = 0, max_pages_per_seq = 0, sm_count = 148;
     size_t weight_bytes = 0, kv_pool_bytes = 0;

@@ -1,0 +1,322 @@
+// tp_comm.cu — see tp_comm.hpp.  Cross-GPU all-reduce over NVLink peer memory with the engine's own kernels.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <stdexcept>
+#include <thread>
+
+#include "common.cuh"
+#include "model.hpp"
+#include "tp_comm.hpp"
+
+namespace oa {
+
+static void spin_until(const std::function<bool()>& ok, const char* what, double timeout_s = 120.0) {
+    const auto t0 = std::chrono::steady_clock::now();
+    while (!ok()) {
+        std::this_thread::sleep_for(std::chrono::microseconds(200));
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s)
+            throw std::runtime_error(std::string("tensor-parallel rendezvous timed out: ") + what);
+    }
+}
+
+TpComm::TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, int max_sample)
+    : t_(t), rank_(rank), shm_name_(shm_name) {
+    if (t < 2 || t > TP_MAX || rank < 0 || rank >= t) throw std::runtime_error("tp must be 2..8 and 0 <= tp_rank < tp");
+    // ---- shared-memory segment (leader creates, followers attach) ----
+    int fd = -1;
+    if (rank == 0) {
+        shm_unlink(shm_name.c_str());
+        fd = shm_open(shm_name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd < 0 || ftruncate(fd, sizeof(TpShm)) != 0) throw std::runtime_error("shm_open/ftruncate failed for " + shm_name);
+        owner_ = true;
+    } else {
+        spin_until([&] { fd = shm_open(shm_name.c_str(), O_RDWR, 0600); if (fd < 0) return false;
+                         struct stat st; if (fstat(fd, &st) != 0 || (size_t)st.st_size < sizeof(TpShm)) { close(fd); fd = -1; return false; } return true; },
+                   "follower waiting for the leader's shm segment");
+    }
+    shm_ = reinterpret_cast<TpShm*>(mmap(nullptr, sizeof(TpShm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0));
+    close(fd);
+    if (shm_ == MAP_FAILED) throw std::runtime_error("mmap of the tp shm segment failed");
+    if (rank == 0) {
+        shm_->handles_ready.store(0); shm_->peers_opened.store(0); shm_->seq.store(0);
+        for (int i = 0; i < TP_MAX; ++i) shm_->ack[i].store(0);
+        shm_->magic.store(0x4f415450u, std::memory_order_release);
+    } else {
+        spin_until([&] { return shm_->magic.load(std::memory_order_acquire) == 0x4f415450u; }, "leader initialising shm");
+    }
+    // ---- symmetric device buffers + IPC handle exchange ----
+    arg_half_bytes_ = (size_t)max_sample * 8;
+    for (int b = 0; b < 2; ++b) { cuda_check(cudaMalloc(&sym_[b], sym_bytes), "cudaMalloc sym"); cuda_check(cudaMemset(sym_[b], 0, sym_bytes), "memset sym"); }
+    cuda_check(cudaMalloc(reinterpret_cast<void**>(&flags_), TP_MAX * sizeof(uint32_t)), "cudaMalloc flags");
+    cuda_check(cudaMemset(flags_, 0, TP_MAX * sizeof(uint32_t)), "memset flags");
+    cuda_check(cudaMalloc(&arg_, 2 * arg_half_bytes_), "cudaMalloc arg");
+    cuda_check(cudaDeviceSynchronize(), "sync");
+    for (int b = 0; b < 2; ++b) cuda_check(cudaIpcGetMemHandle(&shm_->h_sym[rank][b], sym_[b]), "cudaIpcGetMemHandle sym");
+    cuda_check(cudaIpcGetMemHandle(&shm_->h_flags[rank], flags_), "cudaIpcGetMemHandle flags");
+    cuda_check(cudaIpcGetMemHandle(&shm_->h_arg[rank], arg_), "cudaIpcGetMemHandle arg");
+    shm_->handles_ready.fetch_add(1, std::memory_order_acq_rel);
+    spin_until([&] { return shm_->handles_ready.load(std::memory_order_acquire) >= (uint32_t)t; }, "all ranks publishing IPC handles");
+    for (int p = 0; p < t; ++p) {
+        if (p == rank) { peer_sym_[0][p] = sym_[0]; peer_sym_[1][p] = sym_[1]; peer_flags_[p] = flags_; peer_arg_[p] = arg_; continue; }
+        for (int b = 0; b < 2; ++b) cuda_check(cudaIpcOpenMemHandle(&peer_sym_[b][p], shm_->h_sym[p][b], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle sym");
+        cuda_check(cudaIpcOpenMemHandle(reinterpret_cast<void**>(&peer_flags_[p]), shm_->h_flags[p], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle flags");
+        cuda_check(cudaIpcOpenMemHandle(&peer_arg_[p], shm_->h_arg[p], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle arg");
+    }
+    for (int b = 0; b < 2; ++b) {
+        cuda_check(cudaMalloc(reinterpret_cast<void**>(&d_peer_sym_[b]), TP_MAX * sizeof(void*)), "cudaMalloc ptr table");
+        cuda_check(cudaMemcpy(d_peer_sym_[b], peer_sym_[b], TP_MAX * sizeof(void*), cudaMemcpyHostToDevice), "ptr table H2D");
+        void* pa[TP_MAX] = {};
+        for (int p = 0; p < t; ++p) pa[p] = reinterpret_cast<char*>(peer_arg_[p]) + (size_t)b * arg_half_bytes_;
+        cuda_check(cudaMalloc(reinterpret_cast<void**>(&d_peer_arg_[b]), TP_MAX * sizeof(void*)), "cudaMalloc ptr table");
+        cuda_check(cudaMemcpy(d_peer_arg_[b], pa, TP_MAX * sizeof(void*), cudaMemcpyHostToDevice), "ptr table H2D");
+    }
+    cuda_check(cudaMalloc(reinterpret_cast<void**>(&d_peer_flags_), TP_MAX * sizeof(uint32_t*)), "cudaMalloc ptr table");
+    cuda_check(cudaMemcpy(d_peer_flags_, peer_flags_, TP_MAX * sizeof(uint32_t*), cudaMemcpyHostToDevice), "ptr table H2D");
+    shm_->peers_opened.fetch_add(1, std::memory_order_acq_rel);
+    spin_until([&] { return shm_->peers_opened.load(std::memory_order_acquire) >= (uint32_t)t; }, "all ranks mapping their peers");
+}
+
+TpComm::~TpComm() {
+    for (int p = 0; p < t_; ++p) {
+        if (p == rank_) continue;
+        for (int b = 0; b < 2; ++b) if (peer_sym_[b][p]) cudaIpcCloseMemHandle(peer_sym_[b][p]);
+        if (peer_flags_[p]) cudaIpcCloseMemHandle(peer_flags_[p]);
+        if (peer_arg_[p]) cudaIpcCloseMemHandle(peer_arg_[p]);
+    }
+    for (int b = 0; b < 2; ++b) { cudaFree(sym_[b]); cudaFree(d_peer_sym_[b]); cudaFree(d_peer_arg_[b]); }
+    cudaFree(flags_); cudaFree(arg_); cudaFree(d_peer_flags_);
+    if (shm_ && shm_ != MAP_FAILED) munmap(shm_, sizeof(TpShm));
+    if (owner_) shm_unlink(shm_name_.c_str());
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side step broadcast
+// ---------------------------------------------------------------------------------------------
+void TpComm::publish(const StepInput& in) {
+    // the previous message must have been consumed by every follower before it is overwritten
+    const uint64_t cur = shm_->seq.load(std::memory_order_acquire);
+    for (int p = 1; p < t_; ++p)
+        spin_until([&] { return shm_->ack[p].load(std::memory_order_acquire) >= cur; }, "followers acknowledging the previous step", 600.0);
+    int32_t* m = shm_->msg; size_t w = 0;
+    auto put = [&](const void* src, size_t words) { if (w + words > TP_MSG_WORDS) throw std::runtime_error("tp step message overflow"); std::memcpy(m + w, src, words * 4); w += words; };
+    const int32_t hdr[8] = {in.decode ? 1 : 0, (int32_t)in.tokens.size(), (int32_t)in.sample_rows.size(), in.n_seqs, (int32_t)in.block_tables.size(),
+                            (int32_t)in.ctx_lens.size(), (int32_t)in.tiles.size(), 0};
+    put(hdr, 8);
+    put(in.tokens.data(), in.tokens.size()); put(in.positions.data(), in.positions.size()); put(in.slots.data(), in.slots.size());
+    put(in.sample_rows.data(), in.sample_rows.size()); put(in.block_tables.data(), in.block_tables.size());
+    put(in.ctx_lens.data(), in.ctx_lens.size()); put(in.tiles.data(), in.tiles.size() * 4);
+    shm_->msg_words = (uint32_t)w;
+    shm_->seq.store(cur + 1, std::memory_order_release);
+}
+
+bool TpComm::receive(StepInput& in) {
+    uint64_t s = 0;
+    while (true) {
+        s = shm_->seq.load(std::memory_order_acquire);
+        if (s == UINT64_MAX) return false;
+        if (s > seq_local_) break;
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+    const int32_t* m = shm_->msg; size_t w = 0;
+    const int32_t* hdr = m; w += 8;
+    auto get = [&](std::vector<int32_t>& v, int n) { v.assign(m + w, m + w + n); w += n; };
+    in = StepInput();
+    in.decode = hdr[0] != 0; in.n_seqs = hdr[3];
+    get(in.tokens, hdr[1]); get(in.positions, hdr[1]); get(in.slots, hdr[1]); get(in.sample_rows, hdr[2]);
+    get(in.block_tables, hdr[4]); get(in.ctx_lens, hdr[5]);
+    in.tiles.resize(hdr[6]); std::memcpy(in.tiles.data(), m + w, (size_t)hdr[6] * 16); w += (size_t)hdr[6] * 4;
+    seq_local_ = s;
+    shm_->ack[rank_].store(s, std::memory_order_release);
+    return true;
+}
+
+void TpComm::shutdown() { if (shm_ && rank_ == 0) shm_->seq.store(UINT64_MAX, std::memory_order_release); }
+
+// ---------------------------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------------------------
+OA_DEVINL void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+OA_DEVINL uint32_t ld_acquire_sys(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+OA_DEVINL float4 ld_peer_f4(const float* p) { float4 v; asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)); return v; }
+OA_DEVINL uint4 ld_peer_u4(const void* p) { uint4 v; asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v; }
+
+// Thread p tells peer p "rank `rank` has finished everything before epoch e" and waits for peer p's matching flag.
+__global__ void xgpu_barrier_kernel(uint32_t* const* __restrict__ peer_flags, const uint32_t* __restrict__ my_flags, int rank, int t, uint32_t epoch) {
+    griddep_launch(); griddep_wait();
+    const int p = threadIdx.x;
+    if (p < t) {
+        __threadfence_system();
+        st_release_sys(peer_flags[p] + rank, epoch);
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(my_flags + p) - epoch) < 0) {
+            if (clock64() - t0 > (long long)3.0e10) __trap();          // ~15 s: a peer died
+        }
+    }
+}
+cudaError_t TpComm::barrier(cudaStream_t s) {
+    ++epoch_;
+    return launch_k(xgpu_barrier_kernel, dim3(1), dim3(32), 0, s, (uint32_t* const*)d_peer_flags_, (const uint32_t*)flags_, rank_, t_, epoch_);
+}
+
+template <int VPT>
+__global__ void __launch_bounds__(256) ar_resid_rmsnorm_kernel(const float* const* __restrict__ peer, int t, uint4* __restrict__ x,
+                                                               const uint4* __restrict__ g, uint4* __restrict__ y, int H8, float inv_h, float eps) {
+    griddep_launch(); griddep_wait();
+    const int row = blockIdx.x;
+    uint4* xr = x + (size_t)row * H8;
+    uint4 v[VPT];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+        const int i = threadIdx.x + k * 256;
+        if (i < H8) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float4 a[TP_MAX], b[TP_MAX];
+#pragma unroll
+            for (int p = 0; p < TP_MAX; ++p) if (p < t) { const float* src = peer[p] + ((size_t)row * H8 + i) * 8; a[p] = ld_peer_f4(src); b[p] = ld_peer_f4(src + 4); }
+#pragma unroll
+            for (int p = 0; p < TP_MAX; ++p) if (p < t) {      // rank order: every rank computes the identical sum
+                acc[0] += a[p].x; acc[1] += a[p].y; acc[2] += a[p].z; acc[3] += a[p].w; acc[4] += b[p].x; acc[5] += b[p].y; acc[6] += b[p].z; acc[7] += b[p].w;
+            }
+            const uint4 xo = xr[i];
+            uint4 xn;
+            xn.x = pack_bf16x2(bf16lo(xo.x) + acc[0], bf16hi(xo.x) + acc[1]); xn.y = pack_bf16x2(bf16lo(xo.y) + acc[2], bf16hi(xo.y) + acc[3]);
+            xn.z = pack_bf16x2(bf16lo(xo.z) + acc[4], bf16hi(xo.z) + acc[5]); xn.w = pack_bf16x2(bf16lo(xo.w) + acc[6], bf16hi(xo.w) + acc[7]);
+            xr[i] = xn; v[k] = xn;
+            float q;
+            q = bf16lo(xn.x); ss += q * q; q = bf16hi(xn.x); ss += q * q; q = bf16lo(xn.y); ss += q * q; q = bf16hi(xn.y); ss += q * q;
+            q = bf16lo(xn.z); ss += q * q; q = bf16hi(xn.z); ss += q * q; q = bf16lo(xn.w); ss += q * q; q = bf16hi(xn.w); ss += q * q;
+        }
+    }
+    ss = warp_sum(ss);
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float r = 1.0f / sqrtf(tot * inv_h + eps);
+    uint4* yr = y + (size_t)row * H8;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+        const int i = threadIdx.x + k * 256;
+        if (i < H8) {
+            const uint4 gg = g[i]; uint4 o;
+            o.x = pack_bf16x2(bf16lo(v[k].x) * r * bf16lo(gg.x), bf16hi(v[k].x) * r * bf16hi(gg.x));
+            o.y = pack_bf16x2(bf16lo(v[k].y) * r * bf16lo(gg.y), bf16hi(v[k].y) * r * bf16hi(gg.y));
+            o.z = pack_bf16x2(bf16lo(v[k].z) * r * bf16lo(gg.z), bf16hi(v[k].z) * r * bf16hi(gg.z));
+            o.w = pack_bf16x2(bf16lo(v[k].w) * r * bf16lo(gg.w), bf16hi(v[k].w) * r * bf16hi(gg.w));
+            yr[i] = o;
+        }
+    }
+}
+cudaError_t launch_ar_resid_rmsnorm(void* const* d_peer, int t, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s) {
+    if (T <= 0) return cudaSuccess;
+    if (H % 8 != 0 || H > 8192) return cudaErrorInvalidValue;
+    const int H8 = H / 8;
+    auto P = reinterpret_cast<const float* const*>(d_peer);
+    auto X = reinterpret_cast<uint4*>(x); auto G = reinterpret_cast<const uint4*>(gain); auto Y = reinterpret_cast<uint4*>(xn);
+    if (H8 <= 256) return launch_k(ar_resid_rmsnorm_kernel<1>, dim3(T), dim3(256), 0, s, P, t, X, G, Y, H8, 1.0f / H, eps);
+    if (H8 <= 512) return launch_k(ar_resid_rmsnorm_kernel<2>, dim3(T), dim3(256), 0, s, P, t, X, G, Y, H8, 1.0f / H, eps);
+    return launch_k(ar_resid_rmsnorm_kernel<4>, dim3(T), dim3(256), 0, s, P, t, X, G, Y, H8, 1.0f / H, eps);
+}
+
+__global__ void ar_resid_bf16_kernel(const uint16_t* const* __restrict__ peer, int t, uint4* __restrict__ x, size_t n8) {
+    griddep_launch(); griddep_wait();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        uint4 a[TP_MAX];
+#pragma unroll
+        for (int p = 0; p < TP_MAX; ++p) if (p < t) a[p] = ld_peer_u4(peer[p] + i * 8);
+#pragma unroll
+        for (int p = 0; p < TP_MAX; ++p) if (p < t) {
+            acc[0] += bf16lo(a[p].x); acc[1] += bf16hi(a[p].x); acc[2] += bf16lo(a[p].y); acc[3] += bf16hi(a[p].y);
+            acc[4] += bf16lo(a[p].z); acc[5] += bf16hi(a[p].z); acc[6] += bf16lo(a[p].w); acc[7] += bf16hi(a[p].w);
+        }
+        const uint4 xo = x[i]; uint4 xn;
+        xn.x = pack_bf16x2(bf16lo(xo.x) + acc[0], bf16hi(xo.x) + acc[1]); xn.y = pack_bf16x2(bf16lo(xo.y) + acc[2], bf16hi(xo.y) + acc[3]);
+        xn.z = pack_bf16x2(bf16lo(xo.z) + acc[4], bf16hi(xo.z) + acc[5]); xn.w = pack_bf16x2(bf16lo(xo.w) + acc[6], bf16hi(xo.w) + acc[7]);
+        x[i] = xn;
+    }
+}
+cudaError_t launch_ar_resid_bf16(void* const* d_peer, int t, void* x, int T, int H, cudaStream_t s) {
+    if (T <= 0) return cudaSuccess;
+    const size_t n8 = (size_t)T * H / 8;
+    const int blocks = (int)std::min<size_t>((n8 + 255) / 256, 148 * 8);
+    return launch_k(ar_resid_bf16_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const uint16_t* const*>(d_peer), t, reinterpret_cast<uint4*>(x), n8);
+}
+
+__global__ void sk_reduce_f32_rows_kernel(const StreamK sk, float* __restrict__ out, int N8) {
+    griddep_launch(); griddep_wait();
+    const int row = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N8; i += gridDim.x * blockDim.x) {
+        const int col = i * 8;
+        const uint32_t tile = (uint32_t)col / (uint32_t)sk.bn, cc = (uint32_t)col - tile * (uint32_t)sk.bn;
+        const uint32_t ut0 = tile * (uint32_t)sk.kb, G = (uint32_t)sk.G, total = (uint32_t)sk.total;
+        const uint32_t c_first = ((ut0 + 1u) * G - 1u) / total, c_last = ((ut0 + (uint32_t)sk.kb) * G - 1u) / total;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (uint32_t c = c_first; c <= c_last; ++c) {
+            const float4* p = reinterpret_cast<const float4*>(sk.ws + ((size_t)(c + tile) * 128 + row) * sk.bn + cc);
+            const float4 a = __ldcg(p), b = __ldcg(p + 1);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        }
+        float4* o = reinterpret_cast<float4*>(out + ((size_t)row * N8 + i) * 8);
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]); o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+}
+cudaError_t launch_sk_reduce_f32(const StreamK& sk, float* out, int T, int N, cudaStream_t s) {
+    if (T <= 0) return cudaSuccess;
+    return launch_k(sk_reduce_f32_rows_kernel, dim3((N / 8 + 255) / 256, T), dim3(256), 0, s, sk, out, N / 8);
+}
+
+struct ValIdx { float v; int i; };
+__global__ void argmax_reduce_pair_kernel(const float* __restrict__ val, const int* __restrict__ idx, int n_tiles, int idx_offset, ValIdx* __restrict__ out) {
+    griddep_launch(); griddep_wait();
+    const int row = blockIdx.x;
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+        const float v = val[(size_t)row * n_tiles + t]; const int i = idx[(size_t)row * n_tiles + t];
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    __shared__ float sv[8]; __shared__ int si[8];
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
+        out[row].v = bv; out[row].i = (bi == 0x7fffffff ? 0 : bi) + idx_offset;
+    }
+}
+cudaError_t launch_argmax_reduce_pair(const float* amax_val, const int* amax_idx, int M, int n_tiles, int idx_offset, void* pair_out, cudaStream_t s) {
+    return launch_k(argmax_reduce_pair_kernel, dim3(M), dim3(256), 0, s, amax_val, amax_idx, n_tiles, idx_offset, reinterpret_cast<ValIdx*>(pair_out));
+}
+__global__ void ar_argmax_kernel(const ValIdx* const* __restrict__ peer, int t, int M, int32_t* __restrict__ out_ids) {
+    griddep_launch(); griddep_wait();
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= M) return;
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int p = 0; p < t; ++p) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(peer[p] + row);
+        uint32_t a, b;
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(src));
+        const float v = __uint_as_float(a); const int i = (int)b;
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+    out_ids[row] = bi;
+}
+cudaError_t launch_ar_argmax(void* const* d_peer_arg, int t, int M, int32_t* out_ids, cudaStream_t s) {
+    return launch_k(ar_argmax_kernel, dim3((M + 127) / 128), dim3(128), 0, s, reinterpret_cast<const ValIdx* const*>(d_peer_arg), t, M, out_ids);
+}
+
+}  // namespace oa

@@ -1,0 +1,78 @@
+// tp_comm.hpp — tensor-parallel plumbing for models that do not fit one GPU (BASELINE configs[3,4]).
+//
+// One process per GPU on one NVSwitch node.  No NCCL: ranks exchange CUDA-IPC handles of *symmetric* buffers through a
+// POSIX shared-memory segment, map each other's buffers, and the row-parallel projections are all-reduced by the
+// engine's own kernels reading peer memory over NVLink (tp_comm.cu):
+//     partial -> own symmetric buffer;  xgpu_barrier (release/acquire flags in peer memory);
+//     every rank adds the t partials in RANK ORDER (bit-identical result on all ranks) fused with residual add + RMSNorm.
+// Rank 0 (leader) owns the scheduler; each step it publishes the packed step metadata in the shm segment and the
+// followers replay the same forward — they hold no request state.
+#pragma once
+#include <atomic>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "kernels.hpp"
+
+namespace oa {
+
+struct StepInput;
+
+constexpr int TP_MAX = 8;
+constexpr size_t TP_MSG_WORDS = 2u << 20;     // 8 MB step-message area
+
+struct TpShm {                                 // lives in POSIX shared memory
+    std::atomic<uint32_t> magic;
+    std::atomic<uint32_t> handles_ready;       // ranks that published their IPC handles
+    std::atomic<uint32_t> peers_opened;        // ranks that mapped every peer
+    cudaIpcMemHandle_t h_sym[TP_MAX][2];
+    cudaIpcMemHandle_t h_flags[TP_MAX];
+    cudaIpcMemHandle_t h_arg[TP_MAX];
+    std::atomic<uint64_t> seq;                 // step message sequence (UINT64_MAX = shutdown)
+    std::atomic<uint64_t> ack[TP_MAX];
+    uint32_t msg_words;
+    int32_t msg[TP_MSG_WORDS];
+};
+
+class TpComm {
+public:
+    TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, int max_sample);
+    ~TpComm();
+    int size() const { return t_; }
+    int rank() const { return rank_; }
+
+    // ---- device side ----
+    int next_buffer() { return (int)(ar_count_++ & 1); }                // double-buffered symmetric storage
+    void* sym(int b) const { return sym_[b]; }                            // this rank's buffer b
+    void* const* d_peer_sym(int b) const { return d_peer_sym_[b]; }       // device array [t] of peer pointers for buffer b
+    void* arg(int b) const { return reinterpret_cast<char*>(arg_) + (size_t)b * arg_half_bytes_; }
+    void* const* d_peer_arg(int b) const { return d_peer_arg_[b]; }
+    cudaError_t barrier(cudaStream_t s);                                  // every rank's prior writes visible to all
+
+    // ---- host side: leader publishes, followers receive ----
+    void publish(const StepInput& in);
+    bool receive(StepInput& in);                                          // false = shutdown
+    void shutdown();
+
+private:
+    int t_, rank_; std::string shm_name_; TpShm* shm_ = nullptr; bool owner_ = false;
+    void* sym_[2] = {nullptr, nullptr}; void* peer_sym_[2][TP_MAX] = {};
+    void** d_peer_sym_[2] = {nullptr, nullptr};
+    uint32_t* flags_ = nullptr; uint32_t* peer_flags_[TP_MAX] = {}; uint32_t** d_peer_flags_ = nullptr;
+    void* arg_ = nullptr; void* peer_arg_[TP_MAX] = {}; void** d_peer_arg_[2] = {nullptr, nullptr}; size_t arg_half_bytes_ = 0;
+    uint64_t ar_count_ = 0; uint32_t epoch_ = 0; uint64_t seq_local_ = 0;
+};
+
+// x[T,H] (bf16, in place) += sum over ranks (rank order) of fp32 partial rows; xn = rmsnorm(x) * gain   (decode path)
+cudaError_t launch_ar_resid_rmsnorm(void* const* d_peer, int t, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s);
+// x[T,H] += sum over ranks of bf16 partial rows                                                          (prefill path)
+cudaError_t launch_ar_resid_bf16(void* const* d_peer, int t, void* x, int T, int H, cudaStream_t s);
+// stream-K partials -> fp32 rows [T,N] in `out` (this rank's symmetric buffer)
+cudaError_t launch_sk_reduce_f32(const StreamK& sk, float* out, int T, int N, cudaStream_t s);
+// vocab-parallel greedy sampling: (val, global idx) per row into this rank's arg buffer, then combine over ranks
+cudaError_t launch_argmax_reduce_pair(const float* amax_val, const int* amax_idx, int M, int n_tiles, int idx_offset, void* pair_out,
+                                      cudaStream_t s);
+cudaError_t launch_ar_argmax(void* const* d_peer_arg, int t, int M, int32_t* out_ids, cudaStream_t s);
+
+}  // namespace oa
