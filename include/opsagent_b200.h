@@ -69,6 +69,9 @@ typedef struct {
  *  "device":0, "kv_gb":100, "max_batch":128, "max_seq_len":4096, "max_step_tokens":8192, ...} — see DESIGN.md */
 OA_API int oa_engine_create(const char* config_json, oa_engine** out);
 OA_API void oa_engine_destroy(oa_engine*);
+/* tensor-parallel groups (config "tp": t, "tp_rank": r, "tp_shm": name; one process per GPU): rank 0 is the engine callers talk
+ * to; every other rank calls oa_engine_serve(), which replays the leader's steps and returns when the leader is destroyed */
+OA_API int oa_engine_serve(oa_engine*);
 
 /* blocking completion — what (*LocalCUDAClient).Chat calls; replaces CreateChatCompletion (openai.go:79) */
 OA_API int oa_chat_complete(oa_engine*, const oa_chat_req*, oa_chat_resp* out);

@@ -34,7 +34,7 @@ SYMBOLS = [
     "oa_tokens_submit", "oa_count_tokens", "oa_apply_chat_template", "oa_last_error", "oa_engine_stats", "oa_model_info",
     "oa_debug_prefill_logits", "oa_bench_decode", "oa_k_rmsnorm", "oa_k_gemm", "oa_k_init_weight", "oa_k_paged_attention",
     "oa_kernel_launches", "oa_version", "oa_host_apply_chat_template", "oa_host_decode_plan", "oa_host_model_info",
-    "oa_k_gemm_streamk", "oa_debug_kernel_times",
+    "oa_k_gemm_streamk", "oa_debug_kernel_times", "oa_engine_serve",
 ]
 
 _lib = None
@@ -51,6 +51,7 @@ def load() -> C.CDLL:
     vp, i32, u64, f32 = C.c_void_p, C.c_int32, C.c_uint64, C.c_float
     L.oa_engine_create.argtypes = [C.c_char_p, C.POINTER(vp)]; L.oa_engine_create.restype = C.c_int
     L.oa_engine_destroy.argtypes = [vp]; L.oa_engine_destroy.restype = None
+    L.oa_engine_serve.argtypes = [vp]; L.oa_engine_serve.restype = C.c_int
     L.oa_chat_complete.argtypes = [vp, C.POINTER(OaChatReq), C.POINTER(OaChatResp)]; L.oa_chat_complete.restype = C.c_int
     L.oa_chat_submit.argtypes = [vp, C.POINTER(OaChatReq), C.POINTER(u64)]; L.oa_chat_submit.restype = C.c_int
     L.oa_chat_wait.argtypes = [vp, u64, i32, C.POINTER(OaChatResp)]; L.oa_chat_wait.restype = C.c_int

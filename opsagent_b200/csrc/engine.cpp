@@ -47,15 +47,27 @@ public:
     Engine(const ModelConfig& mc, const EngineOptions& eo) : model_(mc, eo), tok_(mc), opt_(eo) {
         free_pages_.reserve(model_.num_pages);
         for (int p = model_.num_pages - 1; p >= 0; --p) free_pages_.push_back(p);
-        if (eo.start_thread) worker_ = std::thread([this] { loop(); });
+        if (eo.tp > 1 && eo.tp_rank > 0) follower_ = std::thread([this] { follow(); });   // tensor-parallel follower: replays the leader's steps
+        else if (eo.start_thread) worker_ = std::thread([this] { loop(); });
     }
     ~Engine() {
         { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
         cv_work_.notify_all();
         if (worker_.joinable()) worker_.join();
+        if (model_.comm && opt_.tp_rank == 0) { std::lock_guard<std::mutex> step(step_mu_); model_.sync(); model_.comm->shutdown(); }
+        if (follower_.joinable()) follower_.join();
+    }
+    bool is_follower() const { return opt_.tp > 1 && opt_.tp_rank > 0; }
+    // blocks a follower process until the leader shuts the group down (returns at once on a leader / single-GPU engine)
+    int serve() {
+        if (!is_follower()) return OA_OK;
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [&] { return follower_done_; });
+        return fatal_ ? fail(OA_ERR_INTERNAL, fatal_msg_) : OA_OK;
     }
 
     int submit_tokens(std::vector<int32_t>&& prompt, int max_new, uint32_t flags, uint64_t* ticket) {
+        if (is_follower()) return fail(OA_ERR_BAD_REQUEST, "tensor-parallel followers take no requests: submit to the leader (tp_rank 0)");
         if (prompt.empty()) return fail(OA_ERR_BAD_REQUEST, "empty prompt");
         if (max_new <= 0) return fail(OA_ERR_BAD_REQUEST, "max_tokens must be positive");
         if ((int)prompt.size() + 1 > opt_.max_seq_len)
@@ -110,13 +122,13 @@ public:
             { std::lock_guard<std::mutex> lk(mu_); if (!alloc_pages_locked(pages, (n + 63) / 64)) return fail(OA_ERR_OVERLOADED, "no free KV pages"); }
             float* d_logits = nullptr;
             cuda_check(cudaMalloc(&d_logits, (size_t)n * V * 4), "cudaMalloc logits");
-            StepInput in; in.decode = false; in.n_seqs = 1;
+            StepInput in; in.decode = false; in.n_seqs = 1; in.want_logits = true;
             in.block_tables.assign(model_.max_pages_per_seq, 0);
             for (size_t i = 0; i < pages.size(); ++i) in.block_tables[i] = pages[i];
             in.ctx_lens = {n};
             for (int i = 0; i < n; ++i) { in.tokens.push_back(toks[i]); in.positions.push_back(i); in.slots.push_back(pages[i / 64] * 64 + i % 64); in.sample_rows.push_back(i); }
             for (int r = 0; r < n; r += 64) in.tiles.push_back(PrefillTile{0, r, r, std::min(64, n - r)});
-            model_.forward(in, d_logits); model_.sync();
+            run_forward(in, d_logits); model_.sync();
             cudaError_t e = cudaMemcpy(logits_out, d_logits, (size_t)n * V * 4, cudaMemcpyDeviceToHost);
             cudaFree(d_logits);
             { std::lock_guard<std::mutex> lk(mu_); for (int p : pages) free_pages_.push_back(p); }
@@ -164,7 +176,7 @@ public:
                         if (off >= P) { off = 0; ++b; }
                     }
                     if (prof_prefill && n_fwd == 1) { model_.sync(); cudaProfilerStart(); }     // the 2nd prefill chunk (warm)
-                    model_.forward(in, nullptr);
+                    run_forward(in, nullptr);
                     if (prof_prefill && n_fwd == 1) { model_.sync(); cudaProfilerStop(); }
                     ++n_fwd;
                 }
@@ -193,7 +205,7 @@ public:
                 }
                 const bool timed = it >= warmup;
                 if (timed) { cudaEventRecord(e0, model_.stream); ctx_sum += pos + 1; }
-                model_.forward(in, nullptr);
+                run_forward(in, nullptr);
                 if (timed) cudaEventRecord(e1, model_.stream);
                 model_.sync();
                 if (timed) { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); total_ms += ms; }
@@ -209,8 +221,8 @@ public:
             out[0] = bracket_ms / steps; if (n_out > 6) out[6] = total_ms / steps; out[1] = prefill_ms; out[2] = (double)(launches1 - launches0) / steps; out[3] = mean_ctx;
             out[4] = model_.profile_attn ? model_.attn_ms_accum / steps : 0.0;
             // W_dec + sum ctx*KVB + B*KVB (the new token's KV write)
-            out[5] = model_.cfg.decode_weight_bytes() + (double)batch * mean_ctx * (double)model_.cfg.kv_bytes_per_token() +
-                     (double)batch * (double)model_.cfg.kv_bytes_per_token();
+            out[5] = (model_.cfg.decode_weight_bytes() + (double)batch * mean_ctx * (double)model_.cfg.kv_bytes_per_token() +
+                      (double)batch * (double)model_.cfg.kv_bytes_per_token()) / opt_.tp;      // per GPU (W_dec/t + ctx*KVB/t)
         } catch (const std::exception& ex) { return fail(OA_ERR_INTERNAL, ex.what()); }
         return OA_OK;
     }
@@ -246,6 +258,23 @@ public:
     DeviceModel& model() { return model_; }
 
 private:
+    // every forward goes through here: the leader of a tensor-parallel group publishes the step for its followers first
+    void run_forward(const StepInput& in, float* logits_out) {
+        if (model_.comm && opt_.tp_rank == 0) model_.comm->publish(in);
+        model_.forward(in, logits_out);
+    }
+    void follow() {
+        cudaSetDevice(opt_.device);
+        try {
+            StepInput in;
+            while (model_.comm->receive(in)) { model_.forward(in, nullptr); model_.sync(); }
+        } catch (const std::exception& ex) {
+            std::lock_guard<std::mutex> lk(mu_); fatal_ = true; fatal_msg_ = ex.what();
+            std::fprintf(stderr, "opsagent_b200 follower %d failed: %s\n", opt_.tp_rank, ex.what());
+        }
+        { std::lock_guard<std::mutex> lk(mu_); follower_done_ = true; }
+        cv_done_.notify_all();
+    }
     bool alloc_pages_locked(std::vector<int32_t>& dst, int n) {
         if ((int)free_pages_.size() < n) return false;
         for (int i = 0; i < n; ++i) { dst.push_back(free_pages_.back()); free_pages_.pop_back(); }
@@ -356,7 +385,7 @@ private:
                 }
             }
         }
-        model_.forward(in, nullptr);
+        run_forward(in, nullptr);
         model_.sync();
         {
             std::lock_guard<std::mutex> lk(mu_);
@@ -389,7 +418,7 @@ private:
     std::vector<int32_t> free_pages_;
     uint64_t next_ticket_ = 1;
     bool stop_ = false, fatal_ = false; std::string fatal_msg_;
-    std::thread worker_;
+    std::thread worker_, follower_; bool follower_done_ = false;
     uint64_t n_completed_ = 0, n_prefill_tokens_ = 0, n_decode_tokens_ = 0, n_prefill_steps_ = 0, n_decode_steps_ = 0, n_preempt_ = 0;
     double busy_ms_ = 0;
 };
@@ -498,6 +527,7 @@ int oa_debug_kernel_times(oa_engine* h, char* buf, size_t n, int32_t reset) {
     s += "}";
     return copy_out(s, buf, n);
 }
+int oa_engine_serve(oa_engine* h) { if (!h) return fail(OA_ERR_BAD_REQUEST, "null engine"); return h->e->serve(); }
 uint64_t oa_kernel_launches(void) { return launches_total(); }
 const char* oa_version(void) { return "opsagent_b200 0.1 (sm_100a)"; }
 

@@ -192,7 +192,8 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
     for (auto& e : ev) cuda_check(cudaEventCreate(&e), "cudaEventCreate");
     if (tp > 1) {
         if (opt.num_pages <= 0) throw std::runtime_error("tensor parallel engines need an explicit num_pages (all ranks must agree on the pool size)");
-        const size_t sym_bytes = std::max((size_t)MR * H * 2, (size_t)128 * H * 4);
+        // bf16 prefill partials | fp32 decode partials | up to 256 rows of this rank's fp32 logits shard (debug parity hook)
+        const size_t sym_bytes = std::max({(size_t)MR * H * 2, (size_t)128 * H * 4, (size_t)256 * V_l * 4});
         comm.reset(new TpComm(tp, tp_rank, opt.tp_shm, sym_bytes, max_sample_));
     }
     cuda_check(cudaStreamSynchronize(stream), "init sync");
@@ -278,8 +279,10 @@ void build_decode_plan(const int32_t* ctx_lens, int n_seqs, int n_kv, int n_ctas
 
 void DeviceModel::forward(const StepInput& in, float* logits_out) {
     const int T = (int)in.tokens.size(), S = (int)in.sample_rows.size();
-    const int H = cfg.hidden, L = cfg.n_layers, F = cfg.ffn, V = cfg.vocab, D = cfg.head_dim;
-    const int qd = cfg.q_dim(), qkvd = cfg.qkv_dim(), nh = cfg.n_heads, nkv = cfg.n_kv_heads;
+    // all projection sizes below are this rank's shard (== the global sizes when tp == 1)
+    const int H = cfg.hidden, L = cfg.n_layers, F = F_l, V = V_l, D = cfg.head_dim;
+    const int nh = nh_l, nkv = nkv_l, qd = nh * D, qkvd = qd + 2 * nkv * D;
+    const bool use_tp = tp > 1;
     if (T <= 0 || T > max_rows_ || S > max_sample_) throw std::runtime_error("forward: bad batch size");
     if (in.decode && in.n_seqs != T) throw std::runtime_error("forward: decode needs one token per sequence");
 
@@ -321,7 +324,7 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
     }
     auto MARK = [&](int id) { if (profile_all && ek < ev_all.size()) { ev_ids[ek] = id; cudaEventRecord(ev_all[ek++], stream); } };
     const float scale_log2e = (1.0f / std::sqrt((float)D)) * 1.4426950408889634f;
-    cuda_check(launch_embed_gather(d_tok, embed, x_, T, H, V, stream), "embed"); MARK(0);
+    cuda_check(launch_embed_gather(d_tok, embed, x_, T, H, cfg.vocab, stream), "embed"); MARK(0);
     const bool use_sk = opt.streamk && T <= 128;
     auto attention = [&](int l) {
         if (profile_attn) cudaEventRecord(ev[2 * l], stream);
@@ -354,12 +357,28 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
             cuda_check(launch_sk_rope_kv_write(sk_qkv, ly.bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, T, nh, stream), "rope (stream-K)"); MARK(3);
             attention(l);
             cuda_check(launch_gemm_streamk(&tm_attn_, ly.o.map(sk_o.bn), T, H, qd, pf_o, stream), "o gemm (stream-K)"); MARK(6);
-            cuda_check(launch_sk_resid_rmsnorm(sk_o, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm2"); MARK(7);
+            if (use_tp) {      // row-parallel projection: all-reduce the rank partials over NVLink peer memory, then residual + norm
+                const int b = comm->next_buffer();
+                cuda_check(launch_sk_reduce_f32(sk_o, reinterpret_cast<float*>(comm->sym(b)), T, H, stream), "o partial -> symmetric buffer");
+                cuda_check(comm->barrier(stream), "xgpu barrier");
+                cuda_check(launch_ar_resid_rmsnorm(comm->d_peer_sym(b), tp, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "allreduce+resid+rmsnorm2");
+            } else {
+                cuda_check(launch_sk_resid_rmsnorm(sk_o, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm2");
+            }
+            MARK(7);
             cuda_check(launch_gemm_streamk(&tm_xn_, ly.gu.map(sk_gu.bn), T, 2 * F, H, pf_gu, stream), "gate_up gemm (stream-K)"); MARK(8);
             cuda_check(launch_sk_swiglu(sk_gu, act_, T, F, stream), "swiglu"); MARK(9);
             cuda_check(launch_gemm_streamk(&tm_act_, ly.down.map(sk_dn.bn), T, H, F, pf_dn, stream), "down gemm (stream-K)"); MARK(10);
             const void* next_gain = (l + 1 < L) ? layers[l + 1].ln1 : final_norm;
-            cuda_check(launch_sk_resid_rmsnorm(sk_dn, x_, next_gain, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm1"); MARK(7);
+            if (use_tp) {
+                const int b = comm->next_buffer();
+                cuda_check(launch_sk_reduce_f32(sk_dn, reinterpret_cast<float*>(comm->sym(b)), T, H, stream), "down partial -> symmetric buffer");
+                cuda_check(comm->barrier(stream), "xgpu barrier");
+                cuda_check(launch_ar_resid_rmsnorm(comm->d_peer_sym(b), tp, x_, next_gain, xn_, T, H, cfg.rms_eps, stream), "allreduce+resid+rmsnorm1");
+            } else {
+                cuda_check(launch_sk_resid_rmsnorm(sk_dn, x_, next_gain, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm1");
+            }
+            MARK(7);
         }
     } else {
         const int bn_qkv = pick_bn(T, qkvd, opt.bn_qkv, false), bn_o = pick_bn(T, H, opt.bn_o, false);
@@ -371,13 +390,29 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
             cuda_check(launch_gemm(&tm_xn_, ly.qkv.map(bn_qkv), g, EPI_STORE, bn_qkv, stream), "qkv gemm"); MARK(2);
             cuda_check(launch_rope_kv_write(qkv_, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, T, nh, stream), "rope"); MARK(3);
             attention(l);
-            GemmParams go{}; go.M = T; go.N = H; go.K = qd; go.out = x_; go.ldo = H; go.resid = x_; go.ldr = H;
-            cuda_check(launch_gemm(&tm_attn_, ly.o.map(bn_o), go, EPI_RESID, bn_o, stream), "o gemm"); MARK(6);
+            if (use_tp) {      // bf16 partial -> symmetric buffer, barrier, x += sum over ranks (rank order)
+                const int b = comm->next_buffer();
+                GemmParams go{}; go.M = T; go.N = H; go.K = qd; go.out = comm->sym(b); go.ldo = H;
+                cuda_check(launch_gemm(&tm_attn_, ly.o.map(bn_o), go, EPI_STORE, bn_o, stream), "o gemm"); MARK(6);
+                cuda_check(comm->barrier(stream), "xgpu barrier");
+                cuda_check(launch_ar_resid_bf16(comm->d_peer_sym(b), tp, x_, T, H, stream), "allreduce+resid");
+            } else {
+                GemmParams go{}; go.M = T; go.N = H; go.K = qd; go.out = x_; go.ldo = H; go.resid = x_; go.ldr = H;
+                cuda_check(launch_gemm(&tm_attn_, ly.o.map(bn_o), go, EPI_RESID, bn_o, stream), "o gemm"); MARK(6);
+            }
             cuda_check(launch_rmsnorm(x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "rmsnorm2"); MARK(1);
             GemmParams gg{}; gg.M = T; gg.N = 2 * F; gg.K = H; gg.out = act_; gg.ldo = F;
             cuda_check(launch_gemm(&tm_xn_, ly.gu.map(bn_gu), gg, EPI_SWIGLU, bn_gu, stream), "gate_up gemm"); MARK(8);
-            GemmParams gd{}; gd.M = T; gd.N = H; gd.K = F; gd.out = x_; gd.ldo = H; gd.resid = x_; gd.ldr = H;
-            cuda_check(launch_gemm(&tm_act_, ly.down.map(bn_down), gd, EPI_RESID, bn_down, stream), "down gemm"); MARK(10);
+            if (use_tp) {
+                const int b = comm->next_buffer();
+                GemmParams gd{}; gd.M = T; gd.N = H; gd.K = F; gd.out = comm->sym(b); gd.ldo = H;
+                cuda_check(launch_gemm(&tm_act_, ly.down.map(bn_down), gd, EPI_STORE, bn_down, stream), "down gemm"); MARK(10);
+                cuda_check(comm->barrier(stream), "xgpu barrier");
+                cuda_check(launch_ar_resid_bf16(comm->d_peer_sym(b), tp, x_, T, H, stream), "allreduce+resid");
+            } else {
+                GemmParams gd{}; gd.M = T; gd.N = H; gd.K = F; gd.out = x_; gd.ldo = H; gd.resid = x_; gd.ldr = H;
+                cuda_check(launch_gemm(&tm_act_, ly.down.map(bn_down), gd, EPI_RESID, bn_down, stream), "down gemm"); MARK(10);
+            }
         }
     }
     if (S > 0) {
@@ -391,8 +426,29 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
         const int bn_lm = pick_bn(S, V, opt.bn_lm, false);
         const int n_tiles = gemm_n_tiles(V, bn_lm);
         GemmParams gl{}; gl.M = S; gl.N = V; gl.K = H; gl.logits = logits_out; gl.ldl = V; gl.amax_val = amax_val_; gl.amax_idx = amax_idx_;
+        int lb = -1;
+        if (use_tp) {          // vocab-parallel head: each rank's fp32 logits shard is staged in its symmetric buffer when asked for
+            gl.logits = nullptr;
+            if (in.want_logits) {
+                if ((size_t)S * V * 4 > comm->sym_bytes()) throw std::runtime_error("debug logits do not fit the symmetric buffer");
+                lb = comm->next_buffer(); gl.logits = reinterpret_cast<float*>(comm->sym(lb)); gl.ldl = V;
+            }
+        }
         cuda_check(launch_gemm(&tm_xsn_, lm_head.map(bn_lm), gl, EPI_LOGITS, bn_lm, stream), "lm_head gemm"); MARK(12);
-        cuda_check(launch_argmax_reduce(amax_val_, amax_idx_, S, n_tiles, d_out_ids_, nullptr, stream), "argmax");
+        if (use_tp) {
+            const int b = comm->next_buffer();
+            cuda_check(launch_argmax_reduce_pair(amax_val_, amax_idx_, S, n_tiles, tp_rank * V, comm->arg(b), stream), "argmax (local shard)");
+            cuda_check(comm->barrier(stream), "xgpu barrier");
+            cuda_check(launch_ar_argmax(comm->d_peer_arg(b), tp, S, d_out_ids_, stream), "argmax (all ranks)");
+            if (lb >= 0 && logits_out) {   // leader assembles the full [S, vocab] logits from the peers' shards over NVLink
+                for (int p = 0; p < tp; ++p)
+                    cuda_check(cudaMemcpy2DAsync(logits_out + (size_t)p * V, (size_t)cfg.vocab * 4, comm->peer_sym_host(lb, p), (size_t)V * 4, (size_t)V * 4, S,
+                                                 cudaMemcpyDeviceToDevice, stream), "logits gather");
+            }
+            if (lb >= 0) cuda_check(comm->barrier(stream), "xgpu barrier");     // peers must not reuse the staged shard before the leader has read it
+        } else {
+            cuda_check(launch_argmax_reduce(amax_val_, amax_idx_, S, n_tiles, d_out_ids_, nullptr, stream), "argmax");
+        }
         cuda_check(cudaMemcpyAsync(h_out_ids, d_out_ids_, (size_t)S * 4, cudaMemcpyDeviceToHost, stream), "ids D2H"); MARK(13);
         d2h_bytes += (size_t)S * 4;
     }

@@ -25,6 +25,7 @@ struct StepInput {
     std::vector<int32_t> block_tables;                // [n_seqs, max_pages_per_seq]
     std::vector<int32_t> ctx_lens;                    // [n_seqs] (decode: tokens in cache incl. the new one)
     std::vector<PrefillTile> tiles;                   // prefill only
+    bool want_logits = false;                         // debug: fp32 logits of the sampled rows (tensor-parallel ranks stage their shard)
 };
 
 struct DecodePlan {

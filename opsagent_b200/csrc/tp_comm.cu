@@ -27,7 +27,7 @@ static void spin_until(const std::function<bool()>& ok, const char* what, double
 }
 
 TpComm::TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, int max_sample)
-    : t_(t), rank_(rank), shm_name_(shm_name) {
+    : t_(t), rank_(rank), shm_name_(shm_name), sym_bytes_(sym_bytes) {
     if (t < 2 || t > TP_MAX || rank < 0 || rank >= t) throw std::runtime_error("tp must be 2..8 and 0 <= tp_rank < tp");
     // ---- shared-memory segment (leader creates, followers attach) ----
     int fd = -1;
@@ -107,7 +107,7 @@ void TpComm::publish(const StepInput& in) {
     int32_t* m = shm_->msg; size_t w = 0;
     auto put = [&](const void* src, size_t words) { if (w + words > TP_MSG_WORDS) throw std::runtime_error("tp step message overflow"); std::memcpy(m + w, src, words * 4); w += words; };
     const int32_t hdr[8] = {in.decode ? 1 : 0, (int32_t)in.tokens.size(), (int32_t)in.sample_rows.size(), in.n_seqs, (int32_t)in.block_tables.size(),
-                            (int32_t)in.ctx_lens.size(), (int32_t)in.tiles.size(), 0};
+                            (int32_t)in.ctx_lens.size(), (int32_t)in.tiles.size(), in.want_logits ? 1 : 0};
     put(hdr, 8);
     put(in.tokens.data(), in.tokens.size()); put(in.positions.data(), in.positions.size()); put(in.slots.data(), in.slots.size());
     put(in.sample_rows.data(), in.sample_rows.size()); put(in.block_tables.data(), in.block_tables.size());
@@ -128,7 +128,7 @@ bool TpComm::receive(StepInput& in) {
     const int32_t* hdr = m; w += 8;
     auto get = [&](std::vector<int32_t>& v, int n) { v.assign(m + w, m + w + n); w += n; };
     in = StepInput();
-    in.decode = hdr[0] != 0; in.n_seqs = hdr[3];
+    in.decode = hdr[0] != 0; in.n_seqs = hdr[3]; in.want_logits = hdr[7] != 0;
     get(in.tokens, hdr[1]); get(in.positions, hdr[1]); get(in.slots, hdr[1]); get(in.sample_rows, hdr[2]);
     get(in.block_tables, hdr[4]); get(in.ctx_lens, hdr[5]);
     in.tiles.resize(hdr[6]); std::memcpy(in.tiles.data(), m + w, (size_t)hdr[6] * 16); w += (size_t)hdr[6] * 4;

@@ -46,6 +46,8 @@ public:
     int next_buffer() { return (int)(ar_count_++ & 1); }                // double-buffered symmetric storage
     void* sym(int b) const { return sym_[b]; }                            // this rank's buffer b
     void* const* d_peer_sym(int b) const { return d_peer_sym_[b]; }       // device array [t] of peer pointers for buffer b
+    void* peer_sym_host(int b, int p) const { return peer_sym_[b][p]; }
+    size_t sym_bytes() const { return sym_bytes_; }
     void* arg(int b) const { return reinterpret_cast<char*>(arg_) + (size_t)b * arg_half_bytes_; }
     void* const* d_peer_arg(int b) const { return d_peer_arg_[b]; }
     cudaError_t barrier(cudaStream_t s);                                  // every rank's prior writes visible to all
@@ -61,7 +63,7 @@ private:
     void** d_peer_sym_[2] = {nullptr, nullptr};
     uint32_t* flags_ = nullptr; uint32_t* peer_flags_[TP_MAX] = {}; uint32_t** d_peer_flags_ = nullptr;
     void* arg_ = nullptr; void* peer_arg_[TP_MAX] = {}; void** d_peer_arg_[2] = {nullptr, nullptr}; size_t arg_half_bytes_ = 0;
-    uint64_t ar_count_ = 0; uint32_t epoch_ = 0; uint64_t seq_local_ = 0;
+    uint64_t ar_count_ = 0; uint32_t epoch_ = 0; uint64_t seq_local_ = 0; size_t sym_bytes_ = 0;
 };
 
 // x[T,H] (bf16, in place) += sum over ranks (rank order) of fp32 partial rows; xn = rmsnorm(x) * gain   (decode path)

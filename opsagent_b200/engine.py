@@ -71,6 +71,10 @@ class Engine:
         _check(fn(self._h, buf, 4096))
         return buf.value.decode()
 
+    def serve(self):
+        """tensor-parallel follower: replay the leader's steps until it shuts the group down"""
+        _check(self._L.oa_engine_serve(self._h))
+
     def stats(self) -> dict:
         return json.loads(self._json(self._L.oa_engine_stats))
 

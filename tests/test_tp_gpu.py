@@ -1,0 +1,22 @@
+"""Tensor parallelism (BASELINE configs[3,4] path) on >= 2 GPUs: column/row-parallel shards, NVLink peer-memory all-reduce
+written in this repo (no NCCL), vocab-parallel arg-max — against the CPU oracle.  Skipped on a 1-GPU box."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("t", [2, 4])
+def test_tensor_parallel_matches_oracle(t):
+    if torch.cuda.device_count() < t:
+        pytest.skip(f"needs {t} GPUs")
+    cmd = [sys.executable, "-u", "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={t}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + t), os.path.join(ROOT, "tests", "tp_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0 and "TP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
