@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/opsagent_b200.h"
+#include "grammar.hpp"
 #include "model.hpp"
 #include "tokenizer.hpp"
 
@@ -30,7 +31,7 @@ __global__ void sk_reduce_f32_kernel(const StreamK sk, float* __restrict__ out, 
         const uint32_t ut0 = tile * (uint32_t)sk.kb, G = (uint32_t)sk.G, total = (uint32_t)sk.total;
         const uint32_t c_first = ((ut0 + 1u) * G - 1u) / total, c_last = ((ut0 + (uint32_t)sk.kb) * G - 1u) / total;
         float acc = 0.f;
-        for (uint32_t c = c_first; c <= c_last; ++c) acc += sk.ws[((size_t)(c + tile) * 128 + row) * sk.bn + cc];
+        for (uint32_t c = c_first; c <= c_last; ++c) acc += sk.ws[((size_t)(c + tile) * sk.rows + row) * sk.bn + cc];
         out[(size_t)row * N + col] = acc;
     }
 }
@@ -42,9 +43,9 @@ int oa_k_gemm_streamk(const void* A, const void* B, int32_t M, int32_t N, int32_
     CUtensorMap tmA, tmB;
     if (make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, 64) != 0) return OA_ERR_INTERNAL;
     if (make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)block_n, 64) != 0) return OA_ERR_INTERNAL;
-    DevBuf ws(streamk_ws_bytes(N, block_n, n_ctas));
+    DevBuf ws(streamk_ws_bytes(N, block_n, n_ctas, M));
     if (!ws.p) return OA_ERR_INTERNAL;
-    StreamK sk = make_streamk((float*)ws.p, N, K, block_n, n_ctas);
+    StreamK sk = make_streamk((float*)ws.p, N, K, block_n, n_ctas, M);
     cudaError_t e = launch_gemm_streamk(&tmA, &tmB, M, N, K, sk, s);
     if (e == cudaSuccess) { sk_reduce_f32_kernel<<<M, 256, 0, s>>>(sk, out_f32, M, N); e = cudaGetLastError(); }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
@@ -159,6 +160,14 @@ int oa_host_decode_plan(const int32_t* ctx_lens, int32_t n_seqs, int32_t n_kv, i
     }
     std::memcpy(cta_ptr_out, plan.cta_ptr.data(), plan.cta_ptr.size() * 4);
     *n_ctas_out = (int32_t)plan.cta_ptr.size() - 1; *n_segs_out = (int32_t)plan.segs.size(); *n_slots_out = plan.n_slots;
+    return OA_OK;
+}
+
+int oa_host_grammar_step(int32_t kind, const uint8_t* prefix, int32_t n, uint32_t* mask_out, int32_t* done_out) {
+    if (kind != GRAMMAR_TOOLCALL && kind != GRAMMAR_FINAL) return OA_ERR_BAD_REQUEST;
+    ToolPromptGrammar g(kind);
+    for (int i = 0; i < n; ++i) if (!g.advance(prefix[i])) return OA_ERR_BAD_REQUEST;
+    g.allowed(mask_out); *done_out = g.done() ? 1 : 0;
     return OA_OK;
 }
 

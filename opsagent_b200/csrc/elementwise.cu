@@ -154,8 +154,8 @@ OA_DEVINL void sk_sum8(const StreamK& sk, int row, int col, float (&acc)[8]) {
     const uint32_t ut0 = tile * (uint32_t)sk.kb, G = (uint32_t)sk.G, total = (uint32_t)sk.total;
     const uint32_t c_first = ((ut0 + 1u) * G - 1u) / total, c_last = ((ut0 + (uint32_t)sk.kb) * G - 1u) / total;
     const int n = (int)(c_last - c_first) + 1;
-    const size_t slot_stride = (size_t)128 * sk.bn;
-    const float* p = sk.ws + ((size_t)(c_first + tile) * 128 + row) * sk.bn + cc;
+    const size_t slot_stride = (size_t)sk.rows * sk.bn;
+    const float* p = sk.ws + ((size_t)(c_first + tile) * sk.rows + row) * sk.bn + cc;
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     // issue up to 6 partials' loads back to back (independent L2 round trips), then add them in CTA order
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256) sk_resid_rmsnorm_kernel(const StreamK sk,
 }
 cudaError_t launch_sk_resid_rmsnorm(const StreamK& sk, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s) {
     if (T <= 0) return cudaSuccess;
-    if (H % 8 != 0 || H > 8192 || T > 128) return cudaErrorInvalidValue;
+    if (H % 8 != 0 || H > 8192 || T > sk.rows) return cudaErrorInvalidValue;
     const int H8 = H / 8;
     auto X = reinterpret_cast<uint4*>(x); auto G = reinterpret_cast<const uint4*>(gain); auto Y = reinterpret_cast<uint4*>(xn);
     if (H8 <= 256) return launch_k(sk_resid_rmsnorm_kernel<1>, dim3(T), dim3(256), 0, s, sk, X, G, Y, H8, 1.0f / H, eps);
@@ -253,7 +253,7 @@ __global__ void sk_swiglu_kernel(const StreamK sk, uint4* __restrict__ act, int 
 }
 cudaError_t launch_sk_swiglu(const StreamK& sk, void* act, int T, int F, cudaStream_t s) {
     if (T <= 0) return cudaSuccess;
-    if (F % 16 != 0 || T > 128) return cudaErrorInvalidValue;
+    if (F % 16 != 0 || T > sk.rows) return cudaErrorInvalidValue;
     return launch_k(sk_swiglu_kernel, dim3((F / 8 + 255) / 256, T), dim3(256), 0, s, sk, reinterpret_cast<uint4*>(act), F / 8);
 }
 
@@ -318,7 +318,7 @@ cudaError_t launch_sk_rope_kv_write(const StreamK& sk, const void* bias, const i
                                     const float* rope_cos, const float* rope_sin, void* q_out, const KvLayout& kv, int layer, int T,
                                     int nh, cudaStream_t s) {
     if (T <= 0) return cudaSuccess;
-    if (kv.head_dim % 16 != 0 || T > 128) return cudaErrorInvalidValue;
+    if (kv.head_dim % 16 != 0 || T > sk.rows) return cudaErrorInvalidValue;
     const int64_t k0 = (int64_t)layer * kv.layer_stride_rows, v0 = k0 + kv.kv_stride_rows;
     const int items = (nh + kv.n_kv) * (kv.head_dim / 16) + kv.n_kv * (kv.head_dim / 8);
     return launch_k(sk_rope_kv_write_kernel, dim3((items + 127) / 128, T), dim3(128), 0, s, sk, reinterpret_cast<const uint16_t*>(bias), positions, slots,

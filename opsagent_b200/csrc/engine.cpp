@@ -20,6 +20,7 @@
 #include <cuda_profiler_api.h>
 
 #include "../../include/opsagent_b200.h"
+#include "grammar.hpp"
 #include "model.hpp"
 #include "tokenizer.hpp"
 
@@ -40,6 +41,7 @@ struct Seq {
     int finish_reason = 1;
     int error = 0; std::string error_msg;
     bool done = false;
+    ToolPromptGrammar grammar;       // inactive unless the request asked for schema-constrained JSON
 };
 
 class Engine {
@@ -76,6 +78,8 @@ public:
         auto s = std::make_shared<Seq>();
         s->n_prompt = (int)prompt.size(); s->tokens = std::move(prompt);
         s->max_new = std::min(max_new, opt_.max_seq_len - s->n_prompt); s->flags = flags;
+        if (flags & OA_FLAG_JSON_TOOLCALL) s->grammar = ToolPromptGrammar(GRAMMAR_TOOLCALL);
+        else if (flags & OA_FLAG_JSON_FINAL) s->grammar = ToolPromptGrammar(GRAMMAR_FINAL);
         {
             std::lock_guard<std::mutex> lk(mu_);
             if (fatal_) return fail(OA_ERR_INTERNAL, "engine is in a failed state: " + fatal_msg_);
@@ -254,6 +258,7 @@ public:
         return b;
     }
     const Tokenizer& tokenizer() const { return tok_; }
+    const EngineOptions& options() const { return opt_; }
     const ModelConfig& config() const { return model_.cfg; }
     DeviceModel& model() { return model_; }
 
@@ -287,6 +292,14 @@ private:
     }
     // Accept a sampled token for s (called with mu_ held). Returns true if the sequence finished.
     bool accept_token_locked(const std::shared_ptr<Seq>& s, int32_t t) {
+        if (s->grammar.active()) {
+            // the masked arg-max can only have produced an allowed byte; a mismatch means the device path is broken
+            if (t < 0 || t > 255 || !s->grammar.advance(t)) { s->error = OA_ERR_INTERNAL; s->error_msg = "grammar-constrained decode produced a disallowed token"; finish_locked(s, 1); return true; }
+            s->tokens.push_back(t); ++s->n_generated;
+            if (s->grammar.done()) { finish_locked(s, 0); return true; }
+            if (s->n_generated >= s->max_new || (int)s->tokens.size() >= opt_.max_seq_len) { finish_locked(s, 1); return true; }
+            return false;
+        }
         const bool eos = tok_.is_eos(t) && !(s->flags & OA_FLAG_IGNORE_EOS);
         if (eos) { finish_locked(s, 0); return true; }
         s->tokens.push_back(t); ++s->n_generated;
@@ -321,6 +334,7 @@ private:
         std::vector<std::shared_ptr<Seq>> batch;      // sequences taking part in this forward
         StepInput in;
         std::vector<int> take_of;                       // prefill: tokens consumed per batch entry
+        std::vector<std::shared_ptr<Seq>> sampled;      // sequences owning this step's sample rows, in row order
         {
             std::lock_guard<std::mutex> lk(mu_);
             // ---- admission: FIFO while pages for the whole current token list (+1) are free ----
@@ -351,7 +365,7 @@ private:
                         in.tokens.push_back(s->tokens[i]); in.positions.push_back(i); in.slots.push_back(s->pages[i / 64] * 64 + i % 64);
                     }
                     for (int r = 0; r < take; r += 64) in.tiles.push_back(PrefillTile{sidx, row0 + r, s->n_cached + r, std::min(64, take - r)});
-                    if (take == remaining) in.sample_rows.push_back(row0 + take - 1);
+                    if (take == remaining) { in.sample_rows.push_back(row0 + take - 1); sampled.push_back(s); }
                     batch.push_back(s); take_of.push_back(take); budget -= take;
                 }
             } else {
@@ -381,8 +395,16 @@ private:
                     for (size_t i = 0; i < s->pages.size(); ++i) in.block_tables[b * model_.max_pages_per_seq + i] = s->pages[i];
                     in.tokens.push_back(s->tokens[pos]); in.positions.push_back(pos); in.slots.push_back(s->pages[pos / 64] * 64 + pos % 64);
                     in.ctx_lens.push_back(pos + 1); in.sample_rows.push_back((int)b);
-                    batch.push_back(s);
+                    batch.push_back(s); sampled.push_back(s);
                 }
+            }
+            // grammar-constrained rows: allowed-byte sets for this step's sampling (9 words per sampled row)
+            bool any = false;
+            for (auto& s : sampled) any |= s->grammar.active();
+            if (any) {
+                in.masks.assign(sampled.size() * 9, 0u);
+                for (size_t i = 0; i < sampled.size(); ++i)
+                    if (sampled[i]->grammar.active()) { sampled[i]->grammar.allowed(&in.masks[i * 9]); in.masks[i * 9 + 8] = 1u; }
             }
         }
         run_forward(in, nullptr);
@@ -463,7 +485,14 @@ static int submit_chat(oa_engine* h, const oa_chat_req* r, uint64_t* ticket) {
     if (r->temperature > 1e-3f) return fail(OA_ERR_BAD_REQUEST, "only greedy decoding is implemented (the reference sends temperature=SmallestNonzeroFloat32)");
     std::vector<ChatMessage> msgs;
     int rc = build_messages(r->msgs, r->n_msgs, msgs); if (rc) return rc;
-    return h->e->submit_tokens(h->e->tokenizer().apply_chat_template(msgs), r->max_tokens, r->flags, ticket);
+    uint32_t flags = r->flags;
+    if (!(flags & (OA_FLAG_JSON_TOOLCALL | OA_FLAG_JSON_FINAL)) && h->e->options().json_mode) {
+        // stateless ReAct policy: the history is resent on every step (simple.go:498-501), so the number of assistant turns
+        // tells which step this is — tool calls first, then the final answer
+        int turns = 0; for (auto& m : msgs) if (m.role == "assistant") ++turns;
+        flags |= (turns < h->e->options().react_tool_steps) ? OA_FLAG_JSON_TOOLCALL : OA_FLAG_JSON_FINAL;
+    }
+    return h->e->submit_tokens(h->e->tokenizer().apply_chat_template(msgs), r->max_tokens, flags, ticket);
 }
 int oa_chat_submit(oa_engine* h, const oa_chat_req* r, uint64_t* ticket) { return submit_chat(h, r, ticket); }
 int oa_chat_wait(oa_engine* h, uint64_t ticket, int32_t timeout_ms, oa_chat_resp* out) {

@@ -199,6 +199,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tcgen05_kernel(const __grid
                         float f = __uint_as_float(v[j]);
                         if (col0 + j < p.N && f > best_v) { best_v = f; best_i = col0 + j; }
                     }
+                    if (p.byte_logits && col0 < 256) {
+                        float* brow = p.byte_logits + (size_t)row * 256 + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(brow + j) =
+                                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    }
                     if (p.logits) {
                         float* lrow = p.logits + (size_t)row * p.ldl;
 #pragma unroll
@@ -479,23 +486,25 @@ static cudaError_t launch_persistent(const CUtensorMap* tmA, const CUtensorMap* 
 // =============================================================================================
 // stream-K (decode, M <= 128): persistent CTAs, balanced weight streaming, fp32 partials
 // =============================================================================================
-template <int BN>
+template <int BN, int MT>     // MT = 128-row tiles of A handled per unit (1: M <= 128, 2: M <= 256)
 struct SkCfg {
-    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int A_BYTES = MT * A_TILE_BYTES;
     static constexpr int B_BYTES = BN * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;          // 4 x 48 KB (BN=256) or 6 x 32 KB (BN=128)
     static constexpr int EPI_ROW_FLOATS = 36;                          // 32 + 4 pad: conflict-free 16-byte smem accesses
     static constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_FLOATS * 4;     // one 32x32 fp32 chunk per epilogue warp
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * EPI_WARP_BYTES + 1024 + 256;
-    static constexpr uint32_t TMEM_COLS = 2 * BN;                      // two accumulator stages
+    static constexpr uint32_t TMEM_COLS = 2 * MT * BN;                 // two accumulator stages of MT row tiles
+    static_assert(TMEM_COLS <= 512, "TMEM holds 512 columns");
 };
 
-template <int BN>
+template <int BN, int MT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                          const __grid_constant__ CUtensorMap tmB, const int M,
                                                                          const StreamK sk) {
-    using Cfg = SkCfg<BN>;
+    using Cfg = SkCfg<BN, MT>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -545,7 +554,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_streamk_kernel(const __g
             for (int i = 0; i < pre; ++i) {
                 const long long u = u0 + i;
                 const int tile = (int)(u / sk.kb), kblk = (int)(u - (long long)tile * sk.kb);
-                tma_load_2d(smem + i * Cfg::STAGE_BYTES, &tmA, &full_bar[i], kblk * BLOCK_K, 0, kEvictLast);
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                    tma_load_2d(smem + i * Cfg::STAGE_BYTES + m * Cfg::A_TILE_BYTES, &tmA, &full_bar[i], kblk * BLOCK_K, m * BLOCK_M, kEvictLast);
             }
             int s = pre == STAGES ? 0 : pre; uint32_t ph = pre == STAGES ? 1 : 0;
             for (long long u = u0 + pre; u < u1; ++u) {
@@ -553,7 +564,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_streamk_kernel(const __g
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
                 mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                tma_load_2d(a_dst, &tmA, &full_bar[s], kblk * BLOCK_K, 0, kEvictLast);
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                    tma_load_2d(a_dst + m * Cfg::A_TILE_BYTES, &tmA, &full_bar[s], kblk * BLOCK_K, m * BLOCK_M, kEvictLast);
                 tma_load_2d(a_dst + Cfg::A_BYTES, &tmB, &full_bar[s], kblk * BLOCK_K, tile * BN, kEvictFirst);
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
@@ -568,15 +581,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_streamk_kernel(const __g
                 const int as = seg & 1;
                 mbar_wait(&acc_empty[as], (((uint32_t)seg >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
                 tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * MT * BN);
                 for (long long uu = u; uu < uend; ++uu) {
                     mbar_wait(&full_bar[s], ph);
                     tcgen05_fence_after();
                     const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                    const uint64_t a_desc = umma_desc_sw128(a_addr), b_desc = umma_desc_sw128(a_addr + Cfg::A_BYTES);
+                    const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                        umma_bf16(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (uu > u || k > 0) ? 1u : 0u);
+                    for (int m = 0; m < MT; ++m) {
+                        const uint64_t a_desc = umma_desc_sw128(a_addr + m * Cfg::A_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_bf16(tmem_d + (uint32_t)(m * BN), a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (uu > u || k > 0) ? 1u : 0u);
+                    }
                     umma_commit(&empty_bar[s]);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -597,12 +614,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_streamk_kernel(const __g
             // TMEM gives each thread one row x 32 columns; transpose through padded smem so that every global store
             // instruction writes four full 128-byte lines (8 lanes per row) instead of 32 scattered 16-byte pieces.
             float* stage = epi_smem + (warp - 2) * (Cfg::EPI_WARP_BYTES / 4);
-            float* dst = sk.ws + ((size_t)(c + tile) * BLOCK_M + q * 32) * BN;
             const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
-            for (int cc = 0; cc < BN; cc += 32) {
+            for (int mc = 0; mc < MT * BN; mc += 32) {
+                const int m = mc / BN, cc = mc - m * BN;
+                float* dst = sk.ws + ((size_t)(c + tile) * (MT * BLOCK_M) + m * BLOCK_M + q * 32) * BN;
                 uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cc), v);
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MT * BN + mc), v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -613,7 +631,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_streamk_kernel(const __g
                 for (int it = 0; it < 8; ++it) {
                     const int r = it * 4 + r_sub;
                     const float4 val = *reinterpret_cast<const float4*>(stage + r * Cfg::EPI_ROW_FLOATS + c4);
-                    if (q * 32 + r < M) *reinterpret_cast<float4*>(dst + (size_t)r * BN + cc + c4) = val;
+                    if (m * BLOCK_M + q * 32 + r < M) *reinterpret_cast<float4*>(dst + (size_t)r * BN + cc + c4) = val;
                 }
                 __syncwarp();
             }
@@ -628,29 +646,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_streamk_kernel(const __g
     if (warp == 1) { tcgen05_fence_after(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
 }
 
-StreamK make_streamk(float* ws, int N, int K, int bn, int G) {
-    StreamK sk{}; sk.ws = ws; sk.bn = bn; sk.kb = (K + BLOCK_K - 1) / BLOCK_K; sk.n_tiles = (N + bn - 1) / bn;
+StreamK make_streamk(float* ws, int N, int K, int bn, int G, int rows) {
+    StreamK sk{}; sk.ws = ws; sk.bn = bn; sk.rows = rows > 128 ? 256 : 128; sk.kb = (K + BLOCK_K - 1) / BLOCK_K; sk.n_tiles = (N + bn - 1) / bn;
     sk.total = (long long)sk.n_tiles * sk.kb; sk.G = (int)std::min<long long>(G, sk.total);
     sk.l2_prefetch_units = 0;
     return sk;
 }
-size_t streamk_ws_bytes(int N, int bn, int G) { return (size_t)(G + (N + bn - 1) / bn) * BLOCK_M * bn * sizeof(float); }
+size_t streamk_ws_bytes(int N, int bn, int G, int rows) { return (size_t)(G + (N + bn - 1) / bn) * (rows > 128 ? 256 : 128) * bn * sizeof(float); }
 
-template <int BN>
+template <int BN, int MT>
 static cudaError_t launch_sk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, const StreamK& sk, cudaStream_t stream) {
-    auto kern = gemm_streamk_kernel<BN>;
+    auto kern = gemm_streamk_kernel<BN, MT>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<BN>::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<BN, MT>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    return launch_k(kern, dim3(sk.G), dim3(GEMM_THREADS), SkCfg<BN>::SMEM_BYTES, stream, *tmA, *tmB, M, sk);
+    return launch_k(kern, dim3(sk.G), dim3(GEMM_THREADS), SkCfg<BN, MT>::SMEM_BYTES, stream, *tmA, *tmB, M, sk);
 }
 cudaError_t launch_gemm_streamk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, cudaStream_t stream) {
-    if (M <= 0 || M > BLOCK_M || (N % 8) != 0 || (K % 8) != 0) return cudaErrorInvalidValue;
-    if (sk.bn == 256) return launch_sk<256>(tmA, tmB, M, sk, stream);
-    if (sk.bn == 128) return launch_sk<128>(tmA, tmB, M, sk, stream);
+    if (M <= 0 || M > sk.rows || (N % 8) != 0 || (K % 8) != 0) return cudaErrorInvalidValue;
+    if (sk.rows == 256) return sk.bn == 128 ? launch_sk<128, 2>(tmA, tmB, M, sk, stream) : cudaErrorInvalidValue;
+    if (sk.bn == 256) return launch_sk<256, 1>(tmA, tmB, M, sk, stream);
+    if (sk.bn == 128) return launch_sk<128, 1>(tmA, tmB, M, sk, stream);
     return cudaErrorInvalidValue;
 }
 
@@ -678,6 +697,35 @@ __global__ void argmax_reduce_kernel(const float* __restrict__ val, const int* _
         out_ids[row] = bi == 0x7fffffff ? 0 : bi;
         if (out_val) out_val[row] = bv;
     }
+}
+
+struct ValIdxPair { float v; int i; };
+__global__ void masked_argmax_kernel(const float* __restrict__ byte_logits, const uint32_t* __restrict__ masks, int M, int32_t* __restrict__ out_ids,
+                                     ValIdxPair* __restrict__ pair_out) {
+    griddep_launch(); griddep_wait();
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const uint32_t* m = masks + (size_t)row * 9;
+    if (m[8] == 0) return;                                  // unconstrained row: keep the full-vocabulary arg-max
+    float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int b = k * 32 + lane;                        // ascending ids per lane => strict '>' keeps the lowest id on ties
+        if ((m[k] >> lane) & 1u) { const float v = byte_logits[(size_t)row * 256 + b]; if (v > bv) { bv = v; bi = b; } }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+        if (bi == 0x7fffffff) bi = 0;
+        if (pair_out) { pair_out[row].v = INFINITY; pair_out[row].i = bi; } else out_ids[row] = bi;
+    }
+}
+cudaError_t launch_masked_argmax(const float* byte_logits, const uint32_t* masks, int M, int32_t* out_ids, void* pair_out, cudaStream_t s) {
+    if (M <= 0) return cudaSuccess;
+    return launch_k(masked_argmax_kernel, dim3((M + 3) / 4), dim3(128), 0, s, byte_logits, masks, M, out_ids, reinterpret_cast<ValIdxPair*>(pair_out));
 }
 
 cudaError_t launch_argmax_reduce(const float* amax_val, const int* amax_idx, int M, int n_tiles, int32_t* out_ids,

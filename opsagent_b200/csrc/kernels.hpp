@@ -29,6 +29,7 @@ struct GemmParams {
     const void* resid; int ldr;     // bf16 [M, ldr]           (EPI_RESID)
     float* logits; int ldl;         // optional fp32 [M, ldl]  (EPI_LOGITS)
     float* amax_val; int* amax_idx; // [M, n_tiles]            (EPI_LOGITS)
+    float* byte_logits;             // optional fp32 [M, 256]: logits of token ids 0..255 for grammar-constrained rows (EPI_LOGITS)
 };
 // tmA: box {64, 128} over A[M,K]; tmB: box {64, block_n} over B[N,K].  block_n in {32,64,128,256}.
 cudaError_t launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int epilogue, int block_n,
@@ -40,11 +41,11 @@ int gemm_n_tiles(int N, int block_n);
 // partials in CTA order — a fixed order, so results are run-to-run deterministic — and apply bias / residual /
 // RMSNorm / RoPE / SwiGLU while they are at it.
 struct StreamK {
-    float* ws; int bn, kb, n_tiles, G; long long total;      // kb = k blocks per tile, total = n_tiles * kb, G = CTAs
+    float* ws; int bn, kb, n_tiles, G, rows; long long total;  // rows = 128 or 256 accumulator rows per slot      // kb = k blocks per tile, total = n_tiles * kb, G = CTAs
     int l2_prefetch_units;                                    // weight tiles each CTA prefetches into L2 before griddepcontrol.wait
 };
-StreamK make_streamk(float* ws, int N, int K, int bn, int G);
-size_t streamk_ws_bytes(int N, int bn, int G);
+StreamK make_streamk(float* ws, int N, int K, int bn, int G, int rows = 128);
+size_t streamk_ws_bytes(int N, int bn, int G, int rows = 128);
 cudaError_t launch_gemm_streamk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, cudaStream_t stream);
 // x[T,H] (bf16, in place) += sum of partials; xn = rmsnorm(x) * gain
 cudaError_t launch_sk_resid_rmsnorm(const StreamK& sk, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s);
@@ -54,6 +55,11 @@ cudaError_t launch_sk_swiglu(const StreamK& sk, void* act, int T, int F, cudaStr
 // reduce EPI_LOGITS partials: out_ids[M] = argmax over n_tiles (ties -> lowest column index)
 cudaError_t launch_argmax_reduce(const float* amax_val, const int* amax_idx, int M, int n_tiles, int32_t* out_ids,
                                  float* out_val, cudaStream_t stream);
+
+// grammar-constrained greedy sampling: masks[row*9 + 0..7] = allowed-byte bitset, masks[row*9 + 8] != 0 marks a constrained
+// row; constrained rows get arg-max over their allowed bytes (ties -> lowest id).  pair_out (tensor parallel, rank 0) receives
+// (+inf, id) so the cross-rank arg-max selects it; otherwise out_ids[row] is overwritten.
+cudaError_t launch_masked_argmax(const float* byte_logits, const uint32_t* masks, int M, int32_t* out_ids, void* pair_out, cudaStream_t s);
 
 // ---- elementwise (elementwise.cu) -----------------------------------------------------------
 cudaError_t launch_embed_gather(const int32_t* ids, const void* table, void* out, int T, int H, int vocab, cudaStream_t s);

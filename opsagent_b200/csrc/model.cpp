@@ -138,6 +138,7 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
     amax_val_ = reinterpret_cast<float*>(dmalloc((size_t)MS * lm_tiles_max * 4));
     amax_idx_ = reinterpret_cast<int*>(dmalloc((size_t)MS * lm_tiles_max * 4));
     d_out_ids_ = reinterpret_cast<int32_t*>(dmalloc((size_t)MS * 4));
+    byte_logits_ = reinterpret_cast<float*>(dmalloc((size_t)MS * 256 * 4));
     cuda_check(cudaMallocHost(&h_out_ids, (size_t)MS * 4), "cudaMallocHost");
 
     // ---- paged KV pool ----
@@ -171,7 +172,7 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
     part_o_ = reinterpret_cast<float*>(dmalloc((size_t)max_part_slots_ * grp * D * 4));
     part_ml_ = reinterpret_cast<float*>(dmalloc((size_t)max_part_slots_ * grp * 2 * 4));
     meta_cap_words_ = (size_t)4 * MR + (size_t)opt.max_batch * (max_pages_per_seq + 2) + (size_t)MR / 64 * 4 + 4 * opt.max_batch +
-                      (size_t)(opt.max_batch * nkv_l + n_ctas + 8) * 8 * 2 + (size_t)n_ctas + 4096;
+                      (size_t)(opt.max_batch * nkv_l + n_ctas + 8) * 8 * 2 + (size_t)n_ctas + 4096 + (size_t)9 * max_sample_;
     for (int i = 0; i < 2; ++i) {
         cuda_check(cudaMallocHost(&h_meta_buf_[i], meta_cap_words_ * 4), "cudaMallocHost meta");
         cuda_check(cudaEventCreateWithFlags(&meta_ev_[i], cudaEventDisableTiming), "cudaEventCreate meta");
@@ -182,7 +183,7 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
     sk_G_ = opt.sk_ctas > 0 ? opt.sk_ctas : sm_count;
     {
         size_t wsb = 0;
-        for (int n : {qkvd, H, 2 * F}) for (int bn : {128, 256}) wsb = std::max(wsb, streamk_ws_bytes(n, bn, sk_G_));
+        for (int n : {qkvd, H, 2 * F}) { wsb = std::max(wsb, streamk_ws_bytes(n, 256, sk_G_, 128)); wsb = std::max(wsb, streamk_ws_bytes(n, 128, sk_G_, 256)); }
         sk_ws_ = reinterpret_cast<float*>(dmalloc(wsb));
         // 32-bit index arithmetic in the consumers: (units of the largest shape + kb) * G must stay below 2^32
         const double worst = ((double)((2 * F + sk_bn_ - 1) / sk_bn_) * ((std::max(H, F) + 63) / 64) + (std::max(H, F) + 63) / 64) * sk_G_;
@@ -193,7 +194,7 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
     if (tp > 1) {
         if (opt.num_pages <= 0) throw std::runtime_error("tensor parallel engines need an explicit num_pages (all ranks must agree on the pool size)");
         // bf16 prefill partials | fp32 decode partials | up to 256 rows of this rank's fp32 logits shard (debug parity hook)
-        const size_t sym_bytes = std::max({(size_t)MR * H * 2, (size_t)128 * H * 4, (size_t)256 * V_l * 4});
+        const size_t sym_bytes = std::max({(size_t)MR * H * 2, (size_t)256 * H * 4, (size_t)256 * V_l * 4});
         comm.reset(new TpComm(tp, tp_rank, opt.tp_shm, sym_bytes, max_sample_));
     }
     cuda_check(cudaStreamSynchronize(stream), "init sync");
@@ -299,6 +300,8 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
     const size_t o_samp = put(in.sample_rows.data(), S);
     const size_t o_bt = put(in.block_tables.data(), in.block_tables.size());
     const size_t o_ctx = put(in.ctx_lens.data(), in.ctx_lens.size());
+    const size_t o_mask = put(in.masks.data(), in.masks.size());
+    if (!in.masks.empty() && (int)in.masks.size() != 9 * S) throw std::runtime_error("forward: grammar masks must be [n_sample, 9]");
     size_t o_segs = 0, o_ptr = 0, o_merge = 0, o_tiles = 0;
     if (in.decode) {
         const int n_ctas = opt.attn_ctas > 0 ? opt.attn_ctas : 2 * sm_count;
@@ -325,7 +328,8 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
     auto MARK = [&](int id) { if (profile_all && ek < ev_all.size()) { ev_ids[ek] = id; cudaEventRecord(ev_all[ek++], stream); } };
     const float scale_log2e = (1.0f / std::sqrt((float)D)) * 1.4426950408889634f;
     cuda_check(launch_embed_gather(d_tok, embed, x_, T, H, cfg.vocab, stream), "embed"); MARK(0);
-    const bool use_sk = opt.streamk && T <= 128;
+    const bool use_sk = opt.streamk && T <= 256;       // decode-sized batches (one or two 128-row tiles)
+    const int sk_rows = T > 128 ? 256 : 128;
     auto attention = [&](int l) {
         if (profile_attn) cudaEventRecord(ev[2 * l], stream);
         if (in.decode) {
@@ -345,10 +349,10 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
     };
     if (use_sk) {
         // decode-sized batch: persistent stream-K projections (fp32 partials) + fused consumers
-        auto bn_of = [&](int o) { return (o == 128 || o == 256) ? o : sk_bn_; };
+        auto bn_of = [&](int o) { return sk_rows == 256 ? 128 : ((o == 128 || o == 256) ? o : sk_bn_); };   // two row tiles need BN=128 (TMEM)
         auto with_pf = [&](StreamK k) { k.l2_prefetch_units = std::max(0, opt.sk_l2_prefetch_kb * 1024 / (k.bn * 128)); return k; };
-        const StreamK sk_qkv = make_streamk(sk_ws_, qkvd, H, bn_of(opt.sk_bn_qkv), sk_G_), sk_o = make_streamk(sk_ws_, H, qd, bn_of(opt.sk_bn_o), sk_G_);
-        const StreamK sk_gu = make_streamk(sk_ws_, 2 * F, H, bn_of(opt.sk_bn_gu), sk_G_), sk_dn = make_streamk(sk_ws_, H, F, bn_of(opt.sk_bn_down), sk_G_);
+        const StreamK sk_qkv = make_streamk(sk_ws_, qkvd, H, bn_of(opt.sk_bn_qkv), sk_G_, sk_rows), sk_o = make_streamk(sk_ws_, H, qd, bn_of(opt.sk_bn_o), sk_G_, sk_rows);
+        const StreamK sk_gu = make_streamk(sk_ws_, 2 * F, H, bn_of(opt.sk_bn_gu), sk_G_, sk_rows), sk_dn = make_streamk(sk_ws_, H, F, bn_of(opt.sk_bn_down), sk_G_, sk_rows);
         cuda_check(launch_rmsnorm(x_, layers[0].ln1, xn_, T, H, cfg.rms_eps, stream), "rmsnorm1"); MARK(1);
         const StreamK pf_qkv = with_pf(sk_qkv), pf_o = with_pf(sk_o), pf_gu = with_pf(sk_gu), pf_dn = with_pf(sk_dn);
         for (int l = 0; l < L; ++l) {
@@ -426,6 +430,9 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
         const int bn_lm = pick_bn(S, V, opt.bn_lm, false);
         const int n_tiles = gemm_n_tiles(V, bn_lm);
         GemmParams gl{}; gl.M = S; gl.N = V; gl.K = H; gl.logits = logits_out; gl.ldl = V; gl.amax_val = amax_val_; gl.amax_idx = amax_idx_;
+        const bool masked = !in.masks.empty();
+        const uint32_t* d_masks = reinterpret_cast<const uint32_t*>(d_meta_ + o_mask);
+        if (masked && tp_rank == 0) gl.byte_logits = byte_logits_;          // ids 0..255 live in rank 0's vocabulary shard
         int lb = -1;
         if (use_tp) {          // vocab-parallel head: each rank's fp32 logits shard is staged in its symmetric buffer when asked for
             gl.logits = nullptr;
@@ -438,6 +445,7 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
         if (use_tp) {
             const int b = comm->next_buffer();
             cuda_check(launch_argmax_reduce_pair(amax_val_, amax_idx_, S, n_tiles, tp_rank * V, comm->arg(b), stream), "argmax (local shard)");
+            if (masked && tp_rank == 0) cuda_check(launch_masked_argmax(byte_logits_, d_masks, S, nullptr, comm->arg(b), stream), "grammar arg-max");
             cuda_check(comm->barrier(stream), "xgpu barrier");
             cuda_check(launch_ar_argmax(comm->d_peer_arg(b), tp, S, d_out_ids_, stream), "argmax (all ranks)");
             if (lb >= 0 && logits_out) {   // leader assembles the full [S, vocab] logits from the peers' shards over NVLink
@@ -448,6 +456,7 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
             if (lb >= 0) cuda_check(comm->barrier(stream), "xgpu barrier");     // peers must not reuse the staged shard before the leader has read it
         } else {
             cuda_check(launch_argmax_reduce(amax_val_, amax_idx_, S, n_tiles, d_out_ids_, nullptr, stream), "argmax");
+            if (masked) cuda_check(launch_masked_argmax(byte_logits_, d_masks, S, d_out_ids_, nullptr, stream), "grammar arg-max");
         }
         cuda_check(cudaMemcpyAsync(h_out_ids, d_out_ids_, (size_t)S * 4, cudaMemcpyDeviceToHost, stream), "ids D2H"); MARK(13);
         d2h_bytes += (size_t)S * 4;

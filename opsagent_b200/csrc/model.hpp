@@ -25,6 +25,7 @@ struct StepInput {
     std::vector<int32_t> block_tables;                // [n_seqs, max_pages_per_seq]
     std::vector<int32_t> ctx_lens;                    // [n_seqs] (decode: tokens in cache incl. the new one)
     std::vector<PrefillTile> tiles;                   // prefill only
+    std::vector<uint32_t> masks;                      // [n_sample, 9] allowed-byte sets of grammar-constrained rows (empty: none)
     bool want_logits = false;                         // debug: fp32 logits of the sampled rows (tensor-parallel ranks stage their shard)
 };
 
@@ -75,7 +76,7 @@ private:
     // activations
     void *x_ = nullptr, *xn_ = nullptr, *qkv_ = nullptr, *q_ = nullptr, *attn_ = nullptr, *act_ = nullptr, *xs_ = nullptr, *xsn_ = nullptr;
     CUtensorMap tm_xn_, tm_attn_, tm_act_, tm_xsn_;
-    float* amax_val_ = nullptr; int* amax_idx_ = nullptr; int32_t* d_out_ids_ = nullptr;
+    float* amax_val_ = nullptr; int* amax_idx_ = nullptr; int32_t* d_out_ids_ = nullptr; float* byte_logits_ = nullptr;
     float *part_o_ = nullptr, *part_ml_ = nullptr; int max_part_slots_ = 0;
     float* sk_ws_ = nullptr; int sk_bn_ = 256, sk_G_ = 148;
     // pinned staging is double-buffered and fenced by events: the host may run ahead of the stream by a whole forward

@@ -106,12 +106,13 @@ void TpComm::publish(const StepInput& in) {
         spin_until([&] { return shm_->ack[p].load(std::memory_order_acquire) >= cur; }, "followers acknowledging the previous step", 600.0);
     int32_t* m = shm_->msg; size_t w = 0;
     auto put = [&](const void* src, size_t words) { if (w + words > TP_MSG_WORDS) throw std::runtime_error("tp step message overflow"); std::memcpy(m + w, src, words * 4); w += words; };
+    const int32_t n_mask = (int32_t)in.masks.size();
     const int32_t hdr[8] = {in.decode ? 1 : 0, (int32_t)in.tokens.size(), (int32_t)in.sample_rows.size(), in.n_seqs, (int32_t)in.block_tables.size(),
-                            (int32_t)in.ctx_lens.size(), (int32_t)in.tiles.size(), in.want_logits ? 1 : 0};
+                            (int32_t)in.ctx_lens.size(), (int32_t)in.tiles.size(), (in.want_logits ? 1 : 0) | (n_mask << 1)};
     put(hdr, 8);
     put(in.tokens.data(), in.tokens.size()); put(in.positions.data(), in.positions.size()); put(in.slots.data(), in.slots.size());
     put(in.sample_rows.data(), in.sample_rows.size()); put(in.block_tables.data(), in.block_tables.size());
-    put(in.ctx_lens.data(), in.ctx_lens.size()); put(in.tiles.data(), in.tiles.size() * 4);
+    put(in.ctx_lens.data(), in.ctx_lens.size()); put(in.tiles.data(), in.tiles.size() * 4); put(in.masks.data(), in.masks.size());
     shm_->msg_words = (uint32_t)w;
     shm_->seq.store(cur + 1, std::memory_order_release);
 }
@@ -128,10 +129,11 @@ bool TpComm::receive(StepInput& in) {
     const int32_t* hdr = m; w += 8;
     auto get = [&](std::vector<int32_t>& v, int n) { v.assign(m + w, m + w + n); w += n; };
     in = StepInput();
-    in.decode = hdr[0] != 0; in.n_seqs = hdr[3]; in.want_logits = hdr[7] != 0;
+    in.decode = hdr[0] != 0; in.n_seqs = hdr[3]; in.want_logits = (hdr[7] & 1) != 0;
     get(in.tokens, hdr[1]); get(in.positions, hdr[1]); get(in.slots, hdr[1]); get(in.sample_rows, hdr[2]);
     get(in.block_tables, hdr[4]); get(in.ctx_lens, hdr[5]);
     in.tiles.resize(hdr[6]); std::memcpy(in.tiles.data(), m + w, (size_t)hdr[6] * 16); w += (size_t)hdr[6] * 4;
+    { const int n_mask = hdr[7] >> 1; in.masks.resize(n_mask); std::memcpy(in.masks.data(), m + w, (size_t)n_mask * 4); w += n_mask; }
     seq_local_ = s;
     shm_->ack[rank_].store(s, std::memory_order_release);
     return true;
@@ -263,7 +265,7 @@ __global__ void sk_reduce_f32_rows_kernel(const StreamK sk, float* __restrict__ 
         const uint32_t c_first = ((ut0 + 1u) * G - 1u) / total, c_last = ((ut0 + (uint32_t)sk.kb) * G - 1u) / total;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (uint32_t c = c_first; c <= c_last; ++c) {
-            const float4* p = reinterpret_cast<const float4*>(sk.ws + ((size_t)(c + tile) * 128 + row) * sk.bn + cc);
+            const float4* p = reinterpret_cast<const float4*>(sk.ws + ((size_t)(c + tile) * sk.rows + row) * sk.bn + cc);
             const float4 a = __ldcg(p), b = __ldcg(p + 1);
             acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
         }

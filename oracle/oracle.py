@@ -266,3 +266,99 @@ def detokenize(ids) -> bytes:
     id t renders as the single byte (t & 0xFF), so random-init models still produce text whose length
     equals the completion length (encode is the identity on bytes 0..255)."""
     return bytes(int(i) & 0xFF for i in ids)
+
+
+# ------------------------------------------------------------------------------------------------
+# Grammar that forces a completion to parse as tools.ToolPrompt (reference pkg/tools/tool.go:29-38).
+# Restatement of opsagent_b200/csrc/grammar.hpp; tests walk both and compare every mask.
+# ------------------------------------------------------------------------------------------------
+TOOLS = ["kubectl", "python", "trivy", "jq", "search"]          # reference pkg/tools/tool.go:20-26
+GRAMMAR_TOOLCALL, GRAMMAR_FINAL = 1, 2
+
+
+class ToolPromptGrammar:
+    def __init__(self, kind: int):
+        L = lambda s: ("lit", s.encode(), 0, 0)
+        S = lambda lo, hi: ("str", b"", lo, hi)
+        if kind == GRAMMAR_TOOLCALL:
+            self.segs = [L('{"question":"'), S(1, 64), L('","thought":"'), S(1, 96), L('","action":{"name":"'), ("enum", b"", 0, 0),
+                         L('","input":"'), S(1, 96), L('"},"observation":"","final_answer":""}')]
+        elif kind == GRAMMAR_FINAL:
+            self.segs = [L('{"question":"'), S(1, 64), L('","thought":"'), S(1, 96),
+                         L('","action":{"name":"","input":""},"observation":"","final_answer":"'), S(10, 160), L('"}')]
+        else:
+            raise ValueError("kind")
+        self.seg, self.off, self.cand = 0, 0, set(range(len(TOOLS)))
+
+    @staticmethod
+    def string_byte(b: int) -> bool:
+        return 0x20 <= b <= 0x7E and b not in (0x22, 0x5C)
+
+    def done(self) -> bool:
+        return self.seg >= len(self.segs)
+
+    def allowed(self) -> set:
+        if self.done():
+            return set()
+        t, lit, lo, hi = self.segs[self.seg]
+        if t == "lit":
+            return {lit[self.off]}
+        if t == "str":
+            a = {b for b in range(0x20, 0x7F) if self.string_byte(b)} if self.off < hi else set()
+            if self.off >= lo:
+                a.add(0x22)
+            return a
+        return {TOOLS[i].encode()[self.off] for i in self.cand}
+
+    def _next(self):
+        self.seg += 1; self.off = 0; self.cand = set(range(len(TOOLS)))
+
+    def advance(self, b: int) -> bool:
+        if self.done() or b not in self.allowed():
+            return False
+        t, lit, lo, hi = self.segs[self.seg]
+        if t == "lit":
+            self.off += 1
+            if self.off == len(lit):
+                self._next()
+        elif t == "str":
+            if b == 0x22:
+                self._next(); self.off = 1
+                if self.off == len(self.segs[self.seg][1]):
+                    self._next()
+            else:
+                self.off += 1
+        else:
+            self.cand = {i for i in self.cand if TOOLS[i].encode()[self.off] == b}
+            self.off += 1
+            if any(self.off == len(TOOLS[i]) for i in self.cand):
+                self._next()
+        return True
+
+    def mask_words(self) -> list:
+        w = [0] * 8
+        for b in self.allowed():
+            w[b >> 5] |= 1 << (b & 31)
+        return w
+
+
+def generate_constrained(orc: "Oracle", prompt, kind: int, max_new: int = 600, slot: int = 0):
+    """Greedy decoding under the ToolPrompt grammar: arg-max over the allowed bytes only (ties -> lowest id).
+    -> (bytes, margins among the allowed set)"""
+    g = ToolPromptGrammar(kind)
+    out, margins = [], []
+    logits = orc.forward(np.ascontiguousarray(prompt, dtype=np.int32), slot=slot)[0]
+    pos = len(prompt)
+    while not g.done() and len(out) < max_new:
+        allowed = sorted(g.allowed())
+        vals = logits[allowed]
+        k = int(np.argmax(vals))                 # first maximum = lowest id
+        tok = allowed[k]
+        rest = np.delete(vals, k)
+        margins.append(float(vals[k] - rest.max()) if len(rest) else float("inf"))
+        out.append(tok); g.advance(tok)
+        if g.done():
+            break
+        logits = orc.forward(np.array([tok], np.int32), pos0=pos, slot=slot)[0]
+        pos += 1
+    return bytes(out), margins

@@ -41,7 +41,7 @@ def pair(request):
 def test_prefill_logits_match_oracle(pair):
     spec, eng, orc = pair
     rng = np.random.default_rng(1)
-    for n in (1, 17, 64, 65, 150):
+    for n in (1, 17, 64, 65, 150, 256):        # <=128: stream-K one row tile; 129..256: two row tiles
         toks = rng.integers(0, spec.vocab, size=n).astype(np.int32)
         got = eng.debug_prefill_logits(toks)
         ref = orc.forward(toks, all_logits=True)
@@ -54,10 +54,10 @@ def test_prefill_logits_through_persistent_gemm(monkeypatch):
     """same parity with every prefill projection forced through the persistent tile GEMM (the 8B prefill path)"""
     monkeypatch.setenv("OA_GEMM_PERSISTENT_MIN_TILES", "1")
     for name in CASES:
-        spec, eng = make_engine(name, bn_qkv=256, bn_o=256, bn_gu=256, bn_down=256)
+        spec, eng = make_engine(name, bn_qkv=256, bn_o=256, bn_gu=256, bn_down=256, max_step_tokens=512)
         orc = O.Oracle(spec, max_pos=512, mode=1)
         rng = np.random.default_rng(11)
-        toks = rng.integers(0, spec.vocab, size=200).astype(np.int32)      # T > 128: tile-GEMM path, not stream-K
+        toks = rng.integers(0, spec.vocab, size=300).astype(np.int32)      # T > 256: tile-GEMM path, not stream-K
         got = eng.debug_prefill_logits(toks)
         ref = orc.forward(toks, all_logits=True)
         assert np.abs(got - ref).max() < LOGIT_TOL
@@ -182,3 +182,50 @@ def test_eos_stops_generation():
     assert out.finish_reason in ("length", "stop")
     assert out.completion_tokens <= 12
     eng.close(); orc.close()
+
+
+@pytest.mark.parametrize("kind,flag", [(O.GRAMMAR_TOOLCALL, 2), (O.GRAMMAR_FINAL, 4)])
+def test_grammar_constrained_completion_is_toolprompt_json_and_matches_oracle(kind, flag):
+    """OA_FLAG_JSON_*: the completion parses as tools.ToolPrompt (reference pkg/tools/tool.go:29-38) and equals the oracle's
+    constrained greedy decode on the same weights wherever the margin among the allowed bytes exceeds the tolerance."""
+    import json as _json
+    spec, eng = make_engine("tiny-llama", max_seq_len=1024, num_pages=64)
+    orc = O.Oracle(spec, max_pos=1024, mode=1)
+    msgs = [("system", "You are a Kubernetes expert."), ("user", "how many namespace in the cluster?")]
+    ids = eng.apply_chat_template(msgs)
+    out = eng.chat_complete(spec.name, msgs, 700, flags=flag)
+    doc = _json.loads(out.content.decode("ascii"))
+    assert list(doc.keys()) == ["question", "thought", "action", "observation", "final_answer"] and out.finish_reason == "stop"
+    if kind == O.GRAMMAR_TOOLCALL:
+        assert doc["action"]["name"] in O.TOOLS and doc["final_answer"] == ""
+    else:
+        assert len(doc["final_answer"]) >= 10
+    ref, margins = O.generate_constrained(orc, np.array(ids, np.int32), kind)
+    got = out.content
+    k = 0
+    while k < min(len(ref), len(got)) and ref[k] == got[k]:
+        k += 1
+    assert k == len(ref) == len(got) or margins[k] <= 2 * LOGIT_TOL, (k, margins[k] if k < len(margins) else None)
+    eng.close(); orc.close()
+
+
+def test_json_mode_drives_a_multi_step_react_loop():
+    """engine option json_mode: tool-call steps first, then a final answer, decided from the resent history
+    (reference pkg/assistants/simple.go:391-501) — mixed with unconstrained requests in the same batch."""
+    import json as _json
+    spec, eng = make_engine("tiny-llama", max_seq_len=4096, num_pages=160, json_mode=1, react_tool_steps=2)
+    history = [("system", "sys"), ("user", "why is pod web-0 crashing?")]
+    names = []
+    for step in range(3):
+        raw = eng.generate(list(range(50, 90)), 8, flags=1)            # an unconstrained request keeps running alongside
+        assert raw.completion_tokens == 8
+        out = eng.chat_complete(spec.name, history, 700)
+        doc = _json.loads(out.content.decode("ascii"))
+        if step < 2:
+            assert doc["action"]["name"] in O.TOOLS and doc["final_answer"] == ""
+            names.append(doc["action"]["name"])
+            doc["observation"] = "NAME READY STATUS\nweb-0 0/1 CrashLoopBackOff"
+            history += [("assistant", out.content.decode("ascii")), ("user", _json.dumps(doc))]
+        else:
+            assert doc["action"]["name"] == "" and len(doc["final_answer"]) >= 10
+    eng.close()

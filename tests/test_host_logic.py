@@ -181,3 +181,44 @@ def test_request_sharding_is_a_partition():
             for i in sh:
                 assert replica_of(i, n, w) == r
         assert seen == list(range(n))
+
+
+# ---- ToolPrompt grammar: C++ automaton (csrc/grammar.hpp) vs the oracle-side restatement ----
+def _cpp_mask(kind, prefix: bytes):
+    L = _lib.load()
+    buf = (C.c_uint8 * max(1, len(prefix)))(*prefix)
+    mask = (C.c_uint32 * 8)(); done = C.c_int32()
+    rc = L.oa_host_grammar_step(kind, buf, len(prefix), mask, C.byref(done))
+    return rc, list(mask), done.value
+
+
+@pytest.mark.parametrize("kind", [O.GRAMMAR_TOOLCALL, O.GRAMMAR_FINAL])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_grammar_random_walks_agree_and_yield_toolprompt_json(kind, seed):
+    rng = np.random.default_rng(seed)
+    g = O.ToolPromptGrammar(kind)
+    out = bytearray()
+    while not g.done():
+        rc, mask, done = _cpp_mask(kind, bytes(out))
+        assert rc == 0 and not done and mask == g.mask_words()
+        allowed = sorted(g.allowed())
+        # bias towards closing strings now and then so walks terminate at varied lengths
+        b = 0x22 if (0x22 in allowed and rng.random() < 0.15) else int(rng.choice(allowed))
+        out.append(b); assert g.advance(b)
+    rc, mask, done = _cpp_mask(kind, bytes(out))
+    assert rc == 0 and done == 1 and mask == [0] * 8
+    doc = json.loads(out.decode("ascii"))
+    # exactly the ToolPrompt fields (reference pkg/tools/tool.go:29-38)
+    assert list(doc.keys()) == ["question", "thought", "action", "observation", "final_answer"]
+    assert list(doc["action"].keys()) == ["name", "input"] and doc["observation"] == ""
+    if kind == O.GRAMMAR_TOOLCALL:
+        assert doc["action"]["name"] in O.TOOLS and doc["action"]["input"] and doc["final_answer"] == ""
+    else:
+        assert doc["action"] == {"name": "", "input": ""} and len(doc["final_answer"]) >= 10   # not a placeholder (simple.go:640-654)
+
+
+def test_grammar_rejects_bytes_outside_the_schema():
+    assert _cpp_mask(1, b"[")[0] == 400
+    assert _cpp_mask(1, b'{"question":"a","thought":"b","action":{"name":"rm')[0] == 400        # not in the tool registry
+    assert _cpp_mask(2, b'{"question":"')[0] == 0
+    assert _cpp_mask(7, b"")[0] == 400

@@ -190,8 +190,11 @@ def test_gemm_persistent_kernel_all_epilogues(L, M, N, K, monkeypatch):
 
 @pytest.mark.parametrize("bn", [128, 256])
 @pytest.mark.parametrize("M,N,K,G", [(128, 4096, 4096, 148), (128, 6144, 4096, 148), (77, 1024, 14336, 148), (1, 320, 320, 148),
-                                      (128, 28672, 4096, 148), (16, 2304, 256, 5), (128, 512, 512, 3), (100, 1000, 192, 148)])
+                                      (128, 28672, 4096, 148), (16, 2304, 256, 5), (128, 512, 512, 3), (100, 1000, 192, 148),
+                                      (256, 4096, 4096, 148), (200, 1792, 5120, 148), (129, 320, 320, 7)])
 def test_gemm_streamk_partials_sum_to_the_product(L, M, N, K, G, bn):
+    if M > 128 and bn != 128:
+        pytest.skip("two 128-row tiles need BN=128 (TMEM columns)")
     g = torch.Generator(device="cpu").manual_seed(N + K + bn + G)
     A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(dev())
     B = (torch.randn(N, K, generator=g) * 0.5).to(torch.bfloat16).to(dev())

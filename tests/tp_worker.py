@@ -25,7 +25,7 @@ for name in cases:
         continue
     orc = O.Oracle(spec, max_pos=512, mode=1)
     rng = np.random.default_rng(1)
-    for n in (1, 17, 64, 150, 200):                      # <=128: stream-K + fp32 all-reduce; >128: tile GEMM + bf16 all-reduce
+    for n in (1, 17, 64, 150, 200, 256):                 # <=256: stream-K + fp32 all-reduce; larger prefill chunks: tile GEMM + bf16 all-reduce
         toks = rng.integers(0, spec.vocab, size=n).astype(np.int32)
         got = eng.debug_prefill_logits(toks)
         ref = orc.forward(toks, all_logits=True)
