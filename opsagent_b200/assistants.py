@@ -1,0 +1,105 @@
+"""assistants — Python host-side mirror of the reference's ReAct loop, the CALLER of the Chat seam
+(reference pkg/assistants/simple.go:292-616 `AssistantWithConfig`).  Same control flow, same strings:
+
+  first Chat -> json.Unmarshal into ToolPrompt; a reply that is not JSON is returned verbatim         (simple.go:343-382)
+  loop (<= maxIterations, default 5):                                                                 (simple.go:391-412)
+      final_answer set, not a template placeholder, and an observation present -> return it           (simple.go:414-419)
+      action.name set -> run tools[name](input); errors/unknown tools become the observation text     (simple.go:421-481)
+      observation = ConstrictPrompt(observation, model, 1024); whole ToolPrompt marshalled as a USER message (simple.go:495-501)
+      Chat again; reply with final_answer -> return it; unparsable reply -> "Summarize all the chat history…" Chat (simple.go:515-600)
+
+Used by bench/tests to drive multi-step tool-calling loops through the engine; `tools` is injectable because the reference's
+pkg/tools shell out to kubectl/trivy (out of scope: SURVEY.md §2 #6)."""
+from __future__ import annotations
+
+import json
+from dataclasses import dataclass, field
+
+from .llms import ChatCompletionMessage, ChatMessageRoleAssistant, ChatMessageRoleUser, ConstrictPrompt
+
+defaultMaxIterations = 5                                     # simple.go:22
+_TEMPLATE_PATTERNS = ["<最终答案", "<final_answer", "<Final answer", "<最终回答", "<回答", "<答案", "使用 Markdown 格式", "使用Markdown格式",
+                      "换行符用 \\n 表示", "换行符用\\n表示"]
+
+
+def isTemplateValue(value: str) -> bool:                     # simple.go:624-657
+    if len(value.encode("utf-8")) < 10:
+        return True
+    if any(p in value for p in _TEMPLATE_PATTERNS):
+        return True
+    return "<" in value and ">" in value
+
+
+@dataclass
+class ToolPrompt:                                            # reference pkg/tools/tool.go:29-38
+    question: str = ""
+    thought: str = ""
+    action: dict = field(default_factory=lambda: {"name": "", "input": ""})
+    observation: str = ""
+    final_answer: str = ""
+
+    @classmethod
+    def unmarshal(cls, text: str) -> "ToolPrompt":
+        d = json.loads(text)
+        if not isinstance(d, dict):
+            raise ValueError("not a JSON object")
+        a = d.get("action") or {}
+        return cls(str(d.get("question", "")), str(d.get("thought", "")), {"name": str(a.get("name", "")), "input": str(a.get("input", ""))},
+                   str(d.get("observation", "")), str(d.get("final_answer", "")))
+
+    def marshal(self) -> str:
+        return json.dumps({"question": self.question, "thought": self.thought, "action": self.action, "observation": self.observation,
+                           "final_answer": self.final_answer}, ensure_ascii=False, separators=(",", ":"))
+
+
+def AssistantWithConfig(model, prompts, maxTokens, countTokens, verbose, maxIterations, client, tools, count_tokens=None):
+    """-> (result, chatHistory).  `client` has Chat(model, maxTokens, prompts); `tools` maps name -> callable(input) -> str."""
+    chatHistory = list(prompts)
+    if not prompts:
+        raise ValueError("prompts cannot be empty")                                          # simple.go:312
+    try:
+        resp = client.Chat(model, maxTokens, chatHistory)                                    # assistant_first_chat
+    except Exception as e:
+        raise RuntimeError(f"chat completion error: {e}") from e
+    chatHistory.append(ChatCompletionMessage(ChatMessageRoleAssistant, resp))
+    try:
+        tp = ToolPrompt.unmarshal(resp)
+    except Exception:
+        return resp, chatHistory                                                             # not JSON: assume final answer
+    iterations = 0
+    if maxIterations <= 0:
+        maxIterations = defaultMaxIterations
+    while True:
+        iterations += 1
+        if iterations > maxIterations:
+            return tp.final_answer, chatHistory
+        if tp.final_answer != "" and not isTemplateValue(tp.final_answer) and tp.observation != "":
+            return tp.final_answer, chatHistory
+        if tp.action["name"] != "":
+            fn = tools.get(tp.action["name"])
+            if fn is not None:
+                try:
+                    observation = fn(tp.action["input"]).strip()
+                except Exception as e:
+                    observation = f"Tool {tp.action['name']} failed with error {e}. Considering refine the inputs for the tool."
+            else:
+                observation = f"Tool {tp.action['name']} is not available. Considering switch to other supported tools."
+            tp.observation = ConstrictPrompt(observation, model, 1024, count_tokens)
+            chatHistory.append(ChatCompletionMessage(ChatMessageRoleUser, tp.marshal()))
+            try:
+                resp = client.Chat(model, maxTokens, chatHistory)                            # assistant_intermediate_chat
+            except Exception as e:
+                raise RuntimeError(f"chat completion error: {e}") from e
+            chatHistory.append(ChatCompletionMessage(ChatMessageRoleAssistant, resp))
+            try:
+                tp = ToolPrompt.unmarshal(resp)
+            except Exception:
+                chatHistory.append(ChatCompletionMessage(ChatMessageRoleUser,
+                                                         "Summarize all the chat history and respond to original question with final answer"))
+                try:
+                    resp = client.Chat(model, maxTokens, chatHistory)                        # assistant_summarize
+                except Exception as e:
+                    raise RuntimeError(f"chat completion error: {e}") from e
+                return resp, chatHistory
+            if tp.final_answer != "":
+                return tp.final_answer, chatHistory

@@ -1,0 +1,80 @@
+"""http_front — OpenAI-compatible /v1/chat/completions in front of the engine.
+
+Lets the UNMODIFIED reference binary use the engine through its existing knobs: `baseUrl` in POST /api/execute
+(reference pkg/handlers/execute.go:21,205) or OPENAI_API_BASE for the swarm flows (pkg/workflows/swarm.go:83).
+Wire format = what go-openai v1.38.0 sends/expects at pkg/llms/openai.go:70-82: request {model, messages[{role,content}],
+max_tokens, temperature}; response {choices[{index, message{role,content}, finish_reason}], usage}; errors
+{error{message,type,code}} with the HTTP status the retry loop switches on (openai.go:85-101)."""
+from __future__ import annotations
+
+import json
+import threading
+import time
+from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+
+from .engine import EngineError
+
+_STATUS_TYPE = {400: "invalid_request_error", 401: "authentication_error", 429: "rate_limit_error", 500: "server_error"}
+
+
+def make_handler(engine, require_key: bool = True):
+    class Handler(BaseHTTPRequestHandler):
+        protocol_version = "HTTP/1.1"
+
+        def log_message(self, *a):      # quiet
+            pass
+
+        def _send(self, status: int, body: dict):
+            data = json.dumps(body, ensure_ascii=False).encode("utf-8")
+            self.send_response(status)
+            self.send_header("Content-Type", "application/json")
+            self.send_header("Content-Length", str(len(data)))
+            self.end_headers()
+            self.wfile.write(data)
+
+        def _error(self, status: int, message: str):
+            self._send(status, {"error": {"message": message, "type": _STATUS_TYPE.get(status, "server_error"), "code": status}})
+
+        def do_GET(self):
+            if self.path.rstrip("/").endswith("/models"):
+                return self._send(200, {"object": "list", "data": [{"id": engine.info["model"], "object": "model", "owned_by": "opsagent_b200"}]})
+            self._error(404, "not found")
+
+        def do_POST(self):
+            if not self.path.rstrip("/").endswith("/chat/completions"):
+                return self._error(404, "not found")
+            auth = self.headers.get("Authorization", "")
+            if require_key and not (auth.startswith("Bearer ") and len(auth) > 7):
+                return self._error(401, "missing bearer token")        # the reference always sends its apiKey (openai.go:44)
+            try:
+                n = int(self.headers.get("Content-Length", "0"))
+                req = json.loads(self.rfile.read(n) or b"{}")
+                msgs = [(m["role"], m.get("content") or "") for m in req["messages"]]
+                if req.get("stream"):
+                    return self._error(400, "streaming is not implemented (the reference does not request it)")
+                if float(req.get("temperature", 0.0) or 0.0) > 1e-3:
+                    return self._error(400, "only greedy decoding is implemented")
+                max_tokens = int(req.get("max_tokens") or req.get("max_completion_tokens") or 1024)
+            except Exception as e:
+                return self._error(400, f"bad request: {e}")
+            try:
+                out = engine.chat_complete(req.get("model", ""), msgs, max_tokens)
+            except EngineError as e:
+                return self._error(e.code if e.code in (400, 401, 429, 500) else 500, e.message)
+            self._send(200, {"id": f"chatcmpl-{int(time.time() * 1e6):x}", "object": "chat.completion", "created": int(time.time()),
+                             "model": req.get("model", ""),
+                             "choices": [{"index": 0, "message": {"role": "assistant", "content": out.content.decode("utf-8", "replace")},
+                                          "finish_reason": out.finish_reason}],
+                             "usage": {"prompt_tokens": out.prompt_tokens, "completion_tokens": out.completion_tokens,
+                                       "total_tokens": out.prompt_tokens + out.completion_tokens}})
+    return Handler
+
+
+def serve(engine, host: str = "127.0.0.1", port: int = 8000, require_key: bool = True):
+    """-> (server, thread).  One OS thread per in-flight request, each blocking in the engine — the same concurrency shape as
+    gin's goroutine-per-request; batching happens inside the engine."""
+    srv = ThreadingHTTPServer((host, port), make_handler(engine, require_key))
+    srv.daemon_threads = True
+    th = threading.Thread(target=srv.serve_forever, daemon=True)
+    th.start()
+    return srv, th

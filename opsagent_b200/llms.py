@@ -66,6 +66,28 @@ class LocalCUDAClient:
         raise RuntimeError(f"OpenAI request throttled after retrying {self.Retries} times")
 
 
+def NumTokensFromMessages(messages, model, count_tokens=None) -> int:
+    """Mirror of pkg/llms/tokens.go:60.  For OpenAI names the reference counts with tiktoken; for local models it logs an error and
+    returns 0 (tokens.go:61-66), which silently disables truncation.  Here the count comes from the engine's own tokenizer + chat
+    template (`count_tokens` = Engine.count_tokens), so it is exact for the model that will read the prompt."""
+    if count_tokens is None:
+        return 0
+    return int(count_tokens([(getattr(m, "Role", "") or "", getattr(m, "Content", "") or "") for m in messages]))
+
+
+def ConstrictPrompt(prompt: str, model: str, tokenLimits: int, count_tokens=None) -> str:
+    """Mirror of pkg/llms/tokens.go:128-144: while the prompt does not fit, drop its first ceil(n/3) lines."""
+    import math
+    while True:
+        if NumTokensFromMessages([ChatCompletionMessage("", prompt)], model, count_tokens) < tokenLimits:
+            return prompt
+        lines = prompt.split("\n")
+        lines = lines[int(math.ceil(len(lines) / 3)):]
+        prompt = "\n".join(lines)
+        if prompt.strip() == "":
+            return ""
+
+
 _ENGINES: dict = {}
 
 

@@ -222,3 +222,124 @@ def test_grammar_rejects_bytes_outside_the_schema():
     assert _cpp_mask(1, b'{"question":"a","thought":"b","action":{"name":"rm')[0] == 400        # not in the tool registry
     assert _cpp_mask(2, b'{"question":"')[0] == 0
     assert _cpp_mask(7, b"")[0] == 400
+
+
+# ---- ConstrictPrompt / ReAct loop / HTTP front (host mirrors of the callers either side of the seam) ----
+from opsagent_b200.llms import ConstrictPrompt                       # noqa: E402
+from opsagent_b200.assistants import AssistantWithConfig, ToolPrompt, isTemplateValue   # noqa: E402
+
+
+def _cl100k_like(messages):
+    """Token counts cl100k_base gives for the reference's own test strings (tokens_test.go:64-90): one token per word /
+    punctuation mark / newline, plus 3 per message and 3 for the reply priming (tokens.go:96-106)."""
+    import re
+    n = 3
+    for _role, content in messages:
+        n += 3 + len(re.findall(r"\w+|[^\w\s]|\n", content))
+    return n
+
+
+@pytest.mark.parametrize("prompt,limit,want", [
+    ("This is a test prompt.", 512, "This is a test prompt."),                       # tokens_test.go:64-72
+    ("This is a test prompt.", 1, ""),                                               # tokens_test.go:73-81
+    ("This is a test prompt.\nhere is another.", 15, "here is another."),            # tokens_test.go:82-90
+])
+def test_constrict_prompt_reproduces_the_reference_golden_cases(prompt, limit, want):
+    assert ConstrictPrompt(prompt, "gpt-3.5-turbo-0613", limit, _cl100k_like) == want
+
+
+def test_constrict_prompt_is_a_noop_without_a_tokenizer_like_the_reference():
+    # tokens.go:61-66: unknown model -> count 0 -> nothing is ever dropped
+    long = "\n".join(f"line {i}" for i in range(5000))
+    assert ConstrictPrompt(long, "llama-3-8b", 1024, None) == long
+
+
+class ScriptedClient:
+    def __init__(self, replies):
+        self.replies, self.calls = list(replies), []
+
+    def Chat(self, model, maxTokens, prompts):
+        self.calls.append([(m.Role, m.Content) for m in prompts])
+        return self.replies.pop(0)
+
+
+def test_react_loop_runs_tools_and_returns_final_answer():
+    step = ToolPrompt("q", "need pods", {"name": "kubectl", "input": "get pods"}, "", "").marshal()
+    final = ToolPrompt("q", "done", {"name": "", "input": ""}, "", "There are 3 crashing pods in ns-1").marshal()
+    cli = ScriptedClient([step, step, final])
+    seen = []
+    res, hist = AssistantWithConfig("m", [ChatCompletionMessage("system", "s"), ChatCompletionMessage("user", "q")], 2048, True, False, 5, cli,
+                                    {"kubectl": lambda i: seen.append(i) or " pod-a Running \n"})
+    assert res == "There are 3 crashing pods in ns-1" and seen == ["get pods", "get pods"] and len(cli.calls) == 3
+    # the observation goes back as a USER message holding the whole ToolPrompt (simple.go:496-501)
+    assert hist[3].Role == "user" and json.loads(hist[3].Content)["observation"] == "pod-a Running"
+    assert [m.Role for m in hist] == ["system", "user", "assistant", "user", "assistant", "user", "assistant"]
+
+
+def test_react_loop_edge_cases_follow_the_reference():
+    msgs = [ChatCompletionMessage("user", "q")]
+    # non-JSON first reply is returned verbatim (simple.go:367-382)
+    assert AssistantWithConfig("m", msgs, 10, False, False, 5, ScriptedClient(["plain text"]), {})[0] == "plain text"
+    # unknown tool / failing tool become observation text (simple.go:455,481)
+    bad = ToolPrompt("q", "t", {"name": "helm", "input": "x"}).marshal()
+    fin = ToolPrompt("q", "t", {"name": "", "input": ""}, "", "a final answer long enough").marshal()
+    cli = ScriptedClient([bad, fin])
+    AssistantWithConfig("m", msgs, 10, False, False, 5, cli, {})
+    assert "Tool helm is not available. Considering switch to other supported tools." in cli.calls[1][-1][1]
+
+    def boom(_):
+        raise RuntimeError("exit status 1")
+    cli = ScriptedClient([ToolPrompt("q", "t", {"name": "kubectl", "input": "x"}).marshal(), fin])
+    AssistantWithConfig("m", msgs, 10, False, False, 5, cli, {"kubectl": boom})
+    assert "Tool kubectl failed with error" in cli.calls[1][-1][1]
+    # unparsable intermediate reply -> one more "Summarize…" Chat (simple.go:558-566)
+    cli = ScriptedClient([ToolPrompt("q", "t", {"name": "kubectl", "input": "x"}).marshal(), "oops", "summary"])
+    res, hist = AssistantWithConfig("m", msgs, 10, False, False, 5, cli, {"kubectl": lambda i: "ok"})
+    assert res == "summary" and hist[-1].Content.startswith("Summarize all the chat history")
+    # iteration cap returns whatever final_answer holds, even empty (simple.go:407-412)
+    loop = ToolPrompt("q", "t", {"name": "kubectl", "input": "x"}).marshal()
+    res, _ = AssistantWithConfig("m", msgs, 10, False, False, 2, ScriptedClient([loop] * 5), {"kubectl": lambda i: "ok"})
+    assert res == ""
+    assert isTemplateValue("short") and isTemplateValue("<final_answer goes here>") and not isTemplateValue("3 namespaces are present")
+    with pytest.raises(ValueError, match="prompts cannot be empty"):
+        AssistantWithConfig("m", [], 10, False, False, 5, ScriptedClient([]), {})
+
+
+def test_http_front_speaks_the_wire_format_go_openai_expects():
+    import urllib.error
+    import urllib.request
+    from opsagent_b200.engine import EngineError
+    from opsagent_b200.http_front import serve
+
+    class Eng:
+        info = {"model": "tiny"}
+
+        def chat_complete(self, model, msgs, max_tokens, flags=0):
+            if model == "nope":
+                raise EngineError(400, "model 'nope' is not loaded")
+            if model == "busy":
+                raise EngineError(429, "request queue full")
+
+            class R:
+                content = ("echo:" + msgs[-1][1]).encode(); prompt_tokens = 7; completion_tokens = 3; finish_reason = "stop"
+            return R()
+
+    srv, _ = serve(Eng(), port=0)
+    base = f"http://127.0.0.1:{srv.server_address[1]}/v1"
+
+    def post(body, key="sk-x"):
+        req = urllib.request.Request(base + "/chat/completions", data=json.dumps(body).encode(),
+                                     headers={"Content-Type": "application/json", **({"Authorization": f"Bearer {key}"} if key else {})})
+        return json.loads(urllib.request.urlopen(req, timeout=10).read())
+
+    r = post({"model": "tiny", "max_tokens": 8192, "temperature": 1.401298464324817e-45, "messages": [{"role": "system", "content": "s"}, {"role": "user", "content": "hi"}]})
+    assert r["choices"][0]["message"] == {"role": "assistant", "content": "echo:hi"} and r["choices"][0]["index"] == 0
+    assert r["usage"]["total_tokens"] == 10 and r["object"] == "chat.completion"
+    for model, status in (("nope", 400), ("busy", 429)):
+        with pytest.raises(urllib.error.HTTPError) as e:
+            post({"model": model, "messages": [{"role": "user", "content": "x"}]})
+        assert e.value.code == status and json.loads(e.value.read())["error"]["code"] == status
+    with pytest.raises(urllib.error.HTTPError) as e:
+        post({"model": "tiny", "messages": [{"role": "user", "content": "x"}]}, key=None)
+    assert e.value.code == 401
+    srv.shutdown()
