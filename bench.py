@@ -125,7 +125,8 @@ def run_ours(args, rank, world, local_rank):
 
     K, W = args.steps, max(args.warmup, 3)
     eng = Engine({"model": MODEL, "device": local_rank, "kv_gb": args.kv_gb, "max_batch": BATCH, "max_seq_len": 2048,
-                  "max_step_tokens": 8192, "seed": 1234})
+                  "max_step_tokens": 8192, "seed": 1234,
+                  "prefix_cache": 0})      # every timed prompt token is really prefilled: no cached outputs inside the timed region
     info = eng.info
     # ------------------------------------------------------------------ value: device-resident decode steps
     # context chosen so that the mean over the K timed steps is MEAN_CTX (=P+G/2)

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <list>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -42,6 +43,7 @@ struct Seq {
     int error = 0; std::string error_msg;
     bool done = false;
     ToolPromptGrammar grammar;       // inactive unless the request asked for schema-constrained JSON
+    int n_registered = 0; uint64_t hash_prev = 0;   // prefix cache: full pages already published / hash of that chain
 };
 
 class Engine {
@@ -49,6 +51,8 @@ public:
     Engine(const ModelConfig& mc, const EngineOptions& eo) : model_(mc, eo), tok_(mc), opt_(eo) {
         free_pages_.reserve(model_.num_pages);
         for (int p = model_.num_pages - 1; p >= 0; --p) free_pages_.push_back(p);
+        page_ref_.assign(model_.num_pages, 0); page_hash_.assign(model_.num_pages, 0); page_parent_.assign(model_.num_pages, 0);
+        page_tokens_.assign((size_t)model_.num_pages * 64, 0); lru_pos_.assign(model_.num_pages, lru_.end());
         if (eo.tp > 1 && eo.tp_rank > 0) follower_ = std::thread([this] { follow(); });   // tensor-parallel follower: replays the leader's steps
         else if (eo.start_thread) worker_ = std::thread([this] { loop(); });
     }
@@ -135,7 +139,7 @@ public:
             run_forward(in, d_logits); model_.sync();
             cudaError_t e = cudaMemcpy(logits_out, d_logits, (size_t)n * V * 4, cudaMemcpyDeviceToHost);
             cudaFree(d_logits);
-            { std::lock_guard<std::mutex> lk(mu_); for (int p : pages) free_pages_.push_back(p); }
+            { std::lock_guard<std::mutex> lk(mu_); for (int p : pages) release_page_locked(p); }
             cuda_check(e, "logits D2H");
         } catch (const std::exception& ex) { return fail(OA_ERR_INTERNAL, ex.what()); }
         return OA_OK;
@@ -152,7 +156,7 @@ public:
             std::vector<std::vector<int32_t>> pages(batch);
             {
                 std::lock_guard<std::mutex> lk(mu_);
-                if ((long long)pages_per * batch > (long long)free_pages_.size()) return fail(OA_ERR_OVERLOADED, "bench_decode: not enough KV pages");
+                if ((long long)pages_per * batch > (long long)available_pages_locked()) return fail(OA_ERR_OVERLOADED, "bench_decode: not enough KV pages");
                 for (int b = 0; b < batch; ++b) alloc_pages_locked(pages[b], pages_per);
             }
             auto synth = [&](int b, int i) { uint64_t h = (uint64_t)(b + 1) * 0x9E3779B97F4A7C15ull + (uint64_t)i * 0xBF58476D1CE4E5B9ull; h ^= h >> 29; return (int32_t)(h % (uint64_t)V); };
@@ -220,7 +224,7 @@ public:
             float bracket_ms = 0; cudaEventElapsedTime(&bracket_ms, eb0, eb1);
             const uint64_t launches1 = launches_total();
             cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(eb0); cudaEventDestroy(eb1);
-            { std::lock_guard<std::mutex> lk(mu_); for (auto& pv : pages) for (int p : pv) free_pages_.push_back(p); }
+            { std::lock_guard<std::mutex> lk(mu_); for (auto& pv : pages) for (int p : pv) release_page_locked(p); }
             const double mean_ctx = ctx_sum / steps;
             out[0] = bracket_ms / steps; if (n_out > 6) out[6] = total_ms / steps; out[1] = prefill_ms; out[2] = (double)(launches1 - launches0) / steps; out[3] = mean_ctx;
             out[4] = model_.profile_attn ? model_.attn_ms_accum / steps : 0.0;
@@ -238,11 +242,11 @@ public:
                       "{\"requests_completed\": %llu, \"prefill_tokens\": %llu, \"decode_tokens\": %llu, \"prefill_steps\": %llu, "
                       "\"decode_steps\": %llu, \"preemptions\": %llu, \"pages_total\": %d, \"pages_free\": %zu, \"running\": %zu, "
                       "\"waiting\": %zu, \"kernel_launches\": %llu, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"weight_bytes\": %zu, "
-                      "\"kv_pool_bytes\": %zu, \"busy_ms\": %.3f}",
+                      "\"kv_pool_bytes\": %zu, \"busy_ms\": %.3f, \"prefix_hit_tokens\": %llu, \"pages_cached\": %zu}",
                       (unsigned long long)n_completed_, (unsigned long long)n_prefill_tokens_, (unsigned long long)n_decode_tokens_,
                       (unsigned long long)n_prefill_steps_, (unsigned long long)n_decode_steps_, (unsigned long long)n_preempt_,
-                      model_.num_pages, free_pages_.size(), running_.size(), waiting_.size(), (unsigned long long)launches_total(),
-                      (unsigned long long)model_.h2d_bytes, (unsigned long long)model_.d2h_bytes, model_.weight_bytes, model_.kv_pool_bytes, busy_ms_);
+                      model_.num_pages, available_pages_locked(), running_.size(), waiting_.size(), (unsigned long long)launches_total(),
+                      (unsigned long long)model_.h2d_bytes, (unsigned long long)model_.d2h_bytes, model_.weight_bytes, model_.kv_pool_bytes, busy_ms_, (unsigned long long)n_prefix_hit_tokens_, cached_.size());
         return b;
     }
     std::string info_json() {
@@ -280,14 +284,72 @@ private:
         { std::lock_guard<std::mutex> lk(mu_); follower_done_ = true; }
         cv_done_.notify_all();
     }
+    // ---- paged-KV allocator with a prefix cache -------------------------------------------------------------------
+    // The ReAct loop resends the whole history on every step (reference pkg/assistants/simple.go:498-501), so step k's
+    // prompt is step k-1's prompt + reply + observation: full 64-token pages are published under a hash chain
+    // (parent hash, 64 token ids) once their KV is complete and are reused, reference-counted, by any later request with
+    // the same prefix.  Unreferenced cached pages sit in an LRU list and are evicted only when no free page is left.
+    size_t available_pages_locked() const { return free_pages_.size() + lru_.size(); }
     bool alloc_pages_locked(std::vector<int32_t>& dst, int n) {
-        if ((int)free_pages_.size() < n) return false;
-        for (int i = 0; i < n; ++i) { dst.push_back(free_pages_.back()); free_pages_.pop_back(); }
+        if ((int)available_pages_locked() < n) return false;
+        for (int i = 0; i < n; ++i) {
+            int p;
+            if (!free_pages_.empty()) { p = free_pages_.back(); free_pages_.pop_back(); }
+            else {                                              // evict the least recently used cached page
+                p = lru_.front(); lru_.pop_front(); lru_pos_[p] = lru_.end();
+                auto it = cached_.find(page_hash_[p]); if (it != cached_.end() && it->second == p) cached_.erase(it);
+                page_hash_[p] = 0;
+            }
+            page_ref_[p] = 1; dst.push_back(p);
+        }
         return true;
+    }
+    void release_page_locked(int p) {
+        if (--page_ref_[p] > 0) return;
+        page_ref_[p] = 0;
+        if (page_hash_[p] != 0) { lru_.push_back(p); lru_pos_[p] = std::prev(lru_.end()); }
+        else free_pages_.push_back(p);
+    }
+    static uint64_t chain_hash(uint64_t parent, const int32_t* toks) {
+        uint64_t h = parent * 0x9E3779B97F4A7C15ull + 0xD6E8FEB86659FD93ull;
+        for (int i = 0; i < 64; ++i) { h ^= (uint64_t)(uint32_t)toks[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 29; }
+        return h ? h : 1;
+    }
+    // reuse cached pages for the longest cached prefix of s->tokens (always leaving >= 1 token to compute)
+    void match_prefix_locked(const std::shared_ptr<Seq>& s) {
+        s->n_registered = 0; s->hash_prev = 0; s->n_cached = 0;
+        if (!opt_.prefix_cache) return;
+        const int max_pages = ((int)s->tokens.size() - 1) / 64;
+        uint64_t h = 0;
+        for (int i = 0; i < max_pages; ++i) {
+            const uint64_t hi = chain_hash(h, s->tokens.data() + (size_t)i * 64);
+            auto it = cached_.find(hi);
+            if (it == cached_.end()) break;
+            const int p = it->second;
+            if (page_parent_[p] != h || std::memcmp(&page_tokens_[(size_t)p * 64], s->tokens.data() + (size_t)i * 64, 256) != 0) break;   // hash collision guard
+            if (page_ref_[p] == 0) { lru_.erase(lru_pos_[p]); lru_pos_[p] = lru_.end(); }
+            ++page_ref_[p]; s->pages.push_back(p);
+            h = hi; s->n_registered = i + 1; s->hash_prev = h; s->n_cached = (i + 1) * 64;
+        }
+        n_prefix_hit_tokens_ += s->n_cached;
+    }
+    // publish the pages of s whose KV became complete (n_cached advanced past their last token)
+    void register_pages_locked(const std::shared_ptr<Seq>& s) {
+        if (!opt_.prefix_cache) return;
+        const int full = std::min(s->n_cached, (int)s->tokens.size()) / 64;
+        for (int i = s->n_registered; i < full; ++i) {
+            const int p = s->pages[i];
+            const uint64_t hi = chain_hash(s->hash_prev, s->tokens.data() + (size_t)i * 64);
+            if (page_hash_[p] == 0 && cached_.find(hi) == cached_.end()) {
+                cached_[hi] = p; page_hash_[p] = hi; page_parent_[p] = s->hash_prev;
+                std::memcpy(&page_tokens_[(size_t)p * 64], s->tokens.data() + (size_t)i * 64, 256);
+            }
+            s->hash_prev = hi; s->n_registered = i + 1;
+        }
     }
     void finish_locked(const std::shared_ptr<Seq>& s, int reason) {
         s->finish_reason = reason; s->state = SeqState::DONE; s->done = true;
-        for (int p : s->pages) free_pages_.push_back(p);
+        for (int p : s->pages) release_page_locked(p);
         s->pages.clear(); ++n_completed_;
     }
     // Accept a sampled token for s (called with mu_ held). Returns true if the sequence finished.
@@ -342,8 +404,13 @@ private:
                 auto& s = waiting_.front();
                 const int need = ((int)s->tokens.size() + 1 + 63) / 64;
                 if (need > model_.num_pages) { s->error = OA_ERR_BAD_REQUEST; s->error_msg = "request larger than the KV pool"; s->done = true; waiting_.pop_front(); cv_done_.notify_all(); continue; }
-                if (!alloc_pages_locked(s->pages, need)) break;
-                s->state = SeqState::PREFILL; s->n_cached = 0;
+                match_prefix_locked(s);                                   // cached prefix pages (ref-counted), s->n_cached set
+                if (!alloc_pages_locked(s->pages, need - (int)s->pages.size())) {
+                    for (int p : s->pages) release_page_locked(p);
+                    s->pages.clear(); s->n_cached = 0; s->n_registered = 0; s->hash_prev = 0;
+                    break;
+                }
+                s->state = SeqState::PREFILL;
                 running_.push_back(s); waiting_.pop_front();
             }
             if (running_.empty()) return;
@@ -372,7 +439,7 @@ private:
                 in.decode = true;
                 // every decoding sequence needs a slot for its newest token; preempt (recompute later) if the pool is dry
                 auto preempt = [&](const std::shared_ptr<Seq>& v) {
-                    for (int p : v->pages) free_pages_.push_back(p);
+                    for (int p : v->pages) release_page_locked(p);
                     v->pages.clear(); v->n_cached = 0; v->state = SeqState::WAITING;
                     waiting_.push_front(v); ++n_preempt_;
                 };
@@ -414,13 +481,16 @@ private:
             bool any_done = false;
             if (in.decode) {
                 ++n_decode_steps_; n_decode_tokens_ += batch.size();
-                for (size_t b = 0; b < batch.size(); ++b) { batch[b]->n_cached = (int)batch[b]->tokens.size(); any_done |= accept_token_locked(batch[b], model_.h_out_ids[b]); }
+                for (size_t b = 0; b < batch.size(); ++b) {
+                    batch[b]->n_cached = (int)batch[b]->tokens.size(); register_pages_locked(batch[b]);
+                    any_done |= accept_token_locked(batch[b], model_.h_out_ids[b]);
+                }
             } else {
                 ++n_prefill_steps_; n_prefill_tokens_ += in.tokens.size();
                 int si = 0;
                 for (size_t b = 0; b < batch.size(); ++b) {
                     auto& s = batch[b];
-                    s->n_cached += take_of[b];
+                    s->n_cached += take_of[b]; register_pages_locked(s);
                     if (s->n_cached == (int)s->tokens.size()) { s->state = SeqState::DECODE; any_done |= accept_token_locked(s, model_.h_out_ids[si++]); }
                 }
             }
@@ -438,6 +508,9 @@ private:
     std::vector<std::shared_ptr<Seq>> running_;
     std::unordered_map<uint64_t, std::shared_ptr<Seq>> by_ticket_;
     std::vector<int32_t> free_pages_;
+    std::vector<int32_t> page_ref_; std::vector<uint64_t> page_hash_, page_parent_; std::vector<int32_t> page_tokens_;
+    std::unordered_map<uint64_t, int> cached_; std::list<int> lru_; std::vector<std::list<int>::iterator> lru_pos_;
+    uint64_t n_prefix_hit_tokens_ = 0;
     uint64_t next_ticket_ = 1;
     bool stop_ = false, fatal_ = false; std::string fatal_msg_;
     std::thread worker_, follower_; bool follower_done_ = false;
@@ -486,7 +559,7 @@ static int submit_chat(oa_engine* h, const oa_chat_req* r, uint64_t* ticket) {
     std::vector<ChatMessage> msgs;
     int rc = build_messages(r->msgs, r->n_msgs, msgs); if (rc) return rc;
     uint32_t flags = r->flags;
-    if (!(flags & (OA_FLAG_JSON_TOOLCALL | OA_FLAG_JSON_FINAL)) && h->e->options().json_mode) {
+    if (flags == 0 && h->e->options().json_mode) {        // explicit per-request flags always win
         // stateless ReAct policy: the history is resent on every step (simple.go:498-501), so the number of assistant turns
         // tells which step this is — tool calls first, then the final answer
         int turns = 0; for (auto& m : msgs) if (m.role == "assistant") ++turns;

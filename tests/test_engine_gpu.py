@@ -229,3 +229,42 @@ def test_json_mode_drives_a_multi_step_react_loop():
         else:
             assert doc["action"]["name"] == "" and len(doc["final_answer"]) >= 10
     eng.close()
+
+
+def test_prefix_cache_reuses_history_pages_without_changing_results():
+    """step k of a ReAct conversation resends step k-1's prompt + reply + observation (reference simple.go:498-501): the shared
+    prefix must come from cached KV pages, results must stay oracle-exact, and the pool must drain back to empty."""
+    spec, eng = make_engine("tiny-llama", max_seq_len=1024, num_pages=48, max_batch=8)
+    orc = O.Oracle(spec, max_pos=1024, mode=1)
+    rng = np.random.default_rng(21)
+    base = rng.integers(0, spec.vocab, size=300).astype(np.int32)
+    r1 = eng.generate(base.tolist(), 20, flags=1)
+    s1 = eng.stats()
+    assert s1["prefix_hit_tokens"] == 0 and s1["pages_cached"] >= 4
+    # same prompt again: everything but the last partial page comes from the cache, same tokens out
+    r2 = eng.generate(base.tolist(), 20, flags=1)
+    s2 = eng.stats()
+    assert s2["prefix_hit_tokens"] == 256 and list(r2.token_ids) == list(r1.token_ids)
+    assert s2["prefill_tokens"] - s1["prefill_tokens"] == 300 - 256
+    # next "ReAct step": previous prompt + reply + new observation
+    nxt = np.concatenate([base, np.array(r1.token_ids, np.int32), rng.integers(0, spec.vocab, size=90).astype(np.int32)])
+    r3 = eng.generate(nxt.tolist(), 16, flags=1)
+    s3 = eng.stats()
+    # 4 full pages: the KV of the last generated token (index 319) is never computed, so page 4 (tokens 256..319) stayed incomplete
+    assert s3["prefix_hit_tokens"] - s2["prefix_hit_tokens"] == 256
+    ref, margins, _ = orc.generate(nxt, 16)
+    k = 0
+    while k < 16 and ref[k] == r3.token_ids[k]:
+        k += 1
+    assert k == 16 or margins[k] <= 2 * LOGIT_TOL
+    # a different prefix does not hit; concurrent identical prompts are all correct
+    other = rng.integers(0, spec.vocab, size=200).astype(np.int32)
+    tickets = [eng.tokens_submit(other.tolist(), 10, flags=1) for _ in range(6)]
+    outs = [eng.wait(t) for t in tickets]
+    assert all(list(o.token_ids) == list(outs[0].token_ids) for o in outs)
+    # eviction: fill the pool with new prefixes, everything still completes and all references are dropped
+    for i in range(12):
+        eng.generate(rng.integers(0, spec.vocab, size=400).astype(np.int32).tolist(), 4, flags=1)
+    st = eng.stats()
+    assert st["pages_free"] == st["pages_total"] and st["pages_cached"] <= st["pages_total"]
+    eng.close(); orc.close()
