@@ -16,7 +16,7 @@
 // The 16-row mma.sync tile is the right tool here: with <= 8 real rows per tile even the legacy tensor path
 // is > 10x faster than the HBM stream it has to keep up with, and tcgen05's 128-row minimum cannot be filled.
 //
-// Prefill kernel: FlashAttention-2 style, 4 warps x 16 query rows per CTA, same TMA ring over the paged cache
+// Prefill kernel: FlashAttention-2 style, 8 warps x 16 query rows per CTA (one TMA-fed K/V stage serves 128 query rows), same TMA ring over the paged cache
 // (new tokens' K/V are written to the cache by rope_kv_write before attention), causal mask by position.
 #include "common.cuh"
 #include "kernels.hpp"
@@ -290,8 +290,11 @@ cudaError_t launch_decode_attention(const CUtensorMap* tm_kv, const KvLayout& kv
 // =============================================================================================
 // prefill (causal, paged)
 // =============================================================================================
+static constexpr int PREFILL_WARPS = PREFILL_TILE_ROWS / 16;            // 8 consumer warps x 16 query rows share every K/V stage
+static constexpr int PREFILL_THREADS = (PREFILL_WARPS + 1) * 32;        // + 1 TMA producer warp
+
 template <int D>
-__global__ void __launch_bounds__(ATT_THREADS, 1) prefill_attention_kernel(const __grid_constant__ CUtensorMap tm_kv,
+__global__ void __launch_bounds__(PREFILL_THREADS, 1) prefill_attention_kernel(const __grid_constant__ CUtensorMap tm_kv,
                                                                            const PrefillAttnParams p, const int64_t layer_row0,
                                                                            const int64_t kv_stride_rows) {
     using Cfg = AttCfg<D>;
@@ -310,14 +313,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) prefill_attention_kernel(const
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_kv);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 4); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], PREFILL_WARPS); }
         fence_barrier_init();
     }
     __syncthreads();
     griddep_launch();
     griddep_wait();
 
-    if (warp == 4) {
+    if (warp == PREFILL_WARPS) {
         if (lane == 0) {
             const int32_t* bt = p.block_tables + (size_t)tile.seq * p.max_pages_per_seq;
             int s = 0; uint32_t ph = 0;
@@ -464,7 +467,7 @@ static cudaError_t launch_prefill_d(const CUtensorMap* tm_kv, const KvLayout& kv
         attr_set = true;
     }
     dim3 grid(p.n_tiles, p.n_heads, 1);
-    return launch_k(kern, grid, dim3(ATT_THREADS), SMEM, s, *tm_kv, p, (int64_t)p.layer * kv.layer_stride_rows, kv.kv_stride_rows);
+    return launch_k(kern, grid, dim3(PREFILL_THREADS), SMEM, s, *tm_kv, p, (int64_t)p.layer * kv.layer_stride_rows, kv.kv_stride_rows);
 }
 
 cudaError_t launch_prefill_attention(const CUtensorMap* tm_kv, const KvLayout& kv, const PrefillAttnParams& p, cudaStream_t s) {

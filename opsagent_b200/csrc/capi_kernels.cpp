@@ -120,7 +120,7 @@ int oa_k_paged_attention(const void* q, void* out, const void* kv_cache, int32_t
     std::vector<PrefillTile> tiles; int row = 0;
     for (int i = 0; i < n_seqs; ++i) {
         const int ql = q_lens[i], p0 = ctx_lens[i] - ql;
-        for (int r = 0; r < ql; r += 64) tiles.push_back(PrefillTile{i, row + r, p0 + r, std::min(64, ql - r)});
+        for (int r = 0; r < ql; r += PREFILL_TILE_ROWS) tiles.push_back(PrefillTile{i, row + r, p0 + r, std::min(PREFILL_TILE_ROWS, ql - r)});
         row += ql;
     }
     (void)total_q;

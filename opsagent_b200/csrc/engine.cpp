@@ -135,7 +135,7 @@ public:
             for (size_t i = 0; i < pages.size(); ++i) in.block_tables[i] = pages[i];
             in.ctx_lens = {n};
             for (int i = 0; i < n; ++i) { in.tokens.push_back(toks[i]); in.positions.push_back(i); in.slots.push_back(pages[i / 64] * 64 + i % 64); in.sample_rows.push_back(i); }
-            for (int r = 0; r < n; r += 64) in.tiles.push_back(PrefillTile{0, r, r, std::min(64, n - r)});
+            for (int r = 0; r < n; r += PREFILL_TILE_ROWS) in.tiles.push_back(PrefillTile{0, r, r, std::min(PREFILL_TILE_ROWS, n - r)});
             run_forward(in, d_logits); model_.sync();
             cudaError_t e = cudaMemcpy(logits_out, d_logits, (size_t)n * V * 4, cudaMemcpyDeviceToHost);
             cudaFree(d_logits);
@@ -179,7 +179,7 @@ public:
                         in.ctx_lens.push_back(off + take);
                         const int row0 = (int)in.tokens.size();
                         for (int i = off; i < off + take; ++i) { in.tokens.push_back(synth(b, i)); in.positions.push_back(i); in.slots.push_back(pages[b][i / 64] * 64 + i % 64); }
-                        for (int r = 0; r < take; r += 64) in.tiles.push_back(PrefillTile{sidx, row0 + r, off + r, std::min(64, take - r)});
+                        for (int r = 0; r < take; r += PREFILL_TILE_ROWS) in.tiles.push_back(PrefillTile{sidx, row0 + r, off + r, std::min(PREFILL_TILE_ROWS, take - r)});
                         budget -= take; off += take;
                         if (off >= P) { off = 0; ++b; }
                     }
@@ -431,7 +431,7 @@ private:
                     for (int i = s->n_cached; i < s->n_cached + take; ++i) {
                         in.tokens.push_back(s->tokens[i]); in.positions.push_back(i); in.slots.push_back(s->pages[i / 64] * 64 + i % 64);
                     }
-                    for (int r = 0; r < take; r += 64) in.tiles.push_back(PrefillTile{sidx, row0 + r, s->n_cached + r, std::min(64, take - r)});
+                    for (int r = 0; r < take; r += PREFILL_TILE_ROWS) in.tiles.push_back(PrefillTile{sidx, row0 + r, s->n_cached + r, std::min(PREFILL_TILE_ROWS, take - r)});
                     if (take == remaining) { in.sample_rows.push_back(row0 + take - 1); sampled.push_back(s); }
                     batch.push_back(s); take_of.push_back(take); budget -= take;
                 }

@@ -110,7 +110,8 @@ struct MergeItem { int32_t seq, kvh, slot_begin, n_slots; };
 cudaError_t launch_decode_merge(const MergeItem* items, int n_items, const float* part_o, const float* part_ml, void* out,
                                 int n_heads, int n_kv, int head_dim, cudaStream_t s);
 
-struct PrefillTile { int32_t seq, q_row0, pos0, n_rows; };  // 64 query rows max; q_row0 = row in the token batch
+constexpr int PREFILL_TILE_ROWS = 128;                     // query rows of one (tile, head) CTA
+struct PrefillTile { int32_t seq, q_row0, pos0, n_rows; };  // <= PREFILL_TILE_ROWS rows of one sequence; q_row0 = row in the token batch
 struct PrefillAttnParams {
     const void* q; void* out;      // bf16 [T, nh*D]
     const int32_t* block_tables; int32_t max_pages_per_seq;

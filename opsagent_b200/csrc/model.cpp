@@ -328,7 +328,7 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
     auto MARK = [&](int id) { if (profile_all && ek < ev_all.size()) { ev_ids[ek] = id; cudaEventRecord(ev_all[ek++], stream); } };
     const float scale_log2e = (1.0f / std::sqrt((float)D)) * 1.4426950408889634f;
     cuda_check(launch_embed_gather(d_tok, embed, x_, T, H, cfg.vocab, stream), "embed"); MARK(0);
-    const bool use_sk = opt.streamk && T <= 256;       // decode-sized batches (one or two 128-row tiles)
+    const bool use_sk = opt.streamk && T <= std::min(256, std::max(128, opt.sk_max_rows));   // decode-sized batches (one or, opt-in, two 128-row tiles)
     const int sk_rows = T > 128 ? 256 : 128;
     auto attention = [&](int l) {
         if (profile_attn) cudaEventRecord(ev[2 * l], stream);

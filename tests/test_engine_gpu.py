@@ -64,6 +64,35 @@ def test_prefill_logits_through_persistent_gemm(monkeypatch):
         eng.close(); orc.close()
 
 
+def test_two_row_tile_streamk_path_matches_oracle():
+    """opt-in sk_max_rows=256: batches of 129..256 rows through the two-row-tile stream-K GEMM"""
+    spec, eng = make_engine("tiny-llama-d128", sk_max_rows=256)
+    orc = O.Oracle(spec, max_pos=512, mode=1)
+    rng = np.random.default_rng(12)
+    for n in (129, 200, 256):
+        toks = rng.integers(0, spec.vocab, size=n).astype(np.int32)
+        assert np.abs(eng.debug_prefill_logits(toks) - orc.forward(toks, all_logits=True)).max() < LOGIT_TOL
+    eng.close(); orc.close()
+
+
+def test_long_context_chunked_prefill_and_decode_match_oracle():
+    """5000-token prompt prefilled in 2048-token chunks over several scheduler steps (each chunk attends to the cached pages of
+    the earlier ones), then decode over ~80 pages with split/merged attention segments — llama3 RoPE scaling, head_dim 128."""
+    spec, eng = make_engine("tiny-llama-d128", max_seq_len=8192, num_pages=200, max_step_tokens=2048, max_batch=4)
+    orc = O.Oracle(spec, max_pos=5200, mode=1)
+    rng = np.random.default_rng(31)
+    prompt = rng.integers(0, spec.vocab, size=5000).astype(np.int32)
+    ref, margins, _ = orc.generate(prompt, 12)
+    out = eng.generate(prompt.tolist(), 12, flags=1)
+    k = 0
+    while k < 12 and ref[k] == out.token_ids[k]:
+        k += 1
+    assert k == 12 or margins[k] <= 2 * LOGIT_TOL, (k, margins[k])
+    st = eng.stats()
+    assert st["prefill_steps"] >= 3 and st["prefill_tokens"] == 5000
+    eng.close(); orc.close()
+
+
 def test_greedy_generation_matches_oracle(pair):
     spec, eng, orc = pair
     rng = np.random.default_rng(2)
