@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -123,13 +124,18 @@ int oa_k_paged_attention(const void* q, void* out, const void* kv_cache, int32_t
         for (int r = 0; r < ql; r += PREFILL_TILE_ROWS) tiles.push_back(PrefillTile{i, row + r, p0 + r, std::min(PREFILL_TILE_ROWS, ql - r)});
         row += ql;
     }
-    (void)total_q;
     DevBuf d_tiles(tiles.size() * sizeof(PrefillTile));
     if (!d_tiles.p) return OA_ERR_INTERNAL;
     cudaMemcpyAsync(d_tiles.p, tiles.data(), tiles.size() * sizeof(PrefillTile), cudaMemcpyHostToDevice, s);
     PrefillAttnParams a{}; a.q = q; a.out = out; a.block_tables = (const int32_t*)d_bt.p; a.max_pages_per_seq = max_pages_per_seq;
     a.tiles = (const PrefillTile*)d_tiles.p; a.n_tiles = (int)tiles.size(); a.layer = 0; a.n_heads = n_heads; a.n_kv = n_kv; a.scale_log2e = scale_log2e;
-    e = launch_prefill_attention(&tm, kv, a, s);
+    const char* leg = std::getenv("OA_PREFILL_ATTN");
+    if (leg && std::string(leg) == "legacy") e = launch_prefill_attention(&tm, kv, a, s);
+    else {
+        CUtensorMap tmq;
+        if (make_tmap_bf16_2d(&tmq, q, (uint64_t)total_q, (uint64_t)n_heads * head_dim, (uint64_t)n_heads * head_dim, 128, 64) != 0) return OA_ERR_INTERNAL;
+        e = launch_prefill_attention_tc(&tmq, &tm, kv, a, s);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     return rc_of(e);
 }

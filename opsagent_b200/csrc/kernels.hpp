@@ -119,7 +119,9 @@ struct PrefillAttnParams {
     int32_t layer, n_heads, n_kv;
     float scale_log2e;
 };
-cudaError_t launch_prefill_attention(const CUtensorMap* tm_kv, const KvLayout& kv, const PrefillAttnParams& p, cudaStream_t s);
+cudaError_t launch_prefill_attention(const CUtensorMap* tm_kv, const KvLayout& kv, const PrefillAttnParams& p, cudaStream_t s);   // legacy mma.sync path
+// tcgen05 path (attention_prefill_tc.cu): tm_q = box {64 cols, 128 rows} over q[T, nh*D]
+cudaError_t launch_prefill_attention_tc(const CUtensorMap* tm_q, const CUtensorMap* tm_kv, const KvLayout& kv, const PrefillAttnParams& p, cudaStream_t s);
 
 // bookkeeping for bench.py's gpu_launches claim
 uint64_t launches_total();

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -128,7 +129,8 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
         int r = make_tmap_bf16_2d(tm, p, (uint64_t)rows, (uint64_t)cols, (uint64_t)cols, 128, 64);
         if (r != 0) throw std::runtime_error("cuTensorMapEncodeTiled failed for an activation buffer (code " + std::to_string(r) + ")");
     };
-    amap(&tm_xn_, xn_, MR, H); amap(&tm_attn_, attn_, MR, qd); amap(&tm_act_, act_, MR, F);
+    amap(&tm_xn_, xn_, MR, H); amap(&tm_attn_, attn_, MR, qd); amap(&tm_act_, act_, MR, F); amap(&tm_q_, q_, MR, qd);
+    cuda_check(cudaMemsetAsync(q_, 0, (size_t)MR * qd * 2, stream), "memset");
     // sampled rows (debug logits sample every row of a short prefill: up to 2048)
     const int MS = max_sample_;
     xs_ = dmalloc((size_t)MS * H * 2); xsn_ = dmalloc((size_t)MS * H * 2);
@@ -343,7 +345,10 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
             PrefillAttnParams a{}; a.q = q_; a.out = attn_; a.block_tables = d_bt; a.max_pages_per_seq = max_pages_per_seq;
             a.tiles = reinterpret_cast<const PrefillTile*>(d_meta_ + o_tiles); a.n_tiles = (int)in.tiles.size();
             a.layer = l; a.n_heads = nh; a.n_kv = nkv; a.scale_log2e = scale_log2e;
-            cuda_check(launch_prefill_attention(&tm_kv, kv, a, stream), "prefill attention"); MARK(4);
+            static const bool legacy = [] { const char* e = std::getenv("OA_PREFILL_ATTN"); return e && std::string(e) == "legacy"; }();
+            if (legacy) cuda_check(launch_prefill_attention(&tm_kv, kv, a, stream), "prefill attention (mma.sync)");
+            else cuda_check(launch_prefill_attention_tc(&tm_q_, &tm_kv, kv, a, stream), "prefill attention (tcgen05)");
+            MARK(4);
         }
         if (profile_attn) cudaEventRecord(ev[2 * l + 1], stream);
     };

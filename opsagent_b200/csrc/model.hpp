@@ -75,7 +75,7 @@ private:
     std::vector<void*> allocs_;
     // activations
     void *x_ = nullptr, *xn_ = nullptr, *qkv_ = nullptr, *q_ = nullptr, *attn_ = nullptr, *act_ = nullptr, *xs_ = nullptr, *xsn_ = nullptr;
-    CUtensorMap tm_xn_, tm_attn_, tm_act_, tm_xsn_;
+    CUtensorMap tm_xn_, tm_attn_, tm_act_, tm_xsn_, tm_q_;
     float* amax_val_ = nullptr; int* amax_idx_ = nullptr; int32_t* d_out_ids_ = nullptr; float* byte_logits_ = nullptr;
     float *part_o_ = nullptr, *part_ml_ = nullptr; int max_part_slots_ = 0;
     float* sk_ws_ = nullptr; int sk_bn_ = 256, sk_G_ = 148;
