@@ -235,6 +235,38 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) decode_attention_kernel(const 
                     }
                 }
             }
+            if (sg.partial_slot >= 0 && p.merge_counters) {
+                // flash-decoding merge without a second kernel: the CTA that finishes an item's LAST piece combines all pieces.
+                // Counters advance by n_pieces per layer and start each step at zero, so "last" is a multiple of n_pieces.
+                __threadfence();
+                __syncwarp();
+                int last = 0;
+                if (lane == 0) last = ((atomicAdd(p.merge_counters + sg.item, 1) + 1) % sg.n_pieces) == 0;
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    __threadfence();
+                    if (g < grp) {
+                        float m_all = -INFINITY;
+                        for (int i = 0; i < sg.n_pieces; ++i) m_all = fmaxf(m_all, __ldcg(p.part_ml + ((size_t)(sg.slot_begin + i) * grp + g) * 2));
+                        float l_all = 0.f;
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) { oacc[j][0] = 0.f; oacc[j][1] = 0.f; }
+                        for (int i = 0; i < sg.n_pieces; ++i) {                       // slot order: deterministic
+                            const size_t sl = (size_t)(sg.slot_begin + i) * grp + g;
+                            const float f = exp2f(__ldcg(p.part_ml + sl * 2) - m_all);
+                            l_all += f * __ldcg(p.part_ml + sl * 2 + 1);
+                            const float* pi = p.part_o + sl * D;
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) { const float2 v2 = __ldcg(reinterpret_cast<const float2*>(pi + j * 8 + 2 * t)); oacc[j][0] += f * v2.x; oacc[j][1] += f * v2.y; }
+                        }
+                        const float inv = 1.0f / l_all;
+                        uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + (size_t)sg.seq * p.n_heads * D + (size_t)(sg.kvh * grp + g) * D;
+#pragma unroll
+                        for (int j = 0; j < NT; ++j)
+                            *reinterpret_cast<uint32_t*>(orow + j * 8 + 2 * t) = pack_bf16x2(oacc[j][0] * inv, oacc[j][1] * inv);
+                    }
+                }
+            }
         }
         named_bar_sync(1, 128);   // scratch free for the next segment
     }

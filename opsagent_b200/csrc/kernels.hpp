@@ -92,7 +92,7 @@ cudaError_t launch_init_weight(void* dst, uint64_t seed, uint64_t tensor_id, int
 struct DecodeSeg {        // one contiguous piece of one (sequence, kv head) handled by one CTA
     int32_t seq, kvh, chunk_begin, chunk_end;   // chunks of 64 tokens
     int32_t partial_slot;                        // index into the partial workspace, or -1: single-piece, write final
-    int32_t pad0, pad1, pad2;
+    int32_t slot_begin, n_pieces, item;          // cut items: first slot, piece count and merge-counter index of the (seq, kv head) item
 };
 struct DecodeAttnParams {
     const void* q;                 // bf16 [B, nh*D] (already rotated)
@@ -102,6 +102,7 @@ struct DecodeAttnParams {
     int32_t max_pages_per_seq;
     const DecodeSeg* segs; const int32_t* cta_seg_ptr; int32_t n_ctas;   // CTA c runs segs[ptr[c] .. ptr[c+1])
     float* part_o; float* part_ml; // partial workspace: [slots, group, D] fp32 and [slots, group, 2]
+    int32_t* merge_counters;       // [items], zero at the start of a step; the CTA that completes an item's last piece merges it (null: separate merge kernel)
     int32_t layer, n_heads, n_kv;
     float scale_log2e;             // (1/sqrt(D)) * log2(e)
 };

@@ -243,8 +243,9 @@ void build_decode_plan(const int32_t* ctx_lens, int n_seqs, int n_kv, int n_ctas
             const int pieces = std::min(force_splits, nch), per = (nch + pieces - 1) / pieces;
             const int real = (nch + per - 1) / per;
             MergeItem mi{s, h, out.n_slots, real};
+            const int slot0 = out.n_slots, item = (int)out.merges.size();
             for (int pz = 0; pz < real; ++pz) {
-                DecodeSeg sg{s, h, pz * per, std::min(nch, (pz + 1) * per), real > 1 ? out.n_slots++ : -1, 0, 0, 0};
+                DecodeSeg sg{s, h, pz * per, std::min(nch, (pz + 1) * per), real > 1 ? out.n_slots++ : -1, slot0, real, item};
                 out.segs.push_back(sg); out.cta_ptr.push_back((int32_t)out.segs.size());
             }
             if (real > 1) out.merges.push_back(mi);
@@ -263,9 +264,10 @@ void build_decode_plan(const int32_t* ctx_lens, int n_seqs, int n_kv, int n_ctas
         const long long c_first = g0 / per, c_last = (g1 - 1) / per;
         const int pieces = (int)(c_last - c_first + 1);
         MergeItem mi{s, h, out.n_slots, pieces};
+        const int slot0 = out.n_slots, item = (int)out.merges.size();
         for (long long c = c_first; c <= c_last; ++c) {
             const long long a = std::max(g0, c * per), b = std::min(g1, (c + 1) * per);
-            DecodeSeg sg{s, h, (int32_t)(a - g0), (int32_t)(b - g0), pieces > 1 ? out.n_slots++ : -1, 0, 0, 0};
+            DecodeSeg sg{s, h, (int32_t)(a - g0), (int32_t)(b - g0), pieces > 1 ? out.n_slots++ : -1, slot0, pieces, item};
             out.segs.push_back(sg); cta_of_seg.push_back((int)c);
         }
         if (pieces > 1) out.merges.push_back(mi);
@@ -304,14 +306,15 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
     const size_t o_ctx = put(in.ctx_lens.data(), in.ctx_lens.size());
     const size_t o_mask = put(in.masks.data(), in.masks.size());
     if (!in.masks.empty() && (int)in.masks.size() != 9 * S) throw std::runtime_error("forward: grammar masks must be [n_sample, 9]");
-    size_t o_segs = 0, o_ptr = 0, o_merge = 0, o_tiles = 0;
+    size_t o_segs = 0, o_ptr = 0, o_tiles = 0, o_cnt = 0;
     if (in.decode) {
         const int n_ctas = opt.attn_ctas > 0 ? opt.attn_ctas : 2 * sm_count;
         build_decode_plan(in.ctx_lens.data(), in.n_seqs, nkv, n_ctas, 0, plan_);
         if (plan_.n_slots > max_part_slots_) throw std::runtime_error("forward: partial workspace overflow");
         o_segs = put(plan_.segs.data(), plan_.segs.size() * 8);
         o_ptr = put(plan_.cta_ptr.data(), plan_.cta_ptr.size());
-        o_merge = put(plan_.merges.data(), plan_.merges.size() * 4);
+        zero_counters_.assign(plan_.merges.size() + 1, 0);
+        o_cnt = put(zero_counters_.data(), zero_counters_.size());     // merge counters start every step at zero
     } else {
         o_tiles = put(in.tiles.data(), in.tiles.size() * 4);
     }
@@ -338,9 +341,8 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
             DecodeAttnParams a{}; a.q = q_; a.out = attn_; a.block_tables = d_bt; a.ctx_lens = d_ctx; a.max_pages_per_seq = max_pages_per_seq;
             a.segs = reinterpret_cast<const DecodeSeg*>(d_meta_ + o_segs); a.cta_seg_ptr = d_meta_ + o_ptr; a.n_ctas = (int)plan_.cta_ptr.size() - 1;
             a.part_o = part_o_; a.part_ml = part_ml_; a.layer = l; a.n_heads = nh; a.n_kv = nkv; a.scale_log2e = scale_log2e;
+            a.merge_counters = d_meta_ + o_cnt;      // cut items are merged inside the kernel by the CTA finishing their last piece
             cuda_check(launch_decode_attention(&tm_kv, kv, a, stream), "decode attention"); MARK(4);
-            cuda_check(launch_decode_merge(reinterpret_cast<const MergeItem*>(d_meta_ + o_merge), (int)plan_.merges.size(), part_o_, part_ml_,
-                                           attn_, nh, nkv, D, stream), "decode merge"); MARK(5);
         } else {
             PrefillAttnParams a{}; a.q = q_; a.out = attn_; a.block_tables = d_bt; a.max_pages_per_seq = max_pages_per_seq;
             a.tiles = reinterpret_cast<const PrefillTile*>(d_meta_ + o_tiles); a.n_tiles = (int)in.tiles.size();
