@@ -148,8 +148,14 @@ def run_ours(args, rank, world, local_rank):
     attn_bytes = BATCH * rp["mean_ctx"] * kv_tok / L                      # K and V of every cached token, once
     peak, peak_src = measured_peaks()
     achieved = attn_bytes / (attn_launch_ms * 1e-3) / 1e9 if attn_launch_ms > 0 else 0.0
+    traffic = None
+    try:      # DRAM bytes of the same kernel from the committed `ncu --set full` capture (per launch)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["decode_attention_kernel<128>"]
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "decode_attention_kernel<128>", "achieved": round(achieved, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": attn_bytes, "launch_ms": round(attn_launch_ms, 4),
                 "kernel_share_of_step": round(rp["attn_ms_per_step"] / rp["device_ms_per_step"], 3) if rp["device_ms_per_step"] else None,
                 "step": {"algorithmic_bytes": r["algorithmic_bytes_per_step"],
