@@ -52,11 +52,15 @@ typedef struct {
     float temperature;     /* the reference always sends SmallestNonzeroFloat32: greedy. Values > 1e-3 -> 400 */
     uint64_t seed;         /* unused under greedy decoding; kept for ABI stability */
     uint32_t flags;        /* OA_FLAG_* */
+    const char* functions; /* OA_FLAG_JSON_FUNCTION: "name:param,name:param" — the functions the request's `tools` array offers */
 } oa_chat_req;
 
 #define OA_FLAG_IGNORE_EOS 1u /* throughput runs: always generate exactly max_tokens tokens */
 #define OA_FLAG_JSON_TOOLCALL 2u /* force the completion to parse as tools.ToolPrompt (pkg/tools/tool.go:29-38) with an action from the
                                   * tool registry (tool.go:20-26) and an empty final_answer: one ReAct tool-call step */
+#define OA_FLAG_JSON_FUNCTION 8u /* OpenAI function calling (swarm-go flows, pkg/workflows/swarm.go:14-78): the completion is
+                                  * {"name":"<offered function>","arguments":{"<its parameter>":"..."}} */
+#define OA_FLAG_JSON_TEXT 16u    /* one bounded line of printable text (10..200 bytes), newline-terminated */
 #define OA_FLAG_JSON_FINAL 4u    /* same schema, empty action, final_answer of >= 10 bytes (not a placeholder per simple.go:640-654) */
 
 /* replaces resp.Choices[0].Message.Content (+ usage) at pkg/llms/openai.go:82 */
@@ -132,6 +136,7 @@ OA_API int oa_host_decode_plan(const int32_t* ctx_lens, int32_t n_seqs, int32_t 
 /* grammar automaton, host only: feeds `prefix` (n bytes) to the schema `kind` (1 tool call, 2 final) and returns the allowed-byte
  * bitset for the next position in mask_out[8], *done_out = 1 when the JSON is complete; 400 if the prefix is not derivable */
 OA_API int oa_host_grammar_step(int32_t kind, const uint8_t* prefix, int32_t n, uint32_t* mask_out, int32_t* done_out);
+OA_API int oa_host_grammar_step_ex(int32_t kind, const char* functions, const uint8_t* prefix, int32_t n, uint32_t* mask_out, int32_t* done_out);
 /* resolved architecture + derived byte counts of a config, no device needed */
 OA_API int oa_host_model_info(const char* config_json, char* buf, size_t n);
 OA_API uint64_t oa_kernel_launches(void);

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libopsagent_b200.so")
 
 OA_OK, OA_ERR_BAD_REQUEST, OA_ERR_TIMEOUT, OA_ERR_OVERLOADED, OA_ERR_INTERNAL = 0, 400, 408, 429, 500
-OA_FLAG_IGNORE_EOS, OA_FLAG_JSON_TOOLCALL, OA_FLAG_JSON_FINAL = 1, 2, 4
+OA_FLAG_IGNORE_EOS, OA_FLAG_JSON_TOOLCALL, OA_FLAG_JSON_FINAL, OA_FLAG_JSON_FUNCTION, OA_FLAG_JSON_TEXT = 1, 2, 4, 8, 16
 
 
 class OaMsg(C.Structure):
@@ -20,7 +20,7 @@ class OaMsg(C.Structure):
 
 class OaChatReq(C.Structure):
     _fields_ = [("model", C.c_char_p), ("msgs", C.POINTER(OaMsg)), ("n_msgs", C.c_int32), ("max_tokens", C.c_int32),
-                ("temperature", C.c_float), ("seed", C.c_uint64), ("flags", C.c_uint32)]
+                ("temperature", C.c_float), ("seed", C.c_uint64), ("flags", C.c_uint32), ("functions", C.c_char_p)]
 
 
 class OaChatResp(C.Structure):
@@ -34,7 +34,7 @@ SYMBOLS = [
     "oa_tokens_submit", "oa_count_tokens", "oa_apply_chat_template", "oa_last_error", "oa_engine_stats", "oa_model_info",
     "oa_debug_prefill_logits", "oa_bench_decode", "oa_k_rmsnorm", "oa_k_gemm", "oa_k_init_weight", "oa_k_paged_attention",
     "oa_kernel_launches", "oa_version", "oa_host_apply_chat_template", "oa_host_decode_plan", "oa_host_model_info",
-    "oa_k_gemm_streamk", "oa_debug_kernel_times", "oa_engine_serve", "oa_host_grammar_step",
+    "oa_k_gemm_streamk", "oa_debug_kernel_times", "oa_engine_serve", "oa_host_grammar_step", "oa_host_grammar_step_ex",
 ]
 
 _lib = None
@@ -73,6 +73,7 @@ def load() -> C.CDLL:
     L.oa_host_apply_chat_template.argtypes = [C.c_char_p, C.POINTER(OaMsg), i32, vp, i32, C.POINTER(i32)]; L.oa_host_apply_chat_template.restype = C.c_int
     L.oa_host_decode_plan.argtypes = [vp, i32, i32, i32, i32, vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]; L.oa_host_decode_plan.restype = C.c_int
     L.oa_host_grammar_step.argtypes = [i32, vp, i32, vp, C.POINTER(i32)]; L.oa_host_grammar_step.restype = C.c_int
+    L.oa_host_grammar_step_ex.argtypes = [i32, C.c_char_p, vp, i32, vp, C.POINTER(i32)]; L.oa_host_grammar_step_ex.restype = C.c_int
     L.oa_host_model_info.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]; L.oa_host_model_info.restype = C.c_int
     L.oa_kernel_launches.restype = u64
     L.oa_version.restype = C.c_char_p

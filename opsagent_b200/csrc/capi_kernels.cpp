@@ -170,8 +170,12 @@ int oa_host_decode_plan(const int32_t* ctx_lens, int32_t n_seqs, int32_t n_kv, i
 }
 
 int oa_host_grammar_step(int32_t kind, const uint8_t* prefix, int32_t n, uint32_t* mask_out, int32_t* done_out) {
-    if (kind != GRAMMAR_TOOLCALL && kind != GRAMMAR_FINAL) return OA_ERR_BAD_REQUEST;
-    ToolPromptGrammar g(kind);
+    return oa_host_grammar_step_ex(kind, "", prefix, n, mask_out, done_out);
+}
+int oa_host_grammar_step_ex(int32_t kind, const char* functions, const uint8_t* prefix, int32_t n, uint32_t* mask_out, int32_t* done_out) {
+    if (kind < GRAMMAR_TOOLCALL || kind > GRAMMAR_TEXT) return OA_ERR_BAD_REQUEST;
+    ToolPromptGrammar g(kind, functions ? functions : "");
+    if (!g.active()) return OA_ERR_BAD_REQUEST;
     for (int i = 0; i < n; ++i) if (!g.advance(prefix[i])) return OA_ERR_BAD_REQUEST;
     g.allowed(mask_out); *done_out = g.done() ? 1 : 0;
     return OA_OK;

@@ -72,7 +72,7 @@ public:
         return fatal_ ? fail(OA_ERR_INTERNAL, fatal_msg_) : OA_OK;
     }
 
-    int submit_tokens(std::vector<int32_t>&& prompt, int max_new, uint32_t flags, uint64_t* ticket) {
+    int submit_tokens(std::vector<int32_t>&& prompt, int max_new, uint32_t flags, uint64_t* ticket, const char* functions = nullptr) {
         if (is_follower()) return fail(OA_ERR_BAD_REQUEST, "tensor-parallel followers take no requests: submit to the leader (tp_rank 0)");
         if (prompt.empty()) return fail(OA_ERR_BAD_REQUEST, "empty prompt");
         if (max_new <= 0) return fail(OA_ERR_BAD_REQUEST, "max_tokens must be positive");
@@ -84,6 +84,10 @@ public:
         s->max_new = std::min(max_new, opt_.max_seq_len - s->n_prompt); s->flags = flags;
         if (flags & OA_FLAG_JSON_TOOLCALL) s->grammar = ToolPromptGrammar(GRAMMAR_TOOLCALL);
         else if (flags & OA_FLAG_JSON_FINAL) s->grammar = ToolPromptGrammar(GRAMMAR_FINAL);
+        else if (flags & OA_FLAG_JSON_FUNCTION) {
+            s->grammar = ToolPromptGrammar(GRAMMAR_FUNCTION, functions ? functions : "");
+            if (!s->grammar.active()) return fail(OA_ERR_BAD_REQUEST, "OA_FLAG_JSON_FUNCTION needs functions=\"name:param,...\"");
+        } else if (flags & OA_FLAG_JSON_TEXT) s->grammar = ToolPromptGrammar(GRAMMAR_TEXT);
         {
             std::lock_guard<std::mutex> lk(mu_);
             if (fatal_) return fail(OA_ERR_INTERNAL, "engine is in a failed state: " + fatal_msg_);
@@ -565,7 +569,7 @@ static int submit_chat(oa_engine* h, const oa_chat_req* r, uint64_t* ticket) {
         int turns = 0; for (auto& m : msgs) if (m.role == "assistant") ++turns;
         flags |= (turns < h->e->options().react_tool_steps) ? OA_FLAG_JSON_TOOLCALL : OA_FLAG_JSON_FINAL;
     }
-    return h->e->submit_tokens(h->e->tokenizer().apply_chat_template(msgs), r->max_tokens, flags, ticket);
+    return h->e->submit_tokens(h->e->tokenizer().apply_chat_template(msgs), r->max_tokens, flags, ticket, r->functions);
 }
 int oa_chat_submit(oa_engine* h, const oa_chat_req* r, uint64_t* ticket) { return submit_chat(h, r, ticket); }
 int oa_chat_wait(oa_engine* h, uint64_t ticket, int32_t timeout_ms, oa_chat_resp* out) {

@@ -79,11 +79,12 @@ class Engine:
         return json.loads(self._json(self._L.oa_engine_stats))
 
     # ---- chat path (what LocalCUDAClient.Chat uses) ----
-    def _req(self, model, messages, max_tokens, flags):
+    def _req(self, model, messages, max_tokens, flags, functions=None):
         arr, keep = _msgs(messages)
         m = model.encode() if model else None
-        req = _lib.OaChatReq(m, arr, len(messages), max_tokens, 1.401298464324817e-45, 0, flags)
-        return req, (arr, keep, m)
+        f = functions.encode() if functions else None
+        req = _lib.OaChatReq(m, arr, len(messages), max_tokens, 1.401298464324817e-45, 0, flags, f)
+        return req, (arr, keep, m, f)
 
     def chat_submit(self, model: str, messages, max_tokens: int, flags: int = 0) -> int:
         req, _keep = self._req(model, messages, max_tokens, flags)
@@ -99,8 +100,8 @@ class Engine:
         finally:
             self._L.oa_free_resp(C.byref(resp))
 
-    def chat_complete(self, model: str, messages, max_tokens: int, flags: int = 0) -> Completion:
-        req, _keep = self._req(model, messages, max_tokens, flags)
+    def chat_complete(self, model: str, messages, max_tokens: int, flags: int = 0, functions: str | None = None) -> Completion:
+        req, _keep = self._req(model, messages, max_tokens, flags, functions)
         resp = _lib.OaChatResp()
         _check(self._L.oa_chat_complete(self._h, C.byref(req), C.byref(resp)))
         try:

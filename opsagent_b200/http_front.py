@@ -17,7 +17,7 @@ from .engine import EngineError
 _STATUS_TYPE = {400: "invalid_request_error", 401: "authentication_error", 429: "rate_limit_error", 500: "server_error"}
 
 
-def make_handler(engine, require_key: bool = True):
+def make_handler(engine, require_key: bool = True, tool_steps: int = 3):
     class Handler(BaseHTTPRequestHandler):
         protocol_version = "HTTP/1.1"
 
@@ -49,7 +49,13 @@ def make_handler(engine, require_key: bool = True):
             try:
                 n = int(self.headers.get("Content-Length", "0"))
                 req = json.loads(self.rfile.read(n) or b"{}")
-                msgs = [(m["role"], m.get("content") or "") for m in req["messages"]]
+                msgs = []
+                for m in req["messages"]:            # function-calling turns are flattened into text the byte-level template can carry
+                    if m.get("tool_calls"):
+                        f = m["tool_calls"][0]["function"]
+                        msgs.append((m["role"], '{"name":%s,"arguments":%s}' % (json.dumps(f["name"]), f.get("arguments") or "{}")))
+                    else:
+                        msgs.append((m["role"], m.get("content") or ""))
                 if req.get("stream"):
                     return self._error(400, "streaming is not implemented (the reference does not request it)")
                 if float(req.get("temperature", 0.0) or 0.0) > 1e-3:
@@ -57,23 +63,48 @@ def make_handler(engine, require_key: bool = True):
                 max_tokens = int(req.get("max_tokens") or req.get("max_completion_tokens") or 1024)
             except Exception as e:
                 return self._error(400, f"bad request: {e}")
+            # OpenAI function calling (swarm-go flows, reference pkg/workflows/swarm.go:14-78, analyze.go:47-75): while fewer than
+            # `react_tool_steps` tool results are in the history the reply is a grammar-forced call of one offered function,
+            # afterwards one line of text.
+            flags, functions = 0, None
+            tools = req.get("tools") or []
+            if tools:
+                specs = []
+                for t in tools:
+                    f = t.get("function", {})
+                    props = list((f.get("parameters") or {}).get("properties", {}).keys()) or ["input"]
+                    specs.append(f"{f.get('name', 'fn')}:{props[0]}")
+                n_results = sum(1 for m in req["messages"] if m.get("role") == "tool")
+                if n_results < tool_steps:
+                    flags, functions = 8, ",".join(specs)
+                else:
+                    flags = 16
             try:
-                out = engine.chat_complete(req.get("model", ""), msgs, max_tokens)
+                out = engine.chat_complete(req.get("model", ""), msgs, max_tokens, flags=flags, functions=functions)
             except EngineError as e:
                 return self._error(e.code if e.code in (400, 401, 429, 500) else 500, e.message)
+            if flags == 8:
+                call = json.loads(out.content.decode("utf-8", "replace"))
+                message = {"role": "assistant", "content": None,
+                           "tool_calls": [{"id": f"call_{int(time.time() * 1e6):x}", "type": "function",
+                                           "function": {"name": call["name"], "arguments": json.dumps(call["arguments"])}}]}
+                return self._send(200, {"id": f"chatcmpl-{int(time.time() * 1e6):x}", "object": "chat.completion", "created": int(time.time()),
+                                        "model": req.get("model", ""), "choices": [{"index": 0, "message": message, "finish_reason": "tool_calls"}],
+                                        "usage": {"prompt_tokens": out.prompt_tokens, "completion_tokens": out.completion_tokens,
+                                                  "total_tokens": out.prompt_tokens + out.completion_tokens}})
             self._send(200, {"id": f"chatcmpl-{int(time.time() * 1e6):x}", "object": "chat.completion", "created": int(time.time()),
                              "model": req.get("model", ""),
-                             "choices": [{"index": 0, "message": {"role": "assistant", "content": out.content.decode("utf-8", "replace")},
+                             "choices": [{"index": 0, "message": {"role": "assistant", "content": out.content.decode("utf-8", "replace").rstrip("\n")},
                                           "finish_reason": out.finish_reason}],
                              "usage": {"prompt_tokens": out.prompt_tokens, "completion_tokens": out.completion_tokens,
                                        "total_tokens": out.prompt_tokens + out.completion_tokens}})
     return Handler
 
 
-def serve(engine, host: str = "127.0.0.1", port: int = 8000, require_key: bool = True):
+def serve(engine, host: str = "127.0.0.1", port: int = 8000, require_key: bool = True, tool_steps: int = 3):
     """-> (server, thread).  One OS thread per in-flight request, each blocking in the engine — the same concurrency shape as
     gin's goroutine-per-request; batching happens inside the engine."""
-    srv = ThreadingHTTPServer((host, port), make_handler(engine, require_key))
+    srv = ThreadingHTTPServer((host, port), make_handler(engine, require_key, tool_steps))
     srv.daemon_threads = True
     th = threading.Thread(target=srv.serve_forever, daemon=True)
     th.start()

@@ -273,22 +273,30 @@ def detokenize(ids) -> bytes:
 # Restatement of opsagent_b200/csrc/grammar.hpp; tests walk both and compare every mask.
 # ------------------------------------------------------------------------------------------------
 TOOLS = ["kubectl", "python", "trivy", "jq", "search"]          # reference pkg/tools/tool.go:20-26
-GRAMMAR_TOOLCALL, GRAMMAR_FINAL = 1, 2
+GRAMMAR_TOOLCALL, GRAMMAR_FINAL, GRAMMAR_FUNCTION, GRAMMAR_TEXT = 1, 2, 3, 4
 
 
 class ToolPromptGrammar:
-    def __init__(self, kind: int):
+    def __init__(self, kind: int, functions: str = ""):
         L = lambda s: ("lit", s.encode(), 0, 0)
         S = lambda lo, hi: ("str", b"", lo, hi)
+        self.opts = [t.encode() for t in TOOLS]
+        self.close = 0x22
         if kind == GRAMMAR_TOOLCALL:
             self.segs = [L('{"question":"'), S(1, 64), L('","thought":"'), S(1, 96), L('","action":{"name":"'), ("enum", b"", 0, 0),
                          L('","input":"'), S(1, 96), L('"},"observation":"","final_answer":""}')]
         elif kind == GRAMMAR_FINAL:
             self.segs = [L('{"question":"'), S(1, 64), L('","thought":"'), S(1, 96),
                          L('","action":{"name":"","input":""},"observation":"","final_answer":"'), S(10, 160), L('"}')]
+        elif kind == GRAMMAR_FUNCTION:       # OpenAI function calling: {"name":"<fn>","arguments":{"<param>":"..."}}
+            self.opts = [(n + '","arguments":{"' + p + '":"').encode() for n, p in (it.split(":", 1) for it in functions.split(",") if ":" in it)]
+            self.segs = [L('{"name":"'), ("enum", b"", 0, 0), S(1, 96), L('"}}')]
+        elif kind == GRAMMAR_TEXT:
+            self.close = 0x0A
+            self.segs = [S(10, 200), L("\n")]
         else:
             raise ValueError("kind")
-        self.seg, self.off, self.cand = 0, 0, set(range(len(TOOLS)))
+        self.seg, self.off, self.cand = 0, 0, set(range(len(self.opts)))
 
     @staticmethod
     def string_byte(b: int) -> bool:
@@ -306,12 +314,12 @@ class ToolPromptGrammar:
         if t == "str":
             a = {b for b in range(0x20, 0x7F) if self.string_byte(b)} if self.off < hi else set()
             if self.off >= lo:
-                a.add(0x22)
+                a.add(self.close)
             return a
-        return {TOOLS[i].encode()[self.off] for i in self.cand}
+        return {self.opts[i][self.off] for i in self.cand}
 
     def _next(self):
-        self.seg += 1; self.off = 0; self.cand = set(range(len(TOOLS)))
+        self.seg += 1; self.off = 0; self.cand = set(range(len(self.opts)))
 
     def advance(self, b: int) -> bool:
         if self.done() or b not in self.allowed():
@@ -322,16 +330,16 @@ class ToolPromptGrammar:
             if self.off == len(lit):
                 self._next()
         elif t == "str":
-            if b == 0x22:
+            if b == self.close:
                 self._next(); self.off = 1
                 if self.off == len(self.segs[self.seg][1]):
                     self._next()
             else:
                 self.off += 1
         else:
-            self.cand = {i for i in self.cand if TOOLS[i].encode()[self.off] == b}
+            self.cand = {i for i in self.cand if self.opts[i][self.off] == b}
             self.off += 1
-            if any(self.off == len(TOOLS[i]) for i in self.cand):
+            if any(self.off == len(self.opts[i]) for i in self.cand):
                 self._next()
         return True
 
@@ -342,10 +350,10 @@ class ToolPromptGrammar:
         return w
 
 
-def generate_constrained(orc: "Oracle", prompt, kind: int, max_new: int = 600, slot: int = 0):
+def generate_constrained(orc: "Oracle", prompt, kind: int, max_new: int = 600, slot: int = 0, functions: str = ""):
     """Greedy decoding under the ToolPrompt grammar: arg-max over the allowed bytes only (ties -> lowest id).
     -> (bytes, margins among the allowed set)"""
-    g = ToolPromptGrammar(kind)
+    g = ToolPromptGrammar(kind, functions)
     out, margins = [], []
     logits = orc.forward(np.ascontiguousarray(prompt, dtype=np.int32), slot=slot)[0]
     pos = len(prompt)

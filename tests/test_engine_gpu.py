@@ -341,3 +341,39 @@ def test_full_size_llama_3_8b_matches_oracle():
     """the bench model itself (BASELINE configs[1]): fp32 logits of every prompt position and greedy tokens vs the CPU oracle"""
     msgs = [("user", "why is pod web-0 in CrashLoopBackOff?")]
     print("llama-3-8b:", _full_size_parity("llama-3-8b", msgs, 6, 64))
+
+
+def test_http_front_function_calling_end_to_end_matches_oracle():
+    """the swarm-go wire path (reference pkg/workflows/swarm.go:14-78, analyze.go:47-75): POST /v1/chat/completions with `tools`
+    -> grammar-forced tool_calls whose bytes equal the oracle's constrained greedy decode; then a text answer."""
+    import json as _json
+    import urllib.request
+    from opsagent_b200.http_front import serve
+    spec, eng = make_engine("tiny-llama", max_seq_len=2048, num_pages=96)
+    orc = O.Oracle(spec, max_pos=1024, mode=1)
+    srv, _ = serve(eng, port=0, tool_steps=1)
+    url = f"http://127.0.0.1:{srv.server_address[1]}/v1/chat/completions"
+    tools = [{"type": "function", "function": {"name": "kubectl", "parameters": {"type": "object", "properties": {"command": {"type": "string"}}}}},
+             {"type": "function", "function": {"name": "trivy", "parameters": {"type": "object", "properties": {"image": {"type": "string"}}}}}]
+    msgs = [{"role": "system", "content": "You are an expert Kubernetes analyst."}, {"role": "user", "content": "analyze pod web-0"}]
+
+    def post(body):
+        rq = urllib.request.Request(url, data=_json.dumps(body).encode(), headers={"Content-Type": "application/json", "Authorization": "Bearer sk-local"})
+        return _json.loads(urllib.request.urlopen(rq, timeout=120).read())
+
+    r = post({"model": spec.name, "messages": msgs, "tools": tools, "max_tokens": 400, "temperature": 1.4e-45})
+    tc = r["choices"][0]["message"]["tool_calls"][0]
+    assert r["choices"][0]["finish_reason"] == "tool_calls" and tc["function"]["name"] in ("kubectl", "trivy")
+    args = _json.loads(tc["function"]["arguments"])
+    assert list(args.keys()) == [{"kubectl": "command", "trivy": "image"}[tc["function"]["name"]]]
+    ids = O.apply_chat_template(spec, [(m["role"], m["content"]) for m in msgs])
+    ref, margins = O.generate_constrained(orc, np.array(ids, np.int32), O.GRAMMAR_FUNCTION, functions="kubectl:command,trivy:image")
+    got = ('{"name":"%s","arguments":{"%s":"%s"}}' % (tc["function"]["name"], list(args.keys())[0], list(args.values())[0])).encode()
+    k = 0
+    while k < min(len(ref), len(got)) and ref[k] == got[k]:
+        k += 1
+    assert k == len(ref) == len(got) or margins[k] <= 2 * LOGIT_TOL
+    msgs2 = msgs + [{"role": "assistant", "tool_calls": [tc]}, {"role": "tool", "tool_call_id": tc["id"], "content": "web-0 0/1 CrashLoopBackOff"}]
+    r2 = post({"model": spec.name, "messages": msgs2, "tools": tools, "max_tokens": 400})
+    assert r2["choices"][0]["finish_reason"] == "stop" and 10 <= len(r2["choices"][0]["message"]["content"]) <= 200
+    srv.shutdown(); eng.close(); orc.close()

@@ -217,6 +217,29 @@ def test_grammar_random_walks_agree_and_yield_toolprompt_json(kind, seed):
         assert doc["action"] == {"name": "", "input": ""} and len(doc["final_answer"]) >= 10   # not a placeholder (simple.go:640-654)
 
 
+def test_function_call_and_text_grammars():
+    L = _lib.load()
+    fns = "kubectl:command,trivy:image,python:code"
+    rng = np.random.default_rng(5)
+    for kind in (O.GRAMMAR_FUNCTION, O.GRAMMAR_TEXT):
+        g = O.ToolPromptGrammar(kind, fns)
+        out = bytearray()
+        while not g.done():
+            buf = (C.c_uint8 * max(1, len(out)))(*out); mask = (C.c_uint32 * 8)(); done = C.c_int32()
+            assert L.oa_host_grammar_step_ex(kind, fns.encode(), buf, len(out), mask, C.byref(done)) == 0 and list(mask) == g.mask_words()
+            allowed = sorted(g.allowed())
+            b = g.close if (g.close in allowed and rng.random() < 0.2) else int(rng.choice(allowed))
+            out.append(b); assert g.advance(b)
+        if kind == O.GRAMMAR_FUNCTION:
+            doc = json.loads(out.decode("ascii"))
+            assert doc["name"] in ("kubectl", "trivy", "python")
+            assert list(doc["arguments"].keys()) == [{"kubectl": "command", "trivy": "image", "python": "code"}[doc["name"]]]
+        else:
+            assert out.endswith(b"\n") and 10 <= len(out) - 1 <= 200
+    mask = (C.c_uint32 * 8)(); done = C.c_int32()
+    assert L.oa_host_grammar_step_ex(O.GRAMMAR_FUNCTION, b"", (C.c_uint8 * 1)(), 0, mask, C.byref(done)) == 400     # no functions offered
+
+
 def test_grammar_rejects_bytes_outside_the_schema():
     assert _cpp_mask(1, b"[")[0] == 400
     assert _cpp_mask(1, b'{"question":"a","thought":"b","action":{"name":"rm')[0] == 400        # not in the tool registry
@@ -314,7 +337,13 @@ def test_http_front_speaks_the_wire_format_go_openai_expects():
     class Eng:
         info = {"model": "tiny"}
 
-        def chat_complete(self, model, msgs, max_tokens, flags=0):
+        def chat_complete(self, model, msgs, max_tokens, flags=0, functions=None):
+            if flags == 8:          # function call forced by the grammar
+                assert functions == "kubectl:command,trivy:image"
+
+                class F:
+                    content = b'{"name":"kubectl","arguments":{"command":"get pods -A"}}'; prompt_tokens = 9; completion_tokens = 5; finish_reason = "stop"
+                return F()
             if model == "nope":
                 raise EngineError(400, "model 'nope' is not loaded")
             if model == "busy":
@@ -342,4 +371,15 @@ def test_http_front_speaks_the_wire_format_go_openai_expects():
     with pytest.raises(urllib.error.HTTPError) as e:
         post({"model": "tiny", "messages": [{"role": "user", "content": "x"}]}, key=None)
     assert e.value.code == 401
+    # function calling as the swarm-go flows use it (reference pkg/workflows/swarm.go:14-78)
+    tools = [{"type": "function", "function": {"name": "kubectl", "description": "Run kubectl command", "parameters": {"type": "object", "properties": {"command": {"type": "string"}}, "required": ["command"]}}},
+             {"type": "function", "function": {"name": "trivy", "parameters": {"type": "object", "properties": {"image": {"type": "string"}}}}}]
+    r = post({"model": "tiny", "tools": tools, "messages": [{"role": "user", "content": "analyze"}]})
+    tc = r["choices"][0]["message"]["tool_calls"][0]
+    assert r["choices"][0]["finish_reason"] == "tool_calls" and tc["type"] == "function" and tc["function"]["name"] == "kubectl"
+    assert json.loads(tc["function"]["arguments"]) == {"command": "get pods -A"} and r["choices"][0]["message"]["content"] is None
+    # after `tool_steps` tool results the reply is text again
+    hist = [{"role": "user", "content": "analyze"}] + [{"role": "assistant", "tool_calls": [tc]}, {"role": "tool", "tool_call_id": tc["id"], "content": "ok"}] * 3
+    r = post({"model": "tiny", "tools": tools, "messages": hist})
+    assert r["choices"][0]["finish_reason"] == "stop" and r["choices"][0]["message"]["content"].startswith("echo:")
     srv.shutdown()
