@@ -302,12 +302,8 @@ cudaError_t launch_decode_merge(const MergeItem* items, int n_items, const float
 template <int D>
 static cudaError_t launch_decode_d(const CUtensorMap* tm_kv, const KvLayout& kv, const DecodeAttnParams& p, cudaStream_t s) {
     auto kern = decode_attention_kernel<D>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<D>::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static bool attr_done[16] = {};
+    { cudaError_t e = ensure_dynamic_smem(kern, AttCfg<D>::SMEM_BYTES, attr_done); if (e != cudaSuccess) return e; }
     return launch_k(kern, dim3(p.n_ctas), dim3(ATT_THREADS), AttCfg<D>::SMEM_BYTES, s, *tm_kv, p, (int64_t)p.layer * kv.layer_stride_rows, kv.kv_stride_rows);
 }
 
@@ -492,12 +488,8 @@ template <int D>
 static cudaError_t launch_prefill_d(const CUtensorMap* tm_kv, const KvLayout& kv, const PrefillAttnParams& p, cudaStream_t s) {
     auto kern = prefill_attention_kernel<D>;
     constexpr int SMEM = AttCfg<D>::STAGES * AttCfg<D>::STAGE_BYTES + 2 * AttCfg<D>::STAGES * 8 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static bool attr_done[16] = {};
+    { cudaError_t e = ensure_dynamic_smem(kern, SMEM, attr_done); if (e != cudaSuccess) return e; }
     dim3 grid(p.n_tiles, p.n_heads, 1);
     return launch_k(kern, grid, dim3(PREFILL_THREADS), SMEM, s, *tm_kv, p, (int64_t)p.layer * kv.layer_stride_rows, kv.kv_stride_rows);
 }

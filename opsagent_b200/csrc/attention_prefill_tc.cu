@@ -239,12 +239,8 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
 template <int D>
 static cudaError_t launch_ptc(const CUtensorMap* tm_q, const CUtensorMap* tm_kv, const KvLayout& kv, const PrefillAttnParams& p, cudaStream_t s) {
     auto kern = prefill_attention_tc_kernel<D>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PtcCfg<D>::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static bool attr_done[16] = {};
+    { cudaError_t e = ensure_dynamic_smem(kern, PtcCfg<D>::SMEM_BYTES, attr_done); if (e != cudaSuccess) return e; }
     return launch_k(kern, dim3(p.n_tiles, p.n_heads), dim3(PTC_THREADS), PtcCfg<D>::SMEM_BYTES, s, *tm_q, *tm_kv, p,
                     (int64_t)p.layer * kv.layer_stride_rows, kv.kv_stride_rows);
 }

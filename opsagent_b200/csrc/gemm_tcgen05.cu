@@ -238,12 +238,8 @@ template <int BN, int EPI>
 static cudaError_t launch_one(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     auto kern = gemm_tcgen05_kernel<BN, EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static bool attr_done[16] = {};
+    { cudaError_t e = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done); if (e != cudaSuccess) return e; }
     dim3 grid(((p.N + BN - 1) / BN) * ((p.M + BLOCK_M - 1) / BLOCK_M), 1, 1);
     return launch_k(kern, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, *tmA, *tmB, p);
 }
@@ -472,12 +468,8 @@ static int sm_count_cached() {
 template <int EPI>
 static cudaError_t launch_persistent(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, cudaStream_t stream) {
     auto kern = gemm_persistent_kernel<EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfg::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static bool attr_done[16] = {};
+    { cudaError_t e = ensure_dynamic_smem(kern, PersistCfg::SMEM_BYTES, attr_done); if (e != cudaSuccess) return e; }
     const int tiles = ((p.N + 255) / 256) * ((p.M + BLOCK_M - 1) / BLOCK_M);
     const int grid = tiles < sm_count_cached() ? tiles : sm_count_cached();
     return launch_k(kern, dim3(grid), dim3(GEMM_THREADS), PersistCfg::SMEM_BYTES, stream, *tmA, *tmB, p);
@@ -657,12 +649,8 @@ size_t streamk_ws_bytes(int N, int bn, int G, int rows) { return (size_t)(G + (N
 template <int BN, int MT>
 static cudaError_t launch_sk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, const StreamK& sk, cudaStream_t stream) {
     auto kern = gemm_streamk_kernel<BN, MT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<BN, MT>::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static bool attr_done[16] = {};
+    { cudaError_t e = ensure_dynamic_smem(kern, SkCfg<BN, MT>::SMEM_BYTES, attr_done); if (e != cudaSuccess) return e; }
     return launch_k(kern, dim3(sk.G), dim3(GEMM_THREADS), SkCfg<BN, MT>::SMEM_BYTES, stream, *tmA, *tmB, M, sk);
 }
 cudaError_t launch_gemm_streamk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, cudaStream_t stream) {

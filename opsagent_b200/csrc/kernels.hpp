@@ -130,6 +130,20 @@ bool pdl_enabled();     // OA_PDL=0 disables programmatic dependent launch
 void count_launch();
 
 
+// cudaFuncSetAttribute is per device: remember per (kernel instantiation, device) that the dynamic-smem limit has been raised
+template <typename K>
+inline cudaError_t ensure_dynamic_smem(K kern, int bytes, bool (&done)[16]) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 16 || !done[dev]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 16) done[dev] = true;
+    }
+    return cudaSuccess;
+}
+
 // Every kernel launch goes through here: counts it and (unless OA_PDL=0) marks it for programmatic dependent launch.
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -1,8 +1,10 @@
 // model.cpp — see model.hpp.
 #include "model.hpp"
+#include "safetensors.hpp"
 
 #include <algorithm>
 #include <cmath>
+#include "common.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -107,6 +109,8 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
         }
     }
 
+    if (!opt.weights.empty()) load_checkpoint(opt.weights);
+
     // ---- RoPE table ----
     {
         std::vector<float> cs, sn; rope_table(cfg, opt.max_seq_len, cs, sn);
@@ -200,6 +204,68 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
         comm.reset(new TpComm(tp, tp_rank, opt.tp_shm, sym_bytes, max_sample_));
     }
     cuda_check(cudaStreamSynchronize(stream), "init sync");
+}
+
+// ---- Hugging Face checkpoint loading (Llama / Qwen2 naming) --------------------------------------------------------
+static void to_bf16_rows(const StTensor& t, int64_t C, int64_t row, int64_t col0, int64_t cols, uint16_t* dst) {
+    if (t.dtype == "BF16") { std::memcpy(dst, reinterpret_cast<const uint16_t*>(t.data) + row * C + col0, (size_t)cols * 2); return; }
+    if (t.dtype == "F32") { const float* s = reinterpret_cast<const float*>(t.data) + row * C + col0; for (int64_t i = 0; i < cols; ++i) dst[i] = f32_to_bf16_bits(s[i]); return; }
+    if (t.dtype == "F16") {
+        const uint16_t* s = reinterpret_cast<const uint16_t*>(t.data) + row * C + col0;
+        for (int64_t i = 0; i < cols; ++i) {
+            const uint32_t h = s[i], sign = (h & 0x8000u) << 16, e = (h >> 10) & 31, m = h & 1023; uint32_t f;
+            if (e == 0) { if (m == 0) f = sign; else { int sh = 0; uint32_t mm = m; while (!(mm & 1024)) { mm <<= 1; ++sh; } f = sign | ((uint32_t)(113 - sh) << 23) | ((mm & 1023) << 13); } }
+            else if (e == 31) f = sign | 0x7f800000u | (m << 13);
+            else f = sign | ((e + 112) << 23) | (m << 13);
+            float x; std::memcpy(&x, &f, 4); dst[i] = f32_to_bf16_bits(x);
+        }
+        return;
+    }
+    throw std::runtime_error("unsupported checkpoint dtype " + t.dtype);
+}
+
+void DeviceModel::load_checkpoint(const std::string& path) {
+    SafeTensors st(path);
+    const int H = cfg.hidden, L = cfg.n_layers, D = cfg.head_dim, V = cfg.vocab;
+    const int qd = nh_l * D, kd = nkv_l * D;
+    const int64_t r = tp_rank;
+    std::vector<uint16_t> buf;
+    // logical [R, C] tensor `name`: rows [row0, row0+rows) x cols [col0, col0+cols) -> device dst (row-major [rows, cols])
+    auto slice = [&](const std::string& name, int64_t R, int64_t C, int64_t row0, int64_t rows, int64_t col0, int64_t cols, void* dst) {
+        const StTensor& t = st.get(name);
+        int64_t n = 1; for (auto d : t.shape) n *= d;
+        if (n != R * C) throw std::runtime_error("checkpoint tensor " + name + " has " + std::to_string(n) + " elements, expected " + std::to_string(R * C));
+        buf.resize((size_t)rows * cols);
+        for (int64_t i = 0; i < rows; ++i) to_bf16_rows(t, C, row0 + i, col0, cols, buf.data() + (size_t)i * cols);
+        cuda_check(cudaMemcpy(dst, buf.data(), buf.size() * 2, cudaMemcpyHostToDevice), "checkpoint H2D");
+    };
+    slice("model.embed_tokens.weight", V, H, 0, V, 0, H, embed);
+    slice("model.norm.weight", 1, H, 0, 1, 0, H, final_norm);
+    if (!cfg.tie_embeddings) slice(st.has("lm_head.weight") ? "lm_head.weight" : "model.embed_tokens.weight", V, H, r * V_l, V_l, 0, H, lm_head.ptr);
+    for (int l = 0; l < L; ++l) {
+        Layer& ly = layers[l]; const std::string p = "model.layers." + std::to_string(l) + ".";
+        uint16_t* wq = reinterpret_cast<uint16_t*>(ly.qkv.ptr);
+        slice(p + "self_attn.q_proj.weight", cfg.q_dim(), H, r * qd, qd, 0, H, wq);
+        slice(p + "self_attn.k_proj.weight", cfg.kv_dim(), H, r * kd, kd, 0, H, wq + (size_t)qd * H);
+        slice(p + "self_attn.v_proj.weight", cfg.kv_dim(), H, r * kd, kd, 0, H, wq + (size_t)(qd + kd) * H);
+        slice(p + "self_attn.o_proj.weight", H, cfg.q_dim(), 0, H, r * qd, qd, ly.o.ptr);
+        slice(p + "mlp.down_proj.weight", H, cfg.ffn, 0, H, r * F_l, F_l, ly.down.ptr);
+        slice(p + "input_layernorm.weight", 1, H, 0, 1, 0, H, ly.ln1);
+        slice(p + "post_attention_layernorm.weight", 1, H, 0, 1, 0, H, ly.ln2);
+        if (cfg.qkv_bias) {
+            uint16_t* bq = reinterpret_cast<uint16_t*>(ly.bqkv);
+            slice(p + "self_attn.q_proj.bias", 1, cfg.q_dim(), 0, 1, r * qd, qd, bq);
+            slice(p + "self_attn.k_proj.bias", 1, cfg.kv_dim(), 0, 1, r * kd, kd, bq + qd);
+            slice(p + "self_attn.v_proj.bias", 1, cfg.kv_dim(), 0, 1, r * kd, kd, bq + qd + kd);
+        }
+        // gate/up: physical rows interleaved in blocks of 16 (16 gate rows, 16 up rows)
+        const StTensor& tg = st.get(p + "mlp.gate_proj.weight"); const StTensor& tu = st.get(p + "mlp.up_proj.weight");
+        buf.resize((size_t)2 * F_l * H);
+        for (int64_t blk = 0; blk < F_l / 16; ++blk)
+            for (int64_t w = 0; w < 32; ++w)
+                to_bf16_rows(w < 16 ? tg : tu, H, r * F_l + blk * 16 + (w & 15), 0, H, buf.data() + (size_t)(blk * 32 + w) * H);
+        cuda_check(cudaMemcpy(ly.gu.ptr, buf.data(), buf.size() * 2, cudaMemcpyHostToDevice), "checkpoint H2D");
+    }
 }
 
 DeviceModel::~DeviceModel() {

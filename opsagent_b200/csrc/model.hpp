@@ -69,6 +69,7 @@ public:
 
 private:
     void alloc_weight(WeightMat& w, int N, int K);
+    void load_checkpoint(const std::string& path);     // overwrite the seeded tensors with this rank's slices of an HF checkpoint
     void make_weight_maps(WeightMat& w);
     int pick_bn(int M, int N, int override_bn, bool swiglu) const;
     void* dmalloc(size_t bytes);

@@ -370,3 +370,40 @@ def generate_constrained(orc: "Oracle", prompt, kind: int, max_new: int = 600, s
         logits = orc.forward(np.array([tok], np.int32), pos0=pos, slot=slot)[0]
         pos += 1
     return bytes(out), margins
+
+
+def write_safetensors(orc: "Oracle", path: str, dtype: str = "BF16") -> None:
+    """Dump the oracle's tensors as a Hugging Face style *.safetensors checkpoint (test fixture for the engine's loader)."""
+    import json as _json
+    import struct
+    sp = orc.spec
+    H, qd, kd, F, V = sp.hidden, sp.n_heads * sp.head_dim, sp.n_kv_heads * sp.head_dim, sp.ffn, sp.vocab
+    items = [("model.embed_tokens.weight", orc.tensor(-1, 0, (V, H))), ("model.norm.weight", orc.tensor(-1, 1, (H,)))]
+    if not sp.tie_embeddings:
+        items.append(("lm_head.weight", orc.tensor(-1, 2, (V, H))))
+    for l in range(sp.n_layers):
+        p = f"model.layers.{l}."
+        items += [(p + "self_attn.q_proj.weight", orc.tensor(l, "wq", (qd, H))), (p + "self_attn.k_proj.weight", orc.tensor(l, "wk", (kd, H))),
+                  (p + "self_attn.v_proj.weight", orc.tensor(l, "wv", (kd, H))), (p + "self_attn.o_proj.weight", orc.tensor(l, "wo", (H, qd))),
+                  (p + "mlp.gate_proj.weight", orc.tensor(l, "wg", (F, H))), (p + "mlp.up_proj.weight", orc.tensor(l, "wu", (F, H))),
+                  (p + "mlp.down_proj.weight", orc.tensor(l, "wd", (H, F))), (p + "input_layernorm.weight", orc.tensor(l, "ln1", (H,))),
+                  (p + "post_attention_layernorm.weight", orc.tensor(l, "ln2", (H,)))]
+        if sp.qkv_bias:
+            items += [(p + "self_attn.q_proj.bias", orc.tensor(l, "bq", (qd,))), (p + "self_attn.k_proj.bias", orc.tensor(l, "bk", (kd,))),
+                      (p + "self_attn.v_proj.bias", orc.tensor(l, "bv", (kd,)))]
+    header, blobs, off = {"__metadata__": {"format": "pt"}}, [], 0
+    for name, bits in items:
+        if dtype == "BF16":
+            raw = np.ascontiguousarray(bits).tobytes()
+        elif dtype == "F32":
+            raw = _np_bf16_to_f32(bits).astype(np.float32).tobytes()
+        else:
+            raw = _np_bf16_to_f32(bits).astype(np.float16).tobytes()
+        header[name] = {"dtype": dtype, "shape": list(bits.shape), "data_offsets": [off, off + len(raw)]}
+        blobs.append(raw); off += len(raw)
+    hj = _json.dumps(header, separators=(",", ":")).encode()
+    hj += b" " * ((8 - len(hj) % 8) % 8)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<Q", len(hj))); f.write(hj)
+        for b in blobs:
+            f.write(b)

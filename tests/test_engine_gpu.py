@@ -377,3 +377,23 @@ def test_http_front_function_calling_end_to_end_matches_oracle():
     r2 = post({"model": spec.name, "messages": msgs2, "tools": tools, "max_tokens": 400})
     assert r2["choices"][0]["finish_reason"] == "stop" and 10 <= len(r2["choices"][0]["message"]["content"]) <= 200
     srv.shutdown(); eng.close(); orc.close()
+
+
+@pytest.mark.parametrize("name,dtype", [("tiny-llama", "BF16"), ("tiny-qwen", "F32"), ("tiny-llama-d128", "BF16")])
+def test_safetensors_checkpoint_loading(name, dtype, tmp_path):
+    """weights from a Hugging Face style checkpoint (HF tensor names, fused q|k|v, interleaved gate/up, tied / untied head,
+    qkv bias, fp32 -> bf16 conversion): the engine is created with a DIFFERENT seed, so only a correct load reproduces the oracle."""
+    spec = O.PRESETS[name]
+    orc = O.Oracle(spec, max_pos=512, mode=1)
+    path = str(tmp_path / "model.safetensors")
+    O.write_safetensors(orc, path, dtype)
+    cfg = spec.engine_json(num_pages=32, max_seq_len=512, max_batch=4, max_step_tokens=256, weights=path)
+    cfg["seed"] = 987654321
+    eng = Engine(cfg)
+    rng = np.random.default_rng(17)
+    for n in (9, 150):
+        toks = rng.integers(0, spec.vocab, size=n).astype(np.int32)
+        assert np.abs(eng.debug_prefill_logits(toks) - orc.forward(toks, all_logits=True)).max() < LOGIT_TOL
+    eng.close(); orc.close()
+    with pytest.raises(EngineError):
+        Engine(spec.engine_json(num_pages=32, max_seq_len=512, weights=str(tmp_path / "missing.safetensors")))
