@@ -478,25 +478,25 @@ static cudaError_t launch_persistent(const CUtensorMap* tmA, const CUtensorMap* 
 // =============================================================================================
 // stream-K (decode, M <= 128): persistent CTAs, balanced weight streaming, fp32 partials
 // =============================================================================================
-template <int BN, int MT>     // MT = 128-row tiles of A handled per unit (1: M <= 128, 2: M <= 256)
+template <int BN, int MT, int OCC = 1>     // MT = 128-row tiles of A per unit (1: M <= 128, 2: M <= 256); OCC = CTAs per SM the ring is sized for
 struct SkCfg {
     static constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int A_BYTES = MT * A_TILE_BYTES;
     static constexpr int B_BYTES = BN * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;          // 4 x 48 KB (BN=256) or 6 x 32 KB (BN=128)
+    static constexpr int STAGES = (OCC == 2 ? 92 * 1024 : 200 * 1024) / STAGE_BYTES;   // 6 x 32 KB (BN=128), 4 x 48 KB (BN=256); halved for 2 CTAs/SM
     static constexpr int EPI_ROW_FLOATS = 36;                          // 32 + 4 pad: conflict-free 16-byte smem accesses
     static constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_FLOATS * 4;     // one 32x32 fp32 chunk per epilogue warp
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * EPI_WARP_BYTES + 1024 + 256;
     static constexpr uint32_t TMEM_COLS = 2 * MT * BN;                 // two accumulator stages of MT row tiles
-    static_assert(TMEM_COLS <= 512, "TMEM holds 512 columns");
+    static_assert(TMEM_COLS * OCC <= 512, "TMEM holds 512 columns per SM");
 };
 
-template <int BN, int MT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, int MT, int OCC>
+__global__ void __launch_bounds__(GEMM_THREADS, OCC) gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                          const __grid_constant__ CUtensorMap tmB, const int M,
                                                                          const StreamK sk) {
-    using Cfg = SkCfg<BN, MT>;
+    using Cfg = SkCfg<BN, MT, OCC>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -646,18 +646,18 @@ StreamK make_streamk(float* ws, int N, int K, int bn, int G, int rows) {
 }
 size_t streamk_ws_bytes(int N, int bn, int G, int rows) { return (size_t)(G + (N + bn - 1) / bn) * (rows > 128 ? 256 : 128) * bn * sizeof(float); }
 
-template <int BN, int MT>
+template <int BN, int MT, int OCC = 1>
 static cudaError_t launch_sk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, const StreamK& sk, cudaStream_t stream) {
-    auto kern = gemm_streamk_kernel<BN, MT>;
+    auto kern = gemm_streamk_kernel<BN, MT, OCC>;
     static bool attr_done[16] = {};
-    { cudaError_t e = ensure_dynamic_smem(kern, SkCfg<BN, MT>::SMEM_BYTES, attr_done); if (e != cudaSuccess) return e; }
-    return launch_k(kern, dim3(sk.G), dim3(GEMM_THREADS), SkCfg<BN, MT>::SMEM_BYTES, stream, *tmA, *tmB, M, sk);
+    { cudaError_t e = ensure_dynamic_smem(kern, SkCfg<BN, MT, OCC>::SMEM_BYTES, attr_done); if (e != cudaSuccess) return e; }
+    return launch_k(kern, dim3(sk.G), dim3(GEMM_THREADS), SkCfg<BN, MT, OCC>::SMEM_BYTES, stream, *tmA, *tmB, M, sk);
 }
 cudaError_t launch_gemm_streamk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, cudaStream_t stream) {
     if (M <= 0 || M > sk.rows || (N % 8) != 0 || (K % 8) != 0) return cudaErrorInvalidValue;
     if (sk.rows == 256) return sk.bn == 128 ? launch_sk<128, 2>(tmA, tmB, M, sk, stream) : cudaErrorInvalidValue;
     if (sk.bn == 256) return launch_sk<256, 1>(tmA, tmB, M, sk, stream);
-    if (sk.bn == 128) return launch_sk<128, 1>(tmA, tmB, M, sk, stream);
+    if (sk.bn == 128) return sk.G > sm_count_cached() ? launch_sk<128, 1, 2>(tmA, tmB, M, sk, stream) : launch_sk<128, 1, 1>(tmA, tmB, M, sk, stream);
     return cudaErrorInvalidValue;
 }
 
