@@ -1,7 +1,9 @@
 // attention_prefill_tc.cu — causal prefill attention over the paged KV cache on the 5th-generation tensor cores.
 //
 // One CTA = 128 query rows of one (sequence, head); KV is consumed in tiles of 128 tokens (two 64-token pages):
-//   warp 0    : TMA producer — Q tile once, then K and V pages of each KV tile into a 2-stage ring (128-byte swizzle)
+//   warp 0    : TMA producers — lane 0: Q tile once, then the K pages of each KV tile; lane 1: the V pages.  K and V have SEPARATE
+//               2-stage rings: K_j is released as soon as S_j has been computed, V_j only after P_j·V_j, so the K load of tile
+//               j+2 gets a full tile period of slack instead of being exposed behind the second MMA
 //   warp 1    : tcgen05.mma issuer —  S_j = Q · K_j^T   (M=128, N=128, K=D;   A, B K-major)        -> TMEM S[j&1]
 //                                     O  += P_j · V_j   (M=128, N=D,   K=128; A K-major, B MN-major: V[kv, d] as stored)  -> TMEM O
 //   warps 2-5 : one query row per thread.  tcgen05.ld S_j once (128 values), causal mask, P_j = 2^(s - m_ref) rounded to bf16 into
@@ -45,13 +47,15 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
     uint8_t* p_s = kv_s + 2 * Cfg::STAGE_BYTES;                  // [2][P]
     uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 2 * Cfg::P_BYTES);
     uint64_t* q_full = bars;                  // 1
-    uint64_t* kv_full = bars + 1;             // [2]
-    uint64_t* kv_empty = bars + 3;            // [2]
-    uint64_t* s_full = bars + 5;              // [2]
-    uint64_t* s_empty = bars + 7;             // [2]
-    uint64_t* p_full = bars + 9;              // [2]
-    uint64_t* t_full = bars + 11;             // 1 (one completion per P·V)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* k_full = bars + 1;              // [2]
+    uint64_t* k_empty = bars + 3;             // [2]
+    uint64_t* v_full = bars + 5;              // [2]
+    uint64_t* v_empty = bars + 7;             // [2]
+    uint64_t* s_full = bars + 9;              // [2]
+    uint64_t* s_empty = bars + 11;            // [2]
+    uint64_t* p_full = bars + 13;             // [2]
+    uint64_t* t_full = bars + 15;             // 1 (one completion per P·V)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PrefillTile tile = p.tiles[blockIdx.x];
@@ -62,7 +66,8 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
         mbar_init(q_full, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); mbar_init(&p_full[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+                                      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); mbar_init(&p_full[i], 4); }
         mbar_init(t_full, 1);
         fence_barrier_init();
     }
@@ -74,29 +79,30 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
     griddep_launch();
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (lane < 2) {
+            const bool is_v = lane == 1;
             griddep_wait();
-            mbar_expect_tx(q_full, Cfg::Q_BYTES);
+            if (!is_v) {
+                mbar_expect_tx(q_full, Cfg::Q_BYTES);
 #pragma unroll
-            for (int h = 0; h < HALVES; ++h) tma_load_2d(q_s + h * Cfg::HALF_BYTES, &tm_q, q_full, head * D + h * 64, tile.q_row0, kEvictFirst);
+                for (int h = 0; h < HALVES; ++h) tma_load_2d(q_s + h * Cfg::HALF_BYTES, &tm_q, q_full, head * D + h * 64, tile.q_row0, kEvictFirst);
+            }
             const int32_t* bt = p.block_tables + (size_t)tile.seq * p.max_pages_per_seq;
+            uint64_t* full = is_v ? v_full : k_full;
+            uint64_t* empty = is_v ? v_empty : k_empty;
             for (int j = 0; j < n_kvt; ++j) {
                 const int st = j & 1;
-                mbar_wait(&kv_empty[st], (((uint32_t)j >> 1) & 1) ^ 1);
-                uint8_t* kdst = kv_s + st * Cfg::STAGE_BYTES;
-                uint8_t* vdst = kdst + Cfg::KV_BYTES;
-                mbar_expect_tx(&kv_full[st], Cfg::STAGE_BYTES);
+                mbar_wait(&empty[st], (((uint32_t)j >> 1) & 1) ^ 1);
+                uint8_t* dst = kv_s + st * Cfg::STAGE_BYTES + (is_v ? Cfg::KV_BYTES : 0);
+                mbar_expect_tx(&full[st], Cfg::KV_BYTES);
 #pragma unroll
                 for (int pg = 0; pg < 2; ++pg) {
                     const int pi = 2 * j + pg;
                     const int page = bt[pi < p.max_pages_per_seq ? pi : 2 * j];      // a missing second page is fully masked anyway
-                    const int64_t krow = layer_row0 + ((int64_t)page * p.n_kv + kvh) * 64;
-                    const int64_t vrow = krow + kv_stride_rows;
+                    const int64_t row = layer_row0 + ((int64_t)page * p.n_kv + kvh) * 64 + (is_v ? kv_stride_rows : 0);
 #pragma unroll
-                    for (int h = 0; h < HALVES; ++h) {
-                        tma_load_2d(kdst + h * Cfg::HALF_BYTES + pg * 8192, &tm_kv, &kv_full[st], h * 64, (int32_t)krow, kEvictLast);
-                        tma_load_2d(vdst + h * Cfg::HALF_BYTES + pg * 8192, &tm_kv, &kv_full[st], h * 64, (int32_t)vrow, kEvictLast);
-                    }
+                    for (int h = 0; h < HALVES; ++h)
+                        tma_load_2d(dst + h * Cfg::HALF_BYTES + pg * 8192, &tm_kv, &full[st], h * 64, (int32_t)row, kEvictLast);
                 }
             }
         }
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
             const uint32_t q_addr = smem_u32(q_s);
             auto issue_s = [&](int j) {
                 const int st = j & 1, sb = j & 1;
-                mbar_wait(&kv_full[st], ((uint32_t)j >> 1) & 1);
+                mbar_wait(&k_full[st], ((uint32_t)j >> 1) & 1);
                 mbar_wait(&s_empty[sb], (((uint32_t)j >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
                 const uint32_t k_addr = smem_u32(kv_s + st * Cfg::STAGE_BYTES);
@@ -117,6 +123,7 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
                     umma_bf16(tmem_base + (uint32_t)(sb * 128), umma_desc_sw128(q_addr + off), umma_desc_sw128(k_addr + off), idesc_s, ks > 0 ? 1u : 0u);
                 }
                 umma_commit(&s_full[sb]);
+                umma_commit(&k_empty[st]);                                 // K_j is free once S_j exists
             };
             mbar_wait(q_full, 0);
             issue_s(0);
@@ -124,6 +131,7 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
                 if (j + 1 < n_kvt) issue_s(j + 1);                         // keep the tensor pipe ahead of the softmax warps
                 const int st = j & 1, pb = j & 1;
                 mbar_wait(&p_full[pb], ((uint32_t)j >> 1) & 1);            // P_j is in shared memory
+                mbar_wait(&v_full[st], ((uint32_t)j >> 1) & 1);
                 tcgen05_fence_after();
                 const uint32_t p_addr = smem_u32(p_s + pb * Cfg::P_BYTES);
                 const uint32_t v_addr = smem_u32(kv_s + st * Cfg::STAGE_BYTES + Cfg::KV_BYTES);
@@ -134,7 +142,7 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
                     umma_bf16(tmem_base + Cfg::T_COL, a_desc, b_desc, idesc_t, (j > 0 || ks > 0) ? 1u : 0u);      // O accumulates over all KV tiles
                 }
                 umma_commit(t_full);
-                umma_commit(&kv_empty[st]);
+                umma_commit(&v_empty[st]);
             }
         }
     } else {
@@ -156,16 +164,19 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[sb]);               // S_j is in registers: the tensor core may overwrite the buffer
             const bool diag = (j * KV_TILE + KV_TILE - 1) > tile.pos0;          // some (row, key) pairs of this tile are masked
-            float mx = -INFINITY;
+            if (diag) {                                                         // only the last tile(s) of a row block pay for the mask
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if ((j * KV_TILE + c * 32 + i) > qpos) v[c][i] = 0xff800000u;   // -inf
+            }
+            float mraw = -INFINITY;                                             // max of the raw scores; the scale is positive
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float sv = __uint_as_float(v[c][i]) * p.scale_log2e;
-                    if (diag && (j * KV_TILE + c * 32 + i) > qpos) sv = -INFINITY;
-                    v[c][i] = __float_as_uint(sv);
-                    mx = fmaxf(mx, sv);
-                }
+                for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, __uint_as_float(v[c][i]));
+            const float mx = mraw * p.scale_log2e;
             // lazy rescaling: raise the reference maximum only when a row would overshoot it by more than 2^8
             const bool raise = mx > m_ref + kRescaleThreshold;      // always true on tile 0 (key 0 is visible to every row)
             if (__any_sync(0xffffffffu, raise)) {
@@ -190,11 +201,12 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
             }
             uint8_t* prow = p_s + sb * Cfg::P_BYTES + row * 128;
             float psum = 0.f;
+            const float neg_ref = -m_ref;                                       // p = 2^(s*scale - m_ref): one FFMA + one SFU op per score
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float pr[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { pr[i] = exp2f(__uint_as_float(v[c][i]) - m_ref); psum += pr[i]; }
+                for (int i = 0; i < 32; ++i) { pr[i] = ex2_approx(fmaf(__uint_as_float(v[c][i]), p.scale_log2e, neg_ref)); psum += pr[i]; }
 #pragma unroll
                 for (int g8 = 0; g8 < 4; ++g8) {                    // four 16-byte chunks (8 keys each)
                     const int key0 = c * 32 + g8 * 8, hh = key0 >> 6, chunk = (key0 & 63) >> 3;

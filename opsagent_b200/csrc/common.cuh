@@ -221,6 +221,9 @@ OA_DEVINL void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t 
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// 2^x on the SFU, flush-to-zero, no range fix-up code around it (inputs here are <= ~8; -inf -> 0)
+OA_DEVINL float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 OA_DEVINL float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

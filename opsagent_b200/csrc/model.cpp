@@ -382,7 +382,10 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
         zero_counters_.assign(plan_.merges.size() + 1, 0);
         o_cnt = put(zero_counters_.data(), zero_counters_.size());     // merge counters start every step at zero
     } else {
-        o_tiles = put(in.tiles.data(), in.tiles.size() * 4);
+        // heaviest query tiles (most visible keys) first: the causal triangle otherwise leaves a long tail of big CTAs
+        sorted_tiles_ = in.tiles;
+        std::stable_sort(sorted_tiles_.begin(), sorted_tiles_.end(), [](const PrefillTile& a, const PrefillTile& b) { return a.pos0 + a.n_rows > b.pos0 + b.n_rows; });
+        o_tiles = put(sorted_tiles_.data(), sorted_tiles_.size() * 4);
     }
     cuda_check(cudaMemcpyAsync(d_meta_, h_meta_, w * 4, cudaMemcpyHostToDevice, stream), "meta H2D");
     cuda_check(cudaEventRecord(meta_ev_[meta_idx_], stream), "meta event");

@@ -84,7 +84,7 @@ private:
     int32_t* h_meta_buf_[2] = {nullptr, nullptr}; cudaEvent_t meta_ev_[2] = {nullptr, nullptr}; int meta_idx_ = 0;
     int32_t *h_meta_ = nullptr, *d_meta_ = nullptr; size_t meta_cap_words_ = 0;
     int max_rows_ = 0, max_sample_ = 0;
-    DecodePlan plan_; std::vector<int32_t> zero_counters_;
+    DecodePlan plan_; std::vector<int32_t> zero_counters_; std::vector<PrefillTile> sorted_tiles_;
 };
 
 void cuda_check(cudaError_t e, const char* what);
