@@ -34,18 +34,6 @@ OA_DEVINL uint32_t pack_bf16x2(float a, float b) {
 }
 
 OA_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-OA_DEVINL uint32_t lane_id() { return threadIdx.x & 31; }
-
-OA_DEVINL bool elect_one_sync() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t.reg .b32 R;\n\t"
-        "elect.sync R|P, 0xffffffff;\n\t"
-        "selp.b32 %0, 1, 0, P;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch: every kernel of the forward chain is launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization.  griddep_launch() lets the next kernel's CTAs become resident and

@@ -7,7 +7,6 @@
 
 namespace oa {
 
-typedef uint16_t bf16_t;  // raw bf16 bits on the host side
 
 // ---- TMA descriptors (tma.cpp) --------------------------------------------------------------
 // 2D row-major bf16 tensor [rows, cols] with row pitch `pitch_elems`; box = {box_cols(<=64), box_rows(<=256)},

@@ -19,7 +19,6 @@ from __future__ import annotations
 import time
 from dataclasses import dataclass
 
-from . import _lib
 from .engine import Engine, EngineError
 
 ChatMessageRoleSystem, ChatMessageRoleUser, ChatMessageRoleAssistant = "system", "user", "assistant"

@@ -13,7 +13,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
-from dataclasses import dataclass, field, asdict
+from dataclasses import dataclass, asdict
 
 import numpy as np
 
