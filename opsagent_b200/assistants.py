@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import json
 from dataclasses import dataclass, field
+from .perf import GetPerfStats
 
 from .llms import ChatCompletionMessage, ChatMessageRoleAssistant, ChatMessageRoleUser, ConstrictPrompt
 
@@ -54,13 +55,29 @@ class ToolPrompt:                                            # reference pkg/too
 
 def AssistantWithConfig(model, prompts, maxTokens, countTokens, verbose, maxIterations, client, tools, count_tokens=None):
     """-> (result, chatHistory).  `client` has Chat(model, maxTokens, prompts); `tools` maps name -> callable(input) -> str."""
+    perf = GetPerfStats()
+    total_done = perf.TraceFunc("assistant_total")                                          # simple.go:296
+    try:
+        return _assistant_loop(perf, model, prompts, maxTokens, maxIterations, client, tools, count_tokens)
+    finally:
+        total_done()
+
+
+def _timed_chat(perf, op, client, model, maxTokens, chatHistory):
+    perf.StartTimer(op)
+    try:
+        return client.Chat(model, maxTokens, chatHistory)
+    except Exception as e:
+        raise RuntimeError(f"chat completion error: {e}") from e
+    finally:
+        perf.StopTimer(op)
+
+
+def _assistant_loop(perf, model, prompts, maxTokens, maxIterations, client, tools, count_tokens):
     chatHistory = list(prompts)
     if not prompts:
         raise ValueError("prompts cannot be empty")                                          # simple.go:312
-    try:
-        resp = client.Chat(model, maxTokens, chatHistory)                                    # assistant_first_chat
-    except Exception as e:
-        raise RuntimeError(f"chat completion error: {e}") from e
+    resp = _timed_chat(perf, "assistant_first_chat", client, model, maxTokens, chatHistory)  # simple.go:341-346
     chatHistory.append(ChatCompletionMessage(ChatMessageRoleAssistant, resp))
     try:
         tp = ToolPrompt.unmarshal(resp)
@@ -78,28 +95,25 @@ def AssistantWithConfig(model, prompts, maxTokens, countTokens, verbose, maxIter
         if tp.action["name"] != "":
             fn = tools.get(tp.action["name"])
             if fn is not None:
+                perf.StartTimer("assistant_tool_" + tp.action["name"])                        # simple.go:440-475
                 try:
                     observation = fn(tp.action["input"]).strip()
                 except Exception as e:
                     observation = f"Tool {tp.action['name']} failed with error {e}. Considering refine the inputs for the tool."
+                finally:
+                    perf.StopTimer("assistant_tool_" + tp.action["name"])
             else:
                 observation = f"Tool {tp.action['name']} is not available. Considering switch to other supported tools."
             tp.observation = ConstrictPrompt(observation, model, 1024, count_tokens)
             chatHistory.append(ChatCompletionMessage(ChatMessageRoleUser, tp.marshal()))
-            try:
-                resp = client.Chat(model, maxTokens, chatHistory)                            # assistant_intermediate_chat
-            except Exception as e:
-                raise RuntimeError(f"chat completion error: {e}") from e
+            resp = _timed_chat(perf, "assistant_intermediate_chat", client, model, maxTokens, chatHistory)   # simple.go:513-518
             chatHistory.append(ChatCompletionMessage(ChatMessageRoleAssistant, resp))
             try:
                 tp = ToolPrompt.unmarshal(resp)
             except Exception:
                 chatHistory.append(ChatCompletionMessage(ChatMessageRoleUser,
                                                          "Summarize all the chat history and respond to original question with final answer"))
-                try:
-                    resp = client.Chat(model, maxTokens, chatHistory)                        # assistant_summarize
-                except Exception as e:
-                    raise RuntimeError(f"chat completion error: {e}") from e
+                resp = _timed_chat(perf, "assistant_summarize", client, model, maxTokens, chatHistory)        # simple.go:564-569
                 return resp, chatHistory
             if tp.final_answer != "":
                 return tp.final_answer, chatHistory

@@ -52,6 +52,30 @@ OA_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
 }
 OA_DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 OA_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+OA_DEVINL void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }    // generic-proxy global writes -> later TMA (async proxy) reads
+// grid-wide counter barrier for persistent kernels whose CTAs are all co-resident (grid <= SM count, one CTA per SM)
+OA_DEVINL unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+OA_DEVINL void grid_counter_wait(const unsigned long long* ctr, unsigned long long target) {
+    uint32_t spins = 0;
+    while (ld_acquire_gpu_u64(ctr) < target) {
+        __nanosleep(20);
+        if (++spins > (1u << 26)) { __trap(); }      // a protocol bug traps instead of hanging the GPU
+    }
+}
+OA_DEVINL void grid_counter_wait32(const unsigned int* ctr, unsigned int target) {
+    uint32_t spins = 0;
+    unsigned int v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        if (v >= target) break;
+        __nanosleep(20);
+        if (++spins > (1u << 26)) { __trap(); }
+    } while (true);
+}
 OA_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }

@@ -2,6 +2,7 @@
 // RoPE + paged-KV write.  All use 16-byte vector accesses; one CTA per token row.
 #include "common.cuh"
 #include "kernels.hpp"
+#include "sk_consumers.cuh"
 
 namespace oa {
 
@@ -145,111 +146,28 @@ cudaError_t launch_rope_kv_write(const void* qkv, const int32_t* positions, cons
 
 
 // =============================================================================================
-// stream-K consumers: add a tile's fp32 partials in CTA order (deterministic) and finish the op
+// stream-K consumers (stand-alone kernels; the bodies live in sk_consumers.cuh)
 // =============================================================================================
-// CTAs c_first..c_last own pieces of `tile`; CTA c covers units [c*total/G, (c+1)*total/G), so the CTA holding
-// unit u is floor(((u+1)*G - 1) / total).  All products fit in 32 bits for the decode shapes (host-checked).
-OA_DEVINL void sk_sum8(const StreamK& sk, int row, int col, float (&acc)[8]) {
-    const uint32_t tile = (uint32_t)col / (uint32_t)sk.bn, cc = (uint32_t)col - tile * (uint32_t)sk.bn;
-    const uint32_t ut0 = tile * (uint32_t)sk.kb, G = (uint32_t)sk.G, total = (uint32_t)sk.total;
-    const uint32_t c_first = ((ut0 + 1u) * G - 1u) / total, c_last = ((ut0 + (uint32_t)sk.kb) * G - 1u) / total;
-    const int n = (int)(c_last - c_first) + 1;
-    const size_t slot_stride = (size_t)sk.rows * sk.bn;
-    const float* p = sk.ws + ((size_t)(c_first + tile) * sk.rows + row) * sk.bn + cc;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    // issue up to 6 partials' loads back to back (independent L2 round trips), then add them in CTA order
-    for (int i = 0; i < n; i += 6) {
-        float4 a[6], b[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            if (i + j < n) {
-                const float4* q4 = reinterpret_cast<const float4*>(p + (size_t)(i + j) * slot_stride);
-                a[j] = __ldcg(q4); b[j] = __ldcg(q4 + 1);
-            } else { a[j] = make_float4(0.f, 0.f, 0.f, 0.f); b[j] = a[j]; }
-        }
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            if (i + j < n) {
-                acc[0] += a[j].x; acc[1] += a[j].y; acc[2] += a[j].z; acc[3] += a[j].w;
-                acc[4] += b[j].x; acc[5] += b[j].y; acc[6] += b[j].z; acc[7] += b[j].w;
-            }
-        }
-    }
-}
-
 template <int VPT>
-__global__ void __launch_bounds__(256) sk_resid_rmsnorm_kernel(const StreamK sk, uint4* __restrict__ x, const uint4* __restrict__ g,
-                                                               uint4* __restrict__ y, int H8, float inv_h, float eps) {
+__global__ void __launch_bounds__(SK_RESID_THREADS) sk_resid_rmsnorm_kernel(const StreamK sk, uint4* __restrict__ x, const uint4* __restrict__ g,
+                                                                            uint4* __restrict__ y, int H8, float inv_h, float eps) {
     griddep_launch(); griddep_wait();
-    const int t = blockIdx.x;
-    uint4* xr = x + (size_t)t * H8;
-    uint4 v[VPT];
-    float ss = 0.f;
-#pragma unroll
-    for (int k = 0; k < VPT; ++k) {
-        const int i = threadIdx.x + k * 256;
-        if (i < H8) {
-            float acc[8];
-            sk_sum8(sk, t, i * 8, acc);
-            const uint4 xo = xr[i];
-            uint4 xn;
-            xn.x = pack_bf16x2(bf16lo(xo.x) + acc[0], bf16hi(xo.x) + acc[1]); xn.y = pack_bf16x2(bf16lo(xo.y) + acc[2], bf16hi(xo.y) + acc[3]);
-            xn.z = pack_bf16x2(bf16lo(xo.z) + acc[4], bf16hi(xo.z) + acc[5]); xn.w = pack_bf16x2(bf16lo(xo.w) + acc[6], bf16hi(xo.w) + acc[7]);
-            xr[i] = xn; v[k] = xn;
-            float a;
-            a = bf16lo(xn.x); ss += a * a; a = bf16hi(xn.x); ss += a * a; a = bf16lo(xn.y); ss += a * a; a = bf16hi(xn.y); ss += a * a;
-            a = bf16lo(xn.z); ss += a * a; a = bf16hi(xn.z); ss += a * a; a = bf16lo(xn.w); ss += a * a; a = bf16hi(xn.w); ss += a * a;
-        }
-    }
-    ss = warp_sum(ss);
-    __shared__ float red[8];
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
-    __syncthreads();
-    float tot = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) tot += red[w];
-    const float r = 1.0f / sqrtf(tot * inv_h + eps);
-    uint4* yr = y + (size_t)t * H8;
-#pragma unroll
-    for (int k = 0; k < VPT; ++k) {
-        const int i = threadIdx.x + k * 256;
-        if (i < H8) {
-            const uint4 gg = g[i]; uint4 o;
-            o.x = pack_bf16x2(bf16lo(v[k].x) * r * bf16lo(gg.x), bf16hi(v[k].x) * r * bf16hi(gg.x));
-            o.y = pack_bf16x2(bf16lo(v[k].y) * r * bf16lo(gg.y), bf16hi(v[k].y) * r * bf16hi(gg.y));
-            o.z = pack_bf16x2(bf16lo(v[k].z) * r * bf16lo(gg.z), bf16hi(v[k].z) * r * bf16hi(gg.z));
-            o.w = pack_bf16x2(bf16lo(v[k].w) * r * bf16lo(gg.w), bf16hi(v[k].w) * r * bf16hi(gg.w));
-            yr[i] = o;
-        }
-    }
+    __shared__ float red[SK_RESID_THREADS / 32];
+    sk_resid_rmsnorm_row<VPT>(sk, blockIdx.x, threadIdx.x, red, 0, x, g, y, H8, inv_h, eps);
 }
 cudaError_t launch_sk_resid_rmsnorm(const StreamK& sk, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s) {
     if (T <= 0) return cudaSuccess;
     if (H % 8 != 0 || H > 8192 || T > sk.rows) return cudaErrorInvalidValue;
     const int H8 = H / 8;
     auto X = reinterpret_cast<uint4*>(x); auto G = reinterpret_cast<const uint4*>(gain); auto Y = reinterpret_cast<uint4*>(xn);
-    if (H8 <= 256) return launch_k(sk_resid_rmsnorm_kernel<1>, dim3(T), dim3(256), 0, s, sk, X, G, Y, H8, 1.0f / H, eps);
-    if (H8 <= 512) return launch_k(sk_resid_rmsnorm_kernel<2>, dim3(T), dim3(256), 0, s, sk, X, G, Y, H8, 1.0f / H, eps);
-    return launch_k(sk_resid_rmsnorm_kernel<4>, dim3(T), dim3(256), 0, s, sk, X, G, Y, H8, 1.0f / H, eps);
+    if (H8 <= SK_RESID_THREADS) return launch_k(sk_resid_rmsnorm_kernel<1>, dim3(T), dim3(SK_RESID_THREADS), 0, s, sk, X, G, Y, H8, 1.0f / H, eps);
+    return launch_k(sk_resid_rmsnorm_kernel<2>, dim3(T), dim3(SK_RESID_THREADS), 0, s, sk, X, G, Y, H8, 1.0f / H, eps);
 }
 
-// physical columns of the fused gate/up GEMM: per 32-column block, 16 gate then 16 up
 __global__ void sk_swiglu_kernel(const StreamK sk, uint4* __restrict__ act, int F8) {
     griddep_launch(); griddep_wait();
     const int t = blockIdx.y;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F8; i += gridDim.x * blockDim.x) {
-        const int f0 = i * 8, blk = f0 >> 4, o = f0 & 15;
-        float gt[8], up[8];
-        sk_sum8(sk, t, blk * 32 + o, gt);
-        sk_sum8(sk, t, blk * 32 + 16 + o, up);
-        float f[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = __fdividef(gt[k], 1.0f + __expf(-gt[k])) * up[k];
-        uint4 ov;
-        ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]); ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
-        act[(size_t)t * F8 + i] = ov;
-    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F8; i += gridDim.x * blockDim.x) sk_swiglu_item(sk, t, i, act, F8);
 }
 cudaError_t launch_sk_swiglu(const StreamK& sk, void* act, int T, int F, cudaStream_t s) {
     if (T <= 0) return cudaSuccess;
@@ -257,73 +175,28 @@ cudaError_t launch_sk_swiglu(const StreamK& sk, void* act, int T, int F, cudaStr
     return launch_k(sk_swiglu_kernel, dim3((F / 8 + 255) / 256, T), dim3(256), 0, s, sk, reinterpret_cast<uint4*>(act), F / 8);
 }
 
-OA_DEVINL void sk_load8_bf16(const StreamK& sk, const uint16_t* bias, int row, int col, float (&v)[8]) {
-    sk_sum8(sk, row, col, v);
-    if (bias) {
-        const uint4 bb = *reinterpret_cast<const uint4*>(bias + col);
-        v[0] += bf16lo(bb.x); v[1] += bf16hi(bb.x); v[2] += bf16lo(bb.y); v[3] += bf16hi(bb.y);
-        v[4] += bf16lo(bb.z); v[5] += bf16hi(bb.z); v[6] += bf16lo(bb.w); v[7] += bf16hi(bb.w);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = bf16_bits_to_f32(f32_to_bf16_bits(v[k]));     // the projection output is a bf16 tensor
-}
-
-__global__ void sk_rope_kv_write_kernel(const StreamK sk, const uint16_t* __restrict__ bias, const int32_t* __restrict__ positions,
-                                        const int32_t* __restrict__ slots, const float* __restrict__ rope_cos,
-                                        const float* __restrict__ rope_sin, uint16_t* __restrict__ q_out, uint16_t* __restrict__ kv_base,
-                                        int64_t k_plane_row0, int64_t v_plane_row0, int page_size, int nh, int nkv, int D) {
+__global__ void sk_rope_kv_write_kernel(const StreamK sk, const SkRopeArgs a) {
     griddep_launch(); griddep_wait();
-    const int t = blockIdx.y;
-    const int half = D >> 1, vec_per_head = half >> 3;
-    const int pos = positions[t], slot = slots[t];
-    const int page = slot / page_size, off = slot - page * page_size;
-    const float* cr = rope_cos + (size_t)pos * half;
-    const float* sr = rope_sin + (size_t)pos * half;
-    const int n_rot = (nh + nkv) * vec_per_head;
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
-    for (int w = gtid; w < n_rot; w += gstride) {
-        const int head = w / vec_per_head, i0 = (w - head * vec_per_head) * 8;
-        float av[8], bv[8];
-        sk_load8_bf16(sk, bias, t, head * D + i0, av);
-        sk_load8_bf16(sk, bias, t, head * D + i0 + half, bv);
-        const float4 c0 = *reinterpret_cast<const float4*>(cr + i0), c1 = *reinterpret_cast<const float4*>(cr + i0 + 4);
-        const float4 s0 = *reinterpret_cast<const float4*>(sr + i0), s1 = *reinterpret_cast<const float4*>(sr + i0 + 4);
-        const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        float ra[8], rb[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { ra[k] = av[k] * cv[k] - bv[k] * sv[k]; rb[k] = bv[k] * cv[k] + av[k] * sv[k]; }
-        uint4 oa, ob;
-        oa.x = pack_bf16x2(ra[0], ra[1]); oa.y = pack_bf16x2(ra[2], ra[3]); oa.z = pack_bf16x2(ra[4], ra[5]); oa.w = pack_bf16x2(ra[6], ra[7]);
-        ob.x = pack_bf16x2(rb[0], rb[1]); ob.y = pack_bf16x2(rb[2], rb[3]); ob.z = pack_bf16x2(rb[4], rb[5]); ob.w = pack_bf16x2(rb[6], rb[7]);
-        uint16_t* dst;
-        if (head < nh) dst = q_out + (size_t)t * nh * D + (size_t)head * D;
-        else dst = kv_base + (size_t)(k_plane_row0 + ((int64_t)page * nkv + (head - nh)) * page_size + off) * D;
-        *reinterpret_cast<uint4*>(dst + i0) = oa;
-        *reinterpret_cast<uint4*>(dst + i0 + half) = ob;
-    }
-    const int n_v = nkv * (D >> 3);
-    for (int w = gtid - n_rot; w < n_v; w += gstride) {      // the threads after the rotary items take V
-        if (w < 0) continue;
-        const int head = w / (D >> 3), i0 = (w - head * (D >> 3)) * 8;
-        float vv[8];
-        sk_load8_bf16(sk, bias, t, (nh + nkv + head) * D + i0, vv);
-        uint4 o;
-        o.x = pack_bf16x2(vv[0], vv[1]); o.y = pack_bf16x2(vv[2], vv[3]); o.z = pack_bf16x2(vv[4], vv[5]); o.w = pack_bf16x2(vv[6], vv[7]);
-        uint16_t* dst = kv_base + (size_t)(v_plane_row0 + ((int64_t)page * nkv + head) * page_size + off) * D;
-        *reinterpret_cast<uint4*>(dst + i0) = o;
-    }
+    const int t = blockIdx.y, items = sk_rope_items_per_row(a);
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < items; w += gridDim.x * blockDim.x) sk_rope_item(sk, a, t, w);
+}
+SkRopeArgs make_sk_rope_args(const void* bias, const int32_t* positions, const int32_t* slots, const float* rope_cos, const float* rope_sin,
+                             void* q_out, const KvLayout& kv, int layer, int nh) {
+    SkRopeArgs a{};
+    a.bias = reinterpret_cast<const uint16_t*>(bias); a.positions = positions; a.slots = slots; a.rope_cos = rope_cos; a.rope_sin = rope_sin;
+    a.q_out = reinterpret_cast<uint16_t*>(q_out); a.kv_base = reinterpret_cast<uint16_t*>(kv.base);
+    a.k_plane_row0 = (int64_t)layer * kv.layer_stride_rows; a.v_plane_row0 = a.k_plane_row0 + kv.kv_stride_rows;
+    a.page_size = kv.page_size; a.nh = nh; a.nkv = kv.n_kv; a.D = kv.head_dim;
+    return a;
 }
 cudaError_t launch_sk_rope_kv_write(const StreamK& sk, const void* bias, const int32_t* positions, const int32_t* slots,
                                     const float* rope_cos, const float* rope_sin, void* q_out, const KvLayout& kv, int layer, int T,
                                     int nh, cudaStream_t s) {
     if (T <= 0) return cudaSuccess;
     if (kv.head_dim % 16 != 0 || T > sk.rows) return cudaErrorInvalidValue;
-    const int64_t k0 = (int64_t)layer * kv.layer_stride_rows, v0 = k0 + kv.kv_stride_rows;
+    const SkRopeArgs a = make_sk_rope_args(bias, positions, slots, rope_cos, rope_sin, q_out, kv, layer, nh);
     const int items = (nh + kv.n_kv) * (kv.head_dim / 16) + kv.n_kv * (kv.head_dim / 8);
-    return launch_k(sk_rope_kv_write_kernel, dim3((items + 127) / 128, T), dim3(128), 0, s, sk, reinterpret_cast<const uint16_t*>(bias), positions, slots,
-                    rope_cos, rope_sin, reinterpret_cast<uint16_t*>(q_out), reinterpret_cast<uint16_t*>(kv.base), k0, v0, kv.page_size, nh, kv.n_kv,
-                    kv.head_dim);
+    return launch_k(sk_rope_kv_write_kernel, dim3((items + 127) / 128, T), dim3(128), 0, s, sk, a);
 }
 
 }  // namespace oa

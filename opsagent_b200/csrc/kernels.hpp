@@ -51,6 +51,31 @@ cudaError_t launch_sk_resid_rmsnorm(const StreamK& sk, void* x, const void* gain
 // act[T,F] = silu(gate) * up from the interleaved gate/up partials (N = 2F)
 cudaError_t launch_sk_swiglu(const StreamK& sk, void* act, int T, int F, cudaStream_t s);
 
+// ---- chained decode kernel: up to 4 stream-K GEMMs and their consumers in ONE persistent launch (gemm_tcgen05.cu) ----
+// Phase p = GEMM p (fp32 partials into the shared workspace) -> grid barrier -> consumer p on all CTAs -> grid barrier -> GEMM p+1
+// (whose weight tiles are already streaming).  Same partial layout, reduction order and consumer code as the stand-alone
+// kernels, so results are bit-identical to launching them one by one.
+struct SkRopeArgs {       // q/k/v from the qkv projection's partials (+ bias): sum -> bf16 -> RoPE -> bf16 (the oracle's order)
+    const uint16_t* bias; const int32_t* positions; const int32_t* slots; const float* rope_cos; const float* rope_sin;
+    uint16_t* q_out; uint16_t* kv_base; int64_t k_plane_row0, v_plane_row0; int32_t page_size, nh, nkv, D;
+};
+enum SkConsumer : int { SK_CONSUMER_NONE = 0, SK_CONSUMER_RESID_RMSNORM = 1, SK_CONSUMER_SWIGLU = 2, SK_CONSUMER_ROPE_KV = 3 };
+struct SkChainPhase {
+    StreamK sk; int consumer;
+    void* x; const void* gain; void* xn; int H; float eps;     // SK_CONSUMER_RESID_RMSNORM
+    void* act; int F;                                          // SK_CONSUMER_SWIGLU
+    SkRopeArgs rope;                                           // SK_CONSUMER_ROPE_KV
+};
+constexpr int SK_CHAIN_MAX_PHASES = 4, SK_CHAIN_MAX_TILES = 1024;
+struct SkChain {
+    int n_phases, M; unsigned long long* bar; SkChainPhase ph[SK_CHAIN_MAX_PHASES];
+    unsigned int* tile_flags;       // [SK_CHAIN_MAX_PHASES][SK_CHAIN_MAX_TILES], zero between launches: pieces of a fused-SwiGLU tile published so far
+    int l2_prefetch_units;          // weight tiles of the next phase each CTA pulls into L2 while it waits at a phase boundary
+    unsigned long long* trace;      // null, or [grid][32] clock64 stamps of the phase boundaries (OA_CHAIN_TRACE=1, dev tooling)
+};   // bar: 3 counters, zero between launches (the kernel resets them)
+struct SkChainMaps { CUtensorMap a[SK_CHAIN_MAX_PHASES], b[SK_CHAIN_MAX_PHASES]; };
+cudaError_t launch_sk_chain(const SkChainMaps& maps, const SkChain& chain, int grid, cudaStream_t stream);
+
 // reduce EPI_LOGITS partials: out_ids[M] = argmax over n_tiles (ties -> lowest column index)
 cudaError_t launch_argmax_reduce(const float* amax_val, const int* amax_idx, int M, int n_tiles, int32_t* out_ids,
                                  float* out_val, cudaStream_t stream);
@@ -77,6 +102,8 @@ struct KvLayout {
 cudaError_t launch_sk_rope_kv_write(const StreamK& sk, const void* bias, const int32_t* positions, const int32_t* slots,
                                     const float* rope_cos, const float* rope_sin, void* q_out, const KvLayout& kv, int layer, int T,
                                     int nh, cudaStream_t s);
+SkRopeArgs make_sk_rope_args(const void* bias, const int32_t* positions, const int32_t* slots, const float* rope_cos, const float* rope_sin,
+                             void* q_out, const KvLayout& kv, int layer, int nh);
 cudaError_t launch_rope_kv_write(const void* qkv, const int32_t* positions, const int32_t* slots, const float* rope_cos,
                                  const float* rope_sin, void* q_out, const KvLayout& kv, int layer, int T, int nh,
                                  cudaStream_t s);

@@ -13,6 +13,7 @@ import time
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
 
 from .engine import EngineError
+from .perf import GetPerfStats
 
 _STATUS_TYPE = {400: "invalid_request_error", 401: "authentication_error", 429: "rate_limit_error", 500: "server_error"}
 
@@ -38,9 +39,19 @@ def make_handler(engine, require_key: bool = True, tool_steps: int = 3):
         def do_GET(self):
             if self.path.rstrip("/").endswith("/models"):
                 return self._send(200, {"object": "list", "data": [{"id": engine.info["model"], "object": "model", "owned_by": "opsagent_b200"}]})
+            if self.path.rstrip("/").endswith("/perf/stats"):
+                # the reference's GET /api/perf/stats (pkg/api/router.go:104, pkg/handlers/perf.go:12-25) plus the engine's own
+                # counters (steps, tokens, bytes moved, kernel launches) under "engine" — steps/sec from the product's endpoint
+                stats = GetPerfStats().GetStats()
+                if hasattr(engine, "stats"):
+                    stats["engine"] = engine.stats()
+                return self._send(200, {"stats": stats, "status": "success"})
             self._error(404, "not found")
 
         def do_POST(self):
+            if self.path.rstrip("/").endswith("/perf/reset"):          # pkg/api/router.go:105, pkg/handlers/perf.go:28-39
+                GetPerfStats().Reset()
+                return self._send(200, {"message": "performance statistics reset", "status": "success"})
             if not self.path.rstrip("/").endswith("/chat/completions"):
                 return self._error(404, "not found")
             auth = self.headers.get("Authorization", "")
@@ -79,10 +90,13 @@ def make_handler(engine, require_key: bool = True, tool_steps: int = 3):
                     flags, functions = 8, ",".join(specs)
                 else:
                     flags = 16
+            done = GetPerfStats().TraceFunc("chat_completion")
             try:
                 out = engine.chat_complete(req.get("model", ""), msgs, max_tokens, flags=flags, functions=functions)
             except EngineError as e:
+                GetPerfStats().RecordMetric("chat_completion_failed", done())
                 return self._error(e.code if e.code in (400, 401, 429, 500) else 500, e.message)
+            done()
             if flags == 8:
                 call = json.loads(out.content.decode("utf-8", "replace"))
                 message = {"role": "assistant", "content": None,

@@ -383,3 +383,71 @@ def test_http_front_speaks_the_wire_format_go_openai_expects():
     r = post({"model": "tiny", "tools": tools, "messages": hist})
     assert r["choices"][0]["finish_reason"] == "stop" and r["choices"][0]["message"]["content"].startswith("echo:")
     srv.shutdown()
+
+
+# ---- PerfStats mirror + /api/perf/stats bridge (reference pkg/utils/perf.go, pkg/handlers/perf.go) ----
+def test_perf_stats_mirror_accumulates_counts_and_is_request_safe():
+    import threading
+    from opsagent_b200.perf import PerfStats
+    t = [0]
+    ps = PerfStats(clock=lambda: t[0])
+    ps.StartTimer("op"); t[0] = 1500; assert ps.StopTimer("op") == 1500
+    ps.StartTimer("op"); t[0] = 2000; ps.StopTimer("op")
+    assert ps.StopTimer("never_started") == 0                       # perf.go:87-93: unknown timer -> zero duration, not counted
+    done = ps.TraceFunc("traced"); t[0] = 2600; done()
+    ps.RecordMetric("execute_model_llama-3-8b", 42)
+    st = ps.GetStats()
+    assert st["timers"] == {"op": 2000, "traced": 600, "execute_model_llama-3-8b": 42}
+    assert st["callCounts"] == {"op": 2, "traced": 1, "execute_model_llama-3-8b": 1} and st["lastResetTime"].endswith("Z")
+    # two requests timing the SAME operation concurrently must not clobber each other's start time (the reference's do: perf.go:64-80)
+    real = PerfStats()
+    def worker():
+        real.StartTimer("assistant_first_chat"); real.StopTimer("assistant_first_chat")
+    th = [threading.Thread(target=worker) for _ in range(8)]
+    [x.start() for x in th]; [x.join() for x in th]
+    assert real.GetStats()["callCounts"] == {"assistant_first_chat": 8}
+    ps.Reset()
+    assert ps.GetStats()["timers"] == {} and ps.GetStats()["callCounts"] == {}
+
+
+def test_assistant_loop_records_the_reference_operation_names():
+    from opsagent_b200.perf import GetPerfStats
+    GetPerfStats().Reset()
+    step = '{"question":"q","thought":"t","action":{"name":"kubectl","input":"get ns"},"observation":"","final_answer":""}'
+    final = '{"question":"q","thought":"t","action":{"name":"","input":""},"observation":"5 namespaces","final_answer":"there are 5 namespaces"}'
+    res, _ = AssistantWithConfig("m", [ChatCompletionMessage("system", "s"), ChatCompletionMessage("user", "u")], 64, False, False, 5,
+                                 ScriptedClient([step, final]), {"kubectl": lambda s: "default\nkube-system"})
+    assert res == "there are 5 namespaces"
+    cc = GetPerfStats().GetStats()["callCounts"]
+    assert cc == {"assistant_first_chat": 1, "assistant_tool_kubectl": 1, "assistant_intermediate_chat": 1, "assistant_total": 1}   # simple.go:296,341,440,513
+
+
+def test_http_front_serves_the_perf_stats_endpoints():
+    import urllib.request
+    from opsagent_b200.http_front import serve
+    from opsagent_b200.perf import GetPerfStats
+
+    class Eng:
+        info = {"model": "tiny"}
+
+        def stats(self):
+            return {"decode_steps": 7, "requests_completed": 1}
+
+        def chat_complete(self, model, msgs, max_tokens, flags=0, functions=None):
+            class R:
+                content = b"ok"; prompt_tokens = 2; completion_tokens = 1; finish_reason = "stop"
+            return R()
+
+    GetPerfStats().Reset()
+    srv, _ = serve(Eng(), port=0)
+    root = f"http://127.0.0.1:{srv.server_address[1]}"
+    req = urllib.request.Request(root + "/v1/chat/completions", data=json.dumps({"model": "tiny", "messages": [{"role": "user", "content": "x"}]}).encode(),
+                                 headers={"Content-Type": "application/json", "Authorization": "Bearer k"})
+    urllib.request.urlopen(req, timeout=10).read()
+    r = json.loads(urllib.request.urlopen(root + "/api/perf/stats", timeout=10).read())          # pkg/api/router.go:104
+    assert r["status"] == "success" and r["stats"]["callCounts"] == {"chat_completion": 1} and r["stats"]["timers"]["chat_completion"] > 0
+    assert r["stats"]["engine"] == {"decode_steps": 7, "requests_completed": 1} and "lastResetTime" in r["stats"]
+    r = json.loads(urllib.request.urlopen(urllib.request.Request(root + "/api/perf/reset", data=b"", method="POST"), timeout=10).read())   # router.go:105
+    assert r["status"] == "success"
+    assert json.loads(urllib.request.urlopen(root + "/api/perf/stats", timeout=10).read())["stats"]["callCounts"] == {}
+    srv.shutdown()
