@@ -493,10 +493,12 @@ struct SkCfg {
     static_assert(TMEM_COLS * OCC <= 512, "TMEM holds 512 columns per SM");
 };
 
-template <int BN, int MT, int OCC>
+struct SkFuse { uint16_t* act; int F; unsigned int* tile_flags; };      // FUSE == 1: SwiGLU finished in the epilogue
+
+template <int BN, int MT, int OCC, int FUSE = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, OCC) gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                          const __grid_constant__ CUtensorMap tmB, const int M,
-                                                                         const StreamK sk) {
+                                                                         const StreamK sk, const SkFuse fz) {
     using Cfg = SkCfg<BN, MT, OCC>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -604,6 +606,81 @@ __global__ void __launch_bounds__(GEMM_THREADS, OCC) gemm_streamk_kernel(const _
             const int as = seg & 1;
             mbar_wait(&acc_full[as], ((uint32_t)seg >> 1) & 1);
             tcgen05_fence_after();
+            if constexpr (FUSE == 1) {
+                // Pieces of this tile live in CTAs c_first..c_last (same arithmetic as sk_sum8).  The CTA holding the FIRST k-block
+                // finishes the tile: it reaches this segment last (it is the tail of its unit range, while the other pieces are the
+                // HEAD of their CTAs' ranges), adds the published pieces to its accumulator in CTA order — the stand-alone
+                // consumer's order, so results are bit-identical — and writes silu(gate)*up.  Private piece layout: [col][row],
+                // so that publisher stores and finisher loads are one full 128-byte line per warp instruction.
+                const uint32_t ut0 = (uint32_t)tile * (uint32_t)sk.kb;
+                const int c_first = (int)(((ut0 + 1u) * (uint32_t)sk.G - 1u) / (uint32_t)sk.total);
+                const int c_last = (int)(((ut0 + (uint32_t)sk.kb) * (uint32_t)sk.G - 1u) / (uint32_t)sk.total);
+                const int row = q * 32 + lane;
+                unsigned int* flag = fz.tile_flags + tile;
+                if ((int)c == c_first) {
+                    const int n_other = c_last - c_first;
+                    if (n_other > 0) {
+                        if (threadIdx.x == 64) { grid_counter_wait32(flag, (unsigned int)n_other); *flag = 0u; }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                    }
+                    const float* other = sk.ws + (size_t)(c_first + 1 + tile) * (BLOCK_M * BN) + row;
+                    uint16_t* act_row = fz.act + (size_t)row * fz.F;
+                    const bool live = row < M;
+                    float t[2][32];
+                    auto load_piece = [&](float (&dst)[32], const float* base, int mc) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) dst[j] = live ? __ldcg(base + (size_t)(mc + j) * BLOCK_M) : 0.f;
+                    };
+                    if (n_other > 0) load_piece(t[0], other, 0);
+#pragma unroll
+                    for (int k4 = 0; k4 < BN / 32; ++k4) {
+                        const int mc = k4 * 32;
+                        if (n_other > 0 && k4 + 1 < BN / 32) load_piece(t[(k4 + 1) & 1], other, mc + 32);      // next chunk's piece is in flight during this chunk's math
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + mc), v);
+                        tmem_ld_wait();
+                        float acc[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = 0.f + __uint_as_float(v[j]);      // "0 +" as in sk_sum8
+                        if (n_other > 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[j] += t[k4 & 1][j];
+                        }
+                        for (int o = 1; o < n_other; ++o) {                                      // tiles cut into more than two pieces (small shapes)
+                            float x[32];
+                            load_piece(x, other + (size_t)o * (BLOCK_M * BN), mc);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[j] += x[j];
+                        }
+                        const int f0 = (tile * BN + mc) >> 1;          // 32 physical columns = 16 gate + 16 up -> 16 outputs
+                        if (live && f0 < fz.F) {
+                            float f[16];
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) f[k] = __fdividef(acc[k], 1.0f + __expf(-acc[k])) * acc[16 + k];
+                            uint4 o0, o1;
+                            o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]); o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
+                            o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]); o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                            *reinterpret_cast<uint4*>(act_row + f0) = o0;
+                            *reinterpret_cast<uint4*>(act_row + f0 + 8) = o1;
+                        }
+                    }
+                } else {
+                    float* dst = sk.ws + (size_t)(c + tile) * (BLOCK_M * BN) + row;
+#pragma unroll 1
+                    for (int mc = 0; mc < BN; mc += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + mc), v);
+                        tmem_ld_wait();
+                        if (row < M) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) dst[(size_t)(mc + j) * BLOCK_M] = __uint_as_float(v[j]);
+                        }
+                    }
+                    __threadfence();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (threadIdx.x == 64) atomicAdd(flag, 1u);
+                }
+            } else {
             // TMEM gives each thread one row x 32 columns; transpose through padded smem so that every global store
             // instruction writes four full 128-byte lines (8 lanes per row) instead of 32 scattered 16-byte pieces.
             float* stage = epi_smem + (warp - 2) * (Cfg::EPI_WARP_BYTES / 4);
@@ -628,6 +705,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, OCC) gemm_streamk_kernel(const _
                 }
                 __syncwarp();
             }
+            }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -647,12 +725,18 @@ StreamK make_streamk(float* ws, int N, int K, int bn, int G, int rows) {
 }
 size_t streamk_ws_bytes(int N, int bn, int G, int rows) { return (size_t)(G + (N + bn - 1) / bn) * (rows > 128 ? 256 : 128) * bn * sizeof(float); }
 
-template <int BN, int MT, int OCC = 1>
-static cudaError_t launch_sk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, const StreamK& sk, cudaStream_t stream) {
-    auto kern = gemm_streamk_kernel<BN, MT, OCC>;
+template <int BN, int MT, int OCC = 1, int FUSE = 0>
+static cudaError_t launch_sk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, const StreamK& sk, cudaStream_t stream, SkFuse fz = SkFuse{}) {
+    auto kern = gemm_streamk_kernel<BN, MT, OCC, FUSE>;
     static bool attr_done[16] = {};
     { cudaError_t e = ensure_dynamic_smem(kern, SkCfg<BN, MT, OCC>::SMEM_BYTES, attr_done); if (e != cudaSuccess) return e; }
-    return launch_k(kern, dim3(sk.G), dim3(GEMM_THREADS), SkCfg<BN, MT, OCC>::SMEM_BYTES, stream, *tmA, *tmB, M, sk);
+    return launch_k(kern, dim3(sk.G), dim3(GEMM_THREADS), SkCfg<BN, MT, OCC>::SMEM_BYTES, stream, *tmA, *tmB, M, sk, fz);
+}
+cudaError_t launch_gemm_streamk_swiglu(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int F, int K, const StreamK& sk, void* act,
+                                       unsigned int* tile_flags, cudaStream_t stream) {
+    if (M <= 0 || M > BLOCK_M || sk.rows != 128 || sk.bn != 128 || (F % 16) != 0 || (K % 8) != 0 || !act || !tile_flags) return cudaErrorInvalidValue;
+    if (sk.G > sm_count_cached()) return cudaErrorInvalidValue;      // finishing CTAs wait for publishing CTAs: all must be resident
+    return launch_sk<128, 1, 1, 1>(tmA, tmB, M, sk, stream, SkFuse{reinterpret_cast<uint16_t*>(act), F, tile_flags});
 }
 cudaError_t launch_gemm_streamk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, cudaStream_t stream) {
     if (M <= 0 || M > sk.rows || (N % 8) != 0 || (K % 8) != 0) return cudaErrorInvalidValue;

@@ -46,6 +46,10 @@ struct StreamK {
 StreamK make_streamk(float* ws, int N, int K, int bn, int G, int rows = 128);
 size_t streamk_ws_bytes(int N, int bn, int G, int rows = 128);
 cudaError_t launch_gemm_streamk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, cudaStream_t stream);
+// gate/up projection with the SwiGLU finished inside the GEMM (BN=128, one row tile): act[M,F] = silu(gate)*up, bit-identical to
+// launch_gemm_streamk + launch_sk_swiglu.  tile_flags: >= n_tiles counters, zero between launches (the kernel re-arms them).
+cudaError_t launch_gemm_streamk_swiglu(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int F, int K, const StreamK& sk, void* act,
+                                       unsigned int* tile_flags, cudaStream_t stream);
 // x[T,H] (bf16, in place) += sum of partials; xn = rmsnorm(x) * gain
 cudaError_t launch_sk_resid_rmsnorm(const StreamK& sk, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s);
 // act[T,F] = silu(gate) * up from the interleaved gate/up partials (N = 2F)

@@ -458,6 +458,7 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
         // sk_chain=2, the next layer's qkv -> RoPE/KV write) run as ONE persistent kernel with grid barriers between the phases
         const int chain_mode = (!use_tp && sk_rows == 128 && sk_G_ <= sm_count && sk_gu.n_tiles <= SK_CHAIN_MAX_TILES && sk_qkv.bn == 128 && sk_o.bn == 128 && sk_gu.bn == 128 && sk_dn.bn == 128)
                                    ? opt.sk_chain : 0;
+        const bool fuse_swiglu = opt.sk_fuse_swiglu && sk_rows == 128 && sk_gu.bn == 128 && sk_G_ <= sm_count && sk_gu.n_tiles <= SK_CHAIN_MAX_TILES;
         auto qkv_phase = [&](int l, SkChainPhase& P) {
             P.sk = sk_qkv; P.consumer = SK_CONSUMER_ROPE_KV;
             P.rope = make_sk_rope_args(layers[l].bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, nh);
@@ -500,8 +501,12 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
                 cuda_check(launch_sk_resid_rmsnorm(sk_o, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm2");
             }
             MARK(7);
-            cuda_check(launch_gemm_streamk(&tm_xn_, ly.gu.map(sk_gu.bn), T, 2 * F, H, pf_gu, stream), "gate_up gemm (stream-K)"); MARK(8);
-            cuda_check(launch_sk_swiglu(sk_gu, act_, T, F, stream), "swiglu"); MARK(9);
+            if (fuse_swiglu) {
+                cuda_check(launch_gemm_streamk_swiglu(&tm_xn_, ly.gu.map(128), T, F, H, pf_gu, act_, chain_flags_, stream), "gate_up gemm + SwiGLU (stream-K)"); MARK(8);
+            } else {
+                cuda_check(launch_gemm_streamk(&tm_xn_, ly.gu.map(sk_gu.bn), T, 2 * F, H, pf_gu, stream), "gate_up gemm (stream-K)"); MARK(8);
+                cuda_check(launch_sk_swiglu(sk_gu, act_, T, F, stream), "swiglu"); MARK(9);
+            }
             cuda_check(launch_gemm_streamk(&tm_act_, ly.down.map(sk_dn.bn), T, H, F, pf_dn, stream), "down gemm (stream-K)"); MARK(10);
             const void* next_gain = (l + 1 < L) ? layers[l + 1].ln1 : final_norm;
             if (use_tp) {

@@ -76,33 +76,36 @@ def test_two_row_tile_streamk_path_matches_oracle():
 
 
 @pytest.mark.parametrize("name", CASES + ["llama-3.2-1b"])
-def test_chained_decode_kernel_is_bit_identical_to_separate_kernels(name):
-    """sk_chain=1/2 run o -> resid+norm -> gate_up -> SwiGLU -> down -> resid+norm (-> next qkv -> RoPE/KV) as ONE persistent kernel
-    with grid barriers; partial layout, reduction order and consumer code are shared with the one-kernel-per-op path (sk_chain=0),
-    so logits and generated ids must be EQUAL, not close.  llama-3.2-1b exercises real multi-CTA tile splits on all 148 SMs."""
+def test_fused_decode_epilogues_are_bit_identical_to_separate_kernels(name):
+    """Baseline: one kernel per projection and per consumer (sk_fuse_swiglu=0, sk_chain=0).  Variants: the gate/up projection finishing
+    SwiGLU in its own epilogue (the CTA holding a tile's first k-block adds the other CTAs' pieces in CTA order); and the opt-in chained
+    kernel (sk_chain=1/2: o -> resid+norm -> gate_up+SwiGLU -> down -> resid+norm (-> next qkv -> RoPE/KV) in ONE persistent launch with
+    grid barriers).  Reduction order and consumer code are shared, so logits and generated ids must be EQUAL, not close.
+    llama-3.2-1b exercises real multi-CTA tile splits on all 148 SMs."""
     full = name == "llama-3.2-1b"
     rng = np.random.default_rng(77)
     spec = O.PRESETS[name]
     prompts = [rng.integers(0, spec.vocab if not full else 256, size=n).astype(np.int32) for n in ((1, 33, 128) if not full else (7, 128))]
     gen_prompts = [rng.integers(0, 256, size=n).astype(np.int32).tolist() for n in (3, 19, 40, 64, 90)]
+    variants = [dict(sk_fuse_swiglu=0, sk_chain=0), dict(sk_fuse_swiglu=1, sk_chain=0), dict(sk_chain=1), dict(sk_chain=2)]
     results = []
-    for mode in (0, 1, 2):
+    for kw in variants:
         if full:
-            eng = Engine({"model": name, "num_pages": 64, "max_seq_len": 512, "max_batch": 8, "max_step_tokens": 512, "seed": spec.seed, "sk_chain": mode})
+            eng = Engine({"model": name, "num_pages": 64, "max_seq_len": 512, "max_batch": 8, "max_step_tokens": 512, "seed": spec.seed, **kw})
         else:
-            _, eng = make_engine(name, sk_chain=mode)
+            _, eng = make_engine(name, **kw)
         logits = [eng.debug_prefill_logits(t) for t in prompts]
-        # one request at a time keeps the batch composition (and with it the attention work plan) identical across modes;
-        # twice: the barrier counters must re-arm between launches
+        # one request at a time keeps the batch composition (and with it the attention work plan) identical across variants;
+        # twice: the barrier counters and tile flags must re-arm between launches
         outs = []
         for _ in range(2):
             outs.append([list(eng.generate(pt, 12 if full else 30, flags=1).token_ids) for pt in gen_prompts])
         results.append((logits, outs))
         eng.close()
-    for mode in (1, 2):
-        for a, b in zip(results[0][0], results[mode][0]):
-            assert np.array_equal(a, b), f"sk_chain={mode}: logits differ by {np.abs(a - b).max()}"
-        assert results[0][1] == results[mode][1], f"sk_chain={mode}: generated ids differ"
+    for kw, res in zip(variants[1:], results[1:]):
+        for a, b in zip(results[0][0], res[0]):
+            assert np.array_equal(a, b), f"{kw}: logits differ by {np.abs(a - b).max()}"
+        assert results[0][1] == res[1], f"{kw}: generated ids differ"
     assert results[0][1][0] == results[0][1][1]
 
 
