@@ -172,7 +172,8 @@ public:
             {
                 int b = 0, off = 0, n_fwd = 0;
                 const bool prof_prefill = std::getenv("OA_CUDA_PROFILER_PREFILL") != nullptr;
-                while (b < batch && P > 0) {
+                const bool skip_prefill = std::getenv("OA_BENCH_SKIP_PREFILL") != nullptr;   // dev profiling only: decode over whatever the (zero-initialised) pages hold
+                while (b < batch && P > 0 && !skip_prefill) {
                     StepInput in; in.decode = false;
                     int budget = opt_.max_step_tokens;
                     while (b < batch && budget > 0 && in.n_seqs < opt_.max_batch) {

@@ -44,4 +44,11 @@ line = {"workload": f"{a.model} TP={world} B={a.batch} mean ctx {r['mean_ctx']:.
         "prefill_tokens_per_sec": round(a.batch * (ctx0 - 1) / r["prefill_ms"] * 1e3, 1), "launches_per_step": r["launches_per_step"],
         "kv_pages": pages, "n_gpus": world}
 print(json.dumps(line), flush=True)
+if os.environ.get("OA_SWEEP_KT"):      # in-situ per-class kernel times on the leader (events between launches: breaks PDL overlap, shows where the step goes)
+    os.environ["OA_PROFILE_ALL"] = "1"
+    eng.kernel_times(True)
+    eng.bench_decode(a.batch, ctx0, 8, 2)
+    kt = eng.kernel_times(True)
+    print("in-situ us/launch (launches/step): " + ", ".join(f"{k}={v[0] * 1e3 / max(v[1], 1):.1f}({v[1] // 10})" for k, v in kt.items() if v[1]), flush=True)
+    print("in-situ ms/step by class: " + ", ".join(f"{k}={v[0] / 10:.3f}" for k, v in kt.items() if v[1]), flush=True)
 eng.close()
