@@ -494,9 +494,9 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
             cuda_check(launch_gemm_streamk(&tm_attn_, ly.o.map(sk_o.bn), T, H, qd, pf_o, stream), "o gemm (stream-K)"); MARK(6);
             if (use_tp) {      // row-parallel projection: all-reduce the rank partials over NVLink peer memory, then residual + norm
                 const int b = comm->next_buffer();
-                cuda_check(launch_sk_reduce_f32(sk_o, reinterpret_cast<float*>(comm->sym(b)), T, H, stream), "o partial -> symmetric buffer");
-                cuda_check(comm->barrier(stream), "xgpu barrier");
-                cuda_check(launch_ar_resid_rmsnorm(comm->d_peer_sym(b), tp, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "allreduce+resid+rmsnorm2");
+                const TpComm::Signal sg = comm->next_signal();     // "buffer written" handshake rides on the two kernels: no barrier launch
+                cuda_check(launch_sk_reduce_f32(sk_o, reinterpret_cast<float*>(comm->sym(b)), T, H, stream, &sg), "o partial -> symmetric buffer");
+                cuda_check(launch_ar_resid_rmsnorm(comm->d_peer_sym(b), tp, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream, &sg), "allreduce+resid+rmsnorm2");
             } else {
                 cuda_check(launch_sk_resid_rmsnorm(sk_o, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm2");
             }
@@ -511,9 +511,9 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
             const void* next_gain = (l + 1 < L) ? layers[l + 1].ln1 : final_norm;
             if (use_tp) {
                 const int b = comm->next_buffer();
-                cuda_check(launch_sk_reduce_f32(sk_dn, reinterpret_cast<float*>(comm->sym(b)), T, H, stream), "down partial -> symmetric buffer");
-                cuda_check(comm->barrier(stream), "xgpu barrier");
-                cuda_check(launch_ar_resid_rmsnorm(comm->d_peer_sym(b), tp, x_, next_gain, xn_, T, H, cfg.rms_eps, stream), "allreduce+resid+rmsnorm1");
+                const TpComm::Signal sg = comm->next_signal();
+                cuda_check(launch_sk_reduce_f32(sk_dn, reinterpret_cast<float*>(comm->sym(b)), T, H, stream, &sg), "down partial -> symmetric buffer");
+                cuda_check(launch_ar_resid_rmsnorm(comm->d_peer_sym(b), tp, x_, next_gain, xn_, T, H, cfg.rms_eps, stream, &sg), "allreduce+resid+rmsnorm1");
             } else {
                 cuda_check(launch_sk_resid_rmsnorm(sk_dn, x_, next_gain, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm1");
             }

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "model.hpp"
 #include "tp_comm.hpp"
+#include "sk_consumers.cuh"
 
 namespace oa {
 
@@ -56,6 +57,8 @@ TpComm::TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, i
     for (int b = 0; b < 2; ++b) { cuda_check(cudaMalloc(&sym_[b], sym_bytes), "cudaMalloc sym"); cuda_check(cudaMemset(sym_[b], 0, sym_bytes), "memset sym"); }
     cuda_check(cudaMalloc(reinterpret_cast<void**>(&flags_), TP_MAX * sizeof(uint32_t)), "cudaMalloc flags");
     cuda_check(cudaMemset(flags_, 0, TP_MAX * sizeof(uint32_t)), "memset flags");
+    cuda_check(cudaMalloc(reinterpret_cast<void**>(&done_counter_), 64), "cudaMalloc done counter");
+    cuda_check(cudaMemset(done_counter_, 0, 64), "memset done counter");
     cuda_check(cudaMalloc(&arg_, 2 * arg_half_bytes_), "cudaMalloc arg");
     cuda_check(cudaDeviceSynchronize(), "sync");
     for (int b = 0; b < 2; ++b) cuda_check(cudaIpcGetMemHandle(&shm_->h_sym[rank][b], sym_[b]), "cudaIpcGetMemHandle sym");
@@ -91,7 +94,7 @@ TpComm::~TpComm() {
         if (peer_arg_[p]) cudaIpcCloseMemHandle(peer_arg_[p]);
     }
     for (int b = 0; b < 2; ++b) { cudaFree(sym_[b]); cudaFree(d_peer_sym_[b]); cudaFree(d_peer_arg_[b]); }
-    cudaFree(flags_); cudaFree(arg_); cudaFree(d_peer_flags_);
+    cudaFree(flags_); cudaFree(arg_); cudaFree(d_peer_flags_); cudaFree(done_counter_);
     if (shm_ && shm_ != MAP_FAILED) munmap(shm_, sizeof(TpShm));
     if (owner_) shm_unlink(shm_name_.c_str());
 }
@@ -167,67 +170,82 @@ cudaError_t TpComm::barrier(cudaStream_t s) {
     return launch_k(xgpu_barrier_kernel, dim3(1), dim3(32), 0, s, (uint32_t* const*)d_peer_flags_, (const uint32_t*)flags_, rank_, t_, epoch_);
 }
 
-template <int VPT>
-__global__ void __launch_bounds__(256) ar_resid_rmsnorm_kernel(const float* const* __restrict__ peer, int t, uint4* __restrict__ x,
-                                                               const uint4* __restrict__ g, uint4* __restrict__ y, int H8, float inv_h, float eps) {
-    griddep_launch(); griddep_wait();
-    const int row = blockIdx.x;
-    uint4* xr = x + (size_t)row * H8;
-    uint4 v[VPT];
-    float ss = 0.f;
-#pragma unroll
-    for (int k = 0; k < VPT; ++k) {
-        const int i = threadIdx.x + k * 256;
-        if (i < H8) {
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            float4 a[TP_MAX], b[TP_MAX];
-#pragma unroll
-            for (int p = 0; p < TP_MAX; ++p) if (p < t) { const float* src = peer[p] + ((size_t)row * H8 + i) * 8; a[p] = ld_peer_f4(src); b[p] = ld_peer_f4(src + 4); }
-#pragma unroll
-            for (int p = 0; p < TP_MAX; ++p) if (p < t) {      // rank order: every rank computes the identical sum
-                acc[0] += a[p].x; acc[1] += a[p].y; acc[2] += a[p].z; acc[3] += a[p].w; acc[4] += b[p].x; acc[5] += b[p].y; acc[6] += b[p].z; acc[7] += b[p].w;
-            }
-            const uint4 xo = xr[i];
-            uint4 xn;
-            xn.x = pack_bf16x2(bf16lo(xo.x) + acc[0], bf16hi(xo.x) + acc[1]); xn.y = pack_bf16x2(bf16lo(xo.y) + acc[2], bf16hi(xo.y) + acc[3]);
-            xn.z = pack_bf16x2(bf16lo(xo.z) + acc[4], bf16hi(xo.z) + acc[5]); xn.w = pack_bf16x2(bf16lo(xo.w) + acc[6], bf16hi(xo.w) + acc[7]);
-            xr[i] = xn; v[k] = xn;
-            float q;
-            q = bf16lo(xn.x); ss += q * q; q = bf16hi(xn.x); ss += q * q; q = bf16lo(xn.y); ss += q * q; q = bf16hi(xn.y); ss += q * q;
-            q = bf16lo(xn.z); ss += q * q; q = bf16hi(xn.z); ss += q * q; q = bf16lo(xn.w); ss += q * q; q = bf16hi(xn.w); ss += q * q;
+// producer side of the split handshake: called by every thread of every CTA after its last store to the symmetric buffer
+OA_DEVINL void xgpu_signal_when_grid_done(const TpComm::Signal& sg, unsigned int n_ctas) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int old = atomicAdd(sg.done_counter, 1u);
+        s_last = old == n_ctas - 1u;
+        if (s_last) *sg.done_counter = 0u;            // re-arm for the next collective
+    }
+    __syncthreads();
+    if (s_last && (int)threadIdx.x < sg.t) {
+        __threadfence_system();
+        st_release_sys(sg.peer_flags[threadIdx.x] + sg.rank, sg.epoch);
+    }
+}
+// consumer side: wait until every peer has signalled `epoch`
+OA_DEVINL void xgpu_wait_peers(const TpComm::Signal& sg) {
+    if ((int)threadIdx.x < sg.t) {
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(sg.my_flags + threadIdx.x) - sg.epoch) < 0) {
+            if (clock64() - t0 > (long long)3.0e10) __trap();          // ~15 s: a peer died
         }
     }
+    __syncthreads();
+}
+
+// One CTA per token row, 1024 threads, 16-byte items: lane l of a warp loads bytes [16l, 16l+16) of a 512-byte run, so every
+// peer load instruction is four full 128-byte lines on the NVLink (32-byte items at a 32-byte stride were half-used sectors).
+constexpr int AR_THREADS = 1024;
+__global__ void __launch_bounds__(AR_THREADS) ar_resid_rmsnorm_kernel(const float* const* __restrict__ peer, int t, uint2* __restrict__ x,
+                                                                      const uint2* __restrict__ g, uint2* __restrict__ y, int H4, float inv_h, float eps,
+                                                                      const TpComm::Signal sg, int wait) {
+    griddep_launch(); griddep_wait();
+    if (wait) xgpu_wait_peers(sg);
+    const int row = blockIdx.x;
+    uint2* xr = x + (size_t)row * H4;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < H4; i += AR_THREADS) {
+        float4 a[TP_MAX];
+#pragma unroll
+        for (int p = 0; p < TP_MAX; ++p) if (p < t) a[p] = ld_peer_f4(peer[p] + ((size_t)row * H4 + i) * 4);
+        const uint2 xo = xr[i];
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int p = 0; p < TP_MAX; ++p) if (p < t) { acc[0] += a[p].x; acc[1] += a[p].y; acc[2] += a[p].z; acc[3] += a[p].w; }   // rank order: identical on every rank
+        uint2 xn;
+        xn.x = pack_bf16x2(bf16lo(xo.x) + acc[0], bf16hi(xo.x) + acc[1]); xn.y = pack_bf16x2(bf16lo(xo.y) + acc[2], bf16hi(xo.y) + acc[3]);
+        xr[i] = xn;
+        float q;
+        q = bf16lo(xn.x); ss += q * q; q = bf16hi(xn.x); ss += q * q; q = bf16lo(xn.y); ss += q * q; q = bf16hi(xn.y); ss += q * q;
+    }
     ss = warp_sum(ss);
-    __shared__ float red[8];
+    __shared__ float red[AR_THREADS / 32];
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
     __syncthreads();
     float tot = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) tot += red[w];
+    for (int w = 0; w < AR_THREADS / 32; ++w) tot += red[w];
     const float r = 1.0f / sqrtf(tot * inv_h + eps);
-    uint4* yr = y + (size_t)row * H8;
-#pragma unroll
-    for (int k = 0; k < VPT; ++k) {
-        const int i = threadIdx.x + k * 256;
-        if (i < H8) {
-            const uint4 gg = g[i]; uint4 o;
-            o.x = pack_bf16x2(bf16lo(v[k].x) * r * bf16lo(gg.x), bf16hi(v[k].x) * r * bf16hi(gg.x));
-            o.y = pack_bf16x2(bf16lo(v[k].y) * r * bf16lo(gg.y), bf16hi(v[k].y) * r * bf16hi(gg.y));
-            o.z = pack_bf16x2(bf16lo(v[k].z) * r * bf16lo(gg.z), bf16hi(v[k].z) * r * bf16hi(gg.z));
-            o.w = pack_bf16x2(bf16lo(v[k].w) * r * bf16lo(gg.w), bf16hi(v[k].w) * r * bf16hi(gg.w));
-            yr[i] = o;
-        }
+    uint2* yr = y + (size_t)row * H4;
+    for (int i = threadIdx.x; i < H4; i += AR_THREADS) {      // this thread re-reads exactly what it wrote above
+        const uint2 v = xr[i], gg = g[i]; uint2 o;
+        o.x = pack_bf16x2(bf16lo(v.x) * r * bf16lo(gg.x), bf16hi(v.x) * r * bf16hi(gg.x));
+        o.y = pack_bf16x2(bf16lo(v.y) * r * bf16lo(gg.y), bf16hi(v.y) * r * bf16hi(gg.y));
+        yr[i] = o;
     }
 }
-cudaError_t launch_ar_resid_rmsnorm(void* const* d_peer, int t, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s) {
+cudaError_t launch_ar_resid_rmsnorm(void* const* d_peer, int t, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s,
+                                    const TpComm::Signal* wait) {
     if (T <= 0) return cudaSuccess;
-    if (H % 8 != 0 || H > 8192) return cudaErrorInvalidValue;
-    const int H8 = H / 8;
+    if (H % 8 != 0) return cudaErrorInvalidValue;
     auto P = reinterpret_cast<const float* const*>(d_peer);
-    auto X = reinterpret_cast<uint4*>(x); auto G = reinterpret_cast<const uint4*>(gain); auto Y = reinterpret_cast<uint4*>(xn);
-    if (H8 <= 256) return launch_k(ar_resid_rmsnorm_kernel<1>, dim3(T), dim3(256), 0, s, P, t, X, G, Y, H8, 1.0f / H, eps);
-    if (H8 <= 512) return launch_k(ar_resid_rmsnorm_kernel<2>, dim3(T), dim3(256), 0, s, P, t, X, G, Y, H8, 1.0f / H, eps);
-    return launch_k(ar_resid_rmsnorm_kernel<4>, dim3(T), dim3(256), 0, s, P, t, X, G, Y, H8, 1.0f / H, eps);
+    const TpComm::Signal sg = wait ? *wait : TpComm::Signal{};
+    return launch_k(ar_resid_rmsnorm_kernel, dim3(T), dim3(AR_THREADS), 0, s, P, t, reinterpret_cast<uint2*>(x), reinterpret_cast<const uint2*>(gain),
+                    reinterpret_cast<uint2*>(xn), H / 4, 1.0f / H, eps, sg, wait ? 1 : 0);
 }
 
 __global__ void ar_resid_bf16_kernel(const uint16_t* const* __restrict__ peer, int t, uint4* __restrict__ x, size_t n8) {
@@ -255,27 +273,21 @@ cudaError_t launch_ar_resid_bf16(void* const* d_peer, int t, void* x, int T, int
     return launch_k(ar_resid_bf16_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const uint16_t* const*>(d_peer), t, reinterpret_cast<uint4*>(x), n8);
 }
 
-__global__ void sk_reduce_f32_rows_kernel(const StreamK sk, float* __restrict__ out, int N8) {
+__global__ void sk_reduce_f32_rows_kernel(const StreamK sk, float* __restrict__ out, int N8, const TpComm::Signal sg, int signal) {
     griddep_launch(); griddep_wait();
     const int row = blockIdx.y;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N8; i += gridDim.x * blockDim.x) {
-        const int col = i * 8;
-        const uint32_t tile = (uint32_t)col / (uint32_t)sk.bn, cc = (uint32_t)col - tile * (uint32_t)sk.bn;
-        const uint32_t ut0 = tile * (uint32_t)sk.kb, G = (uint32_t)sk.G, total = (uint32_t)sk.total;
-        const uint32_t c_first = ((ut0 + 1u) * G - 1u) / total, c_last = ((ut0 + (uint32_t)sk.kb) * G - 1u) / total;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (uint32_t c = c_first; c <= c_last; ++c) {
-            const float4* p = reinterpret_cast<const float4*>(sk.ws + ((size_t)(c + tile) * sk.rows + row) * sk.bn + cc);
-            const float4 a = __ldcg(p), b = __ldcg(p + 1);
-            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-        }
+        float acc[8];
+        sk_sum8(sk, row, i * 8, acc);            // CTA order, up to 6 pieces' loads in flight together
         float4* o = reinterpret_cast<float4*>(out + ((size_t)row * N8 + i) * 8);
         o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]); o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
+    if (signal) xgpu_signal_when_grid_done(sg, gridDim.x * gridDim.y);
 }
-cudaError_t launch_sk_reduce_f32(const StreamK& sk, float* out, int T, int N, cudaStream_t s) {
+cudaError_t launch_sk_reduce_f32(const StreamK& sk, float* out, int T, int N, cudaStream_t s, const TpComm::Signal* signal) {
     if (T <= 0) return cudaSuccess;
-    return launch_k(sk_reduce_f32_rows_kernel, dim3((N / 8 + 255) / 256, T), dim3(256), 0, s, sk, out, N / 8);
+    const TpComm::Signal sg = signal ? *signal : TpComm::Signal{};
+    return launch_k(sk_reduce_f32_rows_kernel, dim3((N / 8 + 255) / 256, T), dim3(256), 0, s, sk, out, N / 8, sg, signal ? 1 : 0);
 }
 
 struct ValIdx { float v; int i; };

@@ -51,6 +51,10 @@ public:
     void* arg(int b) const { return reinterpret_cast<char*>(arg_) + (size_t)b * arg_half_bytes_; }
     void* const* d_peer_arg(int b) const { return d_peer_arg_[b]; }
     cudaError_t barrier(cudaStream_t s);                                  // every rank's prior writes visible to all
+    // the same handshake split over two kernels: the producer's last CTA signals "my buffer is written" to every peer, the
+    // consumer's CTAs wait for every peer's signal before their first peer load (no stand-alone barrier launch)
+    struct Signal { uint32_t* const* peer_flags; const uint32_t* my_flags; unsigned int* done_counter; int rank, t; uint32_t epoch; };
+    Signal next_signal() { ++epoch_; return Signal{(uint32_t* const*)d_peer_flags_, flags_, done_counter_, rank_, t_, epoch_}; }
 
     // ---- host side: leader publishes, followers receive ----
     void publish(const StepInput& in);
@@ -61,17 +65,20 @@ private:
     int t_, rank_; std::string shm_name_; TpShm* shm_ = nullptr; bool owner_ = false;
     void* sym_[2] = {nullptr, nullptr}; void* peer_sym_[2][TP_MAX] = {};
     void** d_peer_sym_[2] = {nullptr, nullptr};
-    uint32_t* flags_ = nullptr; uint32_t* peer_flags_[TP_MAX] = {}; uint32_t** d_peer_flags_ = nullptr;
+    uint32_t* flags_ = nullptr; uint32_t* peer_flags_[TP_MAX] = {}; uint32_t** d_peer_flags_ = nullptr; unsigned int* done_counter_ = nullptr;
     void* arg_ = nullptr; void* peer_arg_[TP_MAX] = {}; void** d_peer_arg_[2] = {nullptr, nullptr}; size_t arg_half_bytes_ = 0;
     uint64_t ar_count_ = 0; uint32_t epoch_ = 0; uint64_t seq_local_ = 0; size_t sym_bytes_ = 0;
 };
 
 // x[T,H] (bf16, in place) += sum over ranks (rank order) of fp32 partial rows; xn = rmsnorm(x) * gain   (decode path)
-cudaError_t launch_ar_resid_rmsnorm(void* const* d_peer, int t, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s);
+// `wait` != null: every CTA first waits for all peers' signals of that epoch (TpComm::next_signal) instead of a preceding barrier launch
+cudaError_t launch_ar_resid_rmsnorm(void* const* d_peer, int t, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s,
+                                    const TpComm::Signal* wait = nullptr);
 // x[T,H] += sum over ranks of bf16 partial rows                                                          (prefill path)
 cudaError_t launch_ar_resid_bf16(void* const* d_peer, int t, void* x, int T, int H, cudaStream_t s);
 // stream-K partials -> fp32 rows [T,N] in `out` (this rank's symmetric buffer)
-cudaError_t launch_sk_reduce_f32(const StreamK& sk, float* out, int T, int N, cudaStream_t s);
+// `signal` != null: the last CTA to finish tells every peer that this rank's buffer is complete
+cudaError_t launch_sk_reduce_f32(const StreamK& sk, float* out, int T, int N, cudaStream_t s, const TpComm::Signal* signal = nullptr);
 // vocab-parallel greedy sampling: (val, global idx) per row into this rank's arg buffer, then combine over ranks
 cudaError_t launch_argmax_reduce_pair(const float* amax_val, const int* amax_idx, int M, int n_tiles, int idx_offset, void* pair_out,
                                       cudaStream_t s);
