@@ -212,13 +212,13 @@ def run_ours(args, rank, world, local_rank):
         dist.barrier(); dist.destroy_process_group()
 
 
-def cpu_baseline(n_decode=6, n_prompt=16):
+def cpu_baseline(n_decode=64, n_prompt=32):
     """The oracle (CPU port of the same decoder, same seeded 8B weights) on the host cores: B=1, short bounded sample."""
     from oracle import oracle as O
     import numpy as np
     spec = O.PRESETS[MODEL]
     t0 = time.perf_counter()
-    orc = O.Oracle(spec, max_pos=64, n_slots=1, mode=1)
+    orc = O.Oracle(spec, max_pos=max(64, n_prompt + n_decode + 8), n_slots=1, mode=1)
     t_init = time.perf_counter() - t0
     prompt = (np.arange(n_prompt) * 7919 % 256).astype(np.int32)
     t0 = time.perf_counter(); orc.forward(prompt); t_pre = time.perf_counter() - t0
@@ -242,7 +242,7 @@ def run_reference(args, rank, world):
     this times the CPU port with all host threads on a bounded sample of the same workload."""
     if rank != 0:
         return
-    K = max(1, min(args.steps, 16))
+    K = max(1, min(args.steps, 64))             # ~0.12 s per token on 16 cores: the whole arm stays well under a few minutes
     cb = cpu_baseline(n_decode=K + min(args.warmup, 2))
     v = cb["value"]
     line = {"impl": "reference", "metric": "decode_tokens_per_sec", "value": v, "unit": "tokens/s", "n_gpus": world, "steps": K,
@@ -262,7 +262,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kv-gb", type=float, default=60.0, dest="kv_gb")
-    ap.add_argument("--cpu-tokens", type=int, default=6, dest="cpu_tokens")
+    ap.add_argument("--cpu-tokens", type=int, default=64, dest="cpu_tokens")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))

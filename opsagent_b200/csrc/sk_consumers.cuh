@@ -40,6 +40,41 @@ OA_DEVINL void sk_sum8(const StreamK& sk, int row, int col, float (&acc)[8]) {
     }
 }
 
+// Two 8-column groups of the SAME tile (a RoPE pair: columns c and c + D/2): one index computation, both groups' partial loads in
+// flight together, each summed in CTA order exactly as sk_sum8 does.
+OA_DEVINL void sk_sum8_pair(const StreamK& sk, int row, int col_a, int col_b, float (&acc_a)[8], float (&acc_b)[8]) {
+    const uint32_t tile = (uint32_t)col_a / (uint32_t)sk.bn;
+    if ((uint32_t)col_b / (uint32_t)sk.bn != tile) { sk_sum8(sk, row, col_a, acc_a); sk_sum8(sk, row, col_b, acc_b); return; }
+    const uint32_t ca = (uint32_t)col_a - tile * (uint32_t)sk.bn, cb = (uint32_t)col_b - tile * (uint32_t)sk.bn;
+    const uint32_t ut0 = tile * (uint32_t)sk.kb, G = (uint32_t)sk.G, total = (uint32_t)sk.total;
+    const uint32_t c_first = ((ut0 + 1u) * G - 1u) / total, c_last = ((ut0 + (uint32_t)sk.kb) * G - 1u) / total;
+    const int n = (int)(c_last - c_first) + 1;
+    const size_t slot_stride = (size_t)sk.rows * sk.bn;
+    const float* p = sk.ws + ((size_t)(c_first + tile) * sk.rows + row) * sk.bn;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc_a[i] = 0.f; acc_b[i] = 0.f; }
+    for (int i = 0; i < n; i += 4) {
+        float4 a0[4], a1[4], b0[4], b1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i + j < n) {
+                const float* q = p + (size_t)(i + j) * slot_stride;
+                a0[j] = __ldcg(reinterpret_cast<const float4*>(q + ca)); a1[j] = __ldcg(reinterpret_cast<const float4*>(q + ca) + 1);
+                b0[j] = __ldcg(reinterpret_cast<const float4*>(q + cb)); b1[j] = __ldcg(reinterpret_cast<const float4*>(q + cb) + 1);
+            } else { a0[j] = make_float4(0.f, 0.f, 0.f, 0.f); a1[j] = a0[j]; b0[j] = a0[j]; b1[j] = a0[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i + j < n) {
+                acc_a[0] += a0[j].x; acc_a[1] += a0[j].y; acc_a[2] += a0[j].z; acc_a[3] += a0[j].w;
+                acc_a[4] += a1[j].x; acc_a[5] += a1[j].y; acc_a[6] += a1[j].z; acc_a[7] += a1[j].w;
+                acc_b[0] += b0[j].x; acc_b[1] += b0[j].y; acc_b[2] += b0[j].z; acc_b[3] += b0[j].w;
+                acc_b[4] += b1[j].x; acc_b[5] += b1[j].y; acc_b[6] += b1[j].z; acc_b[7] += b1[j].w;
+            }
+        }
+    }
+}
+
 // x[t,:] += sum of partials (bf16 residual stream), y[t,:] = rmsnorm(x[t,:]) * g.  SK_RESID_THREADS threads (tid) per row, so that
 // at H <= 4096 every thread owns ONE 16-byte item and all its partial loads are in flight together; `red` = 16 floats of
 // shared memory, `bar_id` = a hardware barrier those threads own.
@@ -103,6 +138,16 @@ OA_DEVINL void sk_swiglu_item(const StreamK& sk, int t, int i, uint4* __restrict
     act[(size_t)t * F8 + i] = ov;
 }
 
+// + bias, then round: the projection output is a bf16 tensor
+OA_DEVINL void sk_finish8_bf16(const uint16_t* bias, int col, float (&v)[8]) {
+    if (bias) {
+        const uint4 bb = *reinterpret_cast<const uint4*>(bias + col);
+        v[0] += bf16lo(bb.x); v[1] += bf16hi(bb.x); v[2] += bf16lo(bb.y); v[3] += bf16hi(bb.y);
+        v[4] += bf16lo(bb.z); v[5] += bf16hi(bb.z); v[6] += bf16lo(bb.w); v[7] += bf16hi(bb.w);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = bf16_bits_to_f32(f32_to_bf16_bits(v[k]));
+}
 OA_DEVINL void sk_load8_bf16(const StreamK& sk, const uint16_t* bias, int row, int col, float (&v)[8]) {
     sk_sum8(sk, row, col, v);
     if (bias) {
@@ -127,8 +172,9 @@ OA_DEVINL void sk_rope_item(const StreamK& sk, const SkRopeArgs& a, int t, int w
         const float* sr = a.rope_sin + (size_t)pos * half;
         const int head = w / vec_per_head, i0 = (w - head * vec_per_head) * 8;
         float av[8], bv[8];
-        sk_load8_bf16(sk, a.bias, t, head * D + i0, av);
-        sk_load8_bf16(sk, a.bias, t, head * D + i0 + half, bv);
+        sk_sum8_pair(sk, t, head * D + i0, head * D + i0 + half, av, bv);
+        sk_finish8_bf16(a.bias, head * D + i0, av);
+        sk_finish8_bf16(a.bias, head * D + i0 + half, bv);
         const float4 c0 = *reinterpret_cast<const float4*>(cr + i0), c1 = *reinterpret_cast<const float4*>(cr + i0 + 4);
         const float4 s0 = *reinterpret_cast<const float4*>(sr + i0), s1 = *reinterpret_cast<const float4*>(sr + i0 + 4);
         const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
