@@ -33,6 +33,10 @@ def make_handler(engine, require_key: bool = True, tool_steps: int = 3):
             self.end_headers()
             self.wfile.write(data)
 
+        def _authorised(self) -> bool:
+            auth = self.headers.get("Authorization", "")
+            return (not require_key) or (auth.startswith("Bearer ") and len(auth) > 7)
+
         def _error(self, status: int, message: str):
             self._send(status, {"error": {"message": message, "type": _STATUS_TYPE.get(status, "server_error"), "code": status}})
 
@@ -40,6 +44,8 @@ def make_handler(engine, require_key: bool = True, tool_steps: int = 3):
             if self.path.rstrip("/").endswith("/models"):
                 return self._send(200, {"object": "list", "data": [{"id": engine.info["model"], "object": "model", "owned_by": "opsagent_b200"}]})
             if self.path.rstrip("/").endswith("/perf/stats"):
+                if not self._authorised():
+                    return self._error(401, "missing bearer token")        # the reference serves it from the authenticated group (router.go:91-105)
                 # the reference's GET /api/perf/stats (pkg/api/router.go:104, pkg/handlers/perf.go:12-25) plus the engine's own
                 # counters (steps, tokens, bytes moved, kernel launches) under "engine" — steps/sec from the product's endpoint
                 stats = GetPerfStats().GetStats()
@@ -50,12 +56,13 @@ def make_handler(engine, require_key: bool = True, tool_steps: int = 3):
 
         def do_POST(self):
             if self.path.rstrip("/").endswith("/perf/reset"):          # pkg/api/router.go:105, pkg/handlers/perf.go:28-39
+                if not self._authorised():
+                    return self._error(401, "missing bearer token")
                 GetPerfStats().Reset()
                 return self._send(200, {"message": "performance statistics reset", "status": "success"})
             if not self.path.rstrip("/").endswith("/chat/completions"):
                 return self._error(404, "not found")
-            auth = self.headers.get("Authorization", "")
-            if require_key and not (auth.startswith("Bearer ") and len(auth) > 7):
+            if not self._authorised():
                 return self._error(401, "missing bearer token")        # the reference always sends its apiKey (openai.go:44)
             try:
                 n = int(self.headers.get("Content-Length", "0"))

@@ -423,6 +423,7 @@ def test_assistant_loop_records_the_reference_operation_names():
 
 
 def test_http_front_serves_the_perf_stats_endpoints():
+    import urllib.error
     import urllib.request
     from opsagent_b200.http_front import serve
     from opsagent_b200.perf import GetPerfStats
@@ -444,10 +445,14 @@ def test_http_front_serves_the_perf_stats_endpoints():
     req = urllib.request.Request(root + "/v1/chat/completions", data=json.dumps({"model": "tiny", "messages": [{"role": "user", "content": "x"}]}).encode(),
                                  headers={"Content-Type": "application/json", "Authorization": "Bearer k"})
     urllib.request.urlopen(req, timeout=10).read()
-    r = json.loads(urllib.request.urlopen(root + "/api/perf/stats", timeout=10).read())          # pkg/api/router.go:104
+    hdr = {"Authorization": "Bearer k"}
+    with pytest.raises(urllib.error.HTTPError) as e:                                                # served from the authenticated group
+        urllib.request.urlopen(root + "/api/perf/stats", timeout=10)
+    assert e.value.code == 401
+    r = json.loads(urllib.request.urlopen(urllib.request.Request(root + "/api/perf/stats", headers=hdr), timeout=10).read())          # pkg/api/router.go:104
     assert r["status"] == "success" and r["stats"]["callCounts"] == {"chat_completion": 1} and r["stats"]["timers"]["chat_completion"] > 0
     assert r["stats"]["engine"] == {"decode_steps": 7, "requests_completed": 1} and "lastResetTime" in r["stats"]
-    r = json.loads(urllib.request.urlopen(urllib.request.Request(root + "/api/perf/reset", data=b"", method="POST"), timeout=10).read())   # router.go:105
+    r = json.loads(urllib.request.urlopen(urllib.request.Request(root + "/api/perf/reset", data=b"", method="POST", headers=hdr), timeout=10).read())   # router.go:105
     assert r["status"] == "success"
-    assert json.loads(urllib.request.urlopen(root + "/api/perf/stats", timeout=10).read())["stats"]["callCounts"] == {}
+    assert json.loads(urllib.request.urlopen(urllib.request.Request(root + "/api/perf/stats", headers=hdr), timeout=10).read())["stats"]["callCounts"] == {}
     srv.shutdown()
