@@ -48,12 +48,12 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index=0):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, gpus="0", period_ms=200):
+        self.gpu, self.period, self.rows, self.proc = gpus, period_ms, [], None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.period),
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -131,11 +131,15 @@ def run_ours(args, rank, world, local_rank):
     # ------------------------------------------------------------------ value: device-resident decode steps
     # context chosen so that the mean over the K timed steps is MEAN_CTX (=P+G/2)
     ctx0 = max(64, MEAN_CTX - W - K // 2)
-    clocks = ClockSampler(local_rank); clocks.start()
+    # ONE sampler for the whole job (rank 0, all N GPUs): NVML queries take driver-wide locks, and N polling processes
+    # put measurable gaps between kernel launches of every rank (N=4: 0.5 ms per 8.5 ms step)
+    clocks = ClockSampler(",".join(str(i) for i in range(world)), 200 if world == 1 else 500) if rank == 0 else None
+    if clocks:
+        clocks.start()
     barrier()
     r = eng.bench_decode(BATCH, ctx0, K, W)
     barrier()
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks else None
     ms_step = allmax(r["ms_per_step"])
     value = world * BATCH / (ms_step / 1e3)
     # ------------------------------------------------------------------ roofline: dominant kernel (decode attention)
