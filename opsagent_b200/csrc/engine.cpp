@@ -44,6 +44,9 @@ struct Seq {
     bool done = false;
     ToolPromptGrammar grammar;       // inactive unless the request asked for schema-constrained JSON
     int n_registered = 0; uint64_t hash_prev = 0;   // prefix cache: full pages already published / hash of that chain
+    std::chrono::steady_clock::time_point t_enqueue{};   // arrival (admission batching)
+    bool preempted = false;                              // pushed back by the scheduler: re-admit without waiting
+    int est_uncached = -1;                               // prompt tokens a prefill would have to compute (prefix-cache walk, made once)
 };
 
 class Engine {
@@ -93,6 +96,7 @@ public:
             if (fatal_) return fail(OA_ERR_INTERNAL, "engine is in a failed state: " + fatal_msg_);
             if ((int)waiting_.size() >= opt_.max_queue) return fail(OA_ERR_OVERLOADED, "request queue full");
             s->ticket = next_ticket_++;
+            s->t_enqueue = std::chrono::steady_clock::now();
             waiting_.push_back(s); by_ticket_[s->ticket] = s;
             *ticket = s->ticket;
         }
@@ -247,11 +251,12 @@ public:
                       "{\"requests_completed\": %llu, \"prefill_tokens\": %llu, \"decode_tokens\": %llu, \"prefill_steps\": %llu, "
                       "\"decode_steps\": %llu, \"preemptions\": %llu, \"pages_total\": %d, \"pages_free\": %zu, \"running\": %zu, "
                       "\"waiting\": %zu, \"kernel_launches\": %llu, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"weight_bytes\": %zu, "
-                      "\"kv_pool_bytes\": %zu, \"busy_ms\": %.3f, \"prefix_hit_tokens\": %llu, \"pages_cached\": %zu}",
+                      "\"kv_pool_bytes\": %zu, \"busy_ms\": %.3f, \"prefix_hit_tokens\": %llu, \"pages_cached\": %zu, \"admissions_deferred\": %llu}",
                       (unsigned long long)n_completed_, (unsigned long long)n_prefill_tokens_, (unsigned long long)n_decode_tokens_,
                       (unsigned long long)n_prefill_steps_, (unsigned long long)n_decode_steps_, (unsigned long long)n_preempt_,
                       model_.num_pages, available_pages_locked(), running_.size(), waiting_.size(), (unsigned long long)launches_total(),
-                      (unsigned long long)model_.h2d_bytes, (unsigned long long)model_.d2h_bytes, model_.weight_bytes, model_.kv_pool_bytes, busy_ms_, (unsigned long long)n_prefix_hit_tokens_, cached_.size());
+                      (unsigned long long)model_.h2d_bytes, (unsigned long long)model_.d2h_bytes, model_.weight_bytes, model_.kv_pool_bytes, busy_ms_, (unsigned long long)n_prefix_hit_tokens_, cached_.size(),
+                      (unsigned long long)n_admit_deferred_);
         return b;
     }
     std::string info_json() {
@@ -338,6 +343,21 @@ private:
         }
         n_prefix_hit_tokens_ += s->n_cached;
     }
+    // prompt tokens of a waiting sequence that a prefill would really have to compute (read-only walk of the prefix cache)
+    int uncached_tokens_locked(const Seq& s) const {
+        int hit = 0;
+        if (opt_.prefix_cache) {
+            const int max_pages = ((int)s.tokens.size() - 1) / 64;
+            uint64_t h = 0;
+            for (int i = 0; i < max_pages; ++i) {
+                const uint64_t hi = chain_hash(h, s.tokens.data() + (size_t)i * 64);
+                auto it = cached_.find(hi);
+                if (it == cached_.end() || page_parent_[it->second] != h) break;
+                h = hi; hit = (i + 1) * 64;
+            }
+        }
+        return (int)s.tokens.size() - hit;
+    }
     // publish the pages of s whose KV became complete (n_cached advanced past their last token)
     void register_pages_locked(const std::shared_ptr<Seq>& s) {
         if (!opt_.prefix_cache) return;
@@ -404,8 +424,29 @@ private:
         std::vector<std::shared_ptr<Seq>> sampled;      // sequences owning this step's sample rows, in row order
         {
             std::lock_guard<std::mutex> lk(mu_);
+            // ---- admission batching: a prefill step streams all the weights once, whether it carries one arrival or ten, and the decoding
+            // sequences stall for its duration.  While sequences are decoding, arrivals therefore wait (bounded) until enough uncached prompt
+            // tokens are queued to be worth that pass.  Nothing running, a preempted sequence, or the time limit admit at once. ----
+            bool defer = false;
+            if (opt_.prefill_batch_tokens > 0 && !waiting_.empty() && !running_.empty() && !waiting_.front()->preempted) {
+                bool all_decoding = true;
+                for (auto& s : running_) if (s->state != SeqState::DECODE) { all_decoding = false; break; }
+                if (all_decoding) {
+                    const auto now = std::chrono::steady_clock::now();
+                    long long pending = 0; double oldest_ms = 0;
+                    size_t seen = 0;
+                    for (auto& s : waiting_) {
+                        if (s->est_uncached < 0) s->est_uncached = uncached_tokens_locked(*s);
+                        pending += s->est_uncached;
+                        oldest_ms = std::max(oldest_ms, std::chrono::duration<double, std::milli>(now - s->t_enqueue).count());
+                        if (++seen >= 64 || pending >= opt_.prefill_batch_tokens) break;
+                    }
+                    defer = pending < opt_.prefill_batch_tokens && oldest_ms < (double)opt_.prefill_max_wait_ms && seen == waiting_.size();
+                    if (defer) ++n_admit_deferred_;
+                }
+            }
             // ---- admission: FIFO while pages for the whole current token list (+1) are free ----
-            while (!waiting_.empty() && (int)running_.size() < opt_.max_batch) {
+            while (!defer && !waiting_.empty() && (int)running_.size() < opt_.max_batch) {
                 auto& s = waiting_.front();
                 const int need = ((int)s->tokens.size() + 1 + 63) / 64;
                 if (need > model_.num_pages) { s->error = OA_ERR_BAD_REQUEST; s->error_msg = "request larger than the KV pool"; s->done = true; waiting_.pop_front(); cv_done_.notify_all(); continue; }
@@ -415,7 +456,7 @@ private:
                     s->pages.clear(); s->n_cached = 0; s->n_registered = 0; s->hash_prev = 0;
                     break;
                 }
-                s->state = SeqState::PREFILL;
+                s->state = SeqState::PREFILL; s->preempted = false;
                 running_.push_back(s); waiting_.pop_front();
             }
             if (running_.empty()) return;
@@ -445,7 +486,7 @@ private:
                 // every decoding sequence needs a slot for its newest token; preempt (recompute later) if the pool is dry
                 auto preempt = [&](const std::shared_ptr<Seq>& v) {
                     for (int p : v->pages) release_page_locked(p);
-                    v->pages.clear(); v->n_cached = 0; v->state = SeqState::WAITING;
+                    v->pages.clear(); v->n_cached = 0; v->state = SeqState::WAITING; v->preempted = true;
                     waiting_.push_front(v); ++n_preempt_;
                 };
                 for (size_t i = 0; i < running_.size();) {
@@ -519,7 +560,7 @@ private:
     uint64_t next_ticket_ = 1;
     bool stop_ = false, fatal_ = false; std::string fatal_msg_;
     std::thread worker_, follower_; bool follower_done_ = false;
-    uint64_t n_completed_ = 0, n_prefill_tokens_ = 0, n_decode_tokens_ = 0, n_prefill_steps_ = 0, n_decode_steps_ = 0, n_preempt_ = 0;
+    uint64_t n_admit_deferred_ = 0, n_completed_ = 0, n_prefill_tokens_ = 0, n_decode_tokens_ = 0, n_prefill_steps_ = 0, n_decode_steps_ = 0, n_preempt_ = 0;
     double busy_ms_ = 0;
 };
 

@@ -21,13 +21,14 @@ ap.add_argument("--model", default="llama-3-8b")
 ap.add_argument("--agents", type=int, default=128)
 ap.add_argument("--tool-steps", type=int, default=3)
 ap.add_argument("--prompt-bytes", type=int, default=1200)
+ap.add_argument("--extra", default="{}", help="engine config overrides (JSON), e.g. {\"prefill_batch_tokens\": 0}")
 a = ap.parse_args()
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import synthetic_pod_yaml, ANALYSIS_SYSTEM  # noqa: E402
 
 eng = Engine({"model": a.model, "kv_gb": 60, "max_batch": a.agents, "max_seq_len": 8192, "max_step_tokens": 8192, "json_mode": 1,
-              "react_tool_steps": a.tool_steps})
+              "react_tool_steps": a.tool_steps, **json.loads(a.extra)})
 calls = [0] * a.agents
 results = [None] * a.agents
 
@@ -66,5 +67,6 @@ print(json.dumps({"workload": f"{a.agents} concurrent ReAct conversations, {a.to
                   "react_steps_per_sec": round(n_calls / dt, 2), "chat_calls": n_calls, "seconds": round(dt, 2), "conversations_with_final_answer": ok,
                   "completion_tokens_per_sec": round((s1["decode_tokens"] - s0["decode_tokens"]) / dt, 1),
                   "prefill_tokens": s1["prefill_tokens"] - s0["prefill_tokens"], "decode_steps": s1["decode_steps"] - s0["decode_steps"],
-                  "preemptions": s1["preemptions"] - s0["preemptions"]}), flush=True)
+                  "preemptions": s1["preemptions"] - s0["preemptions"], "prefill_steps": s1["prefill_steps"] - s0["prefill_steps"],
+                  "admissions_deferred": s1.get("admissions_deferred", 0) - s0.get("admissions_deferred", 0), "extra": json.loads(a.extra)}), flush=True)
 eng.close()
