@@ -133,6 +133,14 @@ OA_API int oa_host_apply_chat_template(const char* config_json, const oa_msg* ms
 OA_API int oa_host_decode_plan(const int32_t* ctx_lens, int32_t n_seqs, int32_t n_kv, int32_t n_ctas_target, int32_t force_splits,
                         int32_t* segs_out, int32_t cap_segs, int32_t* cta_ptr_out, int32_t cap_ctas, int32_t* n_ctas_out,
                         int32_t* n_segs_out, int32_t* n_slots_out);
+/* stream-K unit plan of the decode projections (host only, no GPU): CTA c owns k-block units [cta_unit0[c], cta_unit0[c+1]) of
+ * n_tiles x kb units (tile-major); tile_first/tile_last = the CTAs holding a tile's first and last k-block, computed with the
+ * closed form the kernels use (floor(((u+1)*G-1)/total)).  The fused SwiGLU epilogue relies on: pieces of a tile are exactly
+ * CTAs tile_first..tile_last, the first CTA's piece is the LAST segment of that CTA and every other piece is the FIRST segment
+ * of its CTA (so the finishing CTA never waits on a CTA that is itself waiting). */
+OA_API int oa_host_streamk_plan(int32_t N, int32_t K, int32_t block_n, int32_t n_ctas, int64_t* cta_unit0_out, int32_t cap_ctas,
+                         int32_t* tile_first_out, int32_t* tile_last_out, int32_t cap_tiles, int32_t* n_ctas_out, int32_t* n_tiles_out,
+                         int32_t* kb_out);
 /* grammar automaton, host only: feeds `prefix` (n bytes) to the schema `kind` (1 tool call, 2 final) and returns the allowed-byte
  * bitset for the next position in mask_out[8], *done_out = 1 when the JSON is complete; 400 if the prefix is not derivable */
 OA_API int oa_host_grammar_step(int32_t kind, const uint8_t* prefix, int32_t n, uint32_t* mask_out, int32_t* done_out);

@@ -169,6 +169,22 @@ int oa_host_decode_plan(const int32_t* ctx_lens, int32_t n_seqs, int32_t n_kv, i
     return OA_OK;
 }
 
+int oa_host_streamk_plan(int32_t N, int32_t K, int32_t block_n, int32_t n_ctas, int64_t* cta_unit0_out, int32_t cap_ctas,
+                         int32_t* tile_first_out, int32_t* tile_last_out, int32_t cap_tiles, int32_t* n_ctas_out, int32_t* n_tiles_out,
+                         int32_t* kb_out) {
+    if (N <= 0 || K <= 0 || n_ctas <= 0 || (block_n != 128 && block_n != 256)) return OA_ERR_BAD_REQUEST;
+    const StreamK sk = make_streamk(nullptr, N, K, block_n, n_ctas);
+    if (sk.G > cap_ctas || sk.n_tiles > cap_tiles) return OA_ERR_BAD_REQUEST;
+    for (int c = 0; c <= sk.G; ++c) cta_unit0_out[c] = (long long)c * sk.total / sk.G;            // the kernels' u0/u1
+    for (int t = 0; t < sk.n_tiles; ++t) {                                                        // sk_sum8's closed form (32-bit, as on the device)
+        const uint32_t ut0 = (uint32_t)t * (uint32_t)sk.kb, G = (uint32_t)sk.G, total = (uint32_t)sk.total;
+        tile_first_out[t] = (int32_t)(((ut0 + 1u) * G - 1u) / total);
+        tile_last_out[t] = (int32_t)(((ut0 + (uint32_t)sk.kb) * G - 1u) / total);
+    }
+    *n_ctas_out = sk.G; *n_tiles_out = sk.n_tiles; *kb_out = sk.kb;
+    return OA_OK;
+}
+
 int oa_host_grammar_step(int32_t kind, const uint8_t* prefix, int32_t n, uint32_t* mask_out, int32_t* done_out) {
     return oa_host_grammar_step_ex(kind, "", prefix, n, mask_out, done_out);
 }

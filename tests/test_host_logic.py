@@ -456,3 +456,33 @@ def test_http_front_serves_the_perf_stats_endpoints():
     assert r["status"] == "success"
     assert json.loads(urllib.request.urlopen(urllib.request.Request(root + "/api/perf/stats", headers=hdr), timeout=10).read())["stats"]["callCounts"] == {}
     srv.shutdown()
+
+
+# ---- stream-K unit plan: the invariants the fused SwiGLU epilogue and the consumers rely on (host only) ----
+@pytest.mark.parametrize("N,K,G", [(28672, 4096, 148), (6144, 4096, 148), (4096, 4096, 148), (4096, 14336, 148),     # Llama-3-8B decode projections
+                                   (7168, 8192, 148), (1280, 8192, 148), (8192, 1024, 148), (8192, 3584, 148),     # Llama-3-70B TP=8 shards
+                                   (13824, 5120, 148), (352, 128, 148), (128, 64, 148), (640, 256, 7)])           # Qwen-32B TP=4 gate/up, tiny shapes
+def test_streamk_plan_invariants(N, K, G):
+    import ctypes as C
+    from opsagent_b200 import _lib
+    L = _lib.load()
+    cap = 4096
+    u0 = np.zeros(cap + 1, np.int64); tf = np.zeros(cap, np.int32); tl = np.zeros(cap, np.int32)
+    g, nt, kb = C.c_int32(), C.c_int32(), C.c_int32()
+    assert L.oa_host_streamk_plan(N, K, 128, G, u0.ctypes.data, cap, tf.ctypes.data, tl.ctypes.data, cap, C.byref(g), C.byref(nt), C.byref(kb)) == 0
+    g, nt, kb = g.value, nt.value, kb.value
+    total = nt * kb
+    assert nt == -(-N // 128) and kb == -(-K // 64) and g == min(G, total)
+    u0 = u0[: g + 1]
+    assert u0[0] == 0 and u0[-1] == total and (np.diff(u0) >= 1).all()                 # the CTAs' ranges partition the units; nobody is idle
+    assert np.diff(u0).max() - np.diff(u0).min() <= 1                                  # balanced: every SM streams the same weight bytes (+-1 k-block)
+    for t in range(nt):
+        touching = [c for c in range(g) if u0[c] < (t + 1) * kb and u0[c + 1] > t * kb]          # brute force
+        assert touching == list(range(tf[t], tl[t] + 1)), (t, touching, tf[t], tl[t])            # the closed form the kernels use
+        if len(touching) > 1:
+            first = touching[0]
+            assert u0[first + 1] == min((t + 1) * kb, u0[first + 1]) and u0[first + 1] <= (t + 1) * kb      # the finisher's piece is the TAIL of its range
+            for c in touching[1:]:
+                assert u0[c] >= t * kb and u0[c] < (t + 1) * kb                            # ... every other piece is the HEAD of its CTA's range
+                assert u0[c] == max(u0[c], t * kb)
+            # so a finishing CTA only waits on pieces that their CTAs compute FIRST: the wait-for graph has no cycle
