@@ -18,6 +18,7 @@ import "C"
 import (
 	"fmt"
 	"math"
+	"runtime"
 	"sync"
 	"time"
 	"unsafe"
@@ -46,6 +47,8 @@ func NewLocalCUDAClient(apiKey string, baseURL string) (*LocalCUDAClient, error)
 		return nil, fmt.Errorf("OPENAI_API_KEY is not set")
 	}
 	engineOnce.Do(func() {
+		runtime.LockOSThread() // oa_last_error() is thread-local
+		defer runtime.UnlockOSThread()
 		model := "llama-3-8b"
 		if len(baseURL) > len("cuda://") {
 			model = baseURL[len("cuda://"):]
@@ -65,6 +68,12 @@ func NewLocalCUDAClient(apiKey string, baseURL string) (*LocalCUDAClient, error)
 // Chat — same signature and error behaviour as (*OpenAIClient).Chat (openai.go:69-104).  submit + wait keeps the
 // goroutine parked in one cgo call; many goroutines batch inside the engine (continuous batching).
 func (c *LocalCUDAClient) Chat(model string, maxTokens int, prompts []openai.ChatCompletionMessage) (string, error) {
+	if len(prompts) == 0 {
+		return "", fmt.Errorf("prompts cannot be empty") // the caller checks this too (pkg/assistants/simple.go:312)
+	}
+	// oa_last_error() is thread-local: keep this goroutine on one OS thread across the call and the error read
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
 	msgs := (*[1 << 20]C.oa_msg)(C.malloc(C.size_t(len(prompts)) * C.size_t(unsafe.Sizeof(C.oa_msg{}))))[:len(prompts):len(prompts)]
 	defer C.free(unsafe.Pointer(&msgs[0]))
 	for i, p := range prompts {
