@@ -29,8 +29,8 @@ __global__ void sk_reduce_f32_kernel(const StreamK sk, float* __restrict__ out, 
     const int row = blockIdx.x;
     for (int col = threadIdx.x; col < N; col += blockDim.x) {
         const uint32_t tile = (uint32_t)col / (uint32_t)sk.bn, cc = (uint32_t)col - tile * (uint32_t)sk.bn;
-        const uint32_t ut0 = tile * (uint32_t)sk.kb, G = (uint32_t)sk.G, total = (uint32_t)sk.total;
-        const uint32_t c_first = ((ut0 + 1u) * G - 1u) / total, c_last = ((ut0 + (uint32_t)sk.kb) * G - 1u) / total;
+        uint32_t c_first, c_last;
+        sk_tile_ctas(sk, tile, c_first, c_last);
         float acc = 0.f;
         for (uint32_t c = c_first; c <= c_last; ++c) acc += sk.ws[((size_t)(c + tile) * sk.rows + row) * sk.bn + cc];
         out[(size_t)row * N + col] = acc;
@@ -176,10 +176,10 @@ int oa_host_streamk_plan(int32_t N, int32_t K, int32_t block_n, int32_t n_ctas, 
     const StreamK sk = make_streamk(nullptr, N, K, block_n, n_ctas);
     if (sk.G > cap_ctas || sk.n_tiles > cap_tiles) return OA_ERR_BAD_REQUEST;
     for (int c = 0; c <= sk.G; ++c) cta_unit0_out[c] = (long long)c * sk.total / sk.G;            // the kernels' u0/u1
-    for (int t = 0; t < sk.n_tiles; ++t) {                                                        // sk_sum8's closed form (32-bit, as on the device)
-        const uint32_t ut0 = (uint32_t)t * (uint32_t)sk.kb, G = (uint32_t)sk.G, total = (uint32_t)sk.total;
-        tile_first_out[t] = (int32_t)(((ut0 + 1u) * G - 1u) / total);
-        tile_last_out[t] = (int32_t)(((ut0 + (uint32_t)sk.kb) * G - 1u) / total);
+    for (int t = 0; t < sk.n_tiles; ++t) {                                                        // the very function the kernels call
+        uint32_t cf, cl;
+        sk_tile_ctas(sk, (uint32_t)t, cf, cl);
+        tile_first_out[t] = (int32_t)cf; tile_last_out[t] = (int32_t)cl;
     }
     *n_ctas_out = sk.G; *n_tiles_out = sk.n_tiles; *kb_out = sk.kb;
     return OA_OK;

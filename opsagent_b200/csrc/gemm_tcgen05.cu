@@ -612,9 +612,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, OCC) gemm_streamk_kernel(const _
                 // HEAD of their CTAs' ranges), adds the published pieces to its accumulator in CTA order — the stand-alone
                 // consumer's order, so results are bit-identical — and writes silu(gate)*up.  Private piece layout: [col][row],
                 // so that publisher stores and finisher loads are one full 128-byte line per warp instruction.
-                const uint32_t ut0 = (uint32_t)tile * (uint32_t)sk.kb;
-                const int c_first = (int)(((ut0 + 1u) * (uint32_t)sk.G - 1u) / (uint32_t)sk.total);
-                const int c_last = (int)(((ut0 + (uint32_t)sk.kb) * (uint32_t)sk.G - 1u) / (uint32_t)sk.total);
+                uint32_t cf, cl;
+                sk_tile_ctas(sk, (uint32_t)tile, cf, cl);
+                const int c_first = (int)cf, c_last = (int)cl;
                 const int row = q * 32 + lane;
                 unsigned int* flag = fz.tile_flags + tile;
                 if ((int)c == c_first) {
@@ -920,9 +920,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) gemm_sk_chain_kernel(const _
                     const long long uend = min(u1, (long long)(tile + 1) * sk.kb);
                     const int as = seg & 1;
                     // CTAs c_first..c_last hold pieces of this tile (same arithmetic as sk_sum8)
-                    const uint32_t ut0 = (uint32_t)tile * (uint32_t)sk.kb;
-                    const int c_first = (int)(((ut0 + 1u) * (uint32_t)sk.G - 1u) / (uint32_t)sk.total);
-                    const int c_last = (int)(((ut0 + (uint32_t)sk.kb) * (uint32_t)sk.G - 1u) / (uint32_t)sk.total);
+                    uint32_t cf, cl;
+                    sk_tile_ctas(sk, (uint32_t)tile, cf, cl);
+                    const int c_first = (int)cf, c_last = (int)cl;
                     const bool finish = fused && c == c_first;
                     unsigned int* flag = ch.tile_flags + p * SK_CHAIN_MAX_TILES + tile;
                     mbar_wait(&acc_full[as], ((uint32_t)seg >> 1) & 1);

@@ -44,6 +44,17 @@ struct StreamK {
     int l2_prefetch_units;                                    // weight tiles each CTA prefetches into L2 before griddepcontrol.wait
 };
 StreamK make_streamk(float* ws, int N, int K, int bn, int G, int rows = 128);
+// CTA c owns units [c*total/G, (c+1)*total/G), so unit u lives in CTA floor(((u+1)*G - 1) / total): the CTAs holding the first and the
+// last k-block of `tile`.  One definition for the kernels, the consumers and the host plan (32-bit products: host-checked per model).
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline void sk_tile_ctas(const StreamK& sk, uint32_t tile, uint32_t& c_first, uint32_t& c_last) {
+    const uint32_t ut0 = tile * (uint32_t)sk.kb, G = (uint32_t)sk.G, total = (uint32_t)sk.total;
+    c_first = ((ut0 + 1u) * G - 1u) / total;
+    c_last = ((ut0 + (uint32_t)sk.kb) * G - 1u) / total;
+}
+
 size_t streamk_ws_bytes(int N, int bn, int G, int rows = 128);
 cudaError_t launch_gemm_streamk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, cudaStream_t stream);
 // gate/up projection with the SwiGLU finished inside the GEMM (BN=128, one row tile): act[M,F] = silu(gate)*up, bit-identical to

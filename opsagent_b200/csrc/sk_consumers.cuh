@@ -9,12 +9,11 @@ namespace oa {
 
 OA_DEVINL void named_bar_sync(int id, int n_threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory"); }
 
-// CTAs c_first..c_last own pieces of `tile`; CTA c covers units [c*total/G, (c+1)*total/G), so the CTA holding
-// unit u is floor(((u+1)*G - 1) / total).  All products fit in 32 bits for the decode shapes (host-checked).
+// CTAs c_first..c_last own pieces of `tile` (sk_tile_ctas, kernels.hpp); their partials are added in that order.
 OA_DEVINL void sk_sum8(const StreamK& sk, int row, int col, float (&acc)[8]) {
     const uint32_t tile = (uint32_t)col / (uint32_t)sk.bn, cc = (uint32_t)col - tile * (uint32_t)sk.bn;
-    const uint32_t ut0 = tile * (uint32_t)sk.kb, G = (uint32_t)sk.G, total = (uint32_t)sk.total;
-    const uint32_t c_first = ((ut0 + 1u) * G - 1u) / total, c_last = ((ut0 + (uint32_t)sk.kb) * G - 1u) / total;
+    uint32_t c_first, c_last;
+    sk_tile_ctas(sk, tile, c_first, c_last);
     const int n = (int)(c_last - c_first) + 1;
     const size_t slot_stride = (size_t)sk.rows * sk.bn;
     const float* p = sk.ws + ((size_t)(c_first + tile) * sk.rows + row) * sk.bn + cc;
@@ -46,8 +45,8 @@ OA_DEVINL void sk_sum8_pair(const StreamK& sk, int row, int col_a, int col_b, fl
     const uint32_t tile = (uint32_t)col_a / (uint32_t)sk.bn;
     if ((uint32_t)col_b / (uint32_t)sk.bn != tile) { sk_sum8(sk, row, col_a, acc_a); sk_sum8(sk, row, col_b, acc_b); return; }
     const uint32_t ca = (uint32_t)col_a - tile * (uint32_t)sk.bn, cb = (uint32_t)col_b - tile * (uint32_t)sk.bn;
-    const uint32_t ut0 = tile * (uint32_t)sk.kb, G = (uint32_t)sk.G, total = (uint32_t)sk.total;
-    const uint32_t c_first = ((ut0 + 1u) * G - 1u) / total, c_last = ((ut0 + (uint32_t)sk.kb) * G - 1u) / total;
+    uint32_t c_first, c_last;
+    sk_tile_ctas(sk, tile, c_first, c_last);
     const int n = (int)(c_last - c_first) + 1;
     const size_t slot_stride = (size_t)sk.rows * sk.bn;
     const float* p = sk.ws + ((size_t)(c_first + tile) * sk.rows + row) * sk.bn;
