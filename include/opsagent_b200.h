@@ -141,6 +141,12 @@ OA_API int oa_host_decode_plan(const int32_t* ctx_lens, int32_t n_seqs, int32_t 
 OA_API int oa_host_streamk_plan(int32_t N, int32_t K, int32_t block_n, int32_t n_ctas, int64_t* cta_unit0_out, int32_t cap_ctas,
                          int32_t* tile_first_out, int32_t* tile_last_out, int32_t cap_tiles, int32_t* n_ctas_out, int32_t* n_tiles_out,
                          int32_t* kb_out);
+/* byte-level BPE tokenizer read from a Hugging Face tokenizer.json (Llama-3 / Qwen2.5 format), host only: what the engine uses
+ * for text when its config names one ("tokenizer": path) instead of the synthetic byte-level vocabulary.  Loaded files are cached
+ * by path.  encode: *n_out = number of ids (written up to cap; OA_ERR_BAD_REQUEST if cap is too small or the file is unsupported);
+ * decode: bytes of the ids (control tokens render as their literal content). */
+OA_API int oa_host_bpe_encode(const char* tokenizer_json_path, const char* text, int32_t text_len, int32_t* ids_out, int32_t cap, int32_t* n_out);
+OA_API int oa_host_bpe_decode(const char* tokenizer_json_path, const int32_t* ids, int32_t n_ids, char* buf, int32_t cap, int32_t* n_out);
 /* grammar automaton, host only: feeds `prefix` (n bytes) to the schema `kind` (1 tool call, 2 final) and returns the allowed-byte
  * bitset for the next position in mask_out[8], *done_out = 1 when the JSON is complete; 400 if the prefix is not derivable */
 OA_API int oa_host_grammar_step(int32_t kind, const uint8_t* prefix, int32_t n, uint32_t* mask_out, int32_t* done_out);

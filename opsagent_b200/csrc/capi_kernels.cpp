@@ -144,7 +144,7 @@ int oa_k_paged_attention(const void* q, void* out, const void* kv_cache, int32_t
 int oa_host_apply_chat_template(const char* config_json, const oa_msg* msgs, int32_t n_msgs, int32_t* out_ids, int32_t cap, int32_t* n_out) {
     try {
         ModelConfig mc; EngineOptions eo; parse_config(config_json ? config_json : "{}", mc, eo);
-        Tokenizer tok(mc);
+        Tokenizer tok(mc, eo.tokenizer);
         std::vector<ChatMessage> m;
         for (int i = 0; i < n_msgs; ++i) m.push_back(ChatMessage{msgs[i].role, msgs[i].content});
         auto ids = tok.apply_chat_template(m);

@@ -51,7 +51,7 @@ struct Seq {
 
 class Engine {
 public:
-    Engine(const ModelConfig& mc, const EngineOptions& eo) : model_(mc, eo), tok_(mc), opt_(eo) {
+    Engine(const ModelConfig& mc, const EngineOptions& eo) : model_(mc, eo), tok_(mc, eo.tokenizer), opt_(eo) {
         free_pages_.reserve(model_.num_pages);
         for (int p = model_.num_pages - 1; p >= 0; --p) free_pages_.push_back(p);
         page_ref_.assign(model_.num_pages, 0); page_hash_.assign(model_.num_pages, 0); page_parent_.assign(model_.num_pages, 0);
@@ -82,6 +82,8 @@ public:
         if ((int)prompt.size() + 1 > opt_.max_seq_len)
             return fail(OA_ERR_BAD_REQUEST, "prompt of " + std::to_string(prompt.size()) + " tokens exceeds max_seq_len " + std::to_string(opt_.max_seq_len));
         for (int32_t t : prompt) if (t < 0 || t >= model_.cfg.vocab) return fail(OA_ERR_BAD_REQUEST, "token id out of range");
+        if ((flags & (OA_FLAG_JSON_TOOLCALL | OA_FLAG_JSON_FINAL | OA_FLAG_JSON_FUNCTION | OA_FLAG_JSON_TEXT)) && !tok_.byte_level())
+            return fail(OA_ERR_BAD_REQUEST, "schema-constrained decoding masks byte tokens 0..255: not available with a BPE tokenizer (config \"tokenizer\")");
         auto s = std::make_shared<Seq>();
         s->n_prompt = (int)prompt.size(); s->tokens = std::move(prompt);
         s->max_new = std::min(max_new, opt_.max_seq_len - s->n_prompt); s->flags = flags;
@@ -675,6 +677,37 @@ int oa_debug_kernel_times(oa_engine* h, char* buf, size_t n, int32_t reset) {
     s += "}";
     return copy_out(s, buf, n);
 }
+static std::shared_ptr<BpeTokenizer> cached_bpe(const char* path) {
+    static std::mutex mu; static std::map<std::string, std::shared_ptr<BpeTokenizer>> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(path);
+    if (it != cache.end()) return it->second;
+    auto t = BpeTokenizer::load(path);
+    cache[path] = t;
+    return t;
+}
+int oa_host_bpe_encode(const char* tokenizer_json_path, const char* text, int32_t text_len, int32_t* ids_out, int32_t cap, int32_t* n_out) {
+    if (!tokenizer_json_path || (!text && text_len > 0) || text_len < 0 || !n_out) return fail(OA_ERR_BAD_REQUEST, "null argument");
+    try {
+        std::vector<int32_t> ids;
+        cached_bpe(tokenizer_json_path)->encode(std::string(text ? text : "", (size_t)text_len), ids);
+        *n_out = (int32_t)ids.size();
+        if ((int32_t)ids.size() > cap) return fail(OA_ERR_BAD_REQUEST, "ids buffer too small");
+        if (!ids.empty()) std::memcpy(ids_out, ids.data(), ids.size() * 4);
+    } catch (const std::exception& e) { return fail(OA_ERR_BAD_REQUEST, e.what()); }
+    return OA_OK;
+}
+int oa_host_bpe_decode(const char* tokenizer_json_path, const int32_t* ids, int32_t n_ids, char* buf, int32_t cap, int32_t* n_out) {
+    if (!tokenizer_json_path || (!ids && n_ids > 0) || n_ids < 0 || !n_out) return fail(OA_ERR_BAD_REQUEST, "null argument");
+    try {
+        const std::string s = cached_bpe(tokenizer_json_path)->decode(ids, (size_t)n_ids);
+        *n_out = (int32_t)s.size();
+        if ((int32_t)s.size() > cap) return fail(OA_ERR_BAD_REQUEST, "text buffer too small");
+        if (!s.empty()) std::memcpy(buf, s.data(), s.size());
+    } catch (const std::exception& e) { return fail(OA_ERR_BAD_REQUEST, e.what()); }
+    return OA_OK;
+}
+
 int oa_engine_serve(oa_engine* h) { if (!h) return fail(OA_ERR_BAD_REQUEST, "null engine"); return h->e->serve(); }
 uint64_t oa_kernel_launches(void) { return launches_total(); }
 const char* oa_version(void) { return "opsagent_b200 0.1 (sm_100a)"; }

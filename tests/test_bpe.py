@@ -1,0 +1,89 @@
+"""The C++ byte-level BPE tokenizer (opsagent_b200/csrc/bpe.hpp) against the Hugging Face `tokenizers` library itself:
+tests/golden/gen_golden_bpe.py trained two small tokenizers in exactly the Llama-3 and Qwen2.5 tokenizer.json configuration and
+recorded that library's encodings of the probe strings (contractions, digit grouping 1-3 vs 1, CJK / Greek / Cyrillic / Arabic,
+emoji, whitespace runs with and without newlines, CRLF, JSON, YAML, empty input).  Bit-exact ids; decode round-trips."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from opsagent_b200 import _lib
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = json.load(open(os.path.join(GOLDEN, "bpe_cases.json")))
+
+
+def encode(L, path, text):
+    raw = text.encode("utf-8")
+    out = np.zeros(max(16, 4 * len(raw) + 16), np.int32); n = C.c_int32()
+    rc = L.oa_host_bpe_encode(path.encode(), raw, len(raw), out.ctypes.data, len(out), C.byref(n))
+    assert rc == 0, _lib.last_error()
+    return out[: n.value].tolist()
+
+
+def decode(L, path, ids):
+    arr = np.asarray(ids, np.int32); buf = C.create_string_buffer(max(16, 64 * len(ids) + 16)); n = C.c_int32()
+    rc = L.oa_host_bpe_decode(path.encode(), arr.ctypes.data, len(arr), buf, len(buf), C.byref(n))
+    assert rc == 0, _lib.last_error()
+    return buf.raw[: n.value]
+
+
+@pytest.mark.parametrize("name", ["llama3", "qwen2"])
+def test_encode_matches_the_tokenizers_library_bit_for_bit(name):
+    L = _lib.load()
+    path = os.path.join(GOLDEN, f"bpe_{name}_tiny.json")
+    for case in CASES[name]:
+        got = encode(L, path, case["text"])
+        assert got == case["ids"], (case["text"], got, case["ids"])
+        assert decode(L, path, got) == case["text"].encode("utf-8")
+
+
+def test_against_the_live_library_on_random_text():
+    """beyond the committed probes: seeded random mixtures of scripts, digits, punctuation and whitespace, compared with the
+    `tokenizers` library loaded here (skipped where it is not installed)"""
+    tokenizers = pytest.importorskip("tokenizers")
+    import random
+    L = _lib.load()
+    alphabet = (list("abcXYZ'stTreveLLdm ") + list("0123456789") + list("  \t\n\r") + list("!?.,;:{}[]()\"#$%&*+-/<=>@\\^_`|~") +
+                list("集群命名空间节点") + list("éüïßñ") + list("λμπ") + list("жщю") + list("مرحب") + ["🙂", "→", "½", "①", " ", "　", " ", "ſ"])
+    for name in ("llama3", "qwen2"):
+        path = os.path.join(GOLDEN, f"bpe_{name}_tiny.json")
+        ref = tokenizers.Tokenizer.from_file(path)
+        r = random.Random(1234)
+        for _ in range(300):
+            text = "".join(r.choice(alphabet) for _ in range(r.randrange(0, 60)))
+            assert encode(L, path, text) == ref.encode(text, add_special_tokens=False).ids, repr(text)
+
+
+def test_control_tokens_and_error_paths(tmp_path):
+    L = _lib.load()
+    path = os.path.join(GOLDEN, "bpe_llama3_tiny.json")
+    ids = [CASES["llama3_specials"]["<|begin_of_text|>"]] + encode(L, path, "hi") + [CASES["llama3_specials"]["<|eot_id|>"]]
+    assert decode(L, path, ids) == b"<|begin_of_text|>hi<|eot_id|>"
+    assert CASES["llama3_specials"]["<|eot_id|>"] not in encode(L, path, "<|eot_id|>")          # control tokens are never produced from text
+    n = C.c_int32()
+    assert L.oa_host_bpe_encode(str(tmp_path / "missing.json").encode(), b"x", 1, None, 0, C.byref(n)) == 400 and "not found" in _lib.last_error()
+    bad = json.load(open(path)); bad["pre_tokenizer"]["pretokenizers"][0]["pattern"]["Regex"] = r"\w+|\s+"
+    (tmp_path / "bad.json").write_text(json.dumps(bad))
+    assert L.oa_host_bpe_encode(str(tmp_path / "bad.json").encode(), b"x", 1, None, 0, C.byref(n)) == 400 and "unsupported split pattern" in _lib.last_error()
+    out = np.zeros(1, np.int32)
+    assert L.oa_host_bpe_encode(path.encode(), b"hello world", 11, out.ctypes.data, 1, C.byref(n)) == 400 and n.value > 1      # size query
+
+
+def test_chat_template_uses_the_bpe_vocabulary_when_configured():
+    L = _lib.load()
+    path = os.path.join(GOLDEN, "bpe_llama3_tiny.json")
+    sp = CASES["llama3_specials"]
+    cfg = json.dumps({"model": "custom", "hidden": 64, "n_layers": 1, "n_heads": 2, "n_kv_heads": 1, "head_dim": 64, "ffn": 128, "vocab": 704,
+                      "template": "llama3", "tokenizer": path}).encode()
+    msgs = (_lib.OaMsg * 2)(); msgs[0].role = b"system"; msgs[0].content = b"you are a kubectl expert"; msgs[1].role = b"user"; msgs[1].content = "集群 has 5 namespaces".encode()
+    out = np.zeros(512, np.int32); n = C.c_int32()
+    assert L.oa_host_apply_chat_template(cfg, msgs, 2, out.ctypes.data, len(out), C.byref(n)) == 0, _lib.last_error()
+    ids = out[: n.value].tolist()
+    expect = [sp["<|begin_of_text|>"]]
+    for role, content in (("system", "you are a kubectl expert"), ("user", "集群 has 5 namespaces")):
+        expect += [sp["<|start_header_id|>"]] + encode(L, path, role) + [sp["<|end_header_id|>"]] + encode(L, path, "\n\n") + encode(L, path, content) + [sp["<|eot_id|>"]]
+    expect += [sp["<|start_header_id|>"]] + encode(L, path, "assistant") + [sp["<|end_header_id|>"]] + encode(L, path, "\n\n")
+    assert ids == expect
