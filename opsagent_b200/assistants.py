@@ -79,10 +79,13 @@ def _assistant_loop(perf, model, prompts, maxTokens, maxIterations, client, tool
         raise ValueError("prompts cannot be empty")                                          # simple.go:312
     resp = _timed_chat(perf, "assistant_first_chat", client, model, maxTokens, chatHistory)  # simple.go:341-346
     chatHistory.append(ChatCompletionMessage(ChatMessageRoleAssistant, resp))
+    perf.StartTimer("assistant_parse_tool_prompt")                                           # simple.go:364-385
     try:
         tp = ToolPrompt.unmarshal(resp)
     except Exception:
         return resp, chatHistory                                                             # not JSON: assume final answer
+    finally:
+        perf.StopTimer("assistant_parse_tool_prompt")
     iterations = 0
     if maxIterations <= 0:
         maxIterations = defaultMaxIterations
@@ -104,13 +107,18 @@ def _assistant_loop(perf, model, prompts, maxTokens, maxIterations, client, tool
                     perf.StopTimer("assistant_tool_" + tp.action["name"])
             else:
                 observation = f"Tool {tp.action['name']} is not available. Considering switch to other supported tools."
+            perf.StartTimer("assistant_construct_message")                                   # simple.go:491-507
             tp.observation = ConstrictPrompt(observation, model, 1024, count_tokens)
             chatHistory.append(ChatCompletionMessage(ChatMessageRoleUser, tp.marshal()))
+            perf.StopTimer("assistant_construct_message")
             resp = _timed_chat(perf, "assistant_intermediate_chat", client, model, maxTokens, chatHistory)   # simple.go:513-518
             chatHistory.append(ChatCompletionMessage(ChatMessageRoleAssistant, resp))
+            perf.StartTimer("assistant_parse_intermediate")                                  # simple.go:541-603
             try:
                 tp = ToolPrompt.unmarshal(resp)
+                perf.StopTimer("assistant_parse_intermediate")
             except Exception:
+                perf.StopTimer("assistant_parse_intermediate")
                 chatHistory.append(ChatCompletionMessage(ChatMessageRoleUser,
                                                          "Summarize all the chat history and respond to original question with final answer"))
                 resp = _timed_chat(perf, "assistant_summarize", client, model, maxTokens, chatHistory)        # simple.go:564-569

@@ -419,7 +419,8 @@ def test_assistant_loop_records_the_reference_operation_names():
                                  ScriptedClient([step, final]), {"kubectl": lambda s: "default\nkube-system"})
     assert res == "there are 5 namespaces"
     cc = GetPerfStats().GetStats()["callCounts"]
-    assert cc == {"assistant_first_chat": 1, "assistant_tool_kubectl": 1, "assistant_intermediate_chat": 1, "assistant_total": 1}   # simple.go:296,341,440,513
+    assert cc == {"assistant_first_chat": 1, "assistant_parse_tool_prompt": 1, "assistant_tool_kubectl": 1, "assistant_construct_message": 1,
+                  "assistant_intermediate_chat": 1, "assistant_parse_intermediate": 1, "assistant_total": 1}   # simple.go:296,341,364,440,491,513,541
 
 
 def test_http_front_serves_the_perf_stats_endpoints():
