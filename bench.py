@@ -131,8 +131,8 @@ def run_ours(args, rank, world, local_rank):
     # ------------------------------------------------------------------ value: device-resident decode steps
     # context chosen so that the mean over the K timed steps is MEAN_CTX (=P+G/2)
     ctx0 = max(64, MEAN_CTX - W - K // 2)
-    # ONE sampler for the whole job (rank 0, all N GPUs): NVML queries take driver-wide locks, and N polling processes
-    # put measurable gaps between kernel launches of every rank (N=4: 0.5 ms per 8.5 ms step)
+    # ONE sampler for the whole job (rank 0, all N GPUs): NVML queries take driver-wide locks; N polling processes are the
+    # suspected source of the host gaps seen at N=4 (0.5 ms per 8.5 ms step against 0.02 ms at N=1) and one is enough anyway
     clocks = ClockSampler(",".join(str(i) for i in range(world)), 200 if world == 1 else 500) if rank == 0 else None
     if clocks:
         clocks.start()
