@@ -2,6 +2,7 @@
 //   pre-tokenizer  Sequence[ Split(Regex(<pattern>), Isolated), ByteLevel(add_prefix_space=false, use_regex=false) ]
 //   model          BPE { vocab: {token: id}, merges: [[a, b] | "a b", ...], ignore_merges }
 //   added_tokens   control tokens (looked up by content; never produced from text)
+//   normalizer     null or NFC (already-NFC text passes, anything else is refused: see from_json)
 // Host only (no CUDA).  The two published split patterns are recognised by text and matched by a hand-written scanner with the
 // regex engine's semantics (leftmost alternative first, greedy with backtracking, Unicode \p{L} \p{N} \s); anything else is
 // rejected loudly.  Pinned against the `tokenizers` library itself: tests/golden/gen_golden_bpe.py trains two tokenizers in exactly
@@ -39,6 +40,7 @@ inline bool is_S(uint32_t cp) {      // Unicode White_Space
            cp == 0x2029 || cp == 0x202F || cp == 0x205F || cp == 0x3000;
 }
 inline bool is_NL(uint32_t cp) { return cp == '\r' || cp == '\n'; }
+inline bool nfc_unsafe(uint32_t cp) { return cp >= 0x300 && in_ranges(kUnicodeNfcUnsafe, sizeof(kUnicodeNfcUnsafe) / sizeof(kUnicodeNfcUnsafe[0]), cp); }
 
 inline void utf8_append(std::string& o, uint32_t cp) {
     if (cp < 0x80) o += (char)cp;
@@ -160,6 +162,13 @@ public:
         const JVal* type = model->get("type");
         if (type && type->kind == JVal::Str && type->str != "BPE") throw std::runtime_error("tokenizer.json: model type '" + type->str + "' is not BPE");
         if (const JVal* ig = model->get("ignore_merges")) t->ignore_merges_ = ig->kind == JVal::Bool && ig->b;
+        // ---- normaliser: none (Llama-3) or NFC (Qwen2.5).  NFC itself is not implemented: text that is already NFC — no code point that
+        // can decompose, reorder or compose (table from tools/gen_unicode_tables.py) — passes unchanged, anything else is refused ----
+        if (const JVal* nz = root.get("normalizer")) if (nz->kind == JVal::Obj) {
+            const JVal* ty = nz->get("type");
+            if (ty && ty->kind == JVal::Str && ty->str == "NFC") t->nfc_ = true;
+            else throw std::runtime_error("tokenizer.json: unsupported normalizer" + (ty && ty->kind == JVal::Str ? " '" + ty->str + "'" : std::string()));
+        }
         // ---- split pattern ----
         std::string pattern; bool byte_level = false;
         std::vector<const JVal*> pts;
@@ -252,6 +261,7 @@ public:
         using namespace bpe_detail;
         std::vector<uint32_t> cp, off; utf8_decode(text, cp, off);
         const size_t n = cp.size();
+        if (nfc_) for (uint32_t c : cp) if (nfc_unsafe(c)) throw std::runtime_error("text is not in Unicode NFC (this tokenizer normalises to NFC; normalisation is not implemented)");
         size_t i = 0;
         std::vector<int32_t> word;
         while (i < n) {
@@ -330,7 +340,7 @@ private:
         out.insert(out.end(), word.begin(), word.end());
     }
 
-    int digits_ = 3; bool ignore_merges_ = false;
+    int digits_ = 3; bool ignore_merges_ = false, nfc_ = false;
     std::unordered_map<std::string, int> vocab_;                              // raw bytes -> id
     std::unordered_map<uint64_t, std::pair<int, int>> merge_;                 // (id_a, id_b) -> (rank, merged id)
     std::unordered_map<std::string, int> special_;

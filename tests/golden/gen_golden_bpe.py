@@ -6,7 +6,7 @@ import json
 import os
 import random
 
-from tokenizers import Regex, Tokenizer, decoders, models, pre_tokenizers, trainers
+from tokenizers import Regex, Tokenizer, decoders, models, normalizers, pre_tokenizers, trainers
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LLAMA3 = r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+"
@@ -36,8 +36,10 @@ def corpus(seed=7, n=600):
     return out
 
 
-def build(pattern, ignore_merges, specials, vocab_size):
+def build(pattern, ignore_merges, specials, vocab_size, nfc=False):
     tok = Tokenizer(models.BPE(ignore_merges=ignore_merges))
+    if nfc:
+        tok.normalizer = normalizers.NFC()          # as in Qwen2.5's tokenizer.json
     tok.pre_tokenizer = pre_tokenizers.Sequence([pre_tokenizers.Split(Regex(pattern), behavior="isolated", invert=False),
                                                  pre_tokenizers.ByteLevel(add_prefix_space=False, use_regex=False)])
     tok.decoder = decoders.ByteLevel()
@@ -60,7 +62,7 @@ if __name__ == "__main__":
     q2_specials = ["<|endoftext|>", "<|im_start|>", "<|im_end|>"]
     cases = {}
     for name, pattern, ign, sp in (("llama3", LLAMA3, True, l3_specials), ("qwen2", QWEN2, False, q2_specials)):
-        tok = build(pattern, ign, sp, 700)
+        tok = build(pattern, ign, sp, 700, nfc=(name == "qwen2"))
         path = os.path.join(HERE, f"bpe_{name}_tiny.json")
         tok.save(path)
         cases[name] = [{"text": t, "ids": tok.encode(t, add_special_tokens=False).ids} for t in PROBES]

@@ -87,3 +87,38 @@ def test_chat_template_uses_the_bpe_vocabulary_when_configured():
         expect += [sp["<|start_header_id|>"]] + encode(L, path, role) + [sp["<|end_header_id|>"]] + encode(L, path, "\n\n") + encode(L, path, content) + [sp["<|eot_id|>"]]
     expect += [sp["<|start_header_id|>"]] + encode(L, path, "assistant") + [sp["<|end_header_id|>"]] + encode(L, path, "\n\n")
     assert ids == expect
+
+
+def test_nfc_normaliser_is_exact_or_refused():
+    """Qwen2.5's tokenizer.json normalises to NFC.  The C++ side does not implement normalisation: text that is already NFC passes
+    (and must encode exactly as the library does), anything that could change under NFC is refused with 400 — never silently wrong."""
+    tokenizers = pytest.importorskip("tokenizers")
+    import random
+    import unicodedata
+    L = _lib.load()
+    qwen = os.path.join(GOLDEN, "bpe_qwen2_tiny.json"); llama = os.path.join(GOLDEN, "bpe_llama3_tiny.json")
+    ref_q = tokenizers.Tokenizer.from_file(qwen); ref_l = tokenizers.Tokenizer.from_file(llama)
+
+    def try_encode(path, text):
+        raw = text.encode("utf-8"); out = np.zeros(4 * len(raw) + 16, np.int32); n = C.c_int32()
+        rc = L.oa_host_bpe_encode(path.encode(), raw, len(raw), out.ctypes.data, len(out), C.byref(n))
+        return (out[: n.value].tolist() if rc == 0 else None), rc
+
+    ids, rc = try_encode(qwen, "café")                       # e + combining acute: NFC would compose it
+    assert ids is None and rc == 400 and "NFC" in _lib.last_error()
+    assert try_encode(qwen, "café")[0] == ref_q.encode("café", add_special_tokens=False).ids
+    assert try_encode(llama, "café")[0] == ref_l.encode("café", add_special_tokens=False).ids       # Llama-3: no normaliser
+    pool = list("ab 1.\n") + ["é", "́", "̧", "ᄀ", "ᅡ", "ᆨ", "가", "Å", "क़", "া", "̈́", "中", "\U0001f642", "Ω", "̀"]
+    r = random.Random(5)
+    n_ref = n_ok = 0
+    for _ in range(3000):
+        text = "".join(r.choice(pool) for _ in range(r.randrange(1, 10)))
+        ids, rc = try_encode(qwen, text)
+        if ids is None:
+            n_ref += 1
+            assert rc == 400
+        else:
+            n_ok += 1
+            assert unicodedata.is_normalized("NFC", text), repr(text)                 # accepted => really was NFC
+            assert ids == ref_q.encode(text, add_special_tokens=False).ids, repr(text)
+    assert n_ref > 100 and n_ok > 100
