@@ -600,6 +600,13 @@ int oa_engine_create(const char* config_json, oa_engine** out) {
 }
 void oa_engine_destroy(oa_engine* h) { delete h; }
 
+// chat template -> ids; a BPE tokenizer may refuse text (e.g. not NFC): that is the caller's bad request, never an exception across the C ABI
+static int template_ids(oa_engine* h, const std::vector<ChatMessage>& msgs, std::vector<int32_t>& ids) {
+    try { ids = h->e->tokenizer().apply_chat_template(msgs); }
+    catch (const std::exception& ex) { return fail(OA_ERR_BAD_REQUEST, ex.what()); }
+    return OA_OK;
+}
+
 static int submit_chat(oa_engine* h, const oa_chat_req* r, uint64_t* ticket) {
     if (!h || !r || !ticket) return fail(OA_ERR_BAD_REQUEST, "null argument");
     if (r->model && r->model[0] && h->e->config().name != r->model) return fail(OA_ERR_BAD_REQUEST, std::string("model '") + r->model + "' is not loaded (engine serves '" + h->e->config().name + "')");
@@ -613,7 +620,9 @@ static int submit_chat(oa_engine* h, const oa_chat_req* r, uint64_t* ticket) {
         int turns = 0; for (auto& m : msgs) if (m.role == "assistant") ++turns;
         flags |= (turns < h->e->options().react_tool_steps) ? OA_FLAG_JSON_TOOLCALL : OA_FLAG_JSON_FINAL;
     }
-    return h->e->submit_tokens(h->e->tokenizer().apply_chat_template(msgs), r->max_tokens, flags, ticket, r->functions);
+    std::vector<int32_t> ids;
+    rc = template_ids(h, msgs, ids); if (rc) return rc;
+    return h->e->submit_tokens(std::move(ids), r->max_tokens, flags, ticket, r->functions);
 }
 int oa_chat_submit(oa_engine* h, const oa_chat_req* r, uint64_t* ticket) { return submit_chat(h, r, ticket); }
 int oa_chat_wait(oa_engine* h, uint64_t ticket, int32_t timeout_ms, oa_chat_resp* out) {
@@ -634,13 +643,16 @@ int oa_tokens_submit(oa_engine* h, const int32_t* prompt, int32_t n, int32_t max
 int oa_count_tokens(oa_engine* h, const oa_msg* msgs, int32_t n, int32_t* out_tokens) {
     if (!h || !out_tokens) return fail(OA_ERR_BAD_REQUEST, "null argument");
     std::vector<ChatMessage> m; int rc = build_messages(msgs, n, m); if (rc) return rc;
-    *out_tokens = (int32_t)h->e->tokenizer().apply_chat_template(m).size();
+    std::vector<int32_t> ids;
+    rc = template_ids(h, m, ids); if (rc) return rc;
+    *out_tokens = (int32_t)ids.size();
     return OA_OK;
 }
 int oa_apply_chat_template(oa_engine* h, const oa_msg* msgs, int32_t n, int32_t* out_ids, int32_t cap, int32_t* n_out) {
     if (!h || !n_out) return fail(OA_ERR_BAD_REQUEST, "null argument");
     std::vector<ChatMessage> m; int rc = build_messages(msgs, n, m); if (rc) return rc;
-    auto ids = h->e->tokenizer().apply_chat_template(m);
+    std::vector<int32_t> ids;
+    rc = template_ids(h, m, ids); if (rc) return rc;
     *n_out = (int32_t)ids.size();
     if (out_ids) std::memcpy(out_ids, ids.data(), (size_t)std::min<int32_t>(cap, (int32_t)ids.size()) * 4);
     return OA_OK;
