@@ -122,3 +122,24 @@ def test_nfc_normaliser_is_exact_or_refused():
             assert unicodedata.is_normalized("NFC", text), repr(text)                 # accepted => really was NFC
             assert ids == ref_q.encode(text, add_special_tokens=False).ids, repr(text)
     assert n_ref > 100 and n_ok > 100
+
+
+def test_legacy_merge_strings_and_rejections(tmp_path):
+    """older tokenizer.json files write merges as "a b" strings; unsupported files are refused with a reason, not mis-tokenised"""
+    L = _lib.load()
+    src = json.load(open(os.path.join(GOLDEN, "bpe_llama3_tiny.json")))
+    legacy = json.loads(json.dumps(src)); legacy["model"]["merges"] = [" ".join(m) for m in src["model"]["merges"]]
+    (tmp_path / "legacy.json").write_text(json.dumps(legacy, ensure_ascii=True))      # \\uXXXX escapes exercise the JSON reader too
+    for case in CASES["llama3"]:
+        assert encode(L, str(tmp_path / "legacy.json"), case["text"]) == case["ids"]
+    n = C.c_int32()
+    for name, mutate, needle in (
+            ("wordpiece.json", lambda j: j["model"].__setitem__("type", "WordPiece"), "not BPE"),
+            ("nobytelevel.json", lambda j: j["pre_tokenizer"].__setitem__("pretokenizers", j["pre_tokenizer"]["pretokenizers"][:1]), "byte-level"),
+            ("nfkc.json", lambda j: j.__setitem__("normalizer", {"type": "NFKC"}), "unsupported normalizer"),
+            ("prefixspace.json", lambda j: j["pre_tokenizer"]["pretokenizers"][1].__setitem__("add_prefix_space", True), "not supported")):
+        j = json.loads(json.dumps(src)); mutate(j)
+        (tmp_path / name).write_text(json.dumps(j))
+        assert L.oa_host_bpe_encode(str(tmp_path / name).encode(), b"x", 1, None, 0, C.byref(n)) == 400 and needle in _lib.last_error(), (name, _lib.last_error())
+    (tmp_path / "broken.json").write_text("{\"model\": ")
+    assert L.oa_host_bpe_encode(str(tmp_path / "broken.json").encode(), b"x", 1, None, 0, C.byref(n)) == 400 and "tokenizer.json" in _lib.last_error()
