@@ -140,6 +140,9 @@ PRESETS = {
     "tiny-llama": ModelSpec("tiny-llama", 256, 2, 4, 2, 64, 512, 2304, norm_random=1),
     "tiny-llama-d128": ModelSpec("tiny-llama-d128", 512, 3, 4, 1, 128, 1024, 1024, norm_random=1, rope_scaling=1,
                                  tie_embeddings=1),
+    # GQA group 8 (what one rank of Llama-3-70B TP=8 runs: 8 query heads on 1 kv head) and group 1 (MHA)
+    "tiny-llama-g8": ModelSpec("tiny-llama-g8", 512, 2, 8, 1, 64, 512, 1024, norm_random=1),
+    "tiny-llama-mha": ModelSpec("tiny-llama-mha", 256, 2, 4, 4, 64, 512, 1024, norm_random=1),
     # tensor-parallel-able tiny configs (kv heads divisible by the TP degree)
     "tiny-llama-tp": ModelSpec("tiny-llama-tp", 512, 2, 8, 4, 64, 1024, 2048, norm_random=1),
     "tiny-qwen-tp": ModelSpec("tiny-qwen-tp", 512, 2, 8, 2, 128, 512, 1280, qkv_bias=1, rope_theta=1e6, rms_eps=1e-6, norm_random=1,

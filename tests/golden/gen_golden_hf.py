@@ -5,7 +5,7 @@ The reference (myysophia/OpsAgent) ships no model arithmetic and no golden vecto
 (SURVEY.md §8c), so these fixtures are the pin.  Run in the build container (needs transformers +
 torch on CPU; does NOT need /root/reference):
 
-    python tests/golden/gen_golden_hf.py
+    python tests/golden/gen_golden_hf.py [config ...]
 
 Writes tests/golden/hf_<config>.npz with: prompt ids, HF fp32 logits for every prompt position,
 HF greedy continuation and its per-step top1-top2 margins.  The weights are the oracle's own
@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 from oracle import oracle as O  # noqa: E402
 
 CASES = {"tiny-llama": dict(T=24, G=12, seed=7), "tiny-llama-d128": dict(T=20, G=10, seed=8),
-         "tiny-qwen": dict(T=28, G=12, seed=9)}
+         "tiny-qwen": dict(T=28, G=12, seed=9), "tiny-llama-g8": dict(T=22, G=10, seed=10), "tiny-llama-mha": dict(T=18, G=10, seed=11)}
 
 
 def hf_model(spec: O.ModelSpec, orc: O.Oracle):
@@ -67,7 +67,10 @@ def hf_model(spec: O.ModelSpec, orc: O.Oracle):
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])               # optional: regenerate just the named configs
     for name, cs in CASES.items():
+        if only and name not in only:
+            continue
         spec = O.PRESETS[name]
         orc = O.Oracle(spec, max_pos=128, mode=0)
         model = hf_model(spec, orc)

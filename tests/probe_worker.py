@@ -1,0 +1,72 @@
+"""Child process of tests/test_probe_gpu.py: one probe per process, so that a device fault in a configuration that has not been seen
+green yet cannot poison the CUDA context of the main test run.  Exit code 0 = probe passed; anything else = failed (reason on stdout)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from opsagent_b200 import Engine, _lib  # noqa: E402
+from oracle import oracle as O  # noqa: E402  (checker only)
+
+LOGIT_TOL = 2.5e-2
+
+
+def greedy_ok(ref, margins, got):
+    for i, (a, b) in enumerate(zip(got, ref)):
+        if a != b:
+            return margins[i] <= 2 * LOGIT_TOL          # a legitimate near-tie flip; later tokens differ by construction
+    return len(got) == len(ref)
+
+
+def parity(name):
+    spec = O.PRESETS[name]
+    eng = Engine(spec.engine_json(num_pages=64, max_seq_len=512, max_batch=16, max_step_tokens=256))
+    orc = O.Oracle(spec, max_pos=512, n_slots=1, mode=1)
+    rng = np.random.default_rng(21)
+    for n in (1, 17, 65, 150):
+        toks = rng.integers(0, spec.vocab, size=n).astype(np.int32)
+        err = float(np.abs(eng.debug_prefill_logits(toks) - orc.forward(toks, all_logits=True)).max())
+        if not err < LOGIT_TOL:
+            print(f"{name}: prefill logits n={n} err={err}"); return 1
+    for n, g in ((5, 40), (130, 48)):
+        prompt = rng.integers(0, spec.vocab, size=n).astype(np.int32)
+        ref, margins, _ = orc.generate(prompt, g)
+        out = eng.generate(prompt.tolist(), g, flags=1)
+        if not greedy_ok(list(ref), list(margins), list(out.token_ids)):
+            print(f"{name}: greedy decode diverges beyond a near tie (prompt {n})"); return 1
+    eng.close(); orc.close()
+    print(f"{name}: ok"); return 0
+
+
+def bpe():
+    tok = os.path.join(ROOT, "tests", "golden", "bpe_llama3_tiny.json")
+    spec = O.ModelSpec("bpe-probe", 256, 2, 4, 2, 64, 512, 704, norm_random=1)
+    eng = Engine(spec.engine_json(num_pages=64, max_seq_len=512, max_batch=4, max_step_tokens=256, tokenizer=tok))
+    orc = O.Oracle(spec, max_pos=512, n_slots=1, mode=1)
+    msgs = [("system", "you are a kubectl expert"), ("user", "集群 has 5 namespaces, list them")]
+    ids = eng.apply_chat_template(msgs)
+    if eng.count_tokens(msgs) != len(ids):
+        print("bpe: count_tokens disagrees with the template"); return 1
+    out = eng.chat_complete("", msgs, 24, flags=1)
+    ref, margins, _ = orc.generate(np.asarray(ids, np.int32), 24)
+    if not greedy_ok(list(ref), list(margins), list(out.token_ids)):
+        print("bpe: generated ids diverge from the oracle beyond a near tie"); return 1
+    import ctypes as C
+    L = _lib.load(); arr = np.asarray(out.token_ids, np.int32); buf = C.create_string_buffer(4096); n = C.c_int32()
+    if L.oa_host_bpe_decode(tok.encode(), arr.ctypes.data, len(arr), buf, len(buf), C.byref(n)) != 0 or buf.raw[: n.value] != bytes(out.content):
+        print("bpe: completion text is not the BPE decoding of the generated ids"); return 1
+    try:
+        eng.chat_complete("", msgs, 8, flags=2)
+        print("bpe: grammar flag accepted with a BPE tokenizer"); return 1
+    except Exception as e:      # 400: masks address byte tokens
+        if getattr(e, "code", None) != 400:
+            print("bpe: expected 400, got", e); return 1
+    eng.close(); orc.close()
+    print("bpe: ok"); return 0
+
+
+if __name__ == "__main__":
+    sys.exit(bpe() if sys.argv[1] == "bpe" else parity(sys.argv[1]))
