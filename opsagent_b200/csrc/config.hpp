@@ -113,6 +113,7 @@ struct EngineOptions {
     std::string tokenizer;             // path of a Hugging Face tokenizer.json (byte-level BPE, Llama-3 / Qwen2.5 format); empty = synthetic byte-level ids
     int prefill_batch_tokens = 2048;   // while sequences are decoding, new requests wait until this many uncached prompt tokens are queued ...
     int prefill_max_wait_ms = 20;      // ... or the oldest has waited this long: one weight pass then prefills several arrivals (0 tokens = admit at once)
+    int mixed_steps = 0;               // 1: decoding sequences ride along in prefill steps (decode attention for their rows, prefill attention for the chunks) instead of stalling (opt-in: not yet validated on a GPU)
     int react_tool_steps = 3;     // json_mode: conversations with fewer assistant turns than this get a tool call, later ones a final answer
     int tp = 1, tp_rank = 0;      // tensor parallel degree / this process's rank (one process per GPU)
     std::string tp_shm = "/oa_tp"; // POSIX shm name shared by the ranks of one TP group
@@ -135,7 +136,7 @@ inline void parse_config(const std::string& json, ModelConfig& m, EngineOptions&
     I("device", o.device); o.kv_gb = j.f("kv_gb", o.kv_gb); I("num_pages", o.num_pages); I("max_batch", o.max_batch);
     I("max_seq_len", o.max_seq_len); I("max_step_tokens", o.max_step_tokens); I("max_queue", o.max_queue);
     I("bn_qkv", o.bn_qkv); I("bn_o", o.bn_o); I("bn_gu", o.bn_gu); I("bn_down", o.bn_down); I("bn_lm", o.bn_lm);
-    I("attn_ctas", o.attn_ctas); I("streamk", o.streamk); I("sk_bn", o.sk_bn); I("sk_ctas", o.sk_ctas); I("sk_l2_prefetch_kb", o.sk_l2_prefetch_kb); I("sk_max_rows", o.sk_max_rows); I("sk_chain", o.sk_chain); I("sk_fuse_swiglu", o.sk_fuse_swiglu); I("sk_chain_pf_kb", o.sk_chain_pf_kb); I("sk_bn_qkv", o.sk_bn_qkv); I("sk_bn_o", o.sk_bn_o); I("sk_bn_gu", o.sk_bn_gu); I("sk_bn_down", o.sk_bn_down); I("start_thread", o.start_thread); o.weights = j.s("weights", o.weights); o.tokenizer = j.s("tokenizer", o.tokenizer); I("prefix_cache", o.prefix_cache); I("json_mode", o.json_mode); I("react_tool_steps", o.react_tool_steps); I("prefill_batch_tokens", o.prefill_batch_tokens); I("prefill_max_wait_ms", o.prefill_max_wait_ms); I("tp", o.tp); I("tp_rank", o.tp_rank); o.tp_shm = j.s("tp_shm", o.tp_shm);
+    I("attn_ctas", o.attn_ctas); I("streamk", o.streamk); I("sk_bn", o.sk_bn); I("sk_ctas", o.sk_ctas); I("sk_l2_prefetch_kb", o.sk_l2_prefetch_kb); I("sk_max_rows", o.sk_max_rows); I("sk_chain", o.sk_chain); I("sk_fuse_swiglu", o.sk_fuse_swiglu); I("sk_chain_pf_kb", o.sk_chain_pf_kb); I("sk_bn_qkv", o.sk_bn_qkv); I("sk_bn_o", o.sk_bn_o); I("sk_bn_gu", o.sk_bn_gu); I("sk_bn_down", o.sk_bn_down); I("start_thread", o.start_thread); o.weights = j.s("weights", o.weights); o.tokenizer = j.s("tokenizer", o.tokenizer); I("prefix_cache", o.prefix_cache); I("json_mode", o.json_mode); I("react_tool_steps", o.react_tool_steps); I("prefill_batch_tokens", o.prefill_batch_tokens); I("mixed_steps", o.mixed_steps); I("prefill_max_wait_ms", o.prefill_max_wait_ms); I("tp", o.tp); I("tp_rank", o.tp_rank); o.tp_shm = j.s("tp_shm", o.tp_shm);
     if (m.hidden <= 0 || m.n_layers <= 0 || m.n_heads <= 0 || m.n_kv_heads <= 0 || m.ffn <= 0 || m.vocab <= 0)
         throw std::runtime_error("unknown model '" + name + "' and no explicit dimensions given");
     if (m.head_dim != 64 && m.head_dim != 128) throw std::runtime_error("head_dim must be 64 or 128");

@@ -253,12 +253,12 @@ public:
                       "{\"requests_completed\": %llu, \"prefill_tokens\": %llu, \"decode_tokens\": %llu, \"prefill_steps\": %llu, "
                       "\"decode_steps\": %llu, \"preemptions\": %llu, \"pages_total\": %d, \"pages_free\": %zu, \"running\": %zu, "
                       "\"waiting\": %zu, \"kernel_launches\": %llu, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"weight_bytes\": %zu, "
-                      "\"kv_pool_bytes\": %zu, \"busy_ms\": %.3f, \"prefix_hit_tokens\": %llu, \"pages_cached\": %zu, \"admissions_deferred\": %llu}",
+                      "\"kv_pool_bytes\": %zu, \"busy_ms\": %.3f, \"prefix_hit_tokens\": %llu, \"pages_cached\": %zu, \"admissions_deferred\": %llu, \"mixed_steps\": %llu}",
                       (unsigned long long)n_completed_, (unsigned long long)n_prefill_tokens_, (unsigned long long)n_decode_tokens_,
                       (unsigned long long)n_prefill_steps_, (unsigned long long)n_decode_steps_, (unsigned long long)n_preempt_,
                       model_.num_pages, available_pages_locked(), running_.size(), waiting_.size(), (unsigned long long)launches_total(),
                       (unsigned long long)model_.h2d_bytes, (unsigned long long)model_.d2h_bytes, model_.weight_bytes, model_.kv_pool_bytes, busy_ms_, (unsigned long long)n_prefix_hit_tokens_, cached_.size(),
-                      (unsigned long long)n_admit_deferred_);
+                      (unsigned long long)n_admit_deferred_, (unsigned long long)n_mixed_steps_);
         return b;
     }
     std::string info_json() {
@@ -467,6 +467,24 @@ private:
             if (any_prefill) {
                 in.decode = false;
                 int budget = opt_.max_step_tokens;
+                if (opt_.mixed_steps) {
+                    // mixed step: the decoding sequences take rows / sequence slots 0..n_decode-1 (one token each, decode attention) and
+                    // advance with this forward instead of stalling behind the prefill.  A sequence that cannot get the page for its
+                    // newest token sits this step out (preemption stays with the pure decode step).
+                    for (auto& s : running_) {
+                        if (s->state != SeqState::DECODE || budget <= 1) continue;
+                        const int pos = (int)s->tokens.size() - 1;
+                        if (pos / 64 >= (int)s->pages.size() && !alloc_pages_locked(s->pages, 1)) continue;
+                        const int sidx = in.n_seqs++;
+                        in.block_tables.resize((size_t)in.n_seqs * model_.max_pages_per_seq, 0);
+                        for (size_t i = 0; i < s->pages.size(); ++i) in.block_tables[(size_t)sidx * model_.max_pages_per_seq + i] = s->pages[i];
+                        in.ctx_lens.push_back(pos + 1);
+                        in.sample_rows.push_back((int)in.tokens.size());
+                        in.tokens.push_back(s->tokens[pos]); in.positions.push_back(pos); in.slots.push_back(s->pages[pos / 64] * 64 + pos % 64);
+                        batch.push_back(s); take_of.push_back(0); sampled.push_back(s); --budget;
+                    }
+                    in.n_decode = in.n_seqs;
+                }
                 for (auto& s : running_) {
                     if (s->state != SeqState::PREFILL || budget <= 0) continue;
                     const int remaining = (int)s->tokens.size() - s->n_cached;
@@ -534,10 +552,16 @@ private:
                     any_done |= accept_token_locked(batch[b], model_.h_out_ids[b]);
                 }
             } else {
-                ++n_prefill_steps_; n_prefill_tokens_ += in.tokens.size();
+                ++n_prefill_steps_; n_prefill_tokens_ += in.tokens.size() - (size_t)in.n_decode;
+                if (in.n_decode > 0) { ++n_mixed_steps_; n_decode_tokens_ += (uint64_t)in.n_decode; }
                 int si = 0;
                 for (size_t b = 0; b < batch.size(); ++b) {
                     auto& s = batch[b];
+                    if ((int)b < in.n_decode) {          // a decoding sequence that rode along: exactly what a decode step does with it
+                        s->n_cached = (int)s->tokens.size(); register_pages_locked(s);
+                        any_done |= accept_token_locked(s, model_.h_out_ids[si++]);
+                        continue;
+                    }
                     s->n_cached += take_of[b]; register_pages_locked(s);
                     if (s->n_cached == (int)s->tokens.size()) { s->state = SeqState::DECODE; any_done |= accept_token_locked(s, model_.h_out_ids[si++]); }
                 }
@@ -562,7 +586,7 @@ private:
     uint64_t next_ticket_ = 1;
     bool stop_ = false, fatal_ = false; std::string fatal_msg_;
     std::thread worker_, follower_; bool follower_done_ = false;
-    uint64_t n_admit_deferred_ = 0, n_completed_ = 0, n_prefill_tokens_ = 0, n_decode_tokens_ = 0, n_prefill_steps_ = 0, n_decode_steps_ = 0, n_preempt_ = 0;
+    uint64_t n_mixed_steps_ = 0, n_admit_deferred_ = 0, n_completed_ = 0, n_prefill_tokens_ = 0, n_decode_tokens_ = 0, n_prefill_steps_ = 0, n_decode_steps_ = 0, n_preempt_ = 0;
     double busy_ms_ = 0;
 };
 

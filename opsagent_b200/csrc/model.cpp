@@ -396,15 +396,18 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
     const size_t o_mask = put(in.masks.data(), in.masks.size());
     if (!in.masks.empty() && (int)in.masks.size() != 9 * S) throw std::runtime_error("forward: grammar masks must be [n_sample, 9]");
     size_t o_segs = 0, o_ptr = 0, o_tiles = 0, o_cnt = 0;
-    if (in.decode) {
+    const int n_dec = in.decode ? in.n_seqs : in.n_decode;          // sequences served by the decode attention kernel (rows 0..n_dec-1)
+    if (n_dec < 0 || n_dec > in.n_seqs || n_dec > T) throw std::runtime_error("forward: bad n_decode");
+    if (n_dec > 0) {
         const int n_ctas = opt.attn_ctas > 0 ? opt.attn_ctas : 2 * sm_count;
-        build_decode_plan(in.ctx_lens.data(), in.n_seqs, nkv, n_ctas, 0, plan_);
+        build_decode_plan(in.ctx_lens.data(), n_dec, nkv, n_ctas, 0, plan_);
         if (plan_.n_slots > max_part_slots_) throw std::runtime_error("forward: partial workspace overflow");
         o_segs = put(plan_.segs.data(), plan_.segs.size() * 8);
         o_ptr = put(plan_.cta_ptr.data(), plan_.cta_ptr.size());
         zero_counters_.assign(plan_.merges.size() + 1, 0);
         o_cnt = put(zero_counters_.data(), zero_counters_.size());     // merge counters start every step at zero
-    } else {
+    }
+    if (!in.decode) {
         // heaviest query tiles (most visible keys) first: the causal triangle otherwise leaves a long tail of big CTAs
         sorted_tiles_ = in.tiles;
         std::stable_sort(sorted_tiles_.begin(), sorted_tiles_.end(), [](const PrefillTile& a, const PrefillTile& b) { return a.pos0 + a.n_rows > b.pos0 + b.n_rows; });
@@ -429,13 +432,14 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
     const int sk_rows = T > 128 ? 256 : 128;
     auto attention = [&](int l) {
         if (profile_attn) cudaEventRecord(ev[2 * l], stream);
-        if (in.decode) {
+        if (n_dec > 0) {
             DecodeAttnParams a{}; a.q = q_; a.out = attn_; a.block_tables = d_bt; a.ctx_lens = d_ctx; a.max_pages_per_seq = max_pages_per_seq;
             a.segs = reinterpret_cast<const DecodeSeg*>(d_meta_ + o_segs); a.cta_seg_ptr = d_meta_ + o_ptr; a.n_ctas = (int)plan_.cta_ptr.size() - 1;
             a.part_o = part_o_; a.part_ml = part_ml_; a.layer = l; a.n_heads = nh; a.n_kv = nkv; a.scale_log2e = scale_log2e;
             a.merge_counters = d_meta_ + o_cnt;      // cut items are merged inside the kernel by the CTA finishing their last piece
             cuda_check(launch_decode_attention(&tm_kv, kv, a, stream), "decode attention"); MARK(4);
-        } else {
+        }
+        if (!in.decode && !in.tiles.empty()) {     // mixed step: both kernels, disjoint rows of q_/attn_
             PrefillAttnParams a{}; a.q = q_; a.out = attn_; a.block_tables = d_bt; a.max_pages_per_seq = max_pages_per_seq;
             a.tiles = reinterpret_cast<const PrefillTile*>(d_meta_ + o_tiles); a.n_tiles = (int)in.tiles.size();
             a.layer = l; a.n_heads = nh; a.n_kv = nkv; a.scale_log2e = scale_log2e;

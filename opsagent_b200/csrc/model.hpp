@@ -19,6 +19,8 @@ struct WeightMat {
 
 struct StepInput {
     bool decode = false;
+    int n_decode = 0;                                 // mixed step (decode == false): the first n_decode rows / sequences are decoding sequences
+                                                      // (one token each, decode attention); the prefill chunks follow
     std::vector<int32_t> tokens, positions, slots;   // [T]
     std::vector<int32_t> sample_rows;                 // rows whose next token is wanted
     int n_seqs = 0;

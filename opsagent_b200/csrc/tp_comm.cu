@@ -110,7 +110,7 @@ void TpComm::publish(const StepInput& in) {
     int32_t* m = shm_->msg; size_t w = 0;
     auto put = [&](const void* src, size_t words) { if (w + words > TP_MSG_WORDS) throw std::runtime_error("tp step message overflow"); std::memcpy(m + w, src, words * 4); w += words; };
     const int32_t n_mask = (int32_t)in.masks.size();
-    const int32_t hdr[8] = {in.decode ? 1 : 0, (int32_t)in.tokens.size(), (int32_t)in.sample_rows.size(), in.n_seqs, (int32_t)in.block_tables.size(),
+    const int32_t hdr[8] = {(in.decode ? 1 : 0) | (in.n_decode << 1), (int32_t)in.tokens.size(), (int32_t)in.sample_rows.size(), in.n_seqs, (int32_t)in.block_tables.size(),
                             (int32_t)in.ctx_lens.size(), (int32_t)in.tiles.size(), (in.want_logits ? 1 : 0) | (n_mask << 1)};
     put(hdr, 8);
     put(in.tokens.data(), in.tokens.size()); put(in.positions.data(), in.positions.size()); put(in.slots.data(), in.slots.size());
@@ -132,7 +132,7 @@ bool TpComm::receive(StepInput& in) {
     const int32_t* hdr = m; w += 8;
     auto get = [&](std::vector<int32_t>& v, int n) { v.assign(m + w, m + w + n); w += n; };
     in = StepInput();
-    in.decode = hdr[0] != 0; in.n_seqs = hdr[3]; in.want_logits = (hdr[7] & 1) != 0;
+    in.decode = (hdr[0] & 1) != 0; in.n_decode = hdr[0] >> 1; in.n_seqs = hdr[3]; in.want_logits = (hdr[7] & 1) != 0;
     get(in.tokens, hdr[1]); get(in.positions, hdr[1]); get(in.slots, hdr[1]); get(in.sample_rows, hdr[2]);
     get(in.block_tables, hdr[4]); get(in.ctx_lens, hdr[5]);
     in.tiles.resize(hdr[6]); std::memcpy(in.tiles.data(), m + w, (size_t)hdr[6] * 16); w += (size_t)hdr[6] * 4;

@@ -68,5 +68,38 @@ def bpe():
     print("bpe: ok"); return 0
 
 
+def mixed():
+    """decode rows riding along in prefill steps (engine option mixed_steps=1): every request must still match the oracle"""
+    import threading
+    import time
+    spec = O.PRESETS["tiny-llama-d128"]
+    eng = Engine(spec.engine_json(num_pages=96, max_seq_len=512, max_batch=8, max_step_tokens=256, mixed_steps=1, prefill_batch_tokens=0))
+    orc = O.Oracle(spec, max_pos=512, n_slots=1, mode=1)
+    rng = np.random.default_rng(33)
+    jobs = [(20, 160)] + [(int(n), 30) for n in (40, 90, 150, 200, 64, 129)]
+    prompts = [rng.integers(0, spec.vocab, size=n).astype(np.int32) for n, _ in jobs]
+    results = [None] * len(jobs)
+
+    def run(i):
+        results[i] = eng.generate(prompts[i].tolist(), jobs[i][1], flags=1)
+
+    th = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
+    th[0].start(); time.sleep(0.05)                      # the long request is decoding when the others arrive, one by one
+    for t in th[1:]:
+        t.start(); time.sleep(0.01)
+    [t.join() for t in th]
+    st = eng.stats()
+    if st.get("mixed_steps", 0) <= 0:
+        print("mixed: no mixed step was scheduled (inconclusive)"); return 1
+    for i, (n, g) in enumerate(jobs):
+        ref, margins, _ = orc.generate(prompts[i], g)
+        if results[i].completion_tokens != g or not greedy_ok(list(ref), list(margins), list(results[i].token_ids)):
+            print(f"mixed: request {i} (prompt {n}) diverges from the oracle beyond a near tie"); return 1
+    if st["pages_free"] != st["pages_total"]:
+        print("mixed: pages leaked"); return 1
+    eng.close(); orc.close()
+    print(f"mixed: ok ({st['mixed_steps']} mixed steps)"); return 0
+
+
 if __name__ == "__main__":
-    sys.exit(bpe() if sys.argv[1] == "bpe" else parity(sys.argv[1]))
+    sys.exit({"bpe": bpe, "mixed": mixed}.get(sys.argv[1], lambda: parity(sys.argv[1]))())
