@@ -102,4 +102,6 @@ def mixed():
 
 
 if __name__ == "__main__":
+    import faulthandler
+    faulthandler.dump_traceback_later(200, exit=True)        # a hung probe ends itself (the parent's own timeout is 240 s)
     sys.exit({"bpe": bpe, "mixed": mixed}.get(sys.argv[1], lambda: parity(sys.argv[1]))())

@@ -17,5 +17,5 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 @pytest.mark.xfail(reason="added without a GPU run in round 1; promote to a hard test once seen green", strict=False)
 @pytest.mark.parametrize("probe", ["tiny-llama-g8", "tiny-llama-mha", "bpe", "mixed"])
 def test_probe(probe):
-    r = subprocess.run([sys.executable, os.path.join(HERE, "probe_worker.py"), probe], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "probe_worker.py"), probe], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
