@@ -1,6 +1,5 @@
 """Child process of tests/test_probe_gpu.py: one probe per process, so that a device fault in a configuration that has not been seen
 green yet cannot poison the CUDA context of the main test run.  Exit code 0 = probe passed; anything else = failed (reason on stdout)."""
-import json
 import os
 import sys
 
