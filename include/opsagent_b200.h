@@ -85,6 +85,12 @@ OA_API int oa_chat_complete(oa_engine*, const oa_chat_req*, oa_chat_resp* out);
 /* non-blocking pair for callers that must not pin an OS thread per request (Go: submit, then wait) */
 OA_API int oa_chat_submit(oa_engine*, const oa_chat_req*, uint64_t* ticket);
 OA_API int oa_chat_wait(oa_engine*, uint64_t ticket, int32_t timeout_ms, oa_chat_resp* out);
+/* abandon a submitted request (wait timed out, caller's context cancelled): frees its queue slot / KV pages; the ticket dies */
+OA_API int oa_chat_cancel(oa_engine*, uint64_t ticket);
+/* the same pair with the error text copied into a caller buffer instead of the thread-local oa_last_error(): what the cgo binding
+ * uses, so that goroutines need not be pinned to an OS thread with runtime.LockOSThread for the duration of a Chat */
+OA_API int oa_chat_submit_ex(oa_engine*, const oa_chat_req*, uint64_t* ticket, char* errbuf, size_t errcap);
+OA_API int oa_chat_wait_ex(oa_engine*, uint64_t ticket, int32_t timeout_ms, oa_chat_resp* out, char* errbuf, size_t errcap);
 OA_API void oa_free_resp(oa_chat_resp*);
 
 /* same pair on raw token ids (bench + parity tests; bypasses the chat template) */

@@ -34,7 +34,7 @@ SYMBOLS = [
     "oa_tokens_submit", "oa_count_tokens", "oa_apply_chat_template", "oa_last_error", "oa_engine_stats", "oa_model_info",
     "oa_debug_prefill_logits", "oa_bench_decode", "oa_k_rmsnorm", "oa_k_gemm", "oa_k_init_weight", "oa_k_paged_attention",
     "oa_kernel_launches", "oa_version", "oa_host_apply_chat_template", "oa_host_decode_plan", "oa_host_streamk_plan", "oa_host_bpe_encode", "oa_host_bpe_decode", "oa_host_model_info",
-    "oa_k_gemm_streamk", "oa_debug_kernel_times", "oa_engine_serve", "oa_host_grammar_step", "oa_host_grammar_step_ex",
+    "oa_k_gemm_streamk", "oa_debug_kernel_times", "oa_engine_serve", "oa_host_grammar_step", "oa_host_grammar_step_ex", "oa_chat_cancel", "oa_chat_submit_ex", "oa_chat_wait_ex",
 ]
 
 _lib = None
@@ -55,6 +55,9 @@ def load() -> C.CDLL:
     L.oa_chat_complete.argtypes = [vp, C.POINTER(OaChatReq), C.POINTER(OaChatResp)]; L.oa_chat_complete.restype = C.c_int
     L.oa_chat_submit.argtypes = [vp, C.POINTER(OaChatReq), C.POINTER(u64)]; L.oa_chat_submit.restype = C.c_int
     L.oa_chat_wait.argtypes = [vp, u64, i32, C.POINTER(OaChatResp)]; L.oa_chat_wait.restype = C.c_int
+    L.oa_chat_cancel.argtypes = [vp, u64]; L.oa_chat_cancel.restype = C.c_int
+    L.oa_chat_submit_ex.argtypes = [vp, C.POINTER(OaChatReq), C.POINTER(u64), C.c_char_p, C.c_size_t]; L.oa_chat_submit_ex.restype = C.c_int
+    L.oa_chat_wait_ex.argtypes = [vp, u64, i32, C.POINTER(OaChatResp), C.c_char_p, C.c_size_t]; L.oa_chat_wait_ex.restype = C.c_int
     L.oa_free_resp.argtypes = [C.POINTER(OaChatResp)]; L.oa_free_resp.restype = None
     L.oa_tokens_submit.argtypes = [vp, vp, i32, i32, C.c_uint32, C.POINTER(u64)]; L.oa_tokens_submit.restype = C.c_int
     L.oa_count_tokens.argtypes = [vp, C.POINTER(OaMsg), i32, C.POINTER(i32)]; L.oa_count_tokens.restype = C.c_int

@@ -41,16 +41,64 @@ class ToolPrompt:                                            # reference pkg/too
 
     @classmethod
     def unmarshal(cls, text: str) -> "ToolPrompt":
+        """json.Unmarshal([]byte(text), &toolPrompt) (simple.go:366): unknown keys are ignored, missing keys stay "", JSON null leaves the
+        field at its zero value, and any other non-string value for a string field is an UnmarshalTypeError (-> the caller's
+        'not JSON, assume final answer' / 'Summarize…' branches), not a silent coercion."""
         d = json.loads(text)
         if not isinstance(d, dict):
-            raise ValueError("not a JSON object")
-        a = d.get("action") or {}
-        return cls(str(d.get("question", "")), str(d.get("thought", "")), {"name": str(a.get("name", "")), "input": str(a.get("input", ""))},
-                   str(d.get("observation", "")), str(d.get("final_answer", "")))
+            raise ValueError("json: cannot unmarshal non-object into Go value of type tools.ToolPrompt")
+
+        def field_(obj, key):
+            v = obj.get(key)
+            if key not in obj:                       # encoding/json prefers an exact key match and falls back to a case-insensitive one
+                v = next((x for k, x in obj.items() if k.lower() == key), None)
+            if v is None:
+                return ""
+            if not isinstance(v, str):
+                raise ValueError(f"json: cannot unmarshal {type(v).__name__} into Go struct field ToolPrompt.{key} of type string")
+            return v
+
+        a = d.get("action") if "action" in d else next((x for k, x in d.items() if k.lower() == "action"), None)
+        if a is None:
+            a = {}
+        if not isinstance(a, dict):
+            raise ValueError("json: cannot unmarshal non-object into Go struct field ToolPrompt.action")
+        return cls(field_(d, "question"), field_(d, "thought"), {"name": field_(a, "name"), "input": field_(a, "input")},
+                   field_(d, "observation"), field_(d, "final_answer"))
 
     def marshal(self) -> str:
-        return json.dumps({"question": self.question, "thought": self.thought, "action": self.action, "observation": self.observation,
-                           "final_answer": self.final_answer}, ensure_ascii=False, separators=(",", ":"))
+        r"""json.Marshal(toolPrompt) (simple.go:497), byte for byte: struct field order, no spaces, and Go's default HTML-safe string
+        escaping — '<', '>', '&' become \u003c / \u003e / \u0026, U+2028 / U+2029 become \u2028 / \u2029, other non-ASCII stays
+        raw UTF-8, control bytes use \n \r \t or \u00XX.  kubectl's ubiquitous "<none>" would otherwise tokenise differently from
+        what the Go caller sends."""
+        return ("{" + f'"question":{go_json_string(self.question)},"thought":{go_json_string(self.thought)},'
+                f'"action":{{"name":{go_json_string(self.action["name"])},"input":{go_json_string(self.action["input"])}}},'
+                f'"observation":{go_json_string(self.observation)},"final_answer":{go_json_string(self.final_answer)}' + "}")
+
+
+def go_json_string(s: str) -> str:
+    """encoding/json's string encoder with escapeHTML=true (the json.Marshal default)."""
+    out = ['"']
+    for ch in s:
+        o = ord(ch)
+        if ch == '"':
+            out.append('\\"')
+        elif ch == "\\":
+            out.append("\\\\")
+        elif ch == "\n":
+            out.append("\\n")
+        elif ch == "\r":
+            out.append("\\r")
+        elif ch == "\t":
+            out.append("\\t")
+        elif o < 0x20 or ch in "<>&" or o in (0x2028, 0x2029):
+            out.append("\\u%04x" % o)
+        elif 0xD800 <= o <= 0xDFFF:
+            out.append("\\ufffd")          # invalid UTF-8 in a Go string marshals as U+FFFD
+        else:
+            out.append(ch)
+    out.append('"')
+    return "".join(out)
 
 
 def AssistantWithConfig(model, prompts, maxTokens, countTokens, verbose, maxIterations, client, tools, count_tokens=None):

@@ -11,6 +11,7 @@
 // Why it exists: the reference counts tokens with tiktoken BPE for OpenAI models and silently skips truncation for Llama/Qwen names
 // (pkg/llms/tokens.go:60-66,128-144); with a real checkpoint (config "weights") the engine needs the checkpoint's own vocabulary.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <fstream>
@@ -328,6 +329,7 @@ private:
         }
         word.clear();
         for (size_t k = 0; k < len; ++k) word.push_back(byte_id_[(unsigned char)p[k]]);
+        if (len > 24) { merge_long(word); out.insert(out.end(), word.begin(), word.end()); return; }
         while (word.size() > 1) {      // merge the lowest-ranked adjacent pair (leftmost on ties) until none is mergeable
             int best = -1, best_rank = 0x7fffffff, best_id = 0;
             for (size_t k = 0; k + 1 < word.size(); ++k) {
@@ -338,6 +340,37 @@ private:
             word[(size_t)best] = best_id; word.erase(word.begin() + best + 1);
         }
         out.insert(out.end(), word.begin(), word.end());
+    }
+    // The same merge order for long pre-tokens in O(n log n): doubly linked symbols + a min-heap of candidate pairs keyed by
+    // (rank, position of the left symbol); stale heap entries (a symbol changed since the push) are skipped on pop.  A 1 MB run of
+    // '=' or 'A' in a tool observation must not pin the calling thread for minutes (the quadratic rescan above would).
+    void merge_long(std::vector<int32_t>& word) const {
+        const int n = (int)word.size();
+        std::vector<int> prev(n), next(n);
+        for (int i = 0; i < n; ++i) { prev[i] = i - 1; next[i] = i + 1 < n ? i + 1 : -1; }
+        struct Cand { int rank, pos, left_id, right_id, merged; };
+        auto worse = [](const Cand& a, const Cand& b) { return a.rank != b.rank ? a.rank > b.rank : a.pos > b.pos; };
+        std::vector<Cand> heap;
+        auto push = [&](int i) {
+            const int j = next[i]; if (j < 0) return;
+            auto it = merge_.find(((uint64_t)(uint32_t)word[i] << 32) | (uint32_t)word[j]);
+            if (it != merge_.end()) { heap.push_back(Cand{it->second.first, i, word[i], word[j], it->second.second}); std::push_heap(heap.begin(), heap.end(), worse); }
+        };
+        for (int i = 0; i + 1 < n; ++i) push(i);
+        std::vector<uint8_t> dead(n, 0);
+        while (!heap.empty()) {
+            std::pop_heap(heap.begin(), heap.end(), worse);
+            const Cand c = heap.back(); heap.pop_back();
+            const int i = c.pos, j = dead[i] ? -1 : next[i];
+            if (j < 0 || word[i] != c.left_id || word[j] != c.right_id) continue;      // stale
+            word[i] = c.merged; dead[j] = 1;
+            next[i] = next[j]; if (next[j] >= 0) prev[next[j]] = i;
+            if (prev[i] >= 0) push(prev[i]);
+            push(i);
+        }
+        int w = 0;
+        for (int i = 0; i >= 0 && i < n; i = next[i]) word[w++] = word[i];
+        word.resize(w);
     }
 
     int digits_ = 3; bool ignore_merges_ = false, nfc_ = false;

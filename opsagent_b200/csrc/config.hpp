@@ -107,6 +107,7 @@ struct EngineOptions {
     int sk_l2_prefetch_kb = 0;    // per-CTA weight KB prefetched into L2 ahead of the dependency wait (measured: hurts, 8.75 -> 9.3 ms; off)
     int sk_bn_qkv = 0, sk_bn_o = 0, sk_bn_gu = 0, sk_bn_down = 0;   // per-projection overrides (0 = sk_bn)
     int start_thread = 1;
+    std::string model_aliases;    // other model names this engine answers to, comma separated ("*" = any): the reference sends currentModel or "gpt-4" (execute.go:168-171)
     std::string weights;          // path of a Hugging Face *.safetensors file or shard directory (empty: seeded random init)
     int prefix_cache = 1;         // reuse KV pages of shared prompt prefixes across requests (the ReAct loop resends its history)
     int json_mode = 0;            // 1: every chat completion is grammar-forced to parse as tools.ToolPrompt (tool.go:29-38)
@@ -117,6 +118,7 @@ struct EngineOptions {
     int react_tool_steps = 3;     // json_mode: conversations with fewer assistant turns than this get a tool call, later ones a final answer
     int tp = 1, tp_rank = 0;      // tensor parallel degree / this process's rank (one process per GPU)
     std::string tp_shm = "/oa_tp"; // POSIX shm name shared by the ranks of one TP group
+    uint64_t tp_nonce = 0;         // per-launch id shared by the ranks (e.g. the rendezvous port + a timestamp): followers ignore segments of other launches (0 = not checked)
 };
 
 inline void parse_config(const std::string& json, ModelConfig& m, EngineOptions& o) {
@@ -136,7 +138,7 @@ inline void parse_config(const std::string& json, ModelConfig& m, EngineOptions&
     I("device", o.device); o.kv_gb = j.f("kv_gb", o.kv_gb); I("num_pages", o.num_pages); I("max_batch", o.max_batch);
     I("max_seq_len", o.max_seq_len); I("max_step_tokens", o.max_step_tokens); I("max_queue", o.max_queue);
     I("bn_qkv", o.bn_qkv); I("bn_o", o.bn_o); I("bn_gu", o.bn_gu); I("bn_down", o.bn_down); I("bn_lm", o.bn_lm);
-    I("attn_ctas", o.attn_ctas); I("streamk", o.streamk); I("sk_bn", o.sk_bn); I("sk_ctas", o.sk_ctas); I("sk_l2_prefetch_kb", o.sk_l2_prefetch_kb); I("sk_max_rows", o.sk_max_rows); I("sk_chain", o.sk_chain); I("sk_fuse_swiglu", o.sk_fuse_swiglu); I("sk_chain_pf_kb", o.sk_chain_pf_kb); I("sk_bn_qkv", o.sk_bn_qkv); I("sk_bn_o", o.sk_bn_o); I("sk_bn_gu", o.sk_bn_gu); I("sk_bn_down", o.sk_bn_down); I("start_thread", o.start_thread); o.weights = j.s("weights", o.weights); o.tokenizer = j.s("tokenizer", o.tokenizer); I("prefix_cache", o.prefix_cache); I("json_mode", o.json_mode); I("react_tool_steps", o.react_tool_steps); I("prefill_batch_tokens", o.prefill_batch_tokens); I("mixed_steps", o.mixed_steps); I("prefill_max_wait_ms", o.prefill_max_wait_ms); I("tp", o.tp); I("tp_rank", o.tp_rank); o.tp_shm = j.s("tp_shm", o.tp_shm);
+    I("attn_ctas", o.attn_ctas); I("streamk", o.streamk); I("sk_bn", o.sk_bn); I("sk_ctas", o.sk_ctas); I("sk_l2_prefetch_kb", o.sk_l2_prefetch_kb); I("sk_max_rows", o.sk_max_rows); I("sk_chain", o.sk_chain); I("sk_fuse_swiglu", o.sk_fuse_swiglu); I("sk_chain_pf_kb", o.sk_chain_pf_kb); I("sk_bn_qkv", o.sk_bn_qkv); I("sk_bn_o", o.sk_bn_o); I("sk_bn_gu", o.sk_bn_gu); I("sk_bn_down", o.sk_bn_down); I("start_thread", o.start_thread); o.weights = j.s("weights", o.weights); o.model_aliases = j.s("model_aliases", o.model_aliases); o.tokenizer = j.s("tokenizer", o.tokenizer); I("prefix_cache", o.prefix_cache); I("json_mode", o.json_mode); I("react_tool_steps", o.react_tool_steps); I("prefill_batch_tokens", o.prefill_batch_tokens); I("mixed_steps", o.mixed_steps); I("prefill_max_wait_ms", o.prefill_max_wait_ms); I("tp", o.tp); I("tp_rank", o.tp_rank); o.tp_shm = j.s("tp_shm", o.tp_shm); o.tp_nonce = (uint64_t)j.i("tp_nonce", (int64_t)o.tp_nonce);
     if (m.hidden <= 0 || m.n_layers <= 0 || m.n_heads <= 0 || m.n_kv_heads <= 0 || m.ffn <= 0 || m.vocab <= 0)
         throw std::runtime_error("unknown model '" + name + "' and no explicit dimensions given");
     if (m.head_dim != 64 && m.head_dim != 128) throw std::runtime_error("head_dim must be 64 or 128");

@@ -46,6 +46,7 @@ struct Seq {
     int n_registered = 0; uint64_t hash_prev = 0;   // prefix cache: full pages already published / hash of that chain
     std::chrono::steady_clock::time_point t_enqueue{};   // arrival (admission batching)
     bool preempted = false;                              // pushed back by the scheduler: re-admit without waiting
+    bool cancelled = false;                              // oa_chat_cancel: dropped at the next step boundary
     int est_uncached = -1;                               // prompt tokens a prefill would have to compute (prefix-cache walk, made once)
 };
 
@@ -127,6 +128,21 @@ public:
         out->prompt_tokens = s->n_prompt; out->completion_tokens = (int32_t)gen.size(); out->finish_reason = s->finish_reason;
         out->token_ids = (int32_t*)std::malloc(std::max<size_t>(1, gen.size()) * 4);
         std::memcpy(out->token_ids, gen.data(), gen.size() * 4);
+        return OA_OK;
+    }
+
+    // Abandon a request (a caller whose oa_chat_wait timed out, a Go context that was cancelled): a waiting sequence is removed at once, a
+    // running one is dropped by the scheduler at its next step boundary; either way its KV pages go back to the pool and the ticket dies.
+    int cancel(uint64_t ticket) {
+        std::lock_guard<std::mutex> lk(mu_);
+        auto it = by_ticket_.find(ticket);
+        if (it == by_ticket_.end()) return fail(OA_ERR_BAD_REQUEST, "unknown ticket");
+        std::shared_ptr<Seq> s = it->second;
+        by_ticket_.erase(it);
+        if (s->done) return OA_OK;
+        s->cancelled = true; ++n_cancelled_;
+        for (auto w = waiting_.begin(); w != waiting_.end(); ++w)
+            if (*w == s) { waiting_.erase(w); for (int p : s->pages) release_page_locked(p); s->pages.clear(); s->state = SeqState::DONE; s->done = true; break; }
         return OA_OK;
     }
 
@@ -253,12 +269,12 @@ public:
                       "{\"requests_completed\": %llu, \"prefill_tokens\": %llu, \"decode_tokens\": %llu, \"prefill_steps\": %llu, "
                       "\"decode_steps\": %llu, \"preemptions\": %llu, \"pages_total\": %d, \"pages_free\": %zu, \"running\": %zu, "
                       "\"waiting\": %zu, \"kernel_launches\": %llu, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"weight_bytes\": %zu, "
-                      "\"kv_pool_bytes\": %zu, \"busy_ms\": %.3f, \"prefix_hit_tokens\": %llu, \"pages_cached\": %zu, \"admissions_deferred\": %llu, \"mixed_steps\": %llu}",
+                      "\"kv_pool_bytes\": %zu, \"busy_ms\": %.3f, \"prefix_hit_tokens\": %llu, \"pages_cached\": %zu, \"admissions_deferred\": %llu, \"mixed_steps\": %llu, \"cancelled\": %llu}",
                       (unsigned long long)n_completed_, (unsigned long long)n_prefill_tokens_, (unsigned long long)n_decode_tokens_,
                       (unsigned long long)n_prefill_steps_, (unsigned long long)n_decode_steps_, (unsigned long long)n_preempt_,
                       model_.num_pages, available_pages_locked(), running_.size(), waiting_.size(), (unsigned long long)launches_total(),
                       (unsigned long long)model_.h2d_bytes, (unsigned long long)model_.d2h_bytes, model_.weight_bytes, model_.kv_pool_bytes, busy_ms_, (unsigned long long)n_prefix_hit_tokens_, cached_.size(),
-                      (unsigned long long)n_admit_deferred_, (unsigned long long)n_mixed_steps_);
+                      (unsigned long long)n_admit_deferred_, (unsigned long long)n_mixed_steps_, (unsigned long long)n_cancelled_);
         return b;
     }
     std::string info_json() {
@@ -272,6 +288,18 @@ public:
                       c.rope_scaling, c.rope_theta, c.rms_eps, c.chat_template.c_str(), (unsigned long long)c.seed, model_.num_pages,
                       opt_.max_seq_len, opt_.max_batch, model_.sm_count, c.decode_weight_bytes(), c.kv_bytes_per_token());
         return b;
+    }
+    bool serves_model(const std::string& name) const {
+        if (name == model_.cfg.name) return true;
+        const std::string& a = opt_.model_aliases;       // "gpt-4,gpt-4o" or "*": names the unmodified reference sends (execute.go:168-171 defaults to "gpt-4")
+        size_t b = 0;
+        while (b <= a.size()) {
+            size_t e = a.find(',', b); if (e == std::string::npos) e = a.size();
+            const std::string item = a.substr(b, e - b);
+            if (item == "*" || (!item.empty() && item == name)) return true;
+            b = e + 1;
+        }
+        return false;
     }
     const Tokenizer& tokenizer() const { return tok_; }
     const EngineOptions& options() const { return opt_; }
@@ -426,6 +454,11 @@ private:
         std::vector<std::shared_ptr<Seq>> sampled;      // sequences owning this step's sample rows, in row order
         {
             std::lock_guard<std::mutex> lk(mu_);
+            if (n_cancelled_ != n_cancel_seen_) {       // requests abandoned by their callers: free their pages before planning this step
+                n_cancel_seen_ = n_cancelled_;
+                for (auto& s : running_) if (s->cancelled && !s->done) { finish_locked(s, 1); --n_completed_; }
+                running_.erase(std::remove_if(running_.begin(), running_.end(), [](const std::shared_ptr<Seq>& s) { return s->done; }), running_.end());
+            }
             // ---- admission batching: a prefill step streams all the weights once, whether it carries one arrival or ten, and the decoding
             // sequences stall for its duration.  While sequences are decoding, arrivals therefore wait (bounded) until enough uncached prompt
             // tokens are queued to be worth that pass.  Nothing running, a preempted sequence, or the time limit admit at once. ----
@@ -586,6 +619,7 @@ private:
     uint64_t next_ticket_ = 1;
     bool stop_ = false, fatal_ = false; std::string fatal_msg_;
     std::thread worker_, follower_; bool follower_done_ = false;
+    uint64_t n_cancelled_ = 0, n_cancel_seen_ = 0;
     uint64_t n_mixed_steps_ = 0, n_admit_deferred_ = 0, n_completed_ = 0, n_prefill_tokens_ = 0, n_decode_tokens_ = 0, n_prefill_steps_ = 0, n_decode_steps_ = 0, n_preempt_ = 0;
     double busy_ms_ = 0;
 };
@@ -633,10 +667,16 @@ static int template_ids(oa_engine* h, const std::vector<ChatMessage>& msgs, std:
 
 static int submit_chat(oa_engine* h, const oa_chat_req* r, uint64_t* ticket) {
     if (!h || !r || !ticket) return fail(OA_ERR_BAD_REQUEST, "null argument");
-    if (r->model && r->model[0] && h->e->config().name != r->model) return fail(OA_ERR_BAD_REQUEST, std::string("model '") + r->model + "' is not loaded (engine serves '" + h->e->config().name + "')");
+    if (r->model && r->model[0] && !h->e->serves_model(r->model))
+        return fail(OA_ERR_BAD_REQUEST, std::string("model '") + r->model + "' is not loaded (engine serves '" + h->e->config().name + "'; config \"model_aliases\" lists other names it answers to, \"*\" = any)");
     if (r->temperature > 1e-3f) return fail(OA_ERR_BAD_REQUEST, "only greedy decoding is implemented (the reference sends temperature=SmallestNonzeroFloat32)");
     std::vector<ChatMessage> msgs;
     int rc = build_messages(r->msgs, r->n_msgs, msgs); if (rc) return rc;
+    {   // refuse absurd inputs BEFORE tokenising them on the caller's thread: no tokenizer yields fewer than one token per 16 bytes of text
+        size_t bytes = 0; for (auto& m : msgs) bytes += m.content.size() + m.role.size();
+        if (bytes > (size_t)h->e->options().max_seq_len * 16)
+            return fail(OA_ERR_BAD_REQUEST, "prompt of " + std::to_string(bytes) + " bytes cannot fit max_seq_len " + std::to_string(h->e->options().max_seq_len) + " tokens");
+    }
     uint32_t flags = r->flags;
     if (flags == 0 && h->e->options().json_mode) {        // explicit per-request flags always win
         // stateless ReAct policy: the history is resent on every step (simple.go:498-501), so the number of assistant turns
@@ -658,6 +698,12 @@ int oa_chat_complete(oa_engine* h, const oa_chat_req* r, oa_chat_resp* out) {
     uint64_t t = 0; int rc = submit_chat(h, r, &t); if (rc) return rc;
     return oa_chat_wait(h, t, -1, out);
 }
+int oa_chat_cancel(oa_engine* h, uint64_t ticket) { if (!h) return fail(OA_ERR_BAD_REQUEST, "null engine"); return h->e->cancel(ticket); }
+// variants that hand the error text back in a caller buffer: a goroutine may migrate between OS threads around a cgo call, so the
+// thread-local oa_last_error() is only safe under runtime.LockOSThread — these need no pinning
+static int with_err(int rc, char* errbuf, size_t errcap) { if (errbuf && errcap) std::snprintf(errbuf, errcap, "%s", rc ? g_last_error.c_str() : ""); return rc; }
+int oa_chat_submit_ex(oa_engine* h, const oa_chat_req* r, uint64_t* ticket, char* errbuf, size_t errcap) { return with_err(submit_chat(h, r, ticket), errbuf, errcap); }
+int oa_chat_wait_ex(oa_engine* h, uint64_t ticket, int32_t timeout_ms, oa_chat_resp* out, char* errbuf, size_t errcap) { return with_err(oa_chat_wait(h, ticket, timeout_ms, out), errbuf, errcap); }
 void oa_free_resp(oa_chat_resp* r) { if (!r) return; std::free(r->content); std::free(r->token_ids); std::memset(r, 0, sizeof *r); }
 
 int oa_tokens_submit(oa_engine* h, const int32_t* prompt, int32_t n, int32_t max_tokens, uint32_t flags, uint64_t* ticket) {

@@ -209,7 +209,7 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
         if (opt.num_pages <= 0) throw std::runtime_error("tensor parallel engines need an explicit num_pages (all ranks must agree on the pool size)");
         // bf16 prefill partials | fp32 decode partials | up to 256 rows of this rank's fp32 logits shard (debug parity hook)
         const size_t sym_bytes = std::max({(size_t)MR * H * 2, (size_t)256 * H * 4, (size_t)256 * V_l * 4});
-        comm.reset(new TpComm(tp, tp_rank, opt.tp_shm, sym_bytes, max_sample_));
+        comm.reset(new TpComm(tp, tp_rank, opt.tp_shm, sym_bytes, max_sample_, opt.tp_nonce));
     }
     cuda_check(cudaStreamSynchronize(stream), "init sync");
 }
@@ -238,11 +238,22 @@ void DeviceModel::load_checkpoint(const std::string& path) {
     const int qd = nh_l * D, kd = nkv_l * D;
     const int64_t r = tp_rank;
     std::vector<uint16_t> buf;
+    // every tensor must have exactly the logical shape [R, C] (vectors: [C]) this model configuration implies — a transposed, truncated or
+    // wrong-config (hidden / ffn / heads / vocab) checkpoint is refused with a message instead of being read out of bounds
+    auto checked = [&](const std::string& name, int64_t R, int64_t C) -> const StTensor& {
+        const StTensor& t = st.get(name);
+        const bool ok = (t.shape.size() == 2 && t.shape[0] == R && t.shape[1] == C) || (R == 1 && t.shape.size() == 1 && t.shape[0] == C);
+        if (!ok) {
+            std::string got = "["; for (size_t i = 0; i < t.shape.size(); ++i) got += (i ? ", " : "") + std::to_string(t.shape[i]); got += "]";
+            throw std::runtime_error("checkpoint tensor " + name + " has shape " + got + ", this model needs [" + (R == 1 ? "" : std::to_string(R) + ", ") + std::to_string(C) + "]");
+        }
+        if (t.dtype != "BF16" && t.dtype != "F16" && t.dtype != "F32") throw std::runtime_error("checkpoint tensor " + name + " has unsupported dtype " + t.dtype);
+        return t;       // SafeTensors already verified bytes == prod(shape) * sizeof(dtype)
+    };
     // logical [R, C] tensor `name`: rows [row0, row0+rows) x cols [col0, col0+cols) -> device dst (row-major [rows, cols])
     auto slice = [&](const std::string& name, int64_t R, int64_t C, int64_t row0, int64_t rows, int64_t col0, int64_t cols, void* dst) {
-        const StTensor& t = st.get(name);
-        int64_t n = 1; for (auto d : t.shape) n *= d;
-        if (n != R * C) throw std::runtime_error("checkpoint tensor " + name + " has " + std::to_string(n) + " elements, expected " + std::to_string(R * C));
+        const StTensor& t = checked(name, R, C);
+        if (row0 < 0 || col0 < 0 || row0 + rows > R || col0 + cols > C) throw std::runtime_error("checkpoint slice out of range for " + name);
         buf.resize((size_t)rows * cols);
         for (int64_t i = 0; i < rows; ++i) to_bf16_rows(t, C, row0 + i, col0, cols, buf.data() + (size_t)i * cols);
         cuda_check(cudaMemcpy(dst, buf.data(), buf.size() * 2, cudaMemcpyHostToDevice), "checkpoint H2D");
@@ -267,7 +278,7 @@ void DeviceModel::load_checkpoint(const std::string& path) {
             slice(p + "self_attn.v_proj.bias", 1, cfg.kv_dim(), 0, 1, r * kd, kd, bq + qd + kd);
         }
         // gate/up: physical rows interleaved in blocks of 16 (16 gate rows, 16 up rows)
-        const StTensor& tg = st.get(p + "mlp.gate_proj.weight"); const StTensor& tu = st.get(p + "mlp.up_proj.weight");
+        const StTensor& tg = checked(p + "mlp.gate_proj.weight", cfg.ffn, H); const StTensor& tu = checked(p + "mlp.up_proj.weight", cfg.ffn, H);
         buf.resize((size_t)2 * F_l * H);
         for (int64_t blk = 0; blk < F_l / 16; ++blk)
             for (int64_t w = 0; w < 32; ++w)

@@ -43,6 +43,14 @@ public:
         return it->second;
     }
 
+    static size_t dtype_size(const std::string& d) {
+        if (d == "BF16" || d == "F16" || d == "I16" || d == "U16") return 2;
+        if (d == "F32" || d == "I32" || d == "U32") return 4;
+        if (d == "F64" || d == "I64" || d == "U64") return 8;
+        if (d == "I8" || d == "U8" || d == "BOOL" || d == "F8_E4M3" || d == "F8_E5M2") return 1;
+        return 0;
+    }
+
 private:
     void open_file(const std::string& f) {
         int fd = open(f.c_str(), O_RDONLY);
@@ -99,6 +107,12 @@ private:
                 }
                 if (off.size() != 2 || off[0] < 0 || off[1] < off[0] || (size_t)off[1] > data_bytes) throw std::runtime_error("bad data_offsets for " + name + " in " + f);
                 t.data = data + off[0]; t.bytes = (size_t)(off[1] - off[0]);
+                {   // the byte range must hold exactly prod(shape) elements of the declared dtype: a truncated or mislabelled tensor is an error here, not a SIGBUS later
+                    const size_t esz = dtype_size(t.dtype);
+                    if (esz == 0) throw std::runtime_error("unsupported dtype " + t.dtype + " for " + name + " in " + f);
+                    unsigned __int128 n = 1; for (int64_t d : t.shape) { if (d < 0) throw std::runtime_error("negative dimension for " + name + " in " + f); n *= (unsigned __int128)d; }
+                    if (n * esz != (unsigned __int128)t.bytes) throw std::runtime_error("tensor " + name + " in " + f + ": data_offsets span " + std::to_string(t.bytes) + " bytes but shape x dtype needs " + std::to_string((unsigned long long)(n * esz)));
+                }
                 tensors_[name] = t;
             }
             ws(c); if (c.s[c.i] == ',') { ++c.i; continue; } expect(c, '}'); break;

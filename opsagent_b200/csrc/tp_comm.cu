@@ -3,6 +3,8 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <signal.h>
+#include <cerrno>
 
 #include <chrono>
 #include <cstdio>
@@ -27,30 +29,60 @@ static void spin_until(const std::function<bool()>& ok, const char* what, double
     }
 }
 
-TpComm::TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, int max_sample)
+static bool pid_alive(int64_t pid) { return pid > 0 && (kill((pid_t)pid, 0) == 0 || errno != ESRCH); }
+
+TpComm::TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, int max_sample, uint64_t nonce)
     : t_(t), rank_(rank), shm_name_(shm_name), sym_bytes_(sym_bytes) {
     if (t < 2 || t > TP_MAX || rank < 0 || rank >= t) throw std::runtime_error("tp must be 2..8 and 0 <= tp_rank < tp");
     // ---- shared-memory segment (leader creates, followers attach) ----
-    int fd = -1;
+    // A crashed run leaves its segment behind with magic set, handles_ready >= t and possibly seq == UINT64_MAX.  The new leader therefore
+    // first INVALIDATES whatever is linked under the name (magic = 0: a follower that attached to it goes back to waiting), then unlinks
+    // and creates a fresh segment stamped with this launch's nonce and its own pid; followers accept a segment only if the nonce matches
+    // theirs (when one is configured) and the leader process is alive, and otherwise keep polling for the new one.
     if (rank == 0) {
+        int old = shm_open(shm_name.c_str(), O_RDWR, 0600);
+        if (old >= 0) {
+            struct stat st;
+            if (fstat(old, &st) == 0 && (size_t)st.st_size >= sizeof(TpShm)) {
+                void* m = mmap(nullptr, sizeof(TpShm), PROT_READ | PROT_WRITE, MAP_SHARED, old, 0);
+                if (m != MAP_FAILED) {
+                    TpShm* stale = reinterpret_cast<TpShm*>(m);
+                    const int64_t owner = stale->leader_pid.load();
+                    if (stale->magic.load() == 0x4f415450u && owner != (int64_t)getpid() && pid_alive(owner) && stale->seq.load() != UINT64_MAX) {
+                        munmap(m, sizeof(TpShm)); close(old);
+                        throw std::runtime_error("tp shm segment " + shm_name + " belongs to a live tensor-parallel group (leader pid " + std::to_string((long long)owner) +
+                                                 "): give this group its own \"tp_shm\" name");
+                    }
+                    stale->magic.store(0, std::memory_order_release);
+                    munmap(m, sizeof(TpShm));
+                }
+            }
+            close(old);
+        }
         shm_unlink(shm_name.c_str());
-        fd = shm_open(shm_name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+        const int fd = shm_open(shm_name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
         if (fd < 0 || ftruncate(fd, sizeof(TpShm)) != 0) throw std::runtime_error("shm_open/ftruncate failed for " + shm_name);
         owner_ = true;
-    } else {
-        spin_until([&] { fd = shm_open(shm_name.c_str(), O_RDWR, 0600); if (fd < 0) return false;
-                         struct stat st; if (fstat(fd, &st) != 0 || (size_t)st.st_size < sizeof(TpShm)) { close(fd); fd = -1; return false; } return true; },
-                   "follower waiting for the leader's shm segment");
-    }
-    shm_ = reinterpret_cast<TpShm*>(mmap(nullptr, sizeof(TpShm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0));
-    close(fd);
-    if (shm_ == MAP_FAILED) throw std::runtime_error("mmap of the tp shm segment failed");
-    if (rank == 0) {
+        shm_ = reinterpret_cast<TpShm*>(mmap(nullptr, sizeof(TpShm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0));
+        close(fd);
+        if (shm_ == MAP_FAILED) throw std::runtime_error("mmap of the tp shm segment failed");
         shm_->handles_ready.store(0); shm_->peers_opened.store(0); shm_->seq.store(0);
         for (int i = 0; i < TP_MAX; ++i) shm_->ack[i].store(0);
+        shm_->nonce.store(nonce); shm_->leader_pid.store((int64_t)getpid());
         shm_->magic.store(0x4f415450u, std::memory_order_release);
     } else {
-        spin_until([&] { return shm_->magic.load(std::memory_order_acquire) == 0x4f415450u; }, "leader initialising shm");
+        spin_until([&] {
+            const int fd = shm_open(shm_name.c_str(), O_RDWR, 0600); if (fd < 0) return false;
+            struct stat st; if (fstat(fd, &st) != 0 || (size_t)st.st_size < sizeof(TpShm)) { close(fd); return false; }
+            void* m = mmap(nullptr, sizeof(TpShm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+            close(fd);
+            if (m == MAP_FAILED) return false;
+            TpShm* c = reinterpret_cast<TpShm*>(m);
+            const bool ok = c->magic.load(std::memory_order_acquire) == 0x4f415450u && (nonce == 0 || c->nonce.load() == nonce) &&
+                            pid_alive(c->leader_pid.load()) && c->seq.load() != UINT64_MAX;
+            if (!ok) { munmap(m, sizeof(TpShm)); return false; }      // not there yet, stale, or another launch's: keep polling
+            shm_ = c; return true; },
+                   "follower waiting for the leader's shm segment (same tp_shm name and tp_nonce, live leader)");
     }
     // ---- symmetric device buffers + IPC handle exchange ----
     arg_half_bytes_ = (size_t)max_sample * 8;
@@ -127,6 +159,8 @@ bool TpComm::receive(StepInput& in) {
         if (s == UINT64_MAX) return false;
         if (s > seq_local_) break;
         std::this_thread::sleep_for(std::chrono::microseconds(20));
+        if ((++idle_polls_ & 0x3fff) == 0 && !leader_alive())      // every ~0.3 s of idling
+            throw std::runtime_error("tensor-parallel leader (pid " + std::to_string((long long)shm_->leader_pid.load()) + ") is gone");
     }
     const int32_t* m = shm_->msg; size_t w = 0;
     const int32_t* hdr = m; w += 8;
@@ -141,6 +175,8 @@ bool TpComm::receive(StepInput& in) {
     shm_->ack[rank_].store(s, std::memory_order_release);
     return true;
 }
+
+bool TpComm::leader_alive() const { return shm_ && pid_alive(shm_->leader_pid.load()); }
 
 void TpComm::shutdown() { if (shm_ && rank_ == 0) shm_->seq.store(UINT64_MAX, std::memory_order_release); }
 

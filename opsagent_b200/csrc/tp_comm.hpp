@@ -23,7 +23,9 @@ constexpr int TP_MAX = 8;
 constexpr size_t TP_MSG_WORDS = 2u << 20;     // 8 MB step-message area
 
 struct TpShm {                                 // lives in POSIX shared memory
-    std::atomic<uint32_t> magic;
+    std::atomic<uint32_t> magic;               // set LAST by the leader; cleared first thing when a new leader finds a stale segment
+    std::atomic<uint64_t> nonce;               // per-launch id (config "tp_nonce"): followers refuse a segment of another launch
+    std::atomic<int64_t> leader_pid;           // followers refuse a segment whose leader is gone and notice a leader that dies later
     std::atomic<uint32_t> handles_ready;       // ranks that published their IPC handles
     std::atomic<uint32_t> peers_opened;        // ranks that mapped every peer
     cudaIpcMemHandle_t h_sym[TP_MAX][2];
@@ -37,7 +39,7 @@ struct TpShm {                                 // lives in POSIX shared memory
 
 class TpComm {
 public:
-    TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, int max_sample);
+    TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, int max_sample, uint64_t nonce = 0);
     ~TpComm();
     int size() const { return t_; }
     int rank() const { return rank_; }
@@ -58,7 +60,8 @@ public:
 
     // ---- host side: leader publishes, followers receive ----
     void publish(const StepInput& in);
-    bool receive(StepInput& in);                                          // false = shutdown
+    bool receive(StepInput& in);                                          // false = shutdown; throws when the leader process has died
+    bool leader_alive() const;
     void shutdown();
 
 private:
@@ -67,7 +70,7 @@ private:
     void** d_peer_sym_[2] = {nullptr, nullptr};
     uint32_t* flags_ = nullptr; uint32_t* peer_flags_[TP_MAX] = {}; uint32_t** d_peer_flags_ = nullptr; unsigned int* done_counter_ = nullptr;
     void* arg_ = nullptr; void* peer_arg_[TP_MAX] = {}; void** d_peer_arg_[2] = {nullptr, nullptr}; size_t arg_half_bytes_ = 0;
-    uint64_t ar_count_ = 0; uint32_t epoch_ = 0; uint64_t seq_local_ = 0; size_t sym_bytes_ = 0;
+    uint64_t ar_count_ = 0; uint32_t epoch_ = 0; uint64_t seq_local_ = 0; uint64_t idle_polls_ = 0; size_t sym_bytes_ = 0;
 };
 
 // x[T,H] (bf16, in place) += sum over ranks (rank order) of fp32 partial rows; xn = rmsnorm(x) * gain   (decode path)

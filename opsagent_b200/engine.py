@@ -100,6 +100,10 @@ class Engine:
         finally:
             self._L.oa_free_resp(C.byref(resp))
 
+    def cancel(self, ticket: int) -> None:
+        """abandon a submitted request (frees its KV pages at the next step boundary); waiting on the ticket afterwards is an error"""
+        _check(self._L.oa_chat_cancel(self._h, ticket))
+
     def chat_complete(self, model: str, messages, max_tokens: int, flags: int = 0, functions: str | None = None) -> Completion:
         req, _keep = self._req(model, messages, max_tokens, flags, functions)
         resp = _lib.OaChatResp()

@@ -18,9 +18,26 @@ from .perf import GetPerfStats
 _STATUS_TYPE = {400: "invalid_request_error", 401: "authentication_error", 429: "rate_limit_error", 500: "server_error"}
 
 
-def make_handler(engine, require_key: bool = True, tool_steps: int = 3):
+MAX_BODY_BYTES = 64 << 20        # a chat request is a few KB (16k-token observations: ~100 KB); anything near this is not a chat request
+
+
+def make_handler(engine, require_key: bool = True, tool_steps: int = 3, api_key: str | None = None):
+    """`api_key`: when given, the bearer token must equal it; otherwise any non-empty token is accepted — the reference forwards
+    whatever X-API-Key the caller sent (openai.go:40-44) and a local engine has no account to check it against."""
     class Handler(BaseHTTPRequestHandler):
         protocol_version = "HTTP/1.1"
+
+        def _read_body(self):
+            """-> bytes, or None after answering 400/413 (connection closed: the unread body must not be parsed as the next request)"""
+            try:
+                n = int(self.headers.get("Content-Length", "0"))
+            except ValueError:
+                n = -1
+            if n < 0 or n > MAX_BODY_BYTES:
+                self.close_connection = True
+                self._error(400 if n < 0 else 413, "bad Content-Length")
+                return None
+            return self.rfile.read(n) if n else b""
 
         def log_message(self, *a):      # quiet
             pass
@@ -35,7 +52,11 @@ def make_handler(engine, require_key: bool = True, tool_steps: int = 3):
 
         def _authorised(self) -> bool:
             auth = self.headers.get("Authorization", "")
-            return (not require_key) or (auth.startswith("Bearer ") and len(auth) > 7)
+            if not require_key:
+                return True
+            if not (auth.startswith("Bearer ") and len(auth) > 7):
+                return False
+            return api_key is None or auth[7:] == api_key
 
         def _error(self, status: int, message: str):
             self._send(status, {"error": {"message": message, "type": _STATUS_TYPE.get(status, "server_error"), "code": status}})
@@ -55,6 +76,9 @@ def make_handler(engine, require_key: bool = True, tool_steps: int = 3):
             self._error(404, "not found")
 
         def do_POST(self):
+            body = self._read_body()          # always drained first: early 401/404 replies keep the keep-alive connection in sync
+            if body is None:
+                return
             if self.path.rstrip("/").endswith("/perf/reset"):          # pkg/api/router.go:105, pkg/handlers/perf.go:28-39
                 if not self._authorised():
                     return self._error(401, "missing bearer token")
@@ -65,8 +89,7 @@ def make_handler(engine, require_key: bool = True, tool_steps: int = 3):
             if not self._authorised():
                 return self._error(401, "missing bearer token")        # the reference always sends its apiKey (openai.go:44)
             try:
-                n = int(self.headers.get("Content-Length", "0"))
-                req = json.loads(self.rfile.read(n) or b"{}")
+                req = json.loads(body or b"{}")
                 msgs = []
                 for m in req["messages"]:            # function-calling turns are flattened into text the byte-level template can carry
                     if m.get("tool_calls"):
@@ -105,7 +128,14 @@ def make_handler(engine, require_key: bool = True, tool_steps: int = 3):
                 return self._error(e.code if e.code in (400, 401, 429, 500) else 500, e.message)
             done()
             if flags == 8:
-                call = json.loads(out.content.decode("utf-8", "replace"))
+                try:
+                    call = json.loads(out.content.decode("utf-8", "replace"))
+                    call["name"], call["arguments"]
+                except Exception:
+                    # the grammar-forced call was cut off (max_tokens, or max_seq_len minus a long history): nothing parseable to return.
+                    # 400 is what the API answers when the context budget cannot hold the completion; the reference does not retry it.
+                    return self._error(400, f"function call truncated after {out.completion_tokens} tokens (finish_reason={out.finish_reason}): "
+                                            "raise max_tokens or shorten the history")
                 message = {"role": "assistant", "content": None,
                            "tool_calls": [{"id": f"call_{int(time.time() * 1e6):x}", "type": "function",
                                            "function": {"name": call["name"], "arguments": json.dumps(call["arguments"])}}]}
@@ -122,10 +152,10 @@ def make_handler(engine, require_key: bool = True, tool_steps: int = 3):
     return Handler
 
 
-def serve(engine, host: str = "127.0.0.1", port: int = 8000, require_key: bool = True, tool_steps: int = 3):
+def serve(engine, host: str = "127.0.0.1", port: int = 8000, require_key: bool = True, tool_steps: int = 3, api_key: str | None = None):
     """-> (server, thread).  One OS thread per in-flight request, each blocking in the engine — the same concurrency shape as
     gin's goroutine-per-request; batching happens inside the engine."""
-    srv = ThreadingHTTPServer((host, port), make_handler(engine, require_key, tool_steps))
+    srv = ThreadingHTTPServer((host, port), make_handler(engine, require_key, tool_steps, api_key))
     srv.daemon_threads = True
     th = threading.Thread(target=srv.serve_forever, daemon=True)
     th.start()

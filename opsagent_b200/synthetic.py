@@ -3,12 +3,18 @@ run on-box without a cluster: BASELINE.json configs describe 'synthetic Pod YAML
 observations'.  Not on the hot path; used by bench.py / tests as the `tools` argument of assistants.AssistantWithConfig."""
 from __future__ import annotations
 
+import hashlib
 import random
+
+
+def _seed(seed: int, text: str) -> int:
+    """process-independent seed (the built-in hash() of a str is salted per process)"""
+    return int.from_bytes(hashlib.blake2b(f"{seed}\x00{text}".encode("utf-8"), digest_size=8).digest(), "little")
 
 
 def fake_kubectl(seed: int = 0, rows: int = 12):
     def kubectl(inp: str) -> str:
-        r = random.Random(hash((seed, inp)) & 0xFFFFFFFF)
+        r = random.Random(_seed(seed, inp))
         lines = ["NAME                      READY   STATUS             RESTARTS   AGE    IP            NODE"]
         for i in range(rows):
             st = r.choice(["Running", "Running", "Running", "CrashLoopBackOff", "Pending", "Completed"])
@@ -20,7 +26,7 @@ def fake_kubectl(seed: int = 0, rows: int = 12):
 
 def fake_trivy(seed: int = 0, rows: int = 40):
     def trivy(image: str) -> str:
-        r = random.Random(hash((seed, image)) & 0xFFFFFFFF)
+        r = random.Random(_seed(seed, image))
         lines = [f"{image} (debian 12.5)", "Total: %d (HIGH: %d, CRITICAL: %d)" % (rows, rows * 2 // 3, rows // 3), "LIBRARY | VULNERABILITY | SEVERITY | INSTALLED | FIXED | TITLE"]
         for _ in range(rows):
             lines.append(f"lib{r.randrange(400)} | CVE-20{r.randrange(15, 26)}-{r.randrange(1000, 60000)} | {r.choice(['HIGH', 'CRITICAL', 'MEDIUM'])} | "

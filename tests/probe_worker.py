@@ -1,5 +1,5 @@
-"""Child process of tests/test_probe_gpu.py: one probe per process, so that a device fault in a configuration that has not been seen
-green yet cannot poison the CUDA context of the main test run.  Exit code 0 = probe passed; anything else = failed (reason on stdout)."""
+"""Child process of tests/test_probe_gpu.py: one configuration per process, so that a device fault in one of them cannot poison the CUDA
+context of the main test run.  Exit code 0 = probe passed; anything else = failed (reason on stdout)."""
 import os
 import sys
 
@@ -75,7 +75,7 @@ def mixed():
     eng = Engine(spec.engine_json(num_pages=96, max_seq_len=512, max_batch=8, max_step_tokens=256, mixed_steps=1, prefill_batch_tokens=0))
     orc = O.Oracle(spec, max_pos=512, n_slots=1, mode=1)
     rng = np.random.default_rng(33)
-    jobs = [(20, 160)] + [(int(n), 30) for n in (40, 90, 150, 200, 64, 129)]
+    jobs = [(20, 420)] + [(int(n), 30) for n in (40, 90, 150, 200, 64, 129)]
     prompts = [rng.integers(0, spec.vocab, size=n).astype(np.int32) for n, _ in jobs]
     results = [None] * len(jobs)
 
@@ -83,9 +83,12 @@ def mixed():
         results[i] = eng.generate(prompts[i].tolist(), jobs[i][1], flags=1)
 
     th = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
-    th[0].start(); time.sleep(0.05)                      # the long request is decoding when the others arrive, one by one
+    th[0].start()
+    t_end = time.time() + 30
+    while eng.stats()["decode_steps"] < 3 and time.time() < t_end:      # the long request is provably decoding when the others arrive
+        time.sleep(0.0005)
     for t in th[1:]:
-        t.start(); time.sleep(0.01)
+        t.start(); time.sleep(0.002)
     [t.join() for t in th]
     st = eng.stats()
     if st.get("mixed_steps", 0) <= 0:

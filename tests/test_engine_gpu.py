@@ -431,3 +431,83 @@ def test_safetensors_checkpoint_loading(name, dtype, tmp_path):
     eng.close(); orc.close()
     with pytest.raises(EngineError):
         Engine(spec.engine_json(num_pages=32, max_seq_len=512, weights=str(tmp_path / "missing.safetensors")))
+
+
+def test_malformed_checkpoints_are_refused_with_a_message(tmp_path):
+    """wrong-config, transposed and truncated checkpoints must fail engine creation cleanly (no out-of-bounds read of the mapping)"""
+    import struct
+    spec = O.PRESETS["tiny-llama"]
+    orc = O.Oracle(spec, max_pos=64, mode=1)
+    good = str(tmp_path / "good.safetensors")
+    O.write_safetensors(orc, good, "BF16")
+    orc.close()
+    raw = open(good, "rb").read()
+    hl = struct.unpack("<Q", raw[:8])[0]
+    header = json.loads(raw[8:8 + hl])
+
+    def write(path, hdr, body):
+        hj = json.dumps(hdr, separators=(",", ":")).encode()
+        hj += b" " * ((8 - len(hj) % 8) % 8)
+        open(path, "wb").write(struct.pack("<Q", len(hj)) + hj + body)
+
+    # (1) a checkpoint of another architecture: engine configured with twice the ffn
+    cfg = spec.engine_json(num_pages=32, max_seq_len=512, weights=good)
+    cfg["ffn"] = spec.ffn * 2
+    with pytest.raises(EngineError, match="shape"):
+        Engine(cfg)
+    # (2) same element count, transposed shape
+    h2 = json.loads(json.dumps(header))
+    k = "model.layers.0.mlp.down_proj.weight"
+    h2[k]["shape"] = h2[k]["shape"][::-1]
+    p2 = str(tmp_path / "transposed.safetensors"); write(p2, h2, raw[8 + hl:])
+    with pytest.raises(EngineError, match="shape"):
+        Engine(spec.engine_json(num_pages=32, max_seq_len=512, weights=p2))
+    # (3) data_offsets that do not cover prod(shape) * sizeof(dtype)
+    h3 = json.loads(json.dumps(header))
+    k = "model.layers.0.mlp.gate_proj.weight"
+    h3[k]["data_offsets"][1] -= 64
+    p3 = str(tmp_path / "short.safetensors"); write(p3, h3, raw[8 + hl:])
+    with pytest.raises(EngineError, match="data_offsets"):
+        Engine(spec.engine_json(num_pages=32, max_seq_len=512, weights=p3))
+    # (4) file cut in the middle of the tensor data
+    p4 = str(tmp_path / "cut.safetensors"); open(p4, "wb").write(raw[: len(raw) // 2])
+    with pytest.raises(EngineError):
+        Engine(spec.engine_json(num_pages=32, max_seq_len=512, weights=p4))
+
+
+def test_cancel_model_aliases_and_oversize_text():
+    """oa_chat_cancel frees an abandoned request's pages (a timed-out wait would otherwise decode to max_tokens), `model_aliases`
+    lets the engine answer to the names the unmodified reference sends (execute.go:168-171: currentModel or "gpt-4"), and text that
+    cannot possibly fit is refused before it is tokenised"""
+    import time
+    spec, eng = make_engine("tiny-llama", model_aliases="gpt-4,gpt-4o")
+    assert eng.chat_complete("gpt-4", [("user", "hi")], 4, flags=1).completion_tokens == 4
+    with pytest.raises(EngineError) as e:
+        eng.chat_complete("claude", [("user", "hi")], 4)
+    assert e.value.code == 400 and "model_aliases" in e.value.message
+    with pytest.raises(EngineError) as e:
+        eng.chat_complete(spec.name, [("user", "x" * (512 * 16 + 1))], 4)
+    assert e.value.code == 400 and "cannot fit" in e.value.message
+    # a long request is decoding; the caller gives up
+    t = eng.tokens_submit(list(range(1, 40)), 400, flags=1)
+    with pytest.raises(EngineError) as e:
+        eng.wait(t, timeout_ms=1)
+    assert e.value.code == 408
+    eng.cancel(t)
+    with pytest.raises(EngineError):
+        eng.wait(t, timeout_ms=1)                                   # the ticket is gone
+    t_end = time.time() + 10
+    while time.time() < t_end:
+        st = eng.stats()
+        if st["running"] == 0 and st["pages_free"] + st["pages_cached"] == st["pages_total"]:
+            break
+        time.sleep(0.005)
+    st = eng.stats()
+    assert st["cancelled"] == 1 and st["running"] == 0 and st["pages_free"] + st["pages_cached"] == st["pages_total"]
+    # a cancelled WAITING request (engine busy elsewhere) and normal service afterwards
+    out = eng.generate([5, 6, 7], 8, flags=1)
+    assert out.completion_tokens == 8
+    eng.close()
+    spec, eng = make_engine("tiny-llama", model_aliases="*")
+    assert eng.chat_complete("whatever-the-caller-says", [("user", "hi")], 3, flags=1).completion_tokens == 3
+    eng.close()

@@ -487,3 +487,95 @@ def test_streamk_plan_invariants(N, K, G):
                 assert u0[c] >= t * kb and u0[c] < (t + 1) * kb                            # ... every other piece is the HEAD of its CTA's range
                 assert u0[c] == max(u0[c], t * kb)
             # so a finishing CTA only waits on pieces that their CTAs compute FIRST: the wait-for graph has no cycle
+
+
+# ---- reference prompts (verbatim fixtures), Go-faithful marshalling, seeded synthetic tools ---------------------------------------
+import hashlib    # noqa: E402
+import os         # noqa: E402
+import subprocess  # noqa: E402
+import sys        # noqa: E402
+
+PROMPTS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prompts")
+
+
+def test_prompt_fixtures_are_the_reference_constants_verbatim():
+    """byte lengths are the ones SURVEY.md §8a measured (3,233 / 3,109 / 1,965 / 2,164 B); sha256 pins every byte; when the reference
+    tree is present (build container) the fixtures are re-extracted and compared"""
+    idx = json.load(open(os.path.join(PROMPTS_DIR, "index.json")))
+    want = {"executeSystemPrompt_cn": 3233, "diagnoseSystemPrompt": 3109, "analysisPrompt": 1965, "auditPrompt": 2164}
+    for name, meta in idx.items():
+        raw = open(os.path.join(PROMPTS_DIR, name + ".txt"), "rb").read()
+        assert len(raw) == meta["bytes"] and hashlib.sha256(raw).hexdigest() == meta["sha256"], name
+        if name in want:
+            assert len(raw) == want[name]
+    if os.path.isdir("/root/reference/pkg"):
+        sys.path.insert(0, PROMPTS_DIR)
+        import extract_prompts
+        for name, (text, _where, _use) in extract_prompts.extract("/root/reference").items():
+            assert open(os.path.join(PROMPTS_DIR, name + ".txt"), "rb").read() == text.encode("utf-8"), name
+
+
+def test_toolprompt_marshal_is_go_json_marshal_byte_for_byte():
+    """json.Marshal escapes <, >, & and U+2028/9 (simple.go:497 sends this string as the next user message)"""
+    tp = ToolPrompt("q", "t", {"name": "kubectl", "input": "get pods | grep <none> && echo 'a&b'"}, "NODE  <none>\t中 \x01\"\\", "")
+    want = ('{"question":"q","thought":"t","action":{"name":"kubectl","input":"get pods | grep \\u003cnone\\u003e \\u0026\\u0026 echo \'a\\u0026b\'"},'
+            '"observation":"NODE  \\u003cnone\\u003e\\t中\\u2028\\u0001\\"\\\\","final_answer":""}')
+    assert tp.marshal() == want
+    assert ToolPrompt.unmarshal(tp.marshal()) == tp
+    # Unmarshal: wrong types are errors (Go: UnmarshalTypeError), null / missing / unknown keys are not, keys match case-insensitively
+    for bad in ('{"question": 5}', '{"action": "kubectl"}', '{"action": {"name": 1}}', '[1]', '"x"'):
+        with pytest.raises(ValueError):
+            ToolPrompt.unmarshal(bad)
+    got = ToolPrompt.unmarshal('{"Question": "Q", "thought": null, "action": {"NAME": "jq"}, "extra": [1]}')
+    assert (got.question, got.thought, got.action) == ("Q", "", {"name": "jq", "input": ""})
+
+
+def test_synthetic_tools_are_seeded_across_processes():
+    code = ("from opsagent_b200.synthetic import copilot_tools; import hashlib; t = copilot_tools(7); "
+            "print(hashlib.sha256((t['kubectl']('get pods -A') + t['trivy']('nginx:1.25')).encode()).hexdigest())")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, env={**os.environ, "PYTHONHASHSEED": str(s)}).stdout.strip()
+            for s in (1, 2, 3)}
+    assert len(outs) == 1 and len(next(iter(outs))) == 64
+
+
+def test_http_front_survives_bad_clients():
+    """early 401/404 replies drain the request body (HTTP/1.1 keep-alive stays in sync), a truncated grammar-forced call is an
+    OpenAI-style error instead of a dropped connection, Content-Length is bounded, and a configured key is compared"""
+    import http.client
+    from opsagent_b200.http_front import serve
+
+    class Eng:
+        info = {"model": "tiny"}
+
+        def chat_complete(self, model, msgs, max_tokens, flags=0, functions=None):
+            class R:
+                content = (b'{"name":"kubectl","argum' if flags == 8 else b"ok"); prompt_tokens = 3; completion_tokens = 6; finish_reason = "length" if flags == 8 else "stop"
+            return R()
+
+    srv, _ = serve(Eng(), port=0, api_key="sk-right")
+    conn = http.client.HTTPConnection("127.0.0.1", srv.server_address[1], timeout=10)
+    body = json.dumps({"model": "tiny", "messages": [{"role": "user", "content": "x" * 5000}]})
+
+    def post(path, key, b=body, extra=None):
+        h = {"Content-Type": "application/json", "Authorization": f"Bearer {key}"}
+        h.update(extra or {})
+        conn.request("POST", path, body=b, headers=h)
+        r = conn.getresponse()
+        return r.status, json.loads(r.read() or b"{}")
+
+    # three requests on ONE connection: 401 (wrong key, body unread by the handler logic), 404, then a good one must still parse
+    assert post("/v1/chat/completions", "sk-wrong")[0] == 401
+    assert post("/v1/nothing", "sk-right")[0] == 404
+    st, r = post("/v1/chat/completions", "sk-right")
+    assert st == 200 and r["choices"][0]["message"]["content"] == "ok"
+    tools = [{"type": "function", "function": {"name": "kubectl", "parameters": {"type": "object", "properties": {"command": {"type": "string"}}}}}]
+    st, r = post("/v1/chat/completions", "sk-right", json.dumps({"model": "tiny", "tools": tools, "max_tokens": 6, "messages": [{"role": "user", "content": "x"}]}))
+    assert st == 400 and "truncated" in r["error"]["message"]
+    st, r = post("/v1/chat/completions", "sk-right")          # and the connection is still usable afterwards
+    assert st == 200
+    conn.close()
+    conn = http.client.HTTPConnection("127.0.0.1", srv.server_address[1], timeout=10)
+    conn.putrequest("POST", "/v1/chat/completions"); conn.putheader("Content-Length", "-5"); conn.putheader("Authorization", "Bearer sk-right"); conn.endheaders()
+    assert conn.getresponse().status == 400
+    conn.close(); srv.shutdown()
