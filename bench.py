@@ -15,6 +15,11 @@ A "step" is one decode forward of the whole batch (128 sequences, one new token 
            (CUDA events on the engine stream) against the measured HBM copy bandwidth.
   cpu_baseline: the CPU oracle (a port — the reference has no model arithmetic of its own) on the host cores.
 N>1 = data-parallel replicas (BASELINE configs[2]): one engine per GPU, no data-path collective, weak scaling.
+N>=2 additionally runs, AFTER the headline (metric/value unchanged), the tensor-parallel path at t = N over the same N ranks:
+  tp.parity : tests/tp_worker.py at t=N against the CPU oracle (t=4: Qwen2.5-32B TP=4's per-rank head layout, t=8: Llama-3-70B TP=8's)
+  tp.*      : BASELINE configs[3] (Qwen2.5-32B TP=4, B=256, ctx 2048) at N=4, configs[4] (Llama-3-70B TP=8, B=64, ctx 16.9k incl. its
+              1.08M-token prefill) at N=8, Llama-3-8B TP=2 at N=2 — decode ms/step, tokens/s per group and per GPU, fraction of the per-GPU
+              HBM roofline, the all-reduce chain (in-situ us per all-reduce x count per step).
 `--impl reference` times the CPU port alone (rank 0 only), same JSON line shape.
 """
 import argparse
@@ -101,6 +106,61 @@ ANALYSIS_SYSTEM = ("You are an expert Kubernetes and cloud native networking ana
                    "the fields question, thought, action{name,input}, observation, final_answer.")
 
 
+TP_CONFIGS = {2: ("llama-3-8b", 128, 1664, "Llama-3-8B TP=2 (fits one GPU; exercises the collective path at N=2)"),
+              4: ("qwen2.5-32b", 256, 2048, "BASELINE configs[3]: Qwen2.5-32B TP=4 over NVLink, B=256, ctx 2048"),
+              8: ("llama-3-70b", 64, 16896, "BASELINE configs[4]: Llama-3-70B TP=8, B=64, 16k-token trivy observations (ctx 16.9k)")}
+KVB = {"qwen2.5-32b": 262144, "llama-3-70b": 327680, "llama-3-8b": 131072}
+
+
+def run_tp_block(args, rank, world, nonce, log):
+    """Tensor parallelism at t = world over the same ranks: parity first (checker: the CPU oracle on rank 0), then the BASELINE TP
+    config for this N.  Rank 0 returns the "tp" block, followers return None.  Own NVLink peer-memory all-reduce, no NCCL on the data path."""
+    import importlib.util
+    from opsagent_b200 import Engine
+    spec = importlib.util.spec_from_file_location("oa_tp_worker", os.path.join(ROOT, "tests", "tp_worker.py"))
+    tpw = importlib.util.module_from_spec(spec); spec.loader.exec_module(tpw)
+    block = {}
+    if not args.no_tp_parity:
+        par = tpw.run_cases(rank, world, cases=(args.tp_cases.split(",") if args.tp_cases else None), tag=str(nonce), log=log)
+        if rank == 0:
+            block["parity"] = {k: par[k] for k in ("t", "cases", "max_dlogit", "tokens_identical", "tokens_compared", "near_tie_flips", "ok")}
+            block["parity"]["tolerance"] = {"max_dlogit": tpw.LOGIT_TOL, "tokens": "identical wherever the oracle's top1-top2 margin > 2*tol"}
+    model, batch, ctx, what = TP_CONFIGS[world]
+    if args.tp_model:
+        model, batch, ctx, what = args.tp_model, args.tp_batch, args.tp_ctx, f"override: {args.tp_model} TP={world} B={args.tp_batch} ctx {args.tp_ctx}"
+    K, W = min(args.steps, 16), 4
+    max_seq = (ctx + K + W + 64 + 63) // 64 * 64
+    pages = batch * ((max_seq + 63) // 64) + 64
+    eng = Engine({"model": model, "device": rank, "tp": world, "tp_rank": rank, "tp_shm": f"/oa_tp_bench_{nonce}", "tp_nonce": nonce,
+                  "num_pages": pages, "max_batch": batch, "max_seq_len": max_seq, "max_step_tokens": 8192, "seed": 1234, "prefix_cache": 0})
+    if rank > 0:
+        eng.serve(); eng.close()
+        return None
+    ctx0 = ctx - K // 2 - W
+    r = eng.bench_decode(batch, ctx0, K, W)
+    peak, peak_src = measured_peaks()
+    os.environ["OA_PROFILE_ALL"] = "1"          # in-situ per-class kernel times on the leader (events between launches)
+    eng.kernel_times(True)
+    eng.bench_decode(batch, min(ctx0, 256), 4, 2)   # the all-reduce does not depend on the context length: a short prefill is enough
+    kt = eng.kernel_times(True)
+    os.environ["OA_PROFILE_ALL"] = "0"
+    info = eng.info
+    ar_ms, ar_n = kt.get("resid_rmsnorm", [0.0, 0])
+    gb = r["algorithmic_bytes_per_step"]
+    block.update({"config": what, "model": model, "t": world, "batch": batch, "mean_ctx": round(r["mean_ctx"], 1), "steps": K, "warmup": W,
+                  "ms_per_step": round(r["ms_per_step"], 3), "tok_s_group": round(batch / r["ms_per_step"] * 1e3, 1),
+                  "tok_s_per_gpu": round(batch / r["ms_per_step"] * 1e3 / world, 1),
+                  "algorithmic_bytes_per_gpu_per_step": gb, "hbm_GBps_per_gpu": round(gb / r["ms_per_step"] / 1e6, 1),
+                  "roofline_frac_per_gpu": round(gb / r["ms_per_step"] / 1e6 / peak, 4), "peak_source": peak_src,
+                  "allreduce_us": round(ar_ms / max(ar_n, 1) * 1e3, 2), "allreduce_count_per_step": 2 * info["n_layers"],
+                  "allreduce_note": "partial -> symmetric buffer + all-reduce + residual + RMSNorm, in-situ CUDA events on the leader (serialised: upper bound)",
+                  "prefill_tokens": batch * (ctx0 - 1), "prefill_ms": round(r["prefill_ms"], 1),
+                  "prefill_tok_s": round(batch * (ctx0 - 1) / r["prefill_ms"] * 1e3, 1), "launches_per_step": r["launches_per_step"],
+                  "collective": "own one-shot all-reduce over NVLink peer memory (tp_comm.cu), rank-ordered sum, fused with residual + RMSNorm; no NCCL on the data path"})
+    eng.close()
+    return block
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import numpy as np
@@ -123,6 +183,31 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def tp_block():
+        """-> the "tp" block on rank 0 (None on followers); never raises, never hangs the headline: rank 0 gives the leg a deadline"""
+        nt = torch.tensor([int(time.time() * 1e3) % (1 << 40) + int(os.environ.get("MASTER_PORT", "0"))], dtype=torch.int64, device="cuda")
+        dist.broadcast(nt, 0)                     # same launch id on every rank (shm name + nonce of the TP group)
+        res = {}
+
+        def work():
+            try:
+                res["tp"] = run_tp_block(args, rank, world, int(nt.item()), (lambda m: print(m, file=sys.stderr, flush=True)))
+            except Exception as e:                  # the failure is reported, not hidden
+                res["tp"] = {"error": f"{type(e).__name__}: {e}"}
+        th = threading.Thread(target=work, daemon=True)
+        th.start(); th.join(args.tp_deadline)
+        if th.is_alive():
+            return {"error": f"tensor-parallel leg did not finish within {args.tp_deadline} s"}, True
+        return res.get("tp"), False
+
+    if args.tp_only:
+        tp, hung = tp_block()
+        if rank == 0:
+            print(json.dumps({"tp": tp}), flush=True)
+        if hung:
+            os._exit(3)
+        dist.barrier(); dist.destroy_process_group()
+        return
     K, W = args.steps, max(args.warmup, 3)
     eng = Engine({"model": MODEL, "device": local_rank, "kv_gb": args.kv_gb, "max_batch": BATCH, "max_seq_len": 2048,
                   "max_step_tokens": 8192, "seed": 1234,
@@ -208,10 +293,17 @@ def run_ours(args, rank, world, local_rank):
                         "tokens_per_sec": round(BATCH * (ctx0 - 1) / (r["prefill_ms"] / 1e3), 1)}}
     if rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_tokens)
+    eng.close()
+    hung = False
+    if world >= 2 and not args.no_tp:
+        tp, hung = tp_block()
+        if rank == 0:
+            line["tp"] = tp
     if rank == 0:
         print(json.dumps(line), flush=True)      # before any teardown: a hard exit in NCCL/driver teardown must not eat the line
         sys.stdout.flush()
-    eng.close()
+    if hung:
+        os._exit(3)                               # a wedged TP leg: the line is out; let torchrun tear the other ranks down
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
 
@@ -268,6 +360,14 @@ def main():
     ap.add_argument("--kv-gb", type=float, default=60.0, dest="kv_gb")
     ap.add_argument("--cpu-tokens", type=int, default=64, dest="cpu_tokens")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tp", action="store_true", help="N>=2: skip the tensor-parallel block")
+    ap.add_argument("--no-tp-parity", action="store_true")
+    ap.add_argument("--tp-cases", default="", help="comma-separated tiny presets for the TP parity check (default: by degree)")
+    ap.add_argument("--tp-model", default="", help="override the TP bench config (dev): model, with --tp-batch/--tp-ctx")
+    ap.add_argument("--tp-batch", type=int, default=64)
+    ap.add_argument("--tp-ctx", type=int, default=1024)
+    ap.add_argument("--tp-deadline", type=float, default=900.0, dest="tp_deadline")
+    ap.add_argument("--tp-only", action="store_true", help="dev: only the tensor-parallel block (prints {\"tp\": ...}; NOT a bench line)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -147,6 +147,11 @@ PRESETS = {
     "tiny-llama-tp": ModelSpec("tiny-llama-tp", 512, 2, 8, 4, 64, 1024, 2048, norm_random=1),
     "tiny-qwen-tp": ModelSpec("tiny-qwen-tp", 512, 2, 8, 2, 128, 512, 1280, qkv_bias=1, rope_theta=1e6, rms_eps=1e-6, norm_random=1,
                               template="chatml"),
+    # the per-rank layouts of the two BASELINE tensor-parallel configs: Qwen2.5-32B TP=4 (40/8 heads -> 10 query heads on 2 kv heads per
+    # rank, qkv bias) and Llama-3-70B TP=8 (64/8 heads -> 8 query heads on ONE kv head per rank)
+    "tiny-qwen-tp4": ModelSpec("tiny-qwen-tp4", 512, 2, 40, 8, 128, 1024, 1280, qkv_bias=1, rope_theta=1e6, rms_eps=1e-6, norm_random=1,
+                               template="chatml"),
+    "tiny-llama-tp8": ModelSpec("tiny-llama-tp8", 512, 2, 64, 8, 64, 1024, 2048, norm_random=1),
     "tiny-qwen": ModelSpec("tiny-qwen", 320, 2, 5, 1, 64, 768, 1280, qkv_bias=1, rope_theta=1e6, rms_eps=1e-6,
                            norm_random=1, template="chatml"),
 }

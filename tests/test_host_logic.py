@@ -579,3 +579,9 @@ def test_http_front_survives_bad_clients():
     conn.putrequest("POST", "/v1/chat/completions"); conn.putheader("Content-Length", "-5"); conn.putheader("Authorization", "Bearer sk-right"); conn.endheaders()
     assert conn.getresponse().status == 400
     conn.close(); srv.shutdown()
+
+
+def test_follower_side_tiny_presets_equal_the_oracle_presets():
+    from opsagent_b200.presets_tiny import TINY_TP
+    for name, cfg in TINY_TP.items():
+        assert cfg == O.PRESETS[name].engine_json(), name

@@ -1,5 +1,7 @@
 """Tensor parallelism (BASELINE configs[3,4] path) on >= 2 GPUs: column/row-parallel shards, NVLink peer-memory all-reduce
-written in this repo (no NCCL), vocab-parallel arg-max — against the CPU oracle.  Skipped on a 1-GPU box."""
+written in this repo (no NCCL), vocab-parallel arg-max — against the CPU oracle.  t=4 runs the per-rank head layout of Qwen2.5-32B TP=4,
+t=8 that of Llama-3-70B TP=8 (tests/tp_worker.py).  Skipped on a box with fewer GPUs — `bench.py --gpus N` runs the same check at t=N
+so that the driver's scaling runs carry the verdict."""
 import os
 import subprocess
 import sys
@@ -11,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("t", [2, 4])
+@pytest.mark.parametrize("t", [2, 4, 8])
 def test_tensor_parallel_matches_oracle(t):
     if torch.cuda.device_count() < t:
         pytest.skip(f"needs {t} GPUs")
