@@ -83,27 +83,8 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def synthetic_pod_yaml(i: int, n_bytes: int) -> str:
-    """Seeded synthetic Pod manifest text of exactly n_bytes ASCII bytes (byte-level tokenizer: 1 byte = 1 token)."""
-    import random
-    r = random.Random(42 + i)
-    parts = [f"apiVersion: v1\nkind: Pod\nmetadata:\n  name: app-{i:04d}-{r.randrange(16**6):06x}\n  namespace: ns-{r.randrange(40)}\n"
-             f"  labels:\n    app: svc-{r.randrange(200)}\n    tier: {r.choice(['web', 'db', 'cache', 'batch'])}\nspec:\n  containers:\n"]
-    while sum(map(len, parts)) < n_bytes:
-        c = r.randrange(1000)
-        parts.append(f"  - name: c{c}\n    image: registry.local/team{r.randrange(30)}/img{c}:{r.randrange(9)}.{r.randrange(20)}.{r.randrange(50)}\n"
-                     f"    resources:\n      requests: {{cpu: {r.randrange(50, 2000)}m, memory: {r.randrange(64, 4096)}Mi}}\n"
-                     f"      limits: {{cpu: {r.randrange(100, 4000)}m, memory: {r.randrange(128, 8192)}Mi}}\n"
-                     f"    env:\n    - name: VAR_{r.randrange(100)}\n      value: \"{r.randrange(10**8)}\"\n"
-                     f"    livenessProbe: {{httpGet: {{path: /healthz, port: {r.randrange(1024, 9999)}}}, periodSeconds: {r.randrange(5, 60)}}}\n"
-                     f"status:\n  phase: {r.choice(['Running', 'Pending', 'CrashLoopBackOff', 'Failed'])}\n  conditions:\n"
-                     f"  - type: Ready\n    status: \"{r.choice(['True', 'False'])}\"\n    reason: {r.choice(['ContainersNotReady', 'PodCompleted', 'Unschedulable', 'OK'])}\n")
-    return "".join(parts)[:n_bytes]
-
-
-ANALYSIS_SYSTEM = ("You are an expert Kubernetes and cloud native networking analyst. Analyze the given Kubernetes manifest for "
-                   "issues and misconfigurations, reason step by step, call the kubectl tool when needed, and answer in JSON with "
-                   "the fields question, thought, action{name,input}, observation, final_answer.")
+TOKENIZER = os.path.join(ROOT, "tests", "golden", "bpe_k8s_8k.json")     # Llama-3-format byte-level BPE trained on OpsAgent's own kind of text
+REACT_TOOL_STEPS = 3
 
 
 TP_CONFIGS = {2: ("llama-3-8b", 128, 1664, "Llama-3-8B TP=2 (fits one GPU; exercises the collective path at N=2)"),
@@ -161,6 +142,67 @@ def run_tp_block(args, rank, world, nonce, log):
     return block
 
 
+def react_block(args, rank, world, local_rank, barrier, allmax):
+    """Multi-step ReAct loops inside the measurement contract: per GPU, 128 concurrent conversations driven by the mirror of the
+    reference's loop (assistants.AssistantWithConfig <-> pkg/assistants/simple.go:292-616) through LocalCUDAClient.Chat — POST /execute's
+    message shape (verbatim executeSystemPrompt_cn + a question), REACT_TOOL_STEPS grammar-forced kubectl tool calls answered by a seeded
+    synthetic kubectl, then a final answer.  The history is resent on every step (simple.go:498-501), so the prefix cache is ON here and
+    its hit rate is reported.  A ReAct step = one completed Chat call."""
+    from opsagent_b200 import Engine, LocalCUDAClient
+    from opsagent_b200 import workloads as WL
+    from opsagent_b200.assistants import AssistantWithConfig
+    from opsagent_b200.synthetic import copilot_tools
+    n_agents = args.react_agents
+    eng = Engine({"model": MODEL, "device": local_rank, "kv_gb": args.kv_gb, "max_batch": n_agents, "max_seq_len": 8192, "max_step_tokens": 8192,
+                  "seed": 1234, "tokenizer": TOKENIZER, "json_mode": 1, "react_tool_steps": REACT_TOOL_STEPS, "prefix_cache": 1,
+                  **json.loads(args.engine_extra)})
+    calls = [0] * n_agents
+    results = [None] * n_agents
+
+    class CountingClient(LocalCUDAClient):
+        def __init__(self, engine, slot):
+            super().__init__(engine); self.slot = slot
+
+        def Chat(self, model, maxTokens, prompts):
+            calls[self.slot] += 1
+            return super().Chat(model, maxTokens, prompts)
+
+    def agent(i, salt):
+        q = WL.EXECUTE_QUESTIONS[(rank * n_agents + i) % len(WL.EXECUTE_QUESTIONS)]
+        msgs = WL.execute_messages("execute " + q, f"(cluster c{salt}-{rank}-{i})")
+        results[i] = AssistantWithConfig(MODEL, msgs, 2048, True, False, REACT_TOOL_STEPS + 2, CountingClient(eng, i), copilot_tools(1000 * salt + i),
+                                         count_tokens=eng.count_tokens)
+
+    def round_(n, salt):
+        for i in range(n):
+            calls[i] = 0; results[i] = None
+        th = [threading.Thread(target=agent, args=(i, salt)) for i in range(n)]
+        t0 = time.perf_counter()
+        [t.start() for t in th]; [t.join() for t in th]
+        return time.perf_counter() - t0
+
+    round_(min(8, n_agents), 1)                  # warm-up: every kernel shape and grammar state seen once
+    s0 = eng.stats()
+    barrier()
+    dt = round_(n_agents, 2)
+    barrier()
+    s1 = eng.stats()
+    n_calls = sum(calls)
+    ok = sum(1 for r in results if r and len(r[0]) >= 10)
+    dt = allmax(dt)
+    hit = s1["prefix_hit_tokens"] - s0["prefix_hit_tokens"]; pre = s1["prefill_tokens"] - s0["prefill_tokens"]
+    eng.close()
+    return {"workload": f"{n_agents} concurrent ReAct conversations per GPU: verbatim executeSystemPrompt_cn + question, {REACT_TOOL_STEPS} grammar-forced kubectl "
+                        "tool steps (seeded synthetic kubectl tables) + final answer; json_mode, prefix cache on",
+            "react_steps_per_sec": round(world * n_calls / dt, 2), "chat_calls_per_gpu": n_calls, "seconds": round(dt, 2),
+            "conversations_with_final_answer": ok, "conversations": n_agents,
+            "completion_tokens_per_sec": round(world * (s1["decode_tokens"] - s0["decode_tokens"]) / dt, 1),
+            "prefill_tokens": pre, "prefix_hit_tokens": hit, "prefix_hit_rate": round(hit / max(1, hit + pre), 4),
+            "decode_steps": s1["decode_steps"] - s0["decode_steps"], "prefill_steps": s1["prefill_steps"] - s0["prefill_steps"],
+            "mixed_steps": s1.get("mixed_steps", 0) - s0.get("mixed_steps", 0), "preemptions": s1["preemptions"] - s0["preemptions"],
+            "grammar_states_computed": s1.get("grammar_states_computed", 0)}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import numpy as np
@@ -210,8 +252,9 @@ def run_ours(args, rank, world, local_rank):
         return
     K, W = args.steps, max(args.warmup, 3)
     eng = Engine({"model": MODEL, "device": local_rank, "kv_gb": args.kv_gb, "max_batch": BATCH, "max_seq_len": 2048,
-                  "max_step_tokens": 8192, "seed": 1234,
-                  "prefix_cache": 0})      # every timed prompt token is really prefilled: no cached outputs inside the timed region
+                  "max_step_tokens": 8192, "seed": 1234, "tokenizer": TOKENIZER,
+                  "prefix_cache": 0,       # every timed prompt token is really prefilled: no cached outputs inside the timed region
+                  **json.loads(args.engine_extra)})
     info = eng.info
     # ------------------------------------------------------------------ value: device-resident decode steps
     # context chosen so that the mean over the K timed steps is MEAN_CTX (=P+G/2)
@@ -251,18 +294,32 @@ def run_ours(args, rank, world, local_rank):
                          "achieved": round(r["algorithmic_bytes_per_step"] / (ms_step * 1e-3) / 1e9, 1),
                          "frac": round(r["algorithmic_bytes_per_step"] / (ms_step * 1e-3) / 1e9 / peak, 4)}}
     # ------------------------------------------------------------------ e2e: public chat API, host buffers
+    # The reference's own request shapes with its system prompts VERBATIM (opsagent_b200/workloads.py <- tests/golden/prompts/), tokenised
+    # by the engine's byte-level BPE.  N=1: BASELINE configs[1], 128 analyze requests padded with synthetic Pod YAML to P=1536 tokens.
+    # N>=2: configs[2]'s mix per replica: 40 % analyze (P=1536) / 30 % diagnose / 30 % execute (zh prompt); diagnose and execute carry no
+    # bulk payload in the reference, so their prompt length is what the verbatim prompt + question tokenise to.
+    from opsagent_b200 import workloads as WL
     cli = LocalCUDAClient(eng)
-    overhead = eng.count_tokens([("system", ANALYSIS_SYSTEM), ("user", "")])
-    prompts = [[ChatCompletionMessage("system", ANALYSIS_SYSTEM),
-                ChatCompletionMessage("user", synthetic_pod_yaml(rank * BATCH + i, PROMPT - overhead))] for i in range(BATCH)]
+    reqs = []
+    for i in range(BATCH):
+        gi = rank * BATCH + i
+        if world == 1:
+            reqs.append(("analyze", WL.fit_to_tokens(WL.analyze_messages, WL.synthetic_pod_yaml(gi, 12 * PROMPT), PROMPT, eng.count_tokens)))
+        else:
+            reqs.append(WL.mixed_request(gi, eng.count_tokens, p_analyze=PROMPT))
+    prompts = [m for _k, m in reqs]
+    msgs_all = [[(m.Role, m.Content) for m in p] for p in prompts]
+    p_tokens = [eng.count_tokens(m) for m in msgs_all]
+    by_kind = {}
+    for (k, _m), n in zip(reqs, p_tokens):
+        by_kind.setdefault(k, []).append(n)
 
     def one_round():
-        msgs = [[(m.Role, m.Content) for m in p] for p in prompts]
         t0 = time.perf_counter()
-        tickets = [eng.chat_submit(MODEL, m, GEN, flags=1) for m in msgs]       # non-blocking submit, as Go would
+        tickets = [eng.chat_submit(MODEL, m, GEN, flags=1) for m in msgs_all]   # non-blocking submit, as Go would
         outs = [eng.wait(t) for t in tickets]
         dt = time.perf_counter() - t0
-        assert all(o.completion_tokens == GEN and o.prompt_tokens == PROMPT for o in outs)
+        assert all(o.completion_tokens == GEN and o.prompt_tokens == n for o, n in zip(outs, p_tokens))
         return dt, outs
 
     # one blocking Chat() through the Go-mirror client proves the seam itself (untimed)
@@ -277,14 +334,18 @@ def run_ours(args, rank, world, local_rank):
     dt = allmax(dt)
     n_fwd = (s1["prefill_steps"] - s0["prefill_steps"]) + (s1["decode_steps"] - s0["decode_steps"])
     e2e = {"value": round(world * BATCH * GEN / dt, 1), "unit": "tokens/s", "react_steps_per_sec": round(world * BATCH / dt, 2),
-           "seconds_per_round": round(dt, 3), "requests": world * BATCH, "prompt_tokens": PROMPT, "completion_tokens": GEN,
+           "seconds_per_round": round(dt, 3), "requests": world * BATCH, "prompt_tokens": round(sum(p_tokens) / len(p_tokens), 1), "completion_tokens": GEN,
+           "prompt_tokens_by_kind": {k: {"n": len(v), "mean": round(sum(v) / len(v), 1)} for k, v in by_kind.items()},
+           "prompts": "reference system prompts verbatim (tests/golden/prompts), byte-level BPE tests/golden/bpe_k8s_8k.json",
            "h2d_bytes_per_step": int((s1["h2d_bytes"] - s0["h2d_bytes"]) / max(1, n_fwd)),
            "d2h_bytes_per_step": int((s1["d2h_bytes"] - s0["d2h_bytes"]) / max(1, n_fwd)), "forwards": n_fwd}
     launches = int(round(r["launches_per_step"] * K))
     line = {"metric": "decode_tokens_per_sec", "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic (seeded random-init weights seed=1234, synthetic Pod-YAML prompts, byte-level tokenizer)",
-            "config": {"workload": "BASELINE configs[1]: Llama-3-8B bf16, batch=128 concurrent analyze ReAct steps per GPU, "
+            "data": "synthetic (seeded random-init weights seed=1234; the reference's verbatim system prompts + seeded synthetic Pod YAML; "
+                    "byte-level BPE tokenizer trained offline on OpsAgent-domain text)",
+            "config": {"workload": ("BASELINE configs[1]: Llama-3-8B bf16, batch=128 concurrent analyze ReAct steps per GPU, " if world == 1 else
+                                    f"BASELINE configs[2]: Llama-3-8B replicated data-parallel on {world} GPUs, batch={world * BATCH}, e2e mix 40% analyze / 30% diagnose / 30% execute; value: ") +
                                    f"P={PROMPT} G={GEN}, mean decode ctx {r['mean_ctx']:.0f}",
                        "batch_per_gpu": BATCH, "parallelism": f"dp{world}", "l2": "inputs (15 GB weights + 28 GB KV) exceed L2",
                        "kv_page_tokens": 64, "device_ms_per_step_excl_host_gaps": round(r["device_ms_per_step"], 4)},
@@ -294,6 +355,10 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_tokens)
     eng.close()
+    if not args.no_react:
+        rb = react_block(args, rank, world, local_rank, barrier, allmax)
+        if rank == 0:
+            line["react"] = rb
     hung = False
     if world >= 2 and not args.no_tp:
         tp, hung = tp_block()
@@ -360,12 +425,15 @@ def main():
     ap.add_argument("--kv-gb", type=float, default=60.0, dest="kv_gb")
     ap.add_argument("--cpu-tokens", type=int, default=64, dest="cpu_tokens")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-react", action="store_true", help="skip the multi-step ReAct block")
+    ap.add_argument("--react-agents", type=int, default=128, dest="react_agents")
     ap.add_argument("--no-tp", action="store_true", help="N>=2: skip the tensor-parallel block")
     ap.add_argument("--no-tp-parity", action="store_true")
     ap.add_argument("--tp-cases", default="", help="comma-separated tiny presets for the TP parity check (default: by degree)")
     ap.add_argument("--tp-model", default="", help="override the TP bench config (dev): model, with --tp-batch/--tp-ctx")
     ap.add_argument("--tp-batch", type=int, default=64)
     ap.add_argument("--tp-ctx", type=int, default=1024)
+    ap.add_argument("--engine-extra", default="{}", dest="engine_extra", help="dev: JSON of engine options merged into the config (A/B runs)")
     ap.add_argument("--tp-deadline", type=float, default=900.0, dest="tp_deadline")
     ap.add_argument("--tp-only", action="store_true", help="dev: only the tensor-parallel block (prints {\"tp\": ...}; NOT a bench line)")
     args = ap.parse_args()

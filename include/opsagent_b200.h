@@ -157,6 +157,11 @@ OA_API int oa_host_bpe_decode(const char* tokenizer_json_path, const int32_t* id
  * bitset for the next position in mask_out[8], *done_out = 1 when the JSON is complete; 400 if the prefix is not derivable */
 OA_API int oa_host_grammar_step(int32_t kind, const uint8_t* prefix, int32_t n, uint32_t* mask_out, int32_t* done_out);
 OA_API int oa_host_grammar_step_ex(int32_t kind, const char* functions, const uint8_t* prefix, int32_t n, uint32_t* mask_out, int32_t* done_out);
+/* token-level grammar mask, host only: the bitset (ceil(vocab/32) words) of token ids allowed after `prefix` under schema `kind`, for the
+ * byte-level BPE vocabulary of tokenizer_json_path (NULL/"": the synthetic byte-level ids 0..255) — a token is allowed iff all of its bytes
+ * walk the automaton.  key_out receives the canonical cache key of the state (states with equal keys have equal masks). */
+OA_API int oa_host_grammar_token_mask(const char* tokenizer_json_path, int32_t vocab, int32_t kind, const char* functions, const uint8_t* prefix,
+                               int32_t n, uint32_t* mask_out, int32_t cap_words, char* key_out, int32_t key_cap);
 /* resolved architecture + derived byte counts of a config, no device needed */
 OA_API int oa_host_model_info(const char* config_json, char* buf, size_t n);
 OA_API uint64_t oa_kernel_launches(void);

@@ -255,6 +255,8 @@ public:
     }
 
     int vocab_size() const { return (int)id_to_bytes_.size(); }
+    // raw bytes of every TEXT token (control / added tokens and unused ids: empty) — what a grammar may emit
+    std::vector<std::string> text_token_bytes() const { std::vector<std::string> v = id_to_bytes_; for (size_t i = 0; i < v.size(); ++i) if (is_special_[i]) v[i].clear(); return v; }
     int special_id(const std::string& content) const { auto it = special_.find(content); return it == special_.end() ? -1 : it->second; }
 
     // text -> ids (control tokens are never produced from text: the chat template inserts them by id)

@@ -9,7 +9,12 @@
 #include <vector>
 
 #include "../../include/opsagent_b200.h"
+#include <map>
+#include <memory>
+#include <mutex>
 #include "grammar.hpp"
+#include "token_mask.hpp"
+#include "tokenizer.hpp"
 #include "model.hpp"
 #include "tokenizer.hpp"
 
@@ -194,6 +199,35 @@ int oa_host_grammar_step_ex(int32_t kind, const char* functions, const uint8_t* 
     if (!g.active()) return OA_ERR_BAD_REQUEST;
     for (int i = 0; i < n; ++i) if (!g.advance(prefix[i])) return OA_ERR_BAD_REQUEST;
     g.allowed(mask_out); *done_out = g.done() ? 1 : 0;
+    return OA_OK;
+}
+
+int oa_host_grammar_token_mask(const char* tokenizer_json_path, int32_t vocab, int32_t kind, const char* functions, const uint8_t* prefix, int32_t n,
+                               uint32_t* mask_out, int32_t cap_words, char* key_out, int32_t key_cap) {
+    if (kind < GRAMMAR_TOOLCALL || kind > GRAMMAR_TEXT || vocab <= 0 || !mask_out) return OA_ERR_BAD_REQUEST;
+    try {
+        // one trie per (tokenizer, vocab), built once: the same structure the engine builds at start-up
+        static std::mutex mu; static std::map<std::string, std::shared_ptr<TokenTrie>> tries;
+        const std::string tk = std::string(tokenizer_json_path ? tokenizer_json_path : "") + "#" + std::to_string(vocab);
+        std::shared_ptr<TokenTrie> trie;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = tries.find(tk);
+            if (it == tries.end()) {
+                ModelConfig mc; mc.vocab = vocab; mc.chat_template = "llama3";
+                std::vector<std::string> bytes;
+                if (tokenizer_json_path && tokenizer_json_path[0]) bytes = BpeTokenizer::load(tokenizer_json_path)->text_token_bytes();
+                else { bytes.resize(256); for (int b = 0; b < 256; ++b) bytes[b] = std::string(1, (char)b); }
+                trie = std::make_shared<TokenTrie>(); trie->build(bytes, vocab); tries[tk] = trie;
+            } else trie = it->second;
+        }
+        if (trie->words() > cap_words) return OA_ERR_BAD_REQUEST;
+        ToolPromptGrammar g(kind, functions ? functions : "");
+        if (!g.active()) return OA_ERR_BAD_REQUEST;
+        for (int i = 0; i < n; ++i) if (!g.advance(prefix[i])) return OA_ERR_BAD_REQUEST;
+        trie->allowed_tokens(g, g.cursor(), mask_out);
+        if (key_out && key_cap > 0) std::snprintf(key_out, (size_t)key_cap, "%s", grammar_mask_key(g, g.cursor()).c_str());
+    } catch (const std::exception&) { return OA_ERR_BAD_REQUEST; }
     return OA_OK;
 }
 

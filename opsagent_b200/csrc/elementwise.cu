@@ -164,6 +164,21 @@ cudaError_t launch_sk_resid_rmsnorm(const StreamK& sk, void* x, const void* gain
     return launch_k(sk_resid_rmsnorm_kernel<2>, dim3(T), dim3(SK_RESID_THREADS), 0, s, sk, X, G, Y, H8, 1.0f / H, eps);
 }
 
+template <int VPT>
+__global__ void __launch_bounds__(SK_RESID_THREADS) rmsnorm_wide_kernel(uint4* __restrict__ x, const uint4* __restrict__ g, uint4* __restrict__ y, int H8, float inv_h, float eps) {
+    griddep_launch(); griddep_wait();
+    __shared__ float red[SK_RESID_THREADS / 32];
+    sk_resid_rmsnorm_row<VPT, false>(StreamK{}, blockIdx.x, threadIdx.x, red, 0, x, g, y, H8, inv_h, eps);
+}
+cudaError_t launch_rmsnorm_wide(const void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s) {
+    if (T <= 0) return cudaSuccess;
+    if (H % 8 != 0 || H > 8192) return cudaErrorInvalidValue;
+    const int H8 = H / 8;
+    auto X = reinterpret_cast<uint4*>(const_cast<void*>(x)); auto G = reinterpret_cast<const uint4*>(gain); auto Y = reinterpret_cast<uint4*>(xn);
+    if (H8 <= SK_RESID_THREADS) return launch_k(rmsnorm_wide_kernel<1>, dim3(T), dim3(SK_RESID_THREADS), 0, s, X, G, Y, H8, 1.0f / H, eps);
+    return launch_k(rmsnorm_wide_kernel<2>, dim3(T), dim3(SK_RESID_THREADS), 0, s, X, G, Y, H8, 1.0f / H, eps);
+}
+
 __global__ void sk_swiglu_kernel(const StreamK sk, uint4* __restrict__ act, int F8) {
     griddep_launch(); griddep_wait();
     const int t = blockIdx.y;

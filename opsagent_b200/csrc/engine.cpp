@@ -22,6 +22,7 @@
 
 #include "../../include/opsagent_b200.h"
 #include "grammar.hpp"
+#include "token_mask.hpp"
 #include "model.hpp"
 #include "tokenizer.hpp"
 
@@ -57,6 +58,9 @@ public:
         for (int p = model_.num_pages - 1; p >= 0; --p) free_pages_.push_back(p);
         page_ref_.assign(model_.num_pages, 0); page_hash_.assign(model_.num_pages, 0); page_parent_.assign(model_.num_pages, 0);
         page_tokens_.assign((size_t)model_.num_pages * 64, 0); lru_pos_.assign(model_.num_pages, lru_.end());
+        token_bytes_ = tok_.text_token_bytes();
+        trie_.build(token_bytes_, model_.cfg.vocab);
+        mask_key_of_.assign((size_t)model_.mask_slots, std::string()); mask_last_use_.assign((size_t)model_.mask_slots, 0);
         if (eo.tp > 1 && eo.tp_rank > 0) follower_ = std::thread([this] { follow(); });   // tensor-parallel follower: replays the leader's steps
         else if (eo.start_thread) worker_ = std::thread([this] { loop(); });
     }
@@ -83,8 +87,6 @@ public:
         if ((int)prompt.size() + 1 > opt_.max_seq_len)
             return fail(OA_ERR_BAD_REQUEST, "prompt of " + std::to_string(prompt.size()) + " tokens exceeds max_seq_len " + std::to_string(opt_.max_seq_len));
         for (int32_t t : prompt) if (t < 0 || t >= model_.cfg.vocab) return fail(OA_ERR_BAD_REQUEST, "token id out of range");
-        if ((flags & (OA_FLAG_JSON_TOOLCALL | OA_FLAG_JSON_FINAL | OA_FLAG_JSON_FUNCTION | OA_FLAG_JSON_TEXT)) && !tok_.byte_level())
-            return fail(OA_ERR_BAD_REQUEST, "schema-constrained decoding masks byte tokens 0..255: not available with a BPE tokenizer (config \"tokenizer\")");
         auto s = std::make_shared<Seq>();
         s->n_prompt = (int)prompt.size(); s->tokens = std::move(prompt);
         s->max_new = std::min(max_new, opt_.max_seq_len - s->n_prompt); s->flags = flags;
@@ -269,12 +271,12 @@ public:
                       "{\"requests_completed\": %llu, \"prefill_tokens\": %llu, \"decode_tokens\": %llu, \"prefill_steps\": %llu, "
                       "\"decode_steps\": %llu, \"preemptions\": %llu, \"pages_total\": %d, \"pages_free\": %zu, \"running\": %zu, "
                       "\"waiting\": %zu, \"kernel_launches\": %llu, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"weight_bytes\": %zu, "
-                      "\"kv_pool_bytes\": %zu, \"busy_ms\": %.3f, \"prefix_hit_tokens\": %llu, \"pages_cached\": %zu, \"admissions_deferred\": %llu, \"mixed_steps\": %llu, \"cancelled\": %llu}",
+                      "\"kv_pool_bytes\": %zu, \"busy_ms\": %.3f, \"prefix_hit_tokens\": %llu, \"pages_cached\": %zu, \"admissions_deferred\": %llu, \"mixed_steps\": %llu, \"cancelled\": %llu, \"grammar_states_computed\": %llu}",
                       (unsigned long long)n_completed_, (unsigned long long)n_prefill_tokens_, (unsigned long long)n_decode_tokens_,
                       (unsigned long long)n_prefill_steps_, (unsigned long long)n_decode_steps_, (unsigned long long)n_preempt_,
                       model_.num_pages, available_pages_locked(), running_.size(), waiting_.size(), (unsigned long long)launches_total(),
                       (unsigned long long)model_.h2d_bytes, (unsigned long long)model_.d2h_bytes, model_.weight_bytes, model_.kv_pool_bytes, busy_ms_, (unsigned long long)n_prefix_hit_tokens_, cached_.size(),
-                      (unsigned long long)n_admit_deferred_, (unsigned long long)n_mixed_steps_, (unsigned long long)n_cancelled_);
+                      (unsigned long long)n_admit_deferred_, (unsigned long long)n_mixed_steps_, (unsigned long long)n_cancelled_, (unsigned long long)n_mask_states_);
         return b;
     }
     std::string info_json() {
@@ -410,8 +412,10 @@ private:
     // Accept a sampled token for s (called with mu_ held). Returns true if the sequence finished.
     bool accept_token_locked(const std::shared_ptr<Seq>& s, int32_t t) {
         if (s->grammar.active()) {
-            // the masked arg-max can only have produced an allowed byte; a mismatch means the device path is broken
-            if (t < 0 || t > 255 || !s->grammar.advance(t)) { s->error = OA_ERR_INTERNAL; s->error_msg = "grammar-constrained decode produced a disallowed token"; finish_locked(s, 1); return true; }
+            // the masked arg-max can only have produced an allowed token (all of its bytes walk the automaton); a mismatch means the device path is broken
+            bool ok = t >= 0 && (size_t)t < token_bytes_.size() && !token_bytes_[(size_t)t].empty();
+            if (ok) for (unsigned char ch : token_bytes_[(size_t)t]) if (!s->grammar.advance(ch)) { ok = false; break; }
+            if (!ok) { s->error = OA_ERR_INTERNAL; s->error_msg = "grammar-constrained decode produced a disallowed token"; finish_locked(s, 1); return true; }
             s->tokens.push_back(t); ++s->n_generated;
             if (s->grammar.done()) { finish_locked(s, 0); return true; }
             if (s->n_generated >= s->max_new || (int)s->tokens.size() >= opt_.max_seq_len) { finish_locked(s, 1); return true; }
@@ -422,6 +426,28 @@ private:
         s->tokens.push_back(t); ++s->n_generated;
         if (s->n_generated >= s->max_new || (int)s->tokens.size() >= opt_.max_seq_len) { finish_locked(s, 1); return true; }
         return false;
+    }
+
+    // device-table row holding the allowed-token bitset of s's grammar state; computes + schedules the upload on a miss (LRU over rows
+    // not used by the step being built)
+    int32_t mask_slot_locked(const Seq& s, std::vector<uint32_t>& updates) {
+        const std::string key = grammar_mask_key(s.grammar, s.grammar.cursor());
+        auto it = mask_slot_of_.find(key);
+        if (it != mask_slot_of_.end()) { mask_last_use_[(size_t)it->second] = mask_tick_; return it->second; }
+        int victim = -1; uint64_t oldest = UINT64_MAX;
+        for (int i = 0; i < model_.mask_slots; ++i) {
+            if (mask_key_of_[(size_t)i].empty()) { victim = i; break; }
+            if (mask_last_use_[(size_t)i] < mask_tick_ && mask_last_use_[(size_t)i] < oldest) { oldest = mask_last_use_[(size_t)i]; victim = i; }
+        }
+        if (victim < 0) throw std::runtime_error("token-mask table exhausted within one step");      // cannot happen: rows >= 2 * max_batch
+        if (!mask_key_of_[(size_t)victim].empty()) mask_slot_of_.erase(mask_key_of_[(size_t)victim]);
+        mask_key_of_[(size_t)victim] = key; mask_slot_of_[key] = victim; mask_last_use_[(size_t)victim] = mask_tick_;
+        const size_t at = updates.size(), words = (size_t)model_.mask_words;
+        updates.resize(at + 1 + words);
+        updates[at] = (uint32_t)victim;
+        trie_.allowed_tokens(s.grammar, s.grammar.cursor(), &updates[at + 1]);
+        ++n_mask_states_;
+        return victim;
     }
 
     void loop() {
@@ -564,13 +590,15 @@ private:
                     batch.push_back(s); sampled.push_back(s);
                 }
             }
-            // grammar-constrained rows: allowed-byte sets for this step's sampling (9 words per sampled row)
+            // grammar-constrained rows: each samples under the token mask of its automaton state.  Masks live in a device table, one row
+            // per cached (grammar, canonical state); a state seen for the first time is computed here (trie walk) and shipped with this step.
             bool any = false;
             for (auto& s : sampled) any |= s->grammar.active();
             if (any) {
-                in.masks.assign(sampled.size() * 9, 0u);
+                ++mask_tick_;
+                in.mask_slots.assign(sampled.size(), -1);
                 for (size_t i = 0; i < sampled.size(); ++i)
-                    if (sampled[i]->grammar.active()) { sampled[i]->grammar.allowed(&in.masks[i * 9]); in.masks[i * 9 + 8] = 1u; }
+                    if (sampled[i]->grammar.active()) in.mask_slots[i] = mask_slot_locked(*sampled[i], in.mask_updates);
             }
         }
         run_forward(in, nullptr);
@@ -620,6 +648,8 @@ private:
     bool stop_ = false, fatal_ = false; std::string fatal_msg_;
     std::thread worker_, follower_; bool follower_done_ = false;
     uint64_t n_cancelled_ = 0, n_cancel_seen_ = 0;
+    std::vector<std::string> token_bytes_; TokenTrie trie_;
+    std::unordered_map<std::string, int> mask_slot_of_; std::vector<std::string> mask_key_of_; std::vector<uint64_t> mask_last_use_; uint64_t mask_tick_ = 0, n_mask_states_ = 0;
     uint64_t n_mixed_steps_ = 0, n_admit_deferred_ = 0, n_completed_ = 0, n_prefill_tokens_ = 0, n_decode_tokens_ = 0, n_prefill_steps_ = 0, n_decode_steps_ = 0, n_preempt_ = 0;
     double busy_ms_ = 0;
 };

@@ -132,6 +132,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tcgen05_kernel(const __grid
         mbar_wait(acc_bar, 0);
         tcgen05_fence_after();
         float best_v = -INFINITY; int best_i = 0x7fffffff;
+        const uint32_t* mask_row = nullptr;
+        if (EPI == EPI_LOGITS && row_ok && p.mask_slot) { const int ms = p.mask_slot[row]; if (ms >= 0) mask_row = p.mask_table + (size_t)ms * p.mask_words; }
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             uint32_t v[32];
@@ -195,17 +197,24 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tcgen05_kernel(const __grid
                 }
             } else {  // EPI_LOGITS
                 if (row_ok) {
+                    if (mask_row) {
+                        // grammar-constrained row: only token ids allowed in this sequence's automaton state compete.  The 32 columns of
+                        // this chunk are 32 consecutive global ids: at most two words of the bitset.
+                        const uint32_t g0 = (uint32_t)(p.col_offset + col0);
+                        const uint32_t w0 = (g0 >> 5) < (uint32_t)p.mask_words ? __ldg(mask_row + (g0 >> 5)) : 0u;
+                        const uint32_t w1 = ((g0 & 31u) && (g0 >> 5) + 1 < (uint32_t)p.mask_words) ? __ldg(mask_row + (g0 >> 5) + 1) : 0u;
+                        const uint32_t bits = (g0 & 31u) ? __funnelshift_r(w0, w1, g0 & 31u) : w0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float f = __uint_as_float(v[j]);
-                        if (col0 + j < p.N && f > best_v) { best_v = f; best_i = col0 + j; }
-                    }
-                    if (p.byte_logits && col0 < 256) {
-                        float* brow = p.byte_logits + (size_t)row * 256 + col0;
+                        for (int j = 0; j < 32; ++j) {
+                            float f = __uint_as_float(v[j]);
+                            if (((bits >> j) & 1u) && col0 + j < p.N && f > best_v) { best_v = f; best_i = col0 + j; }
+                        }
+                    } else {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(brow + j) =
-                                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        for (int j = 0; j < 32; ++j) {
+                            float f = __uint_as_float(v[j]);
+                            if (col0 + j < p.N && f > best_v) { best_v = f; best_i = col0 + j; }
+                        }
                     }
                     if (p.logits) {
                         float* lrow = p.logits + (size_t)row * p.ldl;
@@ -493,7 +502,16 @@ struct SkCfg {
     static_assert(TMEM_COLS * OCC <= 512, "TMEM holds 512 columns per SM");
 };
 
-struct SkFuse { uint16_t* act; int F; unsigned int* tile_flags; };      // FUSE == 1: SwiGLU finished in the epilogue
+// Epilogues finished INSIDE the stream-K GEMM by the CTA that holds a tile's first k-block (FUSE != 0): it adds the other CTAs' published
+// pieces to its TMEM accumulator in CTA order (the stand-alone consumers' order: bit-identical sums) and writes the final bf16 result.
+//   FUSE 1  gate/up : act = silu(gate) * up
+//   FUSE 2  o / down: x += acc            (residual stream, bf16, in place)
+//   FUSE 3  qkv     : (+ bias) -> bf16 -> RoPE -> q_out / paged K rows; V rows copied
+struct SkFuse {
+    uint16_t* act; int F; unsigned int* tile_flags;
+    uint16_t* x; int ldx; int N;        // FUSE 2 (N = logical output columns; also the bound of FUSE 3)
+    SkRopeArgs rope;                    // FUSE 3
+};
 
 template <int BN, int MT, int OCC, int FUSE = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, OCC) gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -606,7 +624,140 @@ __global__ void __launch_bounds__(GEMM_THREADS, OCC) gemm_streamk_kernel(const _
             const int as = seg & 1;
             mbar_wait(&acc_full[as], ((uint32_t)seg >> 1) & 1);
             tcgen05_fence_after();
-            if constexpr (FUSE == 1) {
+            if constexpr (FUSE == 2 || FUSE == 3) {
+                // Same publish / finish protocol as the SwiGLU epilogue below (see there for why the finishing CTA never waits on a
+                // waiting CTA); only what the finisher does with the summed 128 x 128 tile differs.
+                uint32_t cf, cl;
+                sk_tile_ctas(sk, (uint32_t)tile, cf, cl);
+                const int c_first = (int)cf, c_last = (int)cl;
+                const int row = q * 32 + lane;
+                unsigned int* flag = fz.tile_flags + tile;
+                if ((int)c == c_first) {
+                    const int n_other = c_last - c_first;
+                    if (n_other > 0) {
+                        if (threadIdx.x == 64) { grid_counter_wait32(flag, (unsigned int)n_other); *flag = 0u; }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                    }
+                    const float* other = sk.ws + (size_t)(c_first + 1 + tile) * (BLOCK_M * BN) + row;
+                    const bool live = row < M;
+                    // acc[0..32) = this row's sums of columns [mc, mc+32) of the tile: own accumulator, then the other pieces in CTA order
+                    auto acc_chunk = [&](int mc, float (&acc)[32]) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + mc), v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = 0.f + __uint_as_float(v[j]);      // "0 +" as in sk_sum8
+                        for (int o = 0; o < n_other; ++o) {
+                            const float* pc = other + (size_t)o * (BLOCK_M * BN) + (size_t)mc * BLOCK_M;
+                            float t[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) t[j] = live ? __ldcg(pc + (size_t)j * BLOCK_M) : 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[j] += t[j];
+                        }
+                    };
+                    if constexpr (FUSE == 2) {
+#pragma unroll 1
+                        for (int mc = 0; mc < BN; mc += 32) {
+                            const int col0 = tile * BN + mc;
+                            if (col0 >= fz.N) break;
+                            float acc[32];
+                            acc_chunk(mc, acc);
+                            if (live) {
+                                uint4* xr = reinterpret_cast<uint4*>(fz.x + (size_t)row * fz.ldx + col0);
+#pragma unroll
+                                for (int h = 0; h < 4; ++h) {
+                                    const uint4 xo = __ldcg(xr + h);
+                                    uint4 xn;
+                                    xn.x = pack_bf16x2(bf16lo(xo.x) + acc[8 * h + 0], bf16hi(xo.x) + acc[8 * h + 1]); xn.y = pack_bf16x2(bf16lo(xo.y) + acc[8 * h + 2], bf16hi(xo.y) + acc[8 * h + 3]);
+                                    xn.z = pack_bf16x2(bf16lo(xo.z) + acc[8 * h + 4], bf16hi(xo.z) + acc[8 * h + 5]); xn.w = pack_bf16x2(bf16lo(xo.w) + acc[8 * h + 6], bf16hi(xo.w) + acc[8 * h + 7]);
+                                    xr[h] = xn;
+                                }
+                            }
+                        }
+                    } else {
+                        const SkRopeArgs& a = fz.rope;
+                        const int D = a.D, half = D >> 1;
+                        int pos = 0, page = 0, off = 0;
+                        if (live) { pos = a.positions[row]; const int slot = a.slots[row]; page = slot / a.page_size; off = slot - page * a.page_size; }
+                        auto finish32 = [&](int col, float (&v)[32]) {          // + bias, round: the projection output is a bf16 tensor (sk_finish8_bf16)
+                            if (a.bias) {
+#pragma unroll
+                                for (int h = 0; h < 4; ++h) {
+                                    const uint4 bb = *reinterpret_cast<const uint4*>(a.bias + col + 8 * h);
+                                    v[8 * h + 0] += bf16lo(bb.x); v[8 * h + 1] += bf16hi(bb.x); v[8 * h + 2] += bf16lo(bb.y); v[8 * h + 3] += bf16hi(bb.y);
+                                    v[8 * h + 4] += bf16lo(bb.z); v[8 * h + 5] += bf16hi(bb.z); v[8 * h + 6] += bf16lo(bb.w); v[8 * h + 7] += bf16hi(bb.w);
+                                }
+                            }
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) v[k] = bf16_bits_to_f32(f32_to_bf16_bits(v[k]));
+                        };
+                        auto store32 = [&](uint16_t* dst, const float (&v)[32]) {
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                uint4 o;
+                                o.x = pack_bf16x2(v[8 * h + 0], v[8 * h + 1]); o.y = pack_bf16x2(v[8 * h + 2], v[8 * h + 3]);
+                                o.z = pack_bf16x2(v[8 * h + 4], v[8 * h + 5]); o.w = pack_bf16x2(v[8 * h + 6], v[8 * h + 7]);
+                                reinterpret_cast<uint4*>(dst)[h] = o;
+                            }
+                        };
+#pragma unroll 1
+                        for (int mc = 0; mc < BN; mc += 32) {
+                            const int col0 = tile * BN + mc;
+                            if (col0 >= fz.N) break;
+                            const int head = col0 / D, i0 = col0 - head * D;
+                            if (head >= a.nh + a.nkv) {                    // V: straight copy into the V plane
+                                float vv[32];
+                                acc_chunk(mc, vv);
+                                finish32(col0, vv);
+                                if (live) store32(a.kv_base + (size_t)(a.v_plane_row0 + ((int64_t)page * a.nkv + (head - a.nh - a.nkv)) * a.page_size + off) * D + i0, vv);
+                                continue;
+                            }
+                            if (i0 >= half) continue;                       // the high half is rotated together with its low partner
+                            float av[32], bv[32];
+                            acc_chunk(mc, av);
+                            acc_chunk(mc + half, bv);                       // same tile: BN is a multiple of D
+                            finish32(col0, av);
+                            finish32(col0 + half, bv);
+                            if (live) {
+                                const float* cr = a.rope_cos + (size_t)pos * half + i0;
+                                const float* sr = a.rope_sin + (size_t)pos * half + i0;
+                                float ra[32], rb[32];
+#pragma unroll
+                                for (int h = 0; h < 8; ++h) {
+                                    const float4 c4 = *reinterpret_cast<const float4*>(cr + 4 * h), s4 = *reinterpret_cast<const float4*>(sr + 4 * h);
+                                    const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        ra[4 * h + k] = av[4 * h + k] * cv[k] - bv[4 * h + k] * sv[k];
+                                        rb[4 * h + k] = bv[4 * h + k] * cv[k] + av[4 * h + k] * sv[k];
+                                    }
+                                }
+                                uint16_t* dst;
+                                if (head < a.nh) dst = a.q_out + (size_t)row * a.nh * D + (size_t)head * D;
+                                else dst = a.kv_base + (size_t)(a.k_plane_row0 + ((int64_t)page * a.nkv + (head - a.nh)) * a.page_size + off) * D;
+                                store32(dst + i0, ra);
+                                store32(dst + i0 + half, rb);
+                            }
+                        }
+                    }
+                } else {
+                    float* dst = sk.ws + (size_t)(c + tile) * (BLOCK_M * BN) + row;
+#pragma unroll 1
+                    for (int mc = 0; mc < BN; mc += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + mc), v);
+                        tmem_ld_wait();
+                        if (row < M) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) dst[(size_t)(mc + j) * BLOCK_M] = __uint_as_float(v[j]);
+                        }
+                    }
+                    __threadfence();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (threadIdx.x == 64) atomicAdd(flag, 1u);
+                }
+            } else if constexpr (FUSE == 1) {
                 // Pieces of this tile live in CTAs c_first..c_last (same arithmetic as sk_sum8).  The CTA holding the FIRST k-block
                 // finishes the tile: it reaches this segment last (it is the tail of its unit range, while the other pieces are the
                 // HEAD of their CTAs' ranges), adds the published pieces to its accumulator in CTA order — the stand-alone
@@ -736,13 +887,30 @@ cudaError_t launch_gemm_streamk_swiglu(const CUtensorMap* tmA, const CUtensorMap
                                        unsigned int* tile_flags, cudaStream_t stream) {
     if (M <= 0 || M > BLOCK_M || sk.rows != 128 || sk.bn != 128 || (F % 16) != 0 || (K % 8) != 0 || !act || !tile_flags) return cudaErrorInvalidValue;
     if (sk.G > sm_count_cached()) return cudaErrorInvalidValue;      // finishing CTAs wait for publishing CTAs: all must be resident
-    return launch_sk<128, 1, 1, 1>(tmA, tmB, M, sk, stream, SkFuse{reinterpret_cast<uint16_t*>(act), F, tile_flags});
+    SkFuse fz{}; fz.act = reinterpret_cast<uint16_t*>(act); fz.F = F; fz.tile_flags = tile_flags;
+    return launch_sk<128, 1, 1, 1>(tmA, tmB, M, sk, stream, fz);
+}
+cudaError_t launch_gemm_streamk_resid(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, void* x, int ldx,
+                                      unsigned int* tile_flags, cudaStream_t stream) {
+    if (M <= 0 || M > BLOCK_M || sk.rows != 128 || sk.bn != 128 || (N % 32) != 0 || (K % 8) != 0 || !x || !tile_flags || (ldx % 8) != 0) return cudaErrorInvalidValue;
+    if (sk.G > sm_count_cached()) return cudaErrorInvalidValue;      // finishing CTAs wait for publishing CTAs: all must be resident
+    SkFuse fz{}; fz.tile_flags = tile_flags; fz.x = reinterpret_cast<uint16_t*>(x); fz.ldx = ldx; fz.N = N;
+    return launch_sk<128, 1, 1, 2>(tmA, tmB, M, sk, stream, fz);
+}
+cudaError_t launch_gemm_streamk_rope(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, const SkRopeArgs& rope,
+                                     unsigned int* tile_flags, cudaStream_t stream) {
+    if (M <= 0 || M > BLOCK_M || sk.rows != 128 || sk.bn != 128 || (K % 8) != 0 || !tile_flags) return cudaErrorInvalidValue;
+    if ((rope.D != 64 && rope.D != 128) || N != (rope.nh + 2 * rope.nkv) * rope.D) return cudaErrorInvalidValue;      // BN must be a multiple of D; chunks of 32 never straddle a head
+    if (sk.G > sm_count_cached()) return cudaErrorInvalidValue;
+    SkFuse fz{}; fz.tile_flags = tile_flags; fz.N = N; fz.rope = rope;
+    return launch_sk<128, 1, 1, 3>(tmA, tmB, M, sk, stream, fz);
 }
 cudaError_t launch_gemm_streamk(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, cudaStream_t stream) {
     if (M <= 0 || M > sk.rows || (N % 8) != 0 || (K % 8) != 0) return cudaErrorInvalidValue;
     if (sk.rows == 256) return sk.bn == 128 ? launch_sk<128, 2>(tmA, tmB, M, sk, stream) : cudaErrorInvalidValue;
     if (sk.bn == 256) return launch_sk<256, 1>(tmA, tmB, M, sk, stream);
     if (sk.bn == 128) return sk.G > sm_count_cached() ? launch_sk<128, 1, 2>(tmA, tmB, M, sk, stream) : launch_sk<128, 1, 1>(tmA, tmB, M, sk, stream);
+    if (sk.bn == 64) return launch_sk<64, 1, 1>(tmA, tmB, M, sk, stream);       // half the partial bytes again; per-projection opt-in (sk_bn_o / sk_bn_down / sk_bn_qkv)
     return cudaErrorInvalidValue;
 }
 
@@ -1074,35 +1242,6 @@ __global__ void argmax_reduce_kernel(const float* __restrict__ val, const int* _
         out_ids[row] = bi == 0x7fffffff ? 0 : bi;
         if (out_val) out_val[row] = bv;
     }
-}
-
-struct ValIdxPair { float v; int i; };
-__global__ void masked_argmax_kernel(const float* __restrict__ byte_logits, const uint32_t* __restrict__ masks, int M, int32_t* __restrict__ out_ids,
-                                     ValIdxPair* __restrict__ pair_out) {
-    griddep_launch(); griddep_wait();
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= M) return;
-    const uint32_t* m = masks + (size_t)row * 9;
-    if (m[8] == 0) return;                                  // unconstrained row: keep the full-vocabulary arg-max
-    float bv = -INFINITY; int bi = 0x7fffffff;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int b = k * 32 + lane;                        // ascending ids per lane => strict '>' keeps the lowest id on ties
-        if ((m[k] >> lane) & 1u) { const float v = byte_logits[(size_t)row * 256 + b]; if (v > bv) { bv = v; bi = b; } }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    if (lane == 0) {
-        if (bi == 0x7fffffff) bi = 0;
-        if (pair_out) { pair_out[row].v = INFINITY; pair_out[row].i = bi; } else out_ids[row] = bi;
-    }
-}
-cudaError_t launch_masked_argmax(const float* byte_logits, const uint32_t* masks, int M, int32_t* out_ids, void* pair_out, cudaStream_t s) {
-    if (M <= 0) return cudaSuccess;
-    return launch_k(masked_argmax_kernel, dim3((M + 3) / 4), dim3(128), 0, s, byte_logits, masks, M, out_ids, reinterpret_cast<ValIdxPair*>(pair_out));
 }
 
 cudaError_t launch_argmax_reduce(const float* amax_val, const int* amax_idx, int M, int n_tiles, int32_t* out_ids,

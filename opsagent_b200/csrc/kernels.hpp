@@ -28,7 +28,9 @@ struct GemmParams {
     const void* resid; int ldr;     // bf16 [M, ldr]           (EPI_RESID)
     float* logits; int ldl;         // optional fp32 [M, ldl]  (EPI_LOGITS)
     float* amax_val; int* amax_idx; // [M, n_tiles]            (EPI_LOGITS)
-    float* byte_logits;             // optional fp32 [M, 256]: logits of token ids 0..255 for grammar-constrained rows (EPI_LOGITS)
+    // grammar-constrained rows (EPI_LOGITS): row r with mask_slot[r] >= 0 takes its arg-max only over the token ids whose bit is set in
+    // mask_table[mask_slot[r] * mask_words ...]; bit index = col_offset + column (col_offset: first global id of a vocab-parallel shard)
+    const uint32_t* mask_table; const int32_t* mask_slot; int mask_words, col_offset;
 };
 // tmA: box {64, 128} over A[M,K]; tmB: box {64, block_n} over B[N,K].  block_n in {32,64,128,256}.
 cudaError_t launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int epilogue, int block_n,
@@ -74,6 +76,16 @@ struct SkRopeArgs {       // q/k/v from the qkv projection's partials (+ bias): 
     const uint16_t* bias; const int32_t* positions; const int32_t* slots; const float* rope_cos; const float* rope_sin;
     uint16_t* q_out; uint16_t* kv_base; int64_t k_plane_row0, v_plane_row0; int32_t page_size, nh, nkv, D;
 };
+// o / down projection with the residual add finished inside the GEMM: x[M, ldx] (bf16, in place) += A.B^T, bit-identical to
+// launch_gemm_streamk + the sum/residual half of launch_sk_resid_rmsnorm.  Follow with launch_rmsnorm_wide for the norm.
+cudaError_t launch_gemm_streamk_resid(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, void* x, int ldx,
+                                      unsigned int* tile_flags, cudaStream_t stream);
+// qkv projection with bias + RoPE + the paged-KV write finished inside the GEMM (no qkv tensor, no consumer launch), bit-identical to
+// launch_gemm_streamk + launch_sk_rope_kv_write
+cudaError_t launch_gemm_streamk_rope(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, const SkRopeArgs& rope,
+                                     unsigned int* tile_flags, cudaStream_t stream);
+// xn = rmsnorm(x) * gain with exactly the reduction order of launch_sk_resid_rmsnorm (512 threads per row)
+cudaError_t launch_rmsnorm_wide(const void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s);
 enum SkConsumer : int { SK_CONSUMER_NONE = 0, SK_CONSUMER_RESID_RMSNORM = 1, SK_CONSUMER_SWIGLU = 2, SK_CONSUMER_ROPE_KV = 3 };
 struct SkChainPhase {
     StreamK sk; int consumer;
@@ -95,10 +107,6 @@ cudaError_t launch_sk_chain(const SkChainMaps& maps, const SkChain& chain, int g
 cudaError_t launch_argmax_reduce(const float* amax_val, const int* amax_idx, int M, int n_tiles, int32_t* out_ids,
                                  float* out_val, cudaStream_t stream);
 
-// grammar-constrained greedy sampling: masks[row*9 + 0..7] = allowed-byte bitset, masks[row*9 + 8] != 0 marks a constrained
-// row; constrained rows get arg-max over their allowed bytes (ties -> lowest id).  pair_out (tensor parallel, rank 0) receives
-// (+inf, id) so the cross-rank arg-max selects it; otherwise out_ids[row] is overwritten.
-cudaError_t launch_masked_argmax(const float* byte_logits, const uint32_t* masks, int M, int32_t* out_ids, void* pair_out, cudaStream_t s);
 
 // ---- elementwise (elementwise.cu) -----------------------------------------------------------
 cudaError_t launch_embed_gather(const int32_t* ids, const void* table, void* out, int T, int H, int vocab, cudaStream_t s);

@@ -144,7 +144,12 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
     amax_val_ = reinterpret_cast<float*>(dmalloc((size_t)MS * lm_tiles_max * 4));
     amax_idx_ = reinterpret_cast<int*>(dmalloc((size_t)MS * lm_tiles_max * 4));
     d_out_ids_ = reinterpret_cast<int32_t*>(dmalloc((size_t)MS * 4));
-    byte_logits_ = reinterpret_cast<float*>(dmalloc((size_t)MS * 256 * 4));
+    // token-mask table of the grammar-constrained decoder: one bitset over the whole vocabulary per cached automaton state
+    mask_words = (cfg.vocab + 31) / 32;
+    mask_slots = std::max(1024, 2 * opt.max_batch);
+    max_mask_updates = opt.max_batch;               // a scheduler step samples at most one row per running sequence
+    mask_table_ = reinterpret_cast<uint32_t*>(dmalloc((size_t)mask_slots * mask_words * 4));
+    cuda_check(cudaMemsetAsync(mask_table_, 0, (size_t)mask_slots * mask_words * 4, stream), "mask table memset");
     cuda_check(cudaMallocHost(&h_out_ids, (size_t)MS * 4), "cudaMallocHost");
 
     // ---- paged KV pool ----
@@ -178,7 +183,7 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
     part_o_ = reinterpret_cast<float*>(dmalloc((size_t)max_part_slots_ * grp * D * 4));
     part_ml_ = reinterpret_cast<float*>(dmalloc((size_t)max_part_slots_ * grp * 2 * 4));
     meta_cap_words_ = (size_t)4 * MR + (size_t)opt.max_batch * (max_pages_per_seq + 2) + (size_t)MR / 64 * 4 + 4 * opt.max_batch +
-                      (size_t)(opt.max_batch * nkv_l + n_ctas + 8) * 8 * 2 + (size_t)n_ctas + 4096 + (size_t)9 * max_sample_;
+                      (size_t)(opt.max_batch * nkv_l + n_ctas + 8) * 8 * 2 + (size_t)n_ctas + 4096 + (size_t)max_sample_ + (size_t)max_mask_updates * (mask_words + 4);
     for (int i = 0; i < 2; ++i) {
         cuda_check(cudaMallocHost(&h_meta_buf_[i], meta_cap_words_ * 4), "cudaMallocHost meta");
         cuda_check(cudaEventCreateWithFlags(&meta_ev_[i], cudaEventDisableTiming), "cudaEventCreate meta");
@@ -189,7 +194,7 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
     sk_G_ = opt.sk_ctas > 0 ? opt.sk_ctas : sm_count;
     {
         size_t wsb = 0;
-        for (int n : {qkvd, H, 2 * F}) { wsb = std::max(wsb, streamk_ws_bytes(n, 256, sk_G_, 128)); wsb = std::max(wsb, streamk_ws_bytes(n, 128, sk_G_, 256)); }
+        for (int n : {qkvd, H, 2 * F}) { wsb = std::max(wsb, streamk_ws_bytes(n, 256, sk_G_, 128)); wsb = std::max(wsb, streamk_ws_bytes(n, 128, sk_G_, 256)); wsb = std::max(wsb, streamk_ws_bytes(n, 64, sk_G_, 128)); }
         sk_ws_ = reinterpret_cast<float*>(dmalloc(wsb));
         chain_bar_ = reinterpret_cast<unsigned long long*>(dmalloc(64));
         cuda_check(cudaMemset(chain_bar_, 0, 64), "chain barrier memset");
@@ -404,8 +409,12 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
     const size_t o_samp = put(in.sample_rows.data(), S);
     const size_t o_bt = put(in.block_tables.data(), in.block_tables.size());
     const size_t o_ctx = put(in.ctx_lens.data(), in.ctx_lens.size());
-    const size_t o_mask = put(in.masks.data(), in.masks.size());
-    if (!in.masks.empty() && (int)in.masks.size() != 9 * S) throw std::runtime_error("forward: grammar masks must be [n_sample, 9]");
+    if (!in.mask_slots.empty() && (int)in.mask_slots.size() != S) throw std::runtime_error("forward: mask_slots must be [n_sample]");
+    const size_t rec = (size_t)mask_words + 1, n_upd = in.mask_updates.size() / rec;
+    if (in.mask_updates.size() % rec != 0 || (int)n_upd > max_mask_updates) throw std::runtime_error("forward: malformed or too many token-mask updates");
+    for (int ms : in.mask_slots) if (ms >= mask_slots) throw std::runtime_error("forward: token-mask slot out of range");
+    const size_t o_mslot = put(in.mask_slots.data(), in.mask_slots.size());
+    const size_t o_mupd = put(in.mask_updates.data(), in.mask_updates.size());
     size_t o_segs = 0, o_ptr = 0, o_tiles = 0, o_cnt = 0;
     const int n_dec = in.decode ? in.n_seqs : in.n_decode;          // sequences served by the decode attention kernel (rows 0..n_dec-1)
     if (n_dec < 0 || n_dec > in.n_seqs || n_dec > T) throw std::runtime_error("forward: bad n_decode");
@@ -425,6 +434,11 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
         o_tiles = put(sorted_tiles_.data(), sorted_tiles_.size() * 4);
     }
     cuda_check(cudaMemcpyAsync(d_meta_, h_meta_, w * 4, cudaMemcpyHostToDevice, stream), "meta H2D");
+    for (size_t u = 0; u < n_upd; ++u) {           // new automaton states: bitset rows of the device table (read by the LM-head epilogue below)
+        const uint32_t slot = in.mask_updates[u * rec];
+        if ((int)slot >= mask_slots) throw std::runtime_error("forward: token-mask update slot out of range");
+        cuda_check(cudaMemcpyAsync(mask_table_ + (size_t)slot * mask_words, d_meta_ + o_mupd + u * rec + 1, (size_t)mask_words * 4, cudaMemcpyDeviceToDevice, stream), "token-mask update");
+    }
     cuda_check(cudaEventRecord(meta_ev_[meta_idx_], stream), "meta event");
     h2d_bytes += w * 4;
     const int32_t* d_tok = d_meta_ + o_tok; const int32_t* d_pos = d_meta_ + o_pos; const int32_t* d_slot = d_meta_ + o_slot;
@@ -463,7 +477,7 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
     };
     if (use_sk) {
         // decode-sized batch: persistent stream-K projections (fp32 partials) + fused consumers
-        auto bn_of = [&](int o) { return sk_rows == 256 ? 128 : ((o == 128 || o == 256) ? o : sk_bn_); };   // two row tiles need BN=128 (TMEM)
+        auto bn_of = [&](int o) { return sk_rows == 256 ? 128 : ((o == 64 || o == 128 || o == 256) ? o : sk_bn_); };   // two row tiles need BN=128 (TMEM)
         auto with_pf = [&](StreamK k) { k.l2_prefetch_units = std::max(0, opt.sk_l2_prefetch_kb * 1024 / (k.bn * 128)); return k; };
         const StreamK sk_qkv = make_streamk(sk_ws_, qkvd, H, bn_of(opt.sk_bn_qkv), sk_G_, sk_rows), sk_o = make_streamk(sk_ws_, H, qd, bn_of(opt.sk_bn_o), sk_G_, sk_rows);
         const StreamK sk_gu = make_streamk(sk_ws_, 2 * F, H, bn_of(opt.sk_bn_gu), sk_G_, sk_rows), sk_dn = make_streamk(sk_ws_, H, F, bn_of(opt.sk_bn_down), sk_G_, sk_rows);
@@ -473,6 +487,10 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
         // sk_chain=2, the next layer's qkv -> RoPE/KV write) run as ONE persistent kernel with grid barriers between the phases
         const int chain_mode = (!use_tp && sk_rows == 128 && sk_G_ <= sm_count && sk_gu.n_tiles <= SK_CHAIN_MAX_TILES && sk_qkv.bn == 128 && sk_o.bn == 128 && sk_gu.bn == 128 && sk_dn.bn == 128)
                                    ? opt.sk_chain : 0;
+        // qkv / o / down epilogues finished inside the GEMM (same conditions as the fused SwiGLU; every projection at BN = 128, tile counts within the flag arrays)
+        const bool fuse_ok = sk_rows == 128 && sk_G_ <= sm_count && sk_qkv.bn == 128 && sk_o.bn == 128 && sk_dn.bn == 128 &&
+                              sk_qkv.n_tiles <= SK_CHAIN_MAX_TILES && sk_o.n_tiles <= SK_CHAIN_MAX_TILES && (D == 64 || D == 128);
+        const bool fuse_rope = fuse_ok && (opt.sk_fuse_epi & 1), fuse_o = fuse_ok && !use_tp && (opt.sk_fuse_epi & 2), fuse_dn = fuse_ok && !use_tp && (opt.sk_fuse_epi & 4);
         const bool fuse_swiglu = opt.sk_fuse_swiglu && sk_rows == 128 && sk_gu.bn == 128 && sk_G_ <= sm_count && sk_gu.n_tiles <= SK_CHAIN_MAX_TILES;
         auto qkv_phase = [&](int l, SkChainPhase& P) {
             P.sk = sk_qkv; P.consumer = SK_CONSUMER_ROPE_KV;
@@ -503,9 +521,18 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
                 cuda_check(launch_sk_chain(maps, ch, sk_G_, stream), "chained o/gate_up/down (stream-K)"); MARK(8);
                 continue;
             }
-            cuda_check(launch_gemm_streamk(&tm_xn_, ly.qkv.map(sk_qkv.bn), T, qkvd, H, pf_qkv, stream), "qkv gemm (stream-K)"); MARK(2);
-            cuda_check(launch_sk_rope_kv_write(sk_qkv, ly.bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, T, nh, stream), "rope (stream-K)"); MARK(3);
+            if (fuse_rope) {
+                cuda_check(launch_gemm_streamk_rope(&tm_xn_, ly.qkv.map(128), T, qkvd, H, pf_qkv, make_sk_rope_args(ly.bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, nh),
+                                                    chain_flags_ + 0 * SK_CHAIN_MAX_TILES, stream), "qkv gemm + RoPE + KV write (stream-K)"); MARK(2);
+            } else {
+                cuda_check(launch_gemm_streamk(&tm_xn_, ly.qkv.map(sk_qkv.bn), T, qkvd, H, pf_qkv, stream), "qkv gemm (stream-K)"); MARK(2);
+                cuda_check(launch_sk_rope_kv_write(sk_qkv, ly.bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, T, nh, stream), "rope (stream-K)"); MARK(3);
+            }
             attention(l);
+            if (fuse_o) {
+                cuda_check(launch_gemm_streamk_resid(&tm_attn_, ly.o.map(128), T, H, qd, pf_o, x_, H, chain_flags_ + 1 * SK_CHAIN_MAX_TILES, stream), "o gemm + residual (stream-K)"); MARK(6);
+                cuda_check(launch_rmsnorm_wide(x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "rmsnorm2"); MARK(7);
+            } else {
             cuda_check(launch_gemm_streamk(&tm_attn_, ly.o.map(sk_o.bn), T, H, qd, pf_o, stream), "o gemm (stream-K)"); MARK(6);
             if (use_tp) {      // row-parallel projection: all-reduce the rank partials over NVLink peer memory, then residual + norm
                 const int b = comm->next_buffer();
@@ -516,14 +543,20 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
                 cuda_check(launch_sk_resid_rmsnorm(sk_o, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm2");
             }
             MARK(7);
+            }
             if (fuse_swiglu) {
-                cuda_check(launch_gemm_streamk_swiglu(&tm_xn_, ly.gu.map(128), T, F, H, pf_gu, act_, chain_flags_, stream), "gate_up gemm + SwiGLU (stream-K)"); MARK(8);
+                cuda_check(launch_gemm_streamk_swiglu(&tm_xn_, ly.gu.map(128), T, F, H, pf_gu, act_, chain_flags_ + 2 * SK_CHAIN_MAX_TILES, stream), "gate_up gemm + SwiGLU (stream-K)"); MARK(8);
             } else {
                 cuda_check(launch_gemm_streamk(&tm_xn_, ly.gu.map(sk_gu.bn), T, 2 * F, H, pf_gu, stream), "gate_up gemm (stream-K)"); MARK(8);
                 cuda_check(launch_sk_swiglu(sk_gu, act_, T, F, stream), "swiglu"); MARK(9);
             }
-            cuda_check(launch_gemm_streamk(&tm_act_, ly.down.map(sk_dn.bn), T, H, F, pf_dn, stream), "down gemm (stream-K)"); MARK(10);
             const void* next_gain = (l + 1 < L) ? layers[l + 1].ln1 : final_norm;
+            if (fuse_dn) {
+                cuda_check(launch_gemm_streamk_resid(&tm_act_, ly.down.map(128), T, H, F, pf_dn, x_, H, chain_flags_ + 3 * SK_CHAIN_MAX_TILES, stream), "down gemm + residual (stream-K)"); MARK(10);
+                cuda_check(launch_rmsnorm_wide(x_, next_gain, xn_, T, H, cfg.rms_eps, stream), "rmsnorm1"); MARK(7);
+                continue;
+            }
+            cuda_check(launch_gemm_streamk(&tm_act_, ly.down.map(sk_dn.bn), T, H, F, pf_dn, stream), "down gemm (stream-K)"); MARK(10);
             if (use_tp) {
                 const int b = comm->next_buffer();
                 const TpComm::Signal sg = comm->next_signal();
@@ -580,9 +613,9 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
         const int bn_lm = pick_bn(S, V, opt.bn_lm, false);
         const int n_tiles = gemm_n_tiles(V, bn_lm);
         GemmParams gl{}; gl.M = S; gl.N = V; gl.K = H; gl.logits = logits_out; gl.ldl = V; gl.amax_val = amax_val_; gl.amax_idx = amax_idx_;
-        const bool masked = !in.masks.empty();
-        const uint32_t* d_masks = reinterpret_cast<const uint32_t*>(d_meta_ + o_mask);
-        if (masked && tp_rank == 0) gl.byte_logits = byte_logits_;          // ids 0..255 live in rank 0's vocabulary shard
+        if (!in.mask_slots.empty()) {          // constrained rows: the arg-max runs over their state's allowed tokens, on every vocabulary shard
+            gl.mask_table = mask_table_; gl.mask_slot = d_meta_ + o_mslot; gl.mask_words = mask_words; gl.col_offset = tp_rank * V;
+        }
         int lb = -1;
         if (use_tp) {          // vocab-parallel head: each rank's fp32 logits shard is staged in its symmetric buffer when asked for
             gl.logits = nullptr;
@@ -595,7 +628,6 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
         if (use_tp) {
             const int b = comm->next_buffer();
             cuda_check(launch_argmax_reduce_pair(amax_val_, amax_idx_, S, n_tiles, tp_rank * V, comm->arg(b), stream), "argmax (local shard)");
-            if (masked && tp_rank == 0) cuda_check(launch_masked_argmax(byte_logits_, d_masks, S, nullptr, comm->arg(b), stream), "grammar arg-max");
             cuda_check(comm->barrier(stream), "xgpu barrier");
             cuda_check(launch_ar_argmax(comm->d_peer_arg(b), tp, S, d_out_ids_, stream), "argmax (all ranks)");
             if (lb >= 0 && logits_out) {   // leader assembles the full [S, vocab] logits from the peers' shards over NVLink
@@ -606,7 +638,6 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
             if (lb >= 0) cuda_check(comm->barrier(stream), "xgpu barrier");     // peers must not reuse the staged shard before the leader has read it
         } else {
             cuda_check(launch_argmax_reduce(amax_val_, amax_idx_, S, n_tiles, d_out_ids_, nullptr, stream), "argmax");
-            if (masked) cuda_check(launch_masked_argmax(byte_logits_, d_masks, S, d_out_ids_, nullptr, stream), "grammar arg-max");
         }
         cuda_check(cudaMemcpyAsync(h_out_ids, d_out_ids_, (size_t)S * 4, cudaMemcpyDeviceToHost, stream), "ids D2H"); MARK(13);
         d2h_bytes += (size_t)S * 4;

@@ -27,7 +27,9 @@ struct StepInput {
     std::vector<int32_t> block_tables;                // [n_seqs, max_pages_per_seq]
     std::vector<int32_t> ctx_lens;                    // [n_seqs] (decode: tokens in cache incl. the new one)
     std::vector<PrefillTile> tiles;                   // prefill only
-    std::vector<uint32_t> masks;                      // [n_sample, 9] allowed-byte sets of grammar-constrained rows (empty: none)
+    // grammar-constrained sampling: mask_slots[i] = row of the device token-mask table applied to sampled row i (-1: unconstrained); empty: no
+    // constrained row.  mask_updates = concatenated records {slot, words[mask_words]} to be written into the table before the LM head.
+    std::vector<int32_t> mask_slots; std::vector<uint32_t> mask_updates;
     bool want_logits = false;                         // debug: fp32 logits of the sampled rows (tensor-parallel ranks stage their shard)
 };
 
@@ -55,6 +57,7 @@ public:
     std::unique_ptr<TpComm> comm;
     cudaStream_t stream = nullptr;
     int num_pages = 0, max_pages_per_seq = 0, sm_count = 148;
+    int mask_words = 0, mask_slots = 0, max_mask_updates = 0;    // token-mask table geometry (words = ceil(vocab / 32))
     size_t weight_bytes = 0, kv_pool_bytes = 0;
     KvLayout kv{}; CUtensorMap tm_kv;
     // instrumentation
@@ -79,7 +82,8 @@ private:
     // activations
     void *x_ = nullptr, *xn_ = nullptr, *qkv_ = nullptr, *q_ = nullptr, *attn_ = nullptr, *act_ = nullptr, *xs_ = nullptr, *xsn_ = nullptr;
     CUtensorMap tm_xn_, tm_attn_, tm_act_, tm_xsn_, tm_q_;
-    float* amax_val_ = nullptr; int* amax_idx_ = nullptr; int32_t* d_out_ids_ = nullptr; float* byte_logits_ = nullptr;
+    float* amax_val_ = nullptr; int* amax_idx_ = nullptr; int32_t* d_out_ids_ = nullptr;
+    uint32_t* mask_table_ = nullptr;               // [mask_slots][mask_words] allowed-token bitsets of grammar states (filled on demand by the scheduler)
     float *part_o_ = nullptr, *part_ml_ = nullptr; int max_part_slots_ = 0;
     float* sk_ws_ = nullptr; int sk_bn_ = 256, sk_G_ = 148;
     unsigned long long* chain_trace_ = nullptr;    // OA_CHAIN_TRACE=1: per-CTA clock stamps of the last chained launch, printed at teardown

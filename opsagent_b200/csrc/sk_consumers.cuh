@@ -78,7 +78,7 @@ OA_DEVINL void sk_sum8_pair(const StreamK& sk, int row, int col_a, int col_b, fl
 // at H <= 4096 every thread owns ONE 16-byte item and all its partial loads are in flight together; `red` = 16 floats of
 // shared memory, `bar_id` = a hardware barrier those threads own.
 constexpr int SK_RESID_THREADS = 512;
-template <int VPT>
+template <int VPT, bool SUM = true>     // SUM == false: the residual stream already holds x + projection (fused GEMM epilogue); only normalise
 OA_DEVINL void sk_resid_rmsnorm_row(const StreamK& sk, int t, int tid, float* red, int bar_id, uint4* __restrict__ x,
                                     const uint4* __restrict__ g, uint4* __restrict__ y, int H8, float inv_h, float eps) {
     uint4* xr = x + (size_t)t * H8;
@@ -90,12 +90,15 @@ OA_DEVINL void sk_resid_rmsnorm_row(const StreamK& sk, int t, int tid, float* re
         if (i < H8) {
             const uint4 xo = __ldcg(xr + i);
             gg[k] = g[i];                              // needed only after the reduction: its latency hides behind the partial loads
-            float acc[8];
-            sk_sum8(sk, t, i * 8, acc);
-            uint4 xn;
-            xn.x = pack_bf16x2(bf16lo(xo.x) + acc[0], bf16hi(xo.x) + acc[1]); xn.y = pack_bf16x2(bf16lo(xo.y) + acc[2], bf16hi(xo.y) + acc[3]);
-            xn.z = pack_bf16x2(bf16lo(xo.z) + acc[4], bf16hi(xo.z) + acc[5]); xn.w = pack_bf16x2(bf16lo(xo.w) + acc[6], bf16hi(xo.w) + acc[7]);
-            xr[i] = xn; v[k] = xn;
+            uint4 xn = xo;
+            if constexpr (SUM) {
+                float acc[8];
+                sk_sum8(sk, t, i * 8, acc);
+                xn.x = pack_bf16x2(bf16lo(xo.x) + acc[0], bf16hi(xo.x) + acc[1]); xn.y = pack_bf16x2(bf16lo(xo.y) + acc[2], bf16hi(xo.y) + acc[3]);
+                xn.z = pack_bf16x2(bf16lo(xo.z) + acc[4], bf16hi(xo.z) + acc[5]); xn.w = pack_bf16x2(bf16lo(xo.w) + acc[6], bf16hi(xo.w) + acc[7]);
+                xr[i] = xn;
+            }
+            v[k] = xn;
             float a;
             a = bf16lo(xn.x); ss += a * a; a = bf16hi(xn.x); ss += a * a; a = bf16lo(xn.y); ss += a * a; a = bf16hi(xn.y); ss += a * a;
             a = bf16lo(xn.z); ss += a * a; a = bf16hi(xn.z); ss += a * a; a = bf16lo(xn.w); ss += a * a; a = bf16hi(xn.w); ss += a * a;

@@ -41,7 +41,15 @@ public:
             eos_ = {im_end_, eot_text_};
         }
     }
-    bool byte_level() const { return !bpe_; }       // ids 0..255 are the bytes (what the grammar masks assume)
+    bool byte_level() const { return !bpe_; }       // ids 0..255 are the bytes
+    // bytes of every token a grammar-constrained completion may emit (token_mask.hpp): the checkpoint's text tokens, or ids 0..255 = one byte each
+    std::vector<std::string> text_token_bytes() const {
+        if (bpe_) return bpe_->text_token_bytes();
+        std::vector<std::string> v(256);
+        for (int b = 0; b < 256; ++b) v[b] = std::string(1, (char)b);
+        return v;
+    }
+    int vocab() const { return vocab_; }
     void bytes(const std::string& s, std::vector<int32_t>& out) const {
         if (bpe_) { bpe_->encode(s, out); return; }
         for (unsigned char ch : s) out.push_back((int32_t)ch);

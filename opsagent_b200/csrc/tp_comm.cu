@@ -141,13 +141,12 @@ void TpComm::publish(const StepInput& in) {
         spin_until([&] { return shm_->ack[p].load(std::memory_order_acquire) >= cur; }, "followers acknowledging the previous step", 600.0);
     int32_t* m = shm_->msg; size_t w = 0;
     auto put = [&](const void* src, size_t words) { if (w + words > TP_MSG_WORDS) throw std::runtime_error("tp step message overflow"); std::memcpy(m + w, src, words * 4); w += words; };
-    const int32_t n_mask = (int32_t)in.masks.size();
-    const int32_t hdr[8] = {(in.decode ? 1 : 0) | (in.n_decode << 1), (int32_t)in.tokens.size(), (int32_t)in.sample_rows.size(), in.n_seqs, (int32_t)in.block_tables.size(),
-                            (int32_t)in.ctx_lens.size(), (int32_t)in.tiles.size(), (in.want_logits ? 1 : 0) | (n_mask << 1)};
-    put(hdr, 8);
+    const int32_t hdr[10] = {(in.decode ? 1 : 0) | (in.n_decode << 1), (int32_t)in.tokens.size(), (int32_t)in.sample_rows.size(), in.n_seqs, (int32_t)in.block_tables.size(),
+                             (int32_t)in.ctx_lens.size(), (int32_t)in.tiles.size(), (in.want_logits ? 1 : 0), (int32_t)in.mask_slots.size(), (int32_t)in.mask_updates.size()};
+    put(hdr, 10);
     put(in.tokens.data(), in.tokens.size()); put(in.positions.data(), in.positions.size()); put(in.slots.data(), in.slots.size());
     put(in.sample_rows.data(), in.sample_rows.size()); put(in.block_tables.data(), in.block_tables.size());
-    put(in.ctx_lens.data(), in.ctx_lens.size()); put(in.tiles.data(), in.tiles.size() * 4); put(in.masks.data(), in.masks.size());
+    put(in.ctx_lens.data(), in.ctx_lens.size()); put(in.tiles.data(), in.tiles.size() * 4); put(in.mask_slots.data(), in.mask_slots.size()); put(in.mask_updates.data(), in.mask_updates.size());
     shm_->msg_words = (uint32_t)w;
     shm_->seq.store(cur + 1, std::memory_order_release);
 }
@@ -163,14 +162,15 @@ bool TpComm::receive(StepInput& in) {
             throw std::runtime_error("tensor-parallel leader (pid " + std::to_string((long long)shm_->leader_pid.load()) + ") is gone");
     }
     const int32_t* m = shm_->msg; size_t w = 0;
-    const int32_t* hdr = m; w += 8;
+    const int32_t* hdr = m; w += 10;
     auto get = [&](std::vector<int32_t>& v, int n) { v.assign(m + w, m + w + n); w += n; };
     in = StepInput();
     in.decode = (hdr[0] & 1) != 0; in.n_decode = hdr[0] >> 1; in.n_seqs = hdr[3]; in.want_logits = (hdr[7] & 1) != 0;
     get(in.tokens, hdr[1]); get(in.positions, hdr[1]); get(in.slots, hdr[1]); get(in.sample_rows, hdr[2]);
     get(in.block_tables, hdr[4]); get(in.ctx_lens, hdr[5]);
     in.tiles.resize(hdr[6]); std::memcpy(in.tiles.data(), m + w, (size_t)hdr[6] * 16); w += (size_t)hdr[6] * 4;
-    { const int n_mask = hdr[7] >> 1; in.masks.resize(n_mask); std::memcpy(in.masks.data(), m + w, (size_t)n_mask * 4); w += n_mask; }
+    get(in.mask_slots, hdr[8]);
+    in.mask_updates.resize((size_t)hdr[9]); std::memcpy(in.mask_updates.data(), m + w, (size_t)hdr[9] * 4); w += (size_t)hdr[9];
     seq_local_ = s;
     shm_->ack[rank_].store(s, std::memory_order_release);
     return true;

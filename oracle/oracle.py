@@ -358,26 +358,74 @@ class ToolPromptGrammar:
         return w
 
 
-def generate_constrained(orc: "Oracle", prompt, kind: int, max_new: int = 600, slot: int = 0, functions: str = ""):
-    """Greedy decoding under the ToolPrompt grammar: arg-max over the allowed bytes only (ties -> lowest id).
-    -> (bytes, margins among the allowed set)"""
+GRAMMAR_MAX_TOKEN_BYTES = 32      # restated from opsagent_b200/csrc/token_mask.hpp
+
+
+def byte_level_token_bytes() -> list:
+    """token id -> bytes for the synthetic byte-level vocabulary: ids 0..255 are one byte each, every other id is not a text token"""
+    return [bytes([b]) for b in range(256)]
+
+
+def bpe_token_bytes(tokenizer_json_path: str) -> list:
+    """token id -> raw bytes of a Hugging Face byte-level BPE tokenizer.json (added/control tokens: b"") — parsed from the file itself
+    (GPT-2 byte<->unicode alphabet), independent of opsagent_b200/csrc/bpe.hpp"""
+    import json as _json
+    d = _json.load(open(tokenizer_json_path, encoding="utf-8"))
+    bs = list(range(33, 127)) + list(range(161, 173)) + list(range(174, 256)); cs = bs[:]; n = 0
+    for b in range(256):
+        if b not in bs:
+            bs.append(b); cs.append(256 + n); n += 1
+    u2b = {chr(c): b for b, c in zip(bs, cs)}
+    vocab = d["model"]["vocab"]
+    added = {a["id"] for a in d.get("added_tokens", [])}
+    size = max(max(vocab.values()), max(added) if added else 0) + 1
+    out = [b""] * size
+    for tok, i in vocab.items():
+        if i not in added:
+            out[i] = bytes(u2b[ch] for ch in tok)
+    return out
+
+
+def allowed_tokens(g: "ToolPromptGrammar", token_bytes) -> list:
+    """Token ids allowed in g's current state, by brute force: a token is allowed iff ALL its bytes walk the automaton from here (the JSON
+    may complete exactly at its last byte, never earlier), it is a text token, and it is at most GRAMMAR_MAX_TOKEN_BYTES long.
+    Restates opsagent_b200/csrc/token_mask.hpp (trie walk + canonicalised cache) the slow, obvious way."""
+    import copy
+    out = []
+    first = g.allowed()
+    for tid, bs in enumerate(token_bytes):
+        if not bs or len(bs) > GRAMMAR_MAX_TOKEN_BYTES or bs[0] not in first:
+            continue
+        h = copy.copy(g); h.cand = set(g.cand)
+        if all(h.advance(b) for b in bs):
+            out.append(tid)
+    return out
+
+
+def generate_constrained(orc: "Oracle", prompt, kind: int, max_new: int = 600, slot: int = 0, functions: str = "", token_bytes=None):
+    """Greedy decoding under the ToolPrompt grammar: arg-max over the allowed TOKENS only (ties -> lowest id).  token_bytes: id -> bytes
+    of the engine's tokenizer (default: the synthetic byte-level vocabulary, where tokens are bytes).
+    -> (bytes, margins among the allowed set, token ids)"""
+    token_bytes = token_bytes if token_bytes is not None else byte_level_token_bytes()
     g = ToolPromptGrammar(kind, functions)
-    out, margins = [], []
+    out, margins, ids = [], [], []
     logits = orc.forward(np.ascontiguousarray(prompt, dtype=np.int32), slot=slot)[0]
     pos = len(prompt)
-    while not g.done() and len(out) < max_new:
-        allowed = sorted(g.allowed())
+    while not g.done() and len(ids) < max_new:
+        allowed = allowed_tokens(g, token_bytes)
         vals = logits[allowed]
         k = int(np.argmax(vals))                 # first maximum = lowest id
         tok = allowed[k]
         rest = np.delete(vals, k)
         margins.append(float(vals[k] - rest.max()) if len(rest) else float("inf"))
-        out.append(tok); g.advance(tok)
+        ids.append(tok)
+        for b in token_bytes[tok]:
+            out.append(b); g.advance(b)
         if g.done():
             break
         logits = orc.forward(np.array([tok], np.int32), pos0=pos, slot=slot)[0]
         pos += 1
-    return bytes(out), margins
+    return bytes(out), margins, ids
 
 
 def write_safetensors(orc: "Oracle", path: str, dtype: str = "BF16") -> None:

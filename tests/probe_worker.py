@@ -57,12 +57,24 @@ def bpe():
     L = _lib.load(); arr = np.asarray(out.token_ids, np.int32); buf = C.create_string_buffer(4096); n = C.c_int32()
     if L.oa_host_bpe_decode(tok.encode(), arr.ctypes.data, len(arr), buf, len(buf), C.byref(n)) != 0 or buf.raw[: n.value] != bytes(out.content):
         print("bpe: completion text is not the BPE decoding of the generated ids"); return 1
-    try:
-        eng.chat_complete("", msgs, 8, flags=2)
-        print("bpe: grammar flag accepted with a BPE tokenizer"); return 1
-    except Exception as e:      # 400: masks address byte tokens
-        if getattr(e, "code", None) != 400:
-            print("bpe: expected 400, got", e); return 1
+    # schema-constrained decoding over the BPE vocabulary (token masks: csrc/token_mask.hpp): the completion must parse as tools.ToolPrompt
+    # and equal the oracle's constrained greedy decode over the same token set, token for token (up to a near tie)
+    import json as _json
+    tb = O.bpe_token_bytes(tok)
+    for kind, flag in ((O.GRAMMAR_TOOLCALL, 2), (O.GRAMMAR_FINAL, 4)):
+        out = eng.chat_complete("", msgs, 400, flags=flag)
+        doc = _json.loads(bytes(out.content).decode("utf-8"))
+        if list(doc.keys()) != ["question", "thought", "action", "observation", "final_answer"] or out.finish_reason != "stop":
+            print("bpe: constrained completion is not ToolPrompt JSON:", bytes(out.content)[:200]); return 1
+        _text, margins, ref_ids = O.generate_constrained(orc, np.asarray(ids, np.int32), kind, token_bytes=tb)
+        got = list(out.token_ids)
+        k = 0
+        while k < min(len(ref_ids), len(got)) and ref_ids[k] == got[k]:
+            k += 1
+        if not (k == len(ref_ids) == len(got) or margins[k] <= 2 * LOGIT_TOL):
+            print(f"bpe: constrained decode (kind {kind}) diverges from the oracle at token {k} with margin {margins[k]}"); return 1
+    if eng.stats().get("grammar_states_computed", 0) <= 0:
+        print("bpe: no token mask was computed"); return 1
     eng.close(); orc.close()
     print("bpe: ok"); return 0
 

@@ -143,3 +143,22 @@ def test_legacy_merge_strings_and_rejections(tmp_path):
         assert L.oa_host_bpe_encode(str(tmp_path / name).encode(), b"x", 1, None, 0, C.byref(n)) == 400 and needle in _lib.last_error(), (name, _lib.last_error())
     (tmp_path / "broken.json").write_text("{\"model\": ")
     assert L.oa_host_bpe_encode(str(tmp_path / "broken.json").encode(), b"x", 1, None, 0, C.byref(n)) == 400 and "tokenizer.json" in _lib.last_error()
+
+
+def test_k8s_tokenizer_and_long_runs_match_the_live_library():
+    """the 8k-vocabulary tokenizer the benchmark's end-to-end leg uses (tests/golden/gen_k8s_bpe.py) on the reference's verbatim prompts,
+    synthetic manifests and kubectl/trivy tables, plus long single-character runs that go through the O(n log n) merge path"""
+    tokenizers = pytest.importorskip("tokenizers")
+    from opsagent_b200.synthetic import copilot_tools
+    from opsagent_b200.workloads import prompt, synthetic_pod_yaml
+    L = _lib.load()
+    path = os.path.join(GOLDEN, "bpe_k8s_8k.json")
+    ref = tokenizers.Tokenizer.from_file(path)
+    tools = copilot_tools(3)
+    texts = [prompt(n) for n in ("executeSystemPrompt_cn", "diagnoseSystemPrompt", "analysisPrompt", "auditPrompt", "analysisSystem")]
+    texts += [synthetic_pod_yaml(i, 3000) for i in range(3)] + [tools["kubectl"]("get pods -A"), tools["trivy"]("nginx:1.25")]
+    texts += ["=" * 5000, "namespace" * 700, "ab" * 3000 + "kubectl" * 400, "集群命名空间" * 500, "-" * 200 + "\n" * 50 + " " * 300 + "x"]
+    for t in texts:
+        ids = encode(L, path, t)
+        assert ids == ref.encode(t, add_special_tokens=False).ids, t[:40]
+        assert decode(L, path, ids) == t.encode("utf-8")

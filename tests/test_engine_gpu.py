@@ -77,7 +77,9 @@ def test_two_row_tile_streamk_path_matches_oracle():
 
 @pytest.mark.parametrize("name", CASES + ["llama-3.2-1b"])
 def test_fused_decode_epilogues_are_bit_identical_to_separate_kernels(name):
-    """Baseline: one kernel per projection and per consumer (sk_fuse_swiglu=0, sk_chain=0).  Variants: the gate/up projection finishing
+    """Baseline: one kernel per projection and per consumer (sk_fuse_swiglu=0, sk_fuse_epi=0, sk_chain=0).  Variants: the qkv projection
+    finishing bias + RoPE + the paged-KV write and the o / down projections finishing the residual add in their own epilogues
+    (sk_fuse_epi bitmask 1 / 2 / 4; o and down are followed by a norm-only kernel with the consumer's reduction order); the gate/up projection finishing
     SwiGLU in its own epilogue (the CTA holding a tile's first k-block adds the other CTAs' pieces in CTA order); and the opt-in chained
     kernel (sk_chain=1/2: o -> resid+norm -> gate_up+SwiGLU -> down -> resid+norm (-> next qkv -> RoPE/KV) in ONE persistent launch with
     grid barriers).  Reduction order and consumer code are shared, so logits and generated ids must be EQUAL, not close.
@@ -87,7 +89,8 @@ def test_fused_decode_epilogues_are_bit_identical_to_separate_kernels(name):
     spec = O.PRESETS[name]
     prompts = [rng.integers(0, spec.vocab if not full else 256, size=n).astype(np.int32) for n in ((1, 33, 128) if not full else (7, 128))]
     gen_prompts = [rng.integers(0, 256, size=n).astype(np.int32).tolist() for n in (3, 19, 40, 64, 90)]
-    variants = [dict(sk_fuse_swiglu=0, sk_chain=0), dict(sk_fuse_swiglu=1, sk_chain=0), dict(sk_chain=1), dict(sk_chain=2)]
+    variants = [dict(sk_fuse_swiglu=0, sk_fuse_epi=0, sk_chain=0), dict(sk_fuse_swiglu=1, sk_fuse_epi=0, sk_chain=0), dict(sk_fuse_swiglu=0, sk_fuse_epi=7, sk_chain=0),
+                dict(sk_fuse_swiglu=1, sk_fuse_epi=1, sk_chain=0), dict(sk_fuse_swiglu=1, sk_fuse_epi=6, sk_chain=0), dict(sk_chain=1), dict(sk_chain=2)]
     results = []
     for kw in variants:
         if full:
@@ -263,7 +266,7 @@ def test_grammar_constrained_completion_is_toolprompt_json_and_matches_oracle(ki
         assert doc["action"]["name"] in O.TOOLS and doc["final_answer"] == ""
     else:
         assert len(doc["final_answer"]) >= 10
-    ref, margins = O.generate_constrained(orc, np.array(ids, np.int32), kind)
+    ref, margins, _ = O.generate_constrained(orc, np.array(ids, np.int32), kind)
     got = out.content
     k = 0
     while k < min(len(ref), len(got)) and ref[k] == got[k]:
@@ -401,7 +404,7 @@ def test_http_front_function_calling_end_to_end_matches_oracle():
     args = _json.loads(tc["function"]["arguments"])
     assert list(args.keys()) == [{"kubectl": "command", "trivy": "image"}[tc["function"]["name"]]]
     ids = O.apply_chat_template(spec, [(m["role"], m["content"]) for m in msgs])
-    ref, margins = O.generate_constrained(orc, np.array(ids, np.int32), O.GRAMMAR_FUNCTION, functions="kubectl:command,trivy:image")
+    ref, margins, _ = O.generate_constrained(orc, np.array(ids, np.int32), O.GRAMMAR_FUNCTION, functions="kubectl:command,trivy:image")
     got = ('{"name":"%s","arguments":{"%s":"%s"}}' % (tc["function"]["name"], list(args.keys())[0], list(args.values())[0])).encode()
     k = 0
     while k < min(len(ref), len(got)) and ref[k] == got[k]:

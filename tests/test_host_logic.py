@@ -585,3 +585,40 @@ def test_follower_side_tiny_presets_equal_the_oracle_presets():
     from opsagent_b200.presets_tiny import TINY_TP
     for name, cfg in TINY_TP.items():
         assert cfg == O.PRESETS[name].engine_json(), name
+
+
+# ---- grammar masks over a TOKEN vocabulary (csrc/token_mask.hpp) vs the oracle-side brute force ----
+@pytest.mark.parametrize("tok", ["", "bpe_llama3_tiny.json", "bpe_qwen2_tiny.json"])
+@pytest.mark.parametrize("kind", [O.GRAMMAR_TOOLCALL, O.GRAMMAR_FINAL, O.GRAMMAR_FUNCTION, O.GRAMMAR_TEXT])
+def test_token_masks_equal_brute_force_along_random_token_walks(tok, kind):
+    """the C++ trie walk must allow exactly the tokens whose bytes all walk the automaton; states sharing a canonical cache key must share a mask"""
+    L = _lib.load()
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", tok) if tok else ""
+    if tok:
+        token_bytes = O.bpe_token_bytes(path)
+        vocab = len(token_bytes)
+    else:
+        vocab, token_bytes = 704, O.byte_level_token_bytes()
+    fns = "kubectl:command,trivy:image" if kind == O.GRAMMAR_FUNCTION else ""
+    words = (vocab + 31) // 32
+    rng = np.random.default_rng(5 + kind)
+    by_key = {}
+    for walk in range(3):
+        g = O.ToolPromptGrammar(kind, fns)
+        prefix = bytearray()
+        for _step in range(400):
+            if g.done():
+                break
+            ref = O.allowed_tokens(g, token_bytes)
+            mask = (C.c_uint32 * words)(); key = C.create_string_buffer(256)
+            buf = (C.c_uint8 * max(1, len(prefix))).from_buffer_copy(bytes(prefix) or b"\0")
+            assert L.oa_host_grammar_token_mask(path.encode() if path else None, vocab, kind, fns.encode(), buf, len(prefix), mask, words, key, 256) == 0
+            got = [i for i in range(vocab) if (mask[i >> 5] >> (i & 31)) & 1]
+            assert got == ref, (walk, bytes(prefix), set(got) ^ set(ref))
+            assert ref, "a grammar state must always allow at least one token"
+            by_key.setdefault(key.value, set()).add(tuple(ref))
+            tid = int(rng.choice(ref))
+            for b in token_bytes[tid]:
+                prefix.append(b); assert g.advance(b)
+        assert g.done()
+    assert all(len(v) == 1 for v in by_key.values())
