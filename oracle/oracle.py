@@ -152,6 +152,9 @@ PRESETS = {
     "tiny-qwen-tp4": ModelSpec("tiny-qwen-tp4", 512, 2, 40, 8, 128, 1024, 1280, qkv_bias=1, rope_theta=1e6, rms_eps=1e-6, norm_random=1,
                                template="chatml"),
     "tiny-llama-tp8": ModelSpec("tiny-llama-tp8", 512, 2, 64, 8, 64, 1024, 2048, norm_random=1),
+    # Llama-3-8B's attention geometry (32 query heads on 8 kv heads, head_dim 128, llama3 RoPE scaling) on tiny other dims: what the decode
+    # attention work plan of the BENCHMARKED batch (128 sequences x ctx ~1700 -> 296 CTAs, cut items, in-kernel merges) depends on
+    "tiny-llama-8bheads": ModelSpec("tiny-llama-8bheads", 256, 1, 32, 8, 128, 256, 512, norm_random=1, rope_scaling=1),
     "tiny-qwen": ModelSpec("tiny-qwen", 320, 2, 5, 1, 64, 768, 1280, qkv_bias=1, rope_theta=1e6, rms_eps=1e-6,
                            norm_random=1, template="chatml"),
 }

@@ -23,7 +23,7 @@ from oracle import oracle as O  # noqa: E402
 
 CASES = {"tiny-llama": dict(T=24, G=12, seed=7), "tiny-llama-d128": dict(T=20, G=10, seed=8),
          "tiny-qwen": dict(T=28, G=12, seed=9), "tiny-llama-g8": dict(T=22, G=10, seed=10), "tiny-llama-mha": dict(T=18, G=10, seed=11),
-         "tiny-qwen-tp4": dict(T=20, G=10, seed=12), "tiny-llama-tp8": dict(T=20, G=10, seed=13)}
+         "tiny-qwen-tp4": dict(T=20, G=10, seed=12), "tiny-llama-tp8": dict(T=20, G=10, seed=13), "tiny-llama-8bheads": dict(T=20, G=10, seed=14)}
 
 
 def hf_model(spec: O.ModelSpec, orc: O.Oracle):

@@ -9,7 +9,7 @@ import pytest
 from oracle import oracle as O
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-CASES = ["tiny-llama", "tiny-llama-d128", "tiny-qwen", "tiny-llama-g8", "tiny-llama-mha", "tiny-qwen-tp4", "tiny-llama-tp8"]
+CASES = ["tiny-llama", "tiny-llama-d128", "tiny-qwen", "tiny-llama-g8", "tiny-llama-mha", "tiny-qwen-tp4", "tiny-llama-tp8", "tiny-llama-8bheads"]
 FP32_TOL = 2e-4      # abs, logits are O(1); observed 1.5e-6
 
 

@@ -24,8 +24,7 @@ ap.add_argument("--prompt-bytes", type=int, default=1200)
 ap.add_argument("--extra", default="{}", help="engine config overrides (JSON), e.g. {\"prefill_batch_tokens\": 0}")
 a = ap.parse_args()
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bench import synthetic_pod_yaml, ANALYSIS_SYSTEM  # noqa: E402
+from opsagent_b200 import workloads as WL  # noqa: E402
 
 eng = Engine({"model": a.model, "kv_gb": 60, "max_batch": a.agents, "max_seq_len": 8192, "max_step_tokens": 8192, "json_mode": 1,
               "react_tool_steps": a.tool_steps, **json.loads(a.extra)})
@@ -43,7 +42,7 @@ class CountingClient(LocalCUDAClient):
 
 
 def agent(i):
-    msgs = [ChatCompletionMessage("system", ANALYSIS_SYSTEM), ChatCompletionMessage("user", synthetic_pod_yaml(i, a.prompt_bytes))]
+    msgs = WL.analyze_messages(WL.synthetic_pod_yaml(i, a.prompt_bytes)[: a.prompt_bytes])
     results[i] = AssistantWithConfig(a.model, msgs, 2048, True, False, a.tool_steps + 2, CountingClient(eng, i), copilot_tools(i),
                                      count_tokens=eng.count_tokens)
 
