@@ -142,6 +142,67 @@ def run_tp_block(args, rank, world, nonce, log):
     return block
 
 
+def router_block(args, rank, world, barrier):
+    """BASELINE configs[2] as it would be SERVED: one front process (rank 0) owning one engine per GPU behind the OpenAI-compatible HTTP
+    endpoint (opsagent_b200/router.py + http_front.py; the reference is one process too, pkg/api/router.go:95), world*128 concurrent
+    clients POSTing the 40/30/30 mix with the reference's wire format.  Sticky least-loaded routing, no data-path collective.
+    The other ranks have closed their engines and idle at the barrier."""
+    barrier()
+    out = None
+    if rank == 0:
+        import http.client
+        import resource
+        from opsagent_b200 import workloads as WL
+        from opsagent_b200.http_front import serve
+        from opsagent_b200.router import Router
+        try:
+            soft, hard = resource.getrlimit(resource.RLIMIT_NOFILE)
+            resource.setrlimit(resource.RLIMIT_NOFILE, (min(hard, 65536) if hard > 0 else 65536, hard))
+        except Exception:
+            pass
+        cfg = {"model": MODEL, "kv_gb": args.kv_gb, "max_batch": BATCH, "max_seq_len": 2048, "max_step_tokens": 8192, "seed": 1234, "tokenizer": TOKENIZER,
+               "prefix_cache": 0, "max_queue": 4096, **json.loads(args.engine_extra)}
+        rt = Router.create(cfg, list(range(world)), max_inflight=2 * BATCH)
+        srv, _th = serve(rt, port=0)
+        port = srv.server_address[1]
+        n_req = world * BATCH
+        bodies = []
+        kinds = {}
+        for gi in range(n_req):
+            k, m = WL.mixed_request(gi, rt.count_tokens, p_analyze=PROMPT)
+            kinds[k] = kinds.get(k, 0) + 1
+            bodies.append(json.dumps({"model": MODEL, "max_tokens": GEN, "temperature": 1.401298464324817e-45,
+                                      "messages": [{"role": x.Role, "content": x.Content} for x in m]}).encode("utf-8"))
+        usage = [None] * n_req
+
+        def post(i):
+            c = http.client.HTTPConnection("127.0.0.1", port, timeout=600)
+            c.request("POST", "/v1/chat/completions", body=bodies[i], headers={"Content-Type": "application/json", "Authorization": "Bearer sk-local"})
+            r = c.getresponse(); d = json.loads(r.read()); c.close()
+            usage[i] = d["usage"] if r.status == 200 else {"error": r.status}
+
+        def round_(idx):
+            th = [threading.Thread(target=post, args=(i,)) for i in idx]
+            t0 = time.perf_counter()
+            [t.start() for t in th]; [t.join() for t in th]
+            return time.perf_counter() - t0
+        round_(range(0, n_req, 16))                                # warm-up: a few requests on every replica
+        s0 = rt.stats()
+        dt = round_(range(n_req))
+        s1 = rt.stats()
+        ok = [u for u in usage if u and "error" not in u]
+        comp = sum(u["completion_tokens"] for u in ok)
+        out = {"workload": f"BASELINE configs[2] served: {n_req} concurrent HTTP clients -> one front (router + OpenAI-compatible endpoint) -> {world} engines; "
+                           "mix 40% analyze (P=1536) / 30% diagnose / 30% execute, verbatim reference prompts, max_tokens 256",
+               "requests": n_req, "completed": len(ok), "by_kind": kinds, "seconds": round(dt, 3),
+               "e2e_tokens_per_sec": round(comp / dt, 1), "react_steps_per_sec": round(len(ok) / dt, 2), "completion_tokens": comp,
+               "prompt_tokens_mean": round(sum(u["prompt_tokens"] for u in ok) / max(1, len(ok)), 1),
+               "routed_per_replica": [b - a for a, b in zip(s0["routed"], s1["routed"])], "rejected_429": s1["rejected_429"] - s0["rejected_429"]}
+        srv.shutdown(); rt.close()
+    barrier()
+    return out
+
+
 def react_block(args, rank, world, local_rank, barrier, allmax):
     """Multi-step ReAct loops inside the measurement contract: per GPU, 128 concurrent conversations driven by the mirror of the
     reference's loop (assistants.AssistantWithConfig <-> pkg/assistants/simple.go:292-616) through LocalCUDAClient.Chat — POST /execute's
@@ -218,12 +279,10 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from opsagent_b200 import dp as DP       # host side of the replica mode: request sharding + max-over-ranks timing (tests/test_dp_gloo.py)
+
     def allmax(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return DP.allreduce_max(x, dist, device="cuda")
 
     def tp_block():
         """-> the "tp" block on rank 0 (None on followers); never raises, never hangs the headline: rank 0 gives the leg a deadline"""
@@ -301,8 +360,7 @@ def run_ours(args, rank, world, local_rank):
     from opsagent_b200 import workloads as WL
     cli = LocalCUDAClient(eng)
     reqs = []
-    for i in range(BATCH):
-        gi = rank * BATCH + i
+    for gi in DP.shard_requests(world * BATCH, rank, world):      # this replica's contiguous shard of the job's request ids
         if world == 1:
             reqs.append(("analyze", WL.fit_to_tokens(WL.analyze_messages, WL.synthetic_pod_yaml(gi, 12 * PROMPT), PROMPT, eng.count_tokens)))
         else:
@@ -359,6 +417,14 @@ def run_ours(args, rank, world, local_rank):
         rb = react_block(args, rank, world, local_rank, barrier, allmax)
         if rank == 0:
             line["react"] = rb
+    if world >= 2 and not args.no_router:
+        try:
+            rb = router_block(args, rank, world, barrier)
+        except Exception as e:
+            rb = {"error": f"{type(e).__name__}: {e}"}
+            barrier()
+        if rank == 0:
+            line["router"] = rb
     hung = False
     if world >= 2 and not args.no_tp:
         tp, hung = tp_block()
@@ -425,6 +491,7 @@ def main():
     ap.add_argument("--kv-gb", type=float, default=60.0, dest="kv_gb")
     ap.add_argument("--cpu-tokens", type=int, default=64, dest="cpu_tokens")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-router", action="store_true", help="N>=2: skip the one-front / N-engines serving block")
     ap.add_argument("--no-react", action="store_true", help="skip the multi-step ReAct block")
     ap.add_argument("--react-agents", type=int, default=128, dest="react_agents")
     ap.add_argument("--no-tp", action="store_true", help="N>=2: skip the tensor-parallel block")

@@ -16,9 +16,12 @@ package llms
 import "C"
 
 import (
+	"context"
 	"fmt"
 	"math"
+	"os"
 	"runtime"
+	"strings"
 	"sync"
 	"time"
 	"unsafe"
@@ -49,11 +52,21 @@ func NewLocalCUDAClient(apiKey string, baseURL string) (*LocalCUDAClient, error)
 	engineOnce.Do(func() {
 		runtime.LockOSThread() // oa_last_error() is thread-local
 		defer runtime.UnlockOSThread()
-		model := "llama-3-8b"
-		if len(baseURL) > len("cuda://") {
-			model = baseURL[len("cuda://"):]
+		// cuda://<preset> names the model to load; anything else after the scheme (the handler's "gpt-4" default, execute.go:168-171)
+		// falls back to $OPSAGENT_LOCAL_MODEL or llama-3-8b — requests are then answered under model_aliases "*"
+		model := os.Getenv("OPSAGENT_LOCAL_MODEL")
+		if m := strings.TrimPrefix(baseURL, "cuda://"); m != baseURL {
+			switch m {
+			case "llama-3.2-1b", "llama-3-8b", "qwen2.5-32b", "llama-3-70b":
+				model = m
+			}
 		}
-		cfg := C.CString(fmt.Sprintf(`{"model": %q, "max_batch": 256, "max_seq_len": 16384}`, model))
+		if model == "" {
+			model = "llama-3-8b"
+		}
+		// model_aliases "*": the reference forwards req.CurrentModel, or "gpt-4" when it is empty (pkg/handlers/execute.go:168-171);
+		// a single-model local engine answers to whatever name the unmodified caller sends
+		cfg := C.CString(fmt.Sprintf(`{"model": %q, "max_batch": 256, "max_seq_len": 16384, "model_aliases": "*"}`, model))
 		defer C.free(unsafe.Pointer(cfg))
 		if rc := C.oa_engine_create(cfg, &engineInst); rc != 0 {
 			engineErr = fmt.Errorf("oa_engine_create: %d %s", int(rc), C.GoString(C.oa_last_error()))
@@ -65,15 +78,23 @@ func NewLocalCUDAClient(apiKey string, baseURL string) (*LocalCUDAClient, error)
 	return &LocalCUDAClient{Retries: 5, Backoff: time.Second, engine: engineInst}, nil
 }
 
-// Chat — same signature and error behaviour as (*OpenAIClient).Chat (openai.go:69-104).  submit + wait keeps the
-// goroutine parked in one cgo call; many goroutines batch inside the engine (continuous batching).
+// Chat — same signature and error behaviour as (*OpenAIClient).Chat (openai.go:69-104).
+//
+// Threading: the goroutine blocks in ONE cgo call at a time (oa_chat_wait_ex with a bounded timeout, re-entered until the completion is
+// there), and error text comes back in a caller-owned buffer (the *_ex entry points), never through the thread-local oa_last_error() — so no
+// runtime.LockOSThread: a goroutine may migrate between OS threads around cgo calls and nothing here depends on thread identity.
+// Hundreds of goroutines batch inside the engine (continuous batching); a request whose goroutine gives up is cancelled so that it stops
+// consuming KV pages and decode slots.
 func (c *LocalCUDAClient) Chat(model string, maxTokens int, prompts []openai.ChatCompletionMessage) (string, error) {
+	return c.ChatContext(context.Background(), model, maxTokens, prompts)
+}
+
+// ChatContext is Chat with cancellation (the reference passes context.Background() to CreateChatCompletion, openai.go:79; a caller
+// with a deadline can use this directly).
+func (c *LocalCUDAClient) ChatContext(ctx context.Context, model string, maxTokens int, prompts []openai.ChatCompletionMessage) (string, error) {
 	if len(prompts) == 0 {
 		return "", fmt.Errorf("prompts cannot be empty") // the caller checks this too (pkg/assistants/simple.go:312)
 	}
-	// oa_last_error() is thread-local: keep this goroutine on one OS thread across the call and the error read
-	runtime.LockOSThread()
-	defer runtime.UnlockOSThread()
 	msgs := (*[1 << 20]C.oa_msg)(C.malloc(C.size_t(len(prompts)) * C.size_t(unsafe.Sizeof(C.oa_msg{}))))[:len(prompts):len(prompts)]
 	defer C.free(unsafe.Pointer(&msgs[0]))
 	for i, p := range prompts {
@@ -86,17 +107,32 @@ func (c *LocalCUDAClient) Chat(model string, maxTokens int, prompts []openai.Cha
 	defer C.free(unsafe.Pointer(cmodel))
 	req := C.oa_chat_req{model: cmodel, msgs: &msgs[0], n_msgs: C.int32_t(len(prompts)), max_tokens: C.int32_t(maxTokens),
 		temperature: C.float(math.SmallestNonzeroFloat32)}
+	const errCap = 512
+	errBuf := (*C.char)(C.malloc(errCap))
+	defer C.free(unsafe.Pointer(errBuf))
 
 	backoff := c.Backoff
 	for try := 0; try < c.Retries; try++ {
-		var resp C.oa_chat_resp
-		rc := int(C.oa_chat_complete(c.engine, &req, &resp))
-		if rc == 0 {
-			out := C.GoStringN(resp.content, C.int(resp.content_len))
-			C.oa_free_resp(&resp)
-			return out, nil
+		var ticket C.uint64_t
+		rc := int(C.oa_chat_submit_ex(c.engine, &req, &ticket, errBuf, errCap))
+		for rc == 0 {
+			var resp C.oa_chat_resp
+			rc = int(C.oa_chat_wait_ex(c.engine, ticket, 250 /* ms */, &resp, errBuf, errCap))
+			if rc == 0 {
+				out := C.GoStringN(resp.content, C.int(resp.content_len))
+				C.oa_free_resp(&resp)
+				return out, nil
+			}
+			if rc != 408 { // anything but "not finished yet"
+				break
+			}
+			if err := ctx.Err(); err != nil {
+				C.oa_chat_cancel(c.engine, ticket)
+				return "", err
+			}
+			rc = 0
 		}
-		err := &openai.APIError{HTTPStatusCode: rc, Message: C.GoString(C.oa_last_error())}
+		err := &openai.APIError{HTTPStatusCode: rc, Message: C.GoString(errBuf)}
 		switch rc {
 		case 401:
 			return "", err

@@ -1,5 +1,7 @@
-"""dp — host-side helpers of the data-parallel replica mode (BASELINE configs[2]: one engine per GPU, requests are
-independent, NO data-path collective).  torch.distributed is used only for the bench barrier and the max-over-ranks."""
+"""dp — host-side helpers of the one-process-per-GPU replica mode that bench.py measures (BASELINE configs[2]: one engine per GPU,
+requests are independent, NO data-path collective): which request ids a rank owns, and the max-over-ranks timing / whole-job throughput
+the JSON line reports.  torch.distributed is used only for that barrier/max.  Serving the same replicas behind ONE endpoint — sticky
+routing of live conversations, per-replica admission — is opsagent_b200/router.py."""
 from __future__ import annotations
 
 

@@ -155,7 +155,9 @@ def make_handler(engine, require_key: bool = True, tool_steps: int = 3, api_key:
 def serve(engine, host: str = "127.0.0.1", port: int = 8000, require_key: bool = True, tool_steps: int = 3, api_key: str | None = None):
     """-> (server, thread).  One OS thread per in-flight request, each blocking in the engine — the same concurrency shape as
     gin's goroutine-per-request; batching happens inside the engine."""
-    srv = ThreadingHTTPServer((host, port), make_handler(engine, require_key, tool_steps, api_key))
+    class Server(ThreadingHTTPServer):
+        request_queue_size = 4096          # hundreds of agents connect at once (BASELINE configs[2]: 1024 concurrent requests); the default backlog is 5
+    srv = Server((host, port), make_handler(engine, require_key, tool_steps, api_key))
     srv.daemon_threads = True
     th = threading.Thread(target=srv.serve_forever, daemon=True)
     th.start()

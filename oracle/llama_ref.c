@@ -182,6 +182,25 @@ REF_API void oa_ref_destroy(ref_model *m) {
     free(m->embed); free(m->norm); free(m->rope_cos); free(m->rope_sin); free(m->kcache); free(m->vcache); free(m);
 }
 
+/* TIMING AID for bench.py's cpu_baseline leg only (never used by a parity test): fills cache positions [0, n) of `slot` with seeded
+ * values of a realistic scale, so that the CPU decode step can be timed at the benchmark's context length (ctx 1664: attention over
+ * 1,664 cached tokens per layer) without first spending a minute prefilling them on the host cores. */
+REF_API int oa_ref_fill_kv(ref_model *m, int32_t slot, int32_t n, uint64_t seed) {
+    if (!m || slot < 0 || slot >= m->n_slots || n < 0 || n > m->max_pos) return -1;
+    const size_t kd = (size_t)m->c.n_kv_heads * m->c.head_dim;
+    for (int l = 0; l < m->c.n_layers; ++l) {
+        float *k = m->kcache + ((size_t)slot * m->c.n_layers + l) * m->max_pos * kd;
+        float *v = m->vcache + ((size_t)slot * m->c.n_layers + l) * m->max_pos * kd;
+        const uint64_t key = gen_key(seed, 0x4b56ull + (uint64_t)l);
+        #pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)((size_t)n * kd); ++i) {
+            k[i] = rbf(gen_unit_k(key, (uint64_t)i) * 0.5f);
+            v[i] = rbf(gen_unit_k(key, (uint64_t)i + (1ull << 40)) * 0.5f);
+        }
+    }
+    return 0;
+}
+
 /* expose weight pointers so the HF cross-check can load the very same tensors */
 REF_API const uint16_t *oa_ref_tensor(ref_model *m, int32_t layer, int32_t kind) {
     if (layer < 0) { return kind == TG_EMBED ? m->embed : kind == TG_NORM ? m->norm : m->lm_head; }

@@ -215,6 +215,12 @@ class Oracle:
             raise ValueError("oa_ref_forward: bad slot or position")
         return (logits, hidden) if want_hidden else logits
 
+    def fill_kv(self, n: int, slot: int = 0, seed: int = 99) -> None:
+        """timing aid (bench.py cpu_baseline only): seeded cache contents for positions [0, n) instead of a CPU prefill"""
+        lib().oa_ref_fill_kv.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64]; lib().oa_ref_fill_kv.restype = C.c_int
+        if lib().oa_ref_fill_kv(self._h, slot, n, seed) != 0:
+            raise ValueError("oa_ref_fill_kv: bad slot or length")
+
     def generate(self, prompt, max_new: int, eos=(), slot: int = 0):
         """-> (tokens[int32], margins[float32], first_logits[float32 V])"""
         p = np.ascontiguousarray(prompt, dtype=np.int32)

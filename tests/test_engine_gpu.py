@@ -350,13 +350,15 @@ def _bpe_template_ids(tokenizer_json, msgs):
     return ids + [sp["<|start_header_id|>"]] + enc("assistant") + [sp["<|end_header_id|>"]] + enc("\n\n")
 
 
-def _full_size_parity(name, prompt_msgs, n_new, kv_pages, tokenizer=None, logit_rows=None):
+def _full_size_parity(name, prompt_msgs, n_new, kv_pages, tokenizer=None, logit_rows=None, floor=None):
     """At 16-80 layers the bf16 rounding of every stored activation makes two bf16 computations with different fp32 accumulation
     orders drift apart chaotically: the CPU oracle in bf16-faithful mode itself sits `floor` away from its own fp32 mode.  Stated
     tolerance at full size: the engine's fp32 logits must be as close to the oracle's fp32-activation logits as 1.5x that floor
     (max and mean), and greedy tokens must agree wherever the oracle's top-1 margin exceeds 2x the floor.
     tokenizer: a tokenizer.json (the prompt is then the reference's real text through a real BPE); logit_rows: prompt positions whose
-    logits are compared (default: all) — long prompts keep the comparison to a few rows incl. the last ones."""
+    logits are compared (default: all).  floor = (max, mean) measured by an earlier call on the same model: the fp32-mode oracle pass is
+    then skipped (a 1,536-token prompt costs minutes of CPU per pass) and the engine is compared with the bf16-faithful oracle directly,
+    within 2.5x the floor (triangle inequality: 1.5x to the fp32 oracle + 1x between the oracle's two modes)."""
     spec = O.PRESETS[name]
     cfg = {"model": name, "num_pages": kv_pages, "max_seq_len": 2048, "max_batch": 8, "max_step_tokens": 2048, "seed": spec.seed}
     if tokenizer:
@@ -369,16 +371,31 @@ def _full_size_parity(name, prompt_msgs, n_new, kv_pages, tokenizer=None, logit_
     got = eng.debug_prefill_logits(ids)[rows]
     out = eng.chat_complete(name, prompt_msgs, n_new, flags=1)
     eng.close()
-    orc0 = O.Oracle(spec, max_pos=len(ids) + n_new + 8, mode=0)
-    ref0 = orc0.forward(toks, all_logits=True)[rows]
-    orc0.close()
-    orc1 = O.Oracle(spec, max_pos=len(ids) + n_new + 8, mode=1)
-    ref1 = orc1.forward(toks, all_logits=True)[rows]
-    floor_max, floor_mean = float(np.abs(ref1 - ref0).max()), float(np.abs(ref1 - ref0).mean())
-    err_max, err_mean = float(np.abs(got - ref0).max()), float(np.abs(got - ref0).mean())
     assert np.isfinite(got).all()
-    assert err_max <= 1.5 * floor_max + 1e-3 and err_mean <= 1.5 * floor_mean + 1e-4, (err_max, floor_max, err_mean, floor_mean)
-    ref_t, margins, _ = orc1.generate(toks, n_new)
+    orc1 = O.Oracle(spec, max_pos=len(ids) + n_new + 8, mode=1)
+    ref1_all = orc1.forward(toks, all_logits=True)
+    ref1, ref1_last = ref1_all[rows], ref1_all[-1].copy()
+    del ref1_all
+    if floor is None:
+        orc0 = O.Oracle(spec, max_pos=len(ids) + n_new + 8, mode=0)
+        ref0 = orc0.forward(toks, all_logits=True)[rows]
+        orc0.close()
+        floor_max, floor_mean = float(np.abs(ref1 - ref0).max()), float(np.abs(ref1 - ref0).mean())
+        err_max, err_mean = float(np.abs(got - ref0).max()), float(np.abs(got - ref0).mean())
+        assert err_max <= 1.5 * floor_max + 1e-3 and err_mean <= 1.5 * floor_mean + 1e-4, (err_max, floor_max, err_mean, floor_mean)
+    else:
+        floor_max, floor_mean = floor
+        err_max, err_mean = float(np.abs(got - ref1).max()), float(np.abs(got - ref1).mean())
+        assert err_max <= 2.5 * floor_max + 1e-3 and err_mean <= 2.5 * floor_mean + 1e-4, (err_max, floor_max, err_mean, floor_mean)
+    # greedy continuation from the KV state the prefill above left in the oracle (no second prefill of a long prompt)
+    ref_t, margins = [], []
+    lg = ref1_last
+    for i in range(n_new):
+        order = np.argsort(lg)
+        ref_t.append(int(order[-1]) if lg[order[-1]] > lg[order[-2]] else int(min(order[-1], order[-2])))
+        margins.append(float(abs(lg[order[-1]] - lg[order[-2]])))
+        if i + 1 < n_new:
+            lg = orc1.forward(np.array([ref_t[-1]], np.int32), pos0=len(ids) + i)[0]
     orc1.close()
     k = 0
     while k < n_new and out.token_ids[k] == ref_t[k]:
@@ -406,14 +423,18 @@ def test_full_size_llama_3_8b_matches_oracle():
     1,500) and 32 greedy tokens vs the CPU oracle.  Short prompt first (every position), as in round 1."""
     from opsagent_b200 import workloads as WL
     msgs = [("user", "why is pod web-0 in CrashLoopBackOff?")]
-    print("llama-3-8b short:", _full_size_parity("llama-3-8b", msgs, 6, 64))
-    P = 1536 if (os.cpu_count() or 1) >= 16 else 640      # the CPU oracle prefills ~25 tokens/s on 16 cores, twice (fp32 and bf16-faithful)
+    short = _full_size_parity("llama-3-8b", msgs, 6, 64)
+    print("llama-3-8b short:", short)
+    if os.environ.get("OA_SKIP_SLOW_PARITY"):      # dev iteration only: the long-prompt half costs minutes of CPU oracle time
+        return
+    P = 1536 if (os.cpu_count() or 1) >= 16 else 640      # one bf16-faithful CPU oracle pass: ~3 minutes for 1,536 tokens on 16 cores
     tmp = Engine({"model": "tiny-llama", "hidden": 256, "n_layers": 1, "n_heads": 4, "n_kv_heads": 2, "head_dim": 64, "ffn": 256, "vocab": 8192,
                   "num_pages": 40, "max_seq_len": 2048, "tokenizer": K8S_BPE})             # only its tokenizer is used, to fit the manifest
     m = WL.fit_to_tokens(WL.analyze_messages, WL.synthetic_pod_yaml(7, 12 * P), P, tmp.count_tokens)
     tmp.close()
     msgs = [(x.Role, x.Content) for x in m]
-    res = _full_size_parity("llama-3-8b", msgs, 32, 64, tokenizer=K8S_BPE, logit_rows=[0, 5, 300, P // 2, -130, -64, -3, -2, -1])
+    res = _full_size_parity("llama-3-8b", msgs, 32, 64, tokenizer=K8S_BPE, logit_rows=[0, 5, 300, P // 2, -130, -64, -3, -2, -1],
+                            floor=(short["floor_max"], short["floor_mean"]))
     assert res["prompt_tokens"] == P
     print("llama-3-8b analyze:", res)
 

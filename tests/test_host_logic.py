@@ -622,3 +622,57 @@ def test_token_masks_equal_brute_force_along_random_token_walks(tok, kind):
                 prefix.append(b); assert g.advance(b)
         assert g.done()
     assert all(len(v) == 1 for v in by_key.values())
+
+
+# ---- data-parallel router: one front, N engines (opsagent_b200/router.py; reference pkg/api/router.go:95 is one process) ----
+def test_router_is_sticky_balanced_and_rejects_overload():
+    import threading
+    import time
+    from opsagent_b200.engine import EngineError
+    from opsagent_b200.router import Router, conversation_key
+
+    class FakeEngine:
+        def __init__(self, i):
+            self.i, self.info, self.seen, self.gate = i, {"model": "m"}, [], threading.Event()
+
+        def chat_complete(self, model, msgs, max_tokens, flags=0, functions=None):
+            self.seen.append(conversation_key(msgs))
+            self.gate.wait(5)
+            return self.i
+
+        def stats(self):
+            return {"decode_tokens": len(self.seen), "pages_free": 1}
+
+        def close(self):
+            pass
+
+    engines = [FakeEngine(i) for i in range(4)]
+    rt = Router(engines, max_inflight=2)
+    conv = lambda c, steps: [("system", "sys"), ("user", f"question {c}")] + [("assistant", "a"), ("user", "obs")] * steps      # noqa: E731
+    results = {}
+
+    def call(c, steps):
+        try:
+            results[(c, steps)] = rt.chat_complete("m", conv(c, steps), 8)
+        except EngineError as e:
+            results[(c, steps)] = e.code
+    # 8 new conversations arrive together: least-loaded placement puts exactly 2 on each replica
+    th = [threading.Thread(target=call, args=(c, 0)) for c in range(8)]
+    [t.start() for t in th]
+    t_end = time.time() + 5
+    while sum(rt.stats()["inflight"]) < 8 and time.time() < t_end:
+        time.sleep(0.002)
+    assert rt.stats()["inflight"] == [2, 2, 2, 2]
+    # a 9th conversation finds every replica at its limit -> 429 for the caller's backoff loop (openai.go:91-94)
+    call(99, 0)
+    assert results[(99, 0)] == 429 and rt.stats()["rejected_429"] == 1
+    [e.gate.set() for e in engines]; [t.join() for t in th]
+    home = {c: results[(c, 0)] for c in range(8)}
+    # later steps of a conversation (longer history, same first two messages) go back to the replica that holds its prefix pages
+    for steps in (1, 2, 3):
+        for c in range(8):
+            call(c, steps)
+            assert results[(c, steps)] == home[c]
+    st = rt.stats()
+    assert st["sticky_hits"] == 24 and st["routed"] == [8, 8, 8, 8] and st["decode_tokens"] == 32 and st["replicas"] == 4
+    assert rt.replica_of(conv(3, 7)) == home[3] and rt.replica_of(conv(12345, 0)) is None
