@@ -12,12 +12,14 @@
 //               2^8 (lazy rescaling), so the common tile costs one TMEM read, 128 exp2 and 16 shared-memory stores per thread and
 //               overlaps the tensor-core work of its neighbours (S and P are double-buffered).
 // Row sums use the unrounded p, P·V the bf16-rounded p — the rounding points the oracle mirrors.  TMEM: 2x128 (S) + D (O).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.hpp"
 
 namespace oa {
 
-static constexpr int PTC_THREADS = 192;
+static constexpr int PTC_MAX_THREADS = 64 + 2 * 128;
 static constexpr int KV_TILE = 128;
 
 template <int D>
@@ -28,20 +30,26 @@ struct PtcCfg {
     static constexpr int KV_BYTES = HALVES * HALF_BYTES;         // K (or V) of one 128-token tile
     static constexpr int STAGE_BYTES = 2 * KV_BYTES;
     static constexpr int P_BYTES = 2 * HALF_BYTES;               // [128 q, 128 kv] bf16
-    static constexpr int SMEM_BYTES = Q_BYTES + 2 * STAGE_BYTES + 2 * P_BYTES + 256 + 1024;
+    static constexpr int XCH_BYTES = 2 * 2 * 128 * 4;            // row-statistic exchange between the two softmax warpgroups: [tile parity][warpgroup][row]
+    static constexpr int SMEM_BYTES = Q_BYTES + 2 * STAGE_BYTES + 2 * P_BYTES + 256 + XCH_BYTES;     // D=128: 231,680 B of the 232,448 available — the base is declared 1024-aligned, no slack
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
     static constexpr uint32_t TMEM_COLS = 512;
     static constexpr uint32_t T_COL = 256;                       // S[0] at 0, S[1] at 128, T at 256
 };
 
-template <int D>
-__global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q,
+// NWG = softmax warpgroups.  With one, each SM sub-partition holds a single softmax warp and the 128 exp2 + pack + store chain of a tile
+// (~1.1 us) is longer than its two MMAs (~0.75 us): the tensor pipe idles 70 % of the time (profiles/r01f).  With two, the warps w and w+4
+// share the same 32 query rows (same TMEM lanes) and split every S tile by KEY columns — 64 scores, 64 exp2, 8 P stores per thread, two
+// warps per sub-partition to hide latencies; the halves' row maxima meet through shared memory once per tile, the row sums once at the end.
+template <int D, int NWG>
+__global__ void __launch_bounds__(64 + 128 * NWG, 1) prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q,
                                                                               const __grid_constant__ CUtensorMap tm_kv,
                                                                               const PrefillAttnParams p, const int64_t layer_row0,
                                                                               const int64_t kv_stride_rows) {
     using Cfg = PtcCfg<D>;
     constexpr int HALVES = Cfg::HALVES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];       // 128-byte-swizzled TMA / UMMA tiles need 1024-byte alignment
+    uint8_t* smem = smem_raw;
     uint8_t* q_s = smem;
     uint8_t* kv_s = q_s + Cfg::Q_BYTES;                          // [2 stages][K | V]
     uint8_t* p_s = kv_s + 2 * Cfg::STAGE_BYTES;                  // [2][P]
@@ -56,6 +64,7 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
     uint64_t* p_full = bars + 13;             // [2]
     uint64_t* t_full = bars + 15;             // 1 (one completion per P·V)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    float* xch = reinterpret_cast<float*>(p_s + 2 * Cfg::P_BYTES + 256);       // [2][2][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PrefillTile tile = p.tiles[blockIdx.x];
@@ -67,7 +76,7 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
         tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-                                      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); mbar_init(&p_full[i], 4); }
+                                      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4 * NWG); mbar_init(&p_full[i], 4 * NWG); }
         mbar_init(t_full, 1);
         fence_barrier_init();
     }
@@ -146,19 +155,23 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
             }
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3, wg = (warp - 2) >> 2;               // warps w and w + 4 own the same rows (TMEM lanes 32 * (w % 4) ...)
         const int row = q * 32 + lane;                              // query row of this thread inside the tile
         const int qpos = tile.pos0 + row;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        constexpr int CH = 4 / NWG;                                 // 32-key chunks of a tile this thread handles
+        const int key_base = wg * (KV_TILE / NWG);
+        constexpr int OC = D / NWG;                                 // O columns this thread rescales / writes
+        const int o_base = wg * OC;
         constexpr float kRescaleThreshold = 8.0f;                   // log2 units: p may reach 2^8 before O is rescaled
         float m_ref = -INFINITY, l_run = 0.f;
         for (int j = 0; j < n_kvt; ++j) {
             const int sb = j & 1;
             mbar_wait(&s_full[sb], ((uint32_t)j >> 1) & 1);
             tcgen05_fence_after();
-            uint32_t v[4][32];
+            uint32_t v[CH][32];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_base + lane_addr + (uint32_t)(sb * 128 + c * 32), v[c]);
+            for (int c = 0; c < CH; ++c) tmem_ld_32x32b_x32(tmem_base + lane_addr + (uint32_t)(sb * 128 + key_base + c * 32), v[c]);
             tmem_ld_wait();
             tcgen05_fence_before();
             __syncwarp();
@@ -166,32 +179,37 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
             const bool diag = (j * KV_TILE + KV_TILE - 1) > tile.pos0;          // some (row, key) pairs of this tile are masked
             if (diag) {                                                         // only the last tile(s) of a row block pay for the mask
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < CH; ++c)
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if ((j * KV_TILE + c * 32 + i) > qpos) v[c][i] = 0xff800000u;   // -inf
+                        if ((j * KV_TILE + key_base + c * 32 + i) > qpos) v[c][i] = 0xff800000u;   // -inf
             }
             float mraw = -INFINITY;                                             // max of the raw scores; the scale is positive
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < CH; ++c)
 #pragma unroll
                 for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, __uint_as_float(v[c][i]));
+            if constexpr (NWG == 2) {                                           // the row's other half lives in the partner warpgroup
+                xch[(sb * 2 + wg) * 128 + row] = mraw;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                mraw = fmaxf(mraw, xch[(sb * 2 + (wg ^ 1)) * 128 + row]);
+            }
             const float mx = mraw * p.scale_log2e;
             // lazy rescaling: raise the reference maximum only when a row would overshoot it by more than 2^8
             const bool raise = mx > m_ref + kRescaleThreshold;      // always true on tile 0 (key 0 is visible to every row)
-            if (__any_sync(0xffffffffu, raise)) {
+            if (__any_sync(0xffffffffu, raise)) {                   // both warps of a row pair see the same mx, hence take the same branch
                 if (j > 0) {
                     mbar_wait(t_full, (uint32_t)(j - 1) & 1);       // O += P_{j-1}·V_{j-1} has landed; O += P_j·V_j is not issued before p_full
                     tcgen05_fence_after();
                     const float alpha = raise ? exp2f(m_ref - mx) : 1.0f;
 #pragma unroll 1
-                    for (int c = 0; c < D; c += 32) {
+                    for (int c = 0; c < OC; c += 32) {
                         uint32_t o[32];
-                        tmem_ld_32x32b_x32(tmem_base + lane_addr + Cfg::T_COL + (uint32_t)c, o);
+                        tmem_ld_32x32b_x32(tmem_base + lane_addr + Cfg::T_COL + (uint32_t)(o_base + c), o);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st_32x32b_x32(tmem_base + lane_addr + Cfg::T_COL + (uint32_t)c, o);
+                        tmem_st_32x32b_x32(tmem_base + lane_addr + Cfg::T_COL + (uint32_t)(o_base + c), o);
                     }
                     tmem_st_wait();
                     tcgen05_fence_before();
@@ -203,13 +221,13 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
             float psum = 0.f;
             const float neg_ref = -m_ref;                                       // p = 2^(s*scale - m_ref): one FFMA + one SFU op per score
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < CH; ++c) {
                 float pr[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) { pr[i] = ex2_approx(fmaf(__uint_as_float(v[c][i]), p.scale_log2e, neg_ref)); psum += pr[i]; }
 #pragma unroll
                 for (int g8 = 0; g8 < 4; ++g8) {                    // four 16-byte chunks (8 keys each)
-                    const int key0 = c * 32 + g8 * 8, hh = key0 >> 6, chunk = (key0 & 63) >> 3;
+                    const int key0 = key_base + c * 32 + g8 * 8, hh = key0 >> 6, chunk = (key0 & 63) >> 3;
                     uint4 w;
                     w.x = pack_bf16x2(pr[g8 * 8 + 0], pr[g8 * 8 + 1]); w.y = pack_bf16x2(pr[g8 * 8 + 2], pr[g8 * 8 + 3]);
                     w.z = pack_bf16x2(pr[g8 * 8 + 4], pr[g8 * 8 + 5]); w.w = pack_bf16x2(pr[g8 * 8 + 6], pr[g8 * 8 + 7]);
@@ -223,12 +241,18 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
         }
         mbar_wait(t_full, (uint32_t)(n_kvt - 1) & 1);
         tcgen05_fence_after();
+        if constexpr (NWG == 2) {                                   // row sum = the two key halves' sums (fixed order: half 0 + half 1)
+            const int xb = n_kvt & 1;                               // the buffer the last tile did not use
+            xch[(xb * 2 + wg) * 128 + row] = l_run;
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            l_run = xch[(xb * 2 + 0) * 128 + row] + xch[(xb * 2 + 1) * 128 + row];
+        }
         const float inv = 1.0f / l_run;
         uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + (size_t)(tile.q_row0 + row) * p.n_heads * D + (size_t)head * D;
 #pragma unroll 1
-        for (int c = 0; c < D; c += 32) {
+        for (int c = 0; c < OC; c += 32) {
             uint32_t o[32];
-            tmem_ld_32x32b_x32(tmem_base + lane_addr + Cfg::T_COL + (uint32_t)c, o);
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + Cfg::T_COL + (uint32_t)(o_base + c), o);
             tmem_ld_wait();
             if (row < tile.n_rows) {
 #pragma unroll
@@ -238,7 +262,7 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
                     w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
                     w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
                     w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-                    *reinterpret_cast<uint4*>(orow + c + i) = w;
+                    *reinterpret_cast<uint4*>(orow + o_base + c + i) = w;
                 }
             }
         }
@@ -248,20 +272,21 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) prefill_attention_tc_kernel(co
     if (warp == 1) { tcgen05_fence_after(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
 }
 
-template <int D>
+template <int D, int NWG>
 static cudaError_t launch_ptc(const CUtensorMap* tm_q, const CUtensorMap* tm_kv, const KvLayout& kv, const PrefillAttnParams& p, cudaStream_t s) {
-    auto kern = prefill_attention_tc_kernel<D>;
+    auto kern = prefill_attention_tc_kernel<D, NWG>;
     static bool attr_done[16] = {};
     { cudaError_t e = ensure_dynamic_smem(kern, PtcCfg<D>::SMEM_BYTES, attr_done); if (e != cudaSuccess) return e; }
-    return launch_k(kern, dim3(p.n_tiles, p.n_heads), dim3(PTC_THREADS), PtcCfg<D>::SMEM_BYTES, s, *tm_q, *tm_kv, p,
+    return launch_k(kern, dim3(p.n_tiles, p.n_heads), dim3(64 + 128 * NWG), PtcCfg<D>::SMEM_BYTES, s, *tm_q, *tm_kv, p,
                     (int64_t)p.layer * kv.layer_stride_rows, kv.kv_stride_rows);
 }
 
 cudaError_t launch_prefill_attention_tc(const CUtensorMap* tm_q, const CUtensorMap* tm_kv, const KvLayout& kv, const PrefillAttnParams& p, cudaStream_t s) {
     if (p.n_tiles <= 0) return cudaSuccess;
     if (kv.page_size != 64 || p.n_heads % p.n_kv != 0) return cudaErrorInvalidValue;
-    if (kv.head_dim == 128) return launch_ptc<128>(tm_q, tm_kv, kv, p, s);
-    if (kv.head_dim == 64) return launch_ptc<64>(tm_q, tm_kv, kv, p, s);
+    static const int nwg = [] { const char* e = std::getenv("OA_PREFILL_WG"); return (e && e[0] == '1') ? 1 : 2; }();      // OA_PREFILL_WG=1: the one-warpgroup kernel of round 1 (A/B)
+    if (kv.head_dim == 128) return nwg == 2 ? launch_ptc<128, 2>(tm_q, tm_kv, kv, p, s) : launch_ptc<128, 1>(tm_q, tm_kv, kv, p, s);
+    if (kv.head_dim == 64) return nwg == 2 ? launch_ptc<64, 2>(tm_q, tm_kv, kv, p, s) : launch_ptc<64, 1>(tm_q, tm_kv, kv, p, s);
     return cudaErrorInvalidValue;
 }
 

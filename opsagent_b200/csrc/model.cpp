@@ -537,8 +537,13 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
             if (use_tp) {      // row-parallel projection: all-reduce the rank partials over NVLink peer memory, then residual + norm
                 const int b = comm->next_buffer();
                 const TpComm::Signal sg = comm->next_signal();     // "buffer written" handshake rides on the two kernels: no barrier launch
-                cuda_check(launch_sk_reduce_f32(sk_o, reinterpret_cast<float*>(comm->sym(b)), T, H, stream, &sg), "o partial -> symmetric buffer");
-                cuda_check(launch_ar_resid_rmsnorm(comm->d_peer_sym(b), tp, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream, &sg), "allreduce+resid+rmsnorm2");
+                if (opt.tp_ar_bf16) {
+                    cuda_check(launch_sk_reduce_bf16(sk_o, comm->sym(b), T, H, stream, &sg), "o partial -> symmetric buffer (bf16)");
+                    cuda_check(launch_ar_resid_rmsnorm_bf16in(comm->d_peer_sym(b), tp, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream, &sg), "allreduce+resid+rmsnorm2");
+                } else {
+                    cuda_check(launch_sk_reduce_f32(sk_o, reinterpret_cast<float*>(comm->sym(b)), T, H, stream, &sg), "o partial -> symmetric buffer");
+                    cuda_check(launch_ar_resid_rmsnorm(comm->d_peer_sym(b), tp, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream, &sg), "allreduce+resid+rmsnorm2");
+                }
             } else {
                 cuda_check(launch_sk_resid_rmsnorm(sk_o, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm2");
             }
@@ -560,14 +565,29 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
             if (use_tp) {
                 const int b = comm->next_buffer();
                 const TpComm::Signal sg = comm->next_signal();
-                cuda_check(launch_sk_reduce_f32(sk_dn, reinterpret_cast<float*>(comm->sym(b)), T, H, stream, &sg), "down partial -> symmetric buffer");
-                cuda_check(launch_ar_resid_rmsnorm(comm->d_peer_sym(b), tp, x_, next_gain, xn_, T, H, cfg.rms_eps, stream, &sg), "allreduce+resid+rmsnorm1");
+                if (opt.tp_ar_bf16) {
+                    cuda_check(launch_sk_reduce_bf16(sk_dn, comm->sym(b), T, H, stream, &sg), "down partial -> symmetric buffer (bf16)");
+                    cuda_check(launch_ar_resid_rmsnorm_bf16in(comm->d_peer_sym(b), tp, x_, next_gain, xn_, T, H, cfg.rms_eps, stream, &sg), "allreduce+resid+rmsnorm1");
+                } else {
+                    cuda_check(launch_sk_reduce_f32(sk_dn, reinterpret_cast<float*>(comm->sym(b)), T, H, stream, &sg), "down partial -> symmetric buffer");
+                    cuda_check(launch_ar_resid_rmsnorm(comm->d_peer_sym(b), tp, x_, next_gain, xn_, T, H, cfg.rms_eps, stream, &sg), "allreduce+resid+rmsnorm1");
+                }
             } else {
                 cuda_check(launch_sk_resid_rmsnorm(sk_dn, x_, next_gain, xn_, T, H, cfg.rms_eps, stream), "resid+rmsnorm1");
             }
             MARK(7);
         }
     } else {
+        // x += sum over ranks of the bf16 partials in symmetric buffer b (every rank's partial is complete: barrier passed)
+        auto allreduce_resid_bf16 = [&](int b) {
+            if (T >= opt.tp_two_shot_rows) {
+                cuda_check(launch_ar2_reduce_scatter(comm->d_peer_sym(b), tp, tp_rank, x_, comm->sym(TpComm::GATHER), T, H, stream), "reduce-scatter+resid");
+                cuda_check(comm->barrier(stream), "xgpu barrier");
+                cuda_check(launch_ar2_all_gather(comm->d_peer_sym(TpComm::GATHER), tp, tp_rank, x_, T, H, stream), "all-gather");
+            } else {
+                cuda_check(launch_ar_resid_bf16(comm->d_peer_sym(b), tp, x_, T, H, stream), "allreduce+resid");
+            }
+        };
         const int bn_qkv = pick_bn(T, qkvd, opt.bn_qkv, false), bn_o = pick_bn(T, H, opt.bn_o, false);
         const int bn_gu = pick_bn(T, 2 * F, opt.bn_gu, true), bn_down = pick_bn(T, H, opt.bn_down, false);
         for (int l = 0; l < L; ++l) {
@@ -582,7 +602,7 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
                 GemmParams go{}; go.M = T; go.N = H; go.K = qd; go.out = comm->sym(b); go.ldo = H;
                 cuda_check(launch_gemm(&tm_attn_, ly.o.map(bn_o), go, EPI_STORE, bn_o, stream), "o gemm"); MARK(6);
                 cuda_check(comm->barrier(stream), "xgpu barrier");
-                cuda_check(launch_ar_resid_bf16(comm->d_peer_sym(b), tp, x_, T, H, stream), "allreduce+resid");
+                allreduce_resid_bf16(b);
             } else {
                 GemmParams go{}; go.M = T; go.N = H; go.K = qd; go.out = x_; go.ldo = H; go.resid = x_; go.ldr = H;
                 cuda_check(launch_gemm(&tm_attn_, ly.o.map(bn_o), go, EPI_RESID, bn_o, stream), "o gemm"); MARK(6);
@@ -595,7 +615,7 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
                 GemmParams gd{}; gd.M = T; gd.N = H; gd.K = F; gd.out = comm->sym(b); gd.ldo = H;
                 cuda_check(launch_gemm(&tm_act_, ly.down.map(bn_down), gd, EPI_STORE, bn_down, stream), "down gemm"); MARK(10);
                 cuda_check(comm->barrier(stream), "xgpu barrier");
-                cuda_check(launch_ar_resid_bf16(comm->d_peer_sym(b), tp, x_, T, H, stream), "allreduce+resid");
+                allreduce_resid_bf16(b);
             } else {
                 GemmParams gd{}; gd.M = T; gd.N = H; gd.K = F; gd.out = x_; gd.ldo = H; gd.resid = x_; gd.ldr = H;
                 cuda_check(launch_gemm(&tm_act_, ly.down.map(bn_down), gd, EPI_RESID, bn_down, stream), "down gemm"); MARK(10);

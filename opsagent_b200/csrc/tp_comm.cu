@@ -86,24 +86,26 @@ TpComm::TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, i
     }
     // ---- symmetric device buffers + IPC handle exchange ----
     arg_half_bytes_ = (size_t)max_sample * 8;
-    for (int b = 0; b < 2; ++b) { cuda_check(cudaMalloc(&sym_[b], sym_bytes), "cudaMalloc sym"); cuda_check(cudaMemset(sym_[b], 0, sym_bytes), "memset sym"); }
+    for (int b = 0; b < 3; ++b) { cuda_check(cudaMalloc(&sym_[b], sym_bytes), "cudaMalloc sym"); cuda_check(cudaMemset(sym_[b], 0, sym_bytes), "memset sym"); }
     cuda_check(cudaMalloc(reinterpret_cast<void**>(&flags_), TP_MAX * sizeof(uint32_t)), "cudaMalloc flags");
     cuda_check(cudaMemset(flags_, 0, TP_MAX * sizeof(uint32_t)), "memset flags");
     cuda_check(cudaMalloc(reinterpret_cast<void**>(&done_counter_), 64), "cudaMalloc done counter");
     cuda_check(cudaMemset(done_counter_, 0, 64), "memset done counter");
     cuda_check(cudaMalloc(&arg_, 2 * arg_half_bytes_), "cudaMalloc arg");
     cuda_check(cudaDeviceSynchronize(), "sync");
-    for (int b = 0; b < 2; ++b) cuda_check(cudaIpcGetMemHandle(&shm_->h_sym[rank][b], sym_[b]), "cudaIpcGetMemHandle sym");
+    for (int b = 0; b < 3; ++b) cuda_check(cudaIpcGetMemHandle(&shm_->h_sym[rank][b], sym_[b]), "cudaIpcGetMemHandle sym");
     cuda_check(cudaIpcGetMemHandle(&shm_->h_flags[rank], flags_), "cudaIpcGetMemHandle flags");
     cuda_check(cudaIpcGetMemHandle(&shm_->h_arg[rank], arg_), "cudaIpcGetMemHandle arg");
     shm_->handles_ready.fetch_add(1, std::memory_order_acq_rel);
     spin_until([&] { return shm_->handles_ready.load(std::memory_order_acquire) >= (uint32_t)t; }, "all ranks publishing IPC handles");
     for (int p = 0; p < t; ++p) {
-        if (p == rank) { peer_sym_[0][p] = sym_[0]; peer_sym_[1][p] = sym_[1]; peer_flags_[p] = flags_; peer_arg_[p] = arg_; continue; }
-        for (int b = 0; b < 2; ++b) cuda_check(cudaIpcOpenMemHandle(&peer_sym_[b][p], shm_->h_sym[p][b], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle sym");
+        if (p == rank) { peer_sym_[0][p] = sym_[0]; peer_sym_[1][p] = sym_[1]; peer_sym_[2][p] = sym_[2]; peer_flags_[p] = flags_; peer_arg_[p] = arg_; continue; }
+        for (int b = 0; b < 3; ++b) cuda_check(cudaIpcOpenMemHandle(&peer_sym_[b][p], shm_->h_sym[p][b], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle sym");
         cuda_check(cudaIpcOpenMemHandle(reinterpret_cast<void**>(&peer_flags_[p]), shm_->h_flags[p], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle flags");
         cuda_check(cudaIpcOpenMemHandle(&peer_arg_[p], shm_->h_arg[p], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle arg");
     }
+    cuda_check(cudaMalloc(reinterpret_cast<void**>(&d_peer_sym_[2]), TP_MAX * sizeof(void*)), "cudaMalloc ptr table");
+    cuda_check(cudaMemcpy(d_peer_sym_[2], peer_sym_[2], TP_MAX * sizeof(void*), cudaMemcpyHostToDevice), "ptr table H2D");
     for (int b = 0; b < 2; ++b) {
         cuda_check(cudaMalloc(reinterpret_cast<void**>(&d_peer_sym_[b]), TP_MAX * sizeof(void*)), "cudaMalloc ptr table");
         cuda_check(cudaMemcpy(d_peer_sym_[b], peer_sym_[b], TP_MAX * sizeof(void*), cudaMemcpyHostToDevice), "ptr table H2D");
@@ -121,11 +123,12 @@ TpComm::TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, i
 TpComm::~TpComm() {
     for (int p = 0; p < t_; ++p) {
         if (p == rank_) continue;
-        for (int b = 0; b < 2; ++b) if (peer_sym_[b][p]) cudaIpcCloseMemHandle(peer_sym_[b][p]);
+        for (int b = 0; b < 3; ++b) if (peer_sym_[b][p]) cudaIpcCloseMemHandle(peer_sym_[b][p]);
         if (peer_flags_[p]) cudaIpcCloseMemHandle(peer_flags_[p]);
         if (peer_arg_[p]) cudaIpcCloseMemHandle(peer_arg_[p]);
     }
     for (int b = 0; b < 2; ++b) { cudaFree(sym_[b]); cudaFree(d_peer_sym_[b]); cudaFree(d_peer_arg_[b]); }
+    cudaFree(sym_[2]); cudaFree(d_peer_sym_[2]);
     cudaFree(flags_); cudaFree(arg_); cudaFree(d_peer_flags_); cudaFree(done_counter_);
     if (shm_ && shm_ != MAP_FAILED) munmap(shm_, sizeof(TpShm));
     if (owner_) shm_unlink(shm_name_.c_str());
@@ -284,6 +287,63 @@ cudaError_t launch_ar_resid_rmsnorm(void* const* d_peer, int t, void* x, const v
                     reinterpret_cast<uint2*>(xn), H / 4, 1.0f / H, eps, sg, wait ? 1 : 0);
 }
 
+// The same collective on bf16 partials: half the NVLink bytes (the one-shot all-reduce of a decode step is bandwidth-bound: every rank
+// reads t full partials — 70B TP=8, B=64: 16.8 MB in fp32).  Each rank rounds its fp32 partial to bf16 once (as the prefill path's tile
+// GEMM always did), the sum over ranks is fp32 in rank order, so all ranks still hold bit-identical activations.
+__global__ void __launch_bounds__(AR_THREADS) ar_resid_rmsnorm_bf16in_kernel(const uint16_t* const* __restrict__ peer, int t, uint4* __restrict__ x,
+                                                                             const uint4* __restrict__ g, uint4* __restrict__ y, int H8, float inv_h, float eps,
+                                                                             const TpComm::Signal sg, int wait) {
+    griddep_launch(); griddep_wait();
+    if (wait) xgpu_wait_peers(sg);
+    const int row = blockIdx.x;
+    uint4* xr = x + (size_t)row * H8;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < H8; i += AR_THREADS) {
+        uint4 a[TP_MAX];
+#pragma unroll
+        for (int p = 0; p < TP_MAX; ++p) if (p < t) a[p] = ld_peer_u4(peer[p] + ((size_t)row * H8 + i) * 8);
+        const uint4 xo = xr[i];
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int p = 0; p < TP_MAX; ++p) if (p < t) {      // rank order: identical on every rank
+            acc[0] += bf16lo(a[p].x); acc[1] += bf16hi(a[p].x); acc[2] += bf16lo(a[p].y); acc[3] += bf16hi(a[p].y);
+            acc[4] += bf16lo(a[p].z); acc[5] += bf16hi(a[p].z); acc[6] += bf16lo(a[p].w); acc[7] += bf16hi(a[p].w);
+        }
+        uint4 xn;
+        xn.x = pack_bf16x2(bf16lo(xo.x) + acc[0], bf16hi(xo.x) + acc[1]); xn.y = pack_bf16x2(bf16lo(xo.y) + acc[2], bf16hi(xo.y) + acc[3]);
+        xn.z = pack_bf16x2(bf16lo(xo.z) + acc[4], bf16hi(xo.z) + acc[5]); xn.w = pack_bf16x2(bf16lo(xo.w) + acc[6], bf16hi(xo.w) + acc[7]);
+        xr[i] = xn;
+        float q;
+        q = bf16lo(xn.x); ss += q * q; q = bf16hi(xn.x); ss += q * q; q = bf16lo(xn.y); ss += q * q; q = bf16hi(xn.y); ss += q * q;
+        q = bf16lo(xn.z); ss += q * q; q = bf16hi(xn.z); ss += q * q; q = bf16lo(xn.w); ss += q * q; q = bf16hi(xn.w); ss += q * q;
+    }
+    ss = warp_sum(ss);
+    __shared__ float red[AR_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < AR_THREADS / 32; ++w) tot += red[w];
+    const float r = 1.0f / sqrtf(tot * inv_h + eps);
+    uint4* yr = y + (size_t)row * H8;
+    for (int i = threadIdx.x; i < H8; i += AR_THREADS) {      // this thread re-reads exactly what it wrote above
+        const uint4 v = xr[i], gg = g[i]; uint4 o;
+        o.x = pack_bf16x2(bf16lo(v.x) * r * bf16lo(gg.x), bf16hi(v.x) * r * bf16hi(gg.x));
+        o.y = pack_bf16x2(bf16lo(v.y) * r * bf16lo(gg.y), bf16hi(v.y) * r * bf16hi(gg.y));
+        o.z = pack_bf16x2(bf16lo(v.z) * r * bf16lo(gg.z), bf16hi(v.z) * r * bf16hi(gg.z));
+        o.w = pack_bf16x2(bf16lo(v.w) * r * bf16lo(gg.w), bf16hi(v.w) * r * bf16hi(gg.w));
+        yr[i] = o;
+    }
+}
+cudaError_t launch_ar_resid_rmsnorm_bf16in(void* const* d_peer, int t, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s,
+                                           const TpComm::Signal* wait) {
+    if (T <= 0) return cudaSuccess;
+    if (H % 8 != 0) return cudaErrorInvalidValue;
+    const TpComm::Signal sg = wait ? *wait : TpComm::Signal{};
+    return launch_k(ar_resid_rmsnorm_bf16in_kernel, dim3(T), dim3(AR_THREADS), 0, s, reinterpret_cast<const uint16_t* const*>(d_peer), t, reinterpret_cast<uint4*>(x),
+                    reinterpret_cast<const uint4*>(gain), reinterpret_cast<uint4*>(xn), H / 8, 1.0f / H, eps, sg, wait ? 1 : 0);
+}
+
 __global__ void ar_resid_bf16_kernel(const uint16_t* const* __restrict__ peer, int t, uint4* __restrict__ x, size_t n8) {
     griddep_launch(); griddep_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
@@ -309,6 +369,50 @@ cudaError_t launch_ar_resid_bf16(void* const* d_peer, int t, void* x, int T, int
     return launch_k(ar_resid_bf16_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const uint16_t* const*>(d_peer), t, reinterpret_cast<uint4*>(x), n8);
 }
 
+// ---- two-shot all-reduce for prefill-sized batches (see tp_comm.hpp) ----
+// flat partition of the T*H/8 16-byte vectors into t contiguous slices; slice r belongs to rank r
+OA_DEVINL void ar2_slice(size_t n8, int t, int r, size_t& lo, size_t& hi) { const size_t per = (n8 + (size_t)t - 1) / (size_t)t; lo = (size_t)r * per; hi = lo + per < n8 ? lo + per : n8; if (lo > n8) lo = n8; }
+__global__ void ar2_reduce_scatter_kernel(const uint16_t* const* __restrict__ peer, int t, int rank, uint4* __restrict__ x, uint4* __restrict__ gather, size_t n8) {
+    griddep_launch(); griddep_wait();
+    size_t lo, hi; ar2_slice(n8, t, rank, lo, hi);
+    for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        uint4 a[TP_MAX];
+#pragma unroll
+        for (int p = 0; p < TP_MAX; ++p) if (p < t) a[p] = ld_peer_u4(peer[p] + i * 8);
+#pragma unroll
+        for (int p = 0; p < TP_MAX; ++p) if (p < t) {      // rank order
+            acc[0] += bf16lo(a[p].x); acc[1] += bf16hi(a[p].x); acc[2] += bf16lo(a[p].y); acc[3] += bf16hi(a[p].y);
+            acc[4] += bf16lo(a[p].z); acc[5] += bf16hi(a[p].z); acc[6] += bf16lo(a[p].w); acc[7] += bf16hi(a[p].w);
+        }
+        const uint4 xo = x[i]; uint4 xn;
+        xn.x = pack_bf16x2(bf16lo(xo.x) + acc[0], bf16hi(xo.x) + acc[1]); xn.y = pack_bf16x2(bf16lo(xo.y) + acc[2], bf16hi(xo.y) + acc[3]);
+        xn.z = pack_bf16x2(bf16lo(xo.z) + acc[4], bf16hi(xo.z) + acc[5]); xn.w = pack_bf16x2(bf16lo(xo.w) + acc[6], bf16hi(xo.w) + acc[7]);
+        x[i] = xn; gather[i] = xn;
+    }
+}
+__global__ void ar2_all_gather_kernel(const uint16_t* const* __restrict__ peer, int t, int rank, uint4* __restrict__ x, size_t n8) {
+    griddep_launch(); griddep_wait();
+    for (int q = 1; q < t; ++q) {
+        const int p = (rank + q) % t;                       // start with the next rank: spreads the first reads over all links
+        size_t lo, hi; ar2_slice(n8, t, p, lo, hi);
+        for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) x[i] = ld_peer_u4(peer[p] + i * 8);
+    }
+}
+cudaError_t launch_ar2_reduce_scatter(void* const* d_peer_partial, int t, int rank, void* x, void* gather_mine, int T, int H, cudaStream_t s) {
+    if (T <= 0) return cudaSuccess;
+    const size_t n8 = (size_t)T * H / 8;
+    const int blocks = (int)std::min<size_t>((n8 / t + 255) / 256 + 1, 148 * 8);
+    return launch_k(ar2_reduce_scatter_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const uint16_t* const*>(d_peer_partial), t, rank, reinterpret_cast<uint4*>(x),
+                    reinterpret_cast<uint4*>(gather_mine), n8);
+}
+cudaError_t launch_ar2_all_gather(void* const* d_peer_gather, int t, int rank, void* x, int T, int H, cudaStream_t s) {
+    if (T <= 0) return cudaSuccess;
+    const size_t n8 = (size_t)T * H / 8;
+    const int blocks = (int)std::min<size_t>((n8 / t + 255) / 256 + 1, 148 * 8);
+    return launch_k(ar2_all_gather_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const uint16_t* const*>(d_peer_gather), t, rank, reinterpret_cast<uint4*>(x), n8);
+}
+
 __global__ void sk_reduce_f32_rows_kernel(const StreamK sk, float* __restrict__ out, int N8, const TpComm::Signal sg, int signal) {
     griddep_launch(); griddep_wait();
     const int row = blockIdx.y;
@@ -324,6 +428,24 @@ cudaError_t launch_sk_reduce_f32(const StreamK& sk, float* out, int T, int N, cu
     if (T <= 0) return cudaSuccess;
     const TpComm::Signal sg = signal ? *signal : TpComm::Signal{};
     return launch_k(sk_reduce_f32_rows_kernel, dim3((N / 8 + 255) / 256, T), dim3(256), 0, s, sk, out, N / 8, sg, signal ? 1 : 0);
+}
+
+__global__ void sk_reduce_bf16_rows_kernel(const StreamK sk, uint4* __restrict__ out, int N8, const TpComm::Signal sg, int signal) {
+    griddep_launch(); griddep_wait();
+    const int row = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N8; i += gridDim.x * blockDim.x) {
+        float acc[8];
+        sk_sum8(sk, row, i * 8, acc);            // CTA order, up to 6 pieces' loads in flight together
+        uint4 o;
+        o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]); o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+        out[(size_t)row * N8 + i] = o;
+    }
+    if (signal) xgpu_signal_when_grid_done(sg, gridDim.x * gridDim.y);
+}
+cudaError_t launch_sk_reduce_bf16(const StreamK& sk, void* out, int T, int N, cudaStream_t s, const TpComm::Signal* signal) {
+    if (T <= 0) return cudaSuccess;
+    const TpComm::Signal sg = signal ? *signal : TpComm::Signal{};
+    return launch_k(sk_reduce_bf16_rows_kernel, dim3((N / 8 + 255) / 256, T), dim3(256), 0, s, sk, reinterpret_cast<uint4*>(out), N / 8, sg, signal ? 1 : 0);
 }
 
 struct ValIdx { float v; int i; };

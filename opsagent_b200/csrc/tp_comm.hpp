@@ -28,7 +28,7 @@ struct TpShm {                                 // lives in POSIX shared memory
     std::atomic<int64_t> leader_pid;           // followers refuse a segment whose leader is gone and notice a leader that dies later
     std::atomic<uint32_t> handles_ready;       // ranks that published their IPC handles
     std::atomic<uint32_t> peers_opened;        // ranks that mapped every peer
-    cudaIpcMemHandle_t h_sym[TP_MAX][2];
+    cudaIpcMemHandle_t h_sym[TP_MAX][3];       // [rank][buffer]: 0/1 = double-buffered partials, 2 = the gather buffer of the two-shot all-reduce
     cudaIpcMemHandle_t h_flags[TP_MAX];
     cudaIpcMemHandle_t h_arg[TP_MAX];
     std::atomic<uint64_t> seq;                 // step message sequence (UINT64_MAX = shutdown)
@@ -46,7 +46,8 @@ public:
 
     // ---- device side ----
     int next_buffer() { return (int)(ar_count_++ & 1); }                // double-buffered symmetric storage
-    void* sym(int b) const { return sym_[b]; }                            // this rank's buffer b
+    void* sym(int b) const { return sym_[b]; }                            // this rank's buffer b (0/1: partials, alternating; 2: gather buffer)
+    static constexpr int GATHER = 2;
     void* const* d_peer_sym(int b) const { return d_peer_sym_[b]; }       // device array [t] of peer pointers for buffer b
     void* peer_sym_host(int b, int p) const { return peer_sym_[b][p]; }
     size_t sym_bytes() const { return sym_bytes_; }
@@ -66,8 +67,8 @@ public:
 
 private:
     int t_, rank_; std::string shm_name_; TpShm* shm_ = nullptr; bool owner_ = false;
-    void* sym_[2] = {nullptr, nullptr}; void* peer_sym_[2][TP_MAX] = {};
-    void** d_peer_sym_[2] = {nullptr, nullptr};
+    void* sym_[3] = {nullptr, nullptr, nullptr}; void* peer_sym_[3][TP_MAX] = {};
+    void** d_peer_sym_[3] = {nullptr, nullptr, nullptr};
     uint32_t* flags_ = nullptr; uint32_t* peer_flags_[TP_MAX] = {}; uint32_t** d_peer_flags_ = nullptr; unsigned int* done_counter_ = nullptr;
     void* arg_ = nullptr; void* peer_arg_[TP_MAX] = {}; void** d_peer_arg_[2] = {nullptr, nullptr}; size_t arg_half_bytes_ = 0;
     uint64_t ar_count_ = 0; uint32_t epoch_ = 0; uint64_t seq_local_ = 0; uint64_t idle_polls_ = 0; size_t sym_bytes_ = 0;
@@ -77,8 +78,19 @@ private:
 // `wait` != null: every CTA first waits for all peers' signals of that epoch (TpComm::next_signal) instead of a preceding barrier launch
 cudaError_t launch_ar_resid_rmsnorm(void* const* d_peer, int t, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s,
                                     const TpComm::Signal* wait = nullptr);
+// the same with bf16 partial rows (half the NVLink bytes; engine option tp_ar_bf16)
+cudaError_t launch_ar_resid_rmsnorm_bf16in(void* const* d_peer, int t, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s,
+                                           const TpComm::Signal* wait = nullptr);
+cudaError_t launch_sk_reduce_bf16(const StreamK& sk, void* out, int T, int N, cudaStream_t s, const TpComm::Signal* signal = nullptr);
 // x[T,H] += sum over ranks of bf16 partial rows                                                          (prefill path)
 cudaError_t launch_ar_resid_bf16(void* const* d_peer, int t, void* x, int T, int H, cudaStream_t s);
+// Two-shot variant for large T (prefill chunks): the one-shot kernel above makes every rank read all t full partials — t x T x H x 2 bytes, 1.07 GB
+// per all-reduce for a Llama-3-70B TP=8 chunk of 8192 tokens, 1.2 ms on the NVLink, 160 times per chunk.  Here rank r reduces only slice r
+// (reduce-scatter: reads (t-1)/t of ONE partial's bytes), adds the residual and publishes the finished bf16 slice in its gather buffer; after a
+// barrier every rank copies the other t-1 slices (all-gather).  2 x (t-1)/t x T x H x 2 bytes per rank instead of (t-1) x T x H x 2; each element
+// is computed once, by its slice owner, in rank order — all ranks still hold bit-identical activations.
+cudaError_t launch_ar2_reduce_scatter(void* const* d_peer_partial, int t, int rank, void* x, void* gather_mine, int T, int H, cudaStream_t s);
+cudaError_t launch_ar2_all_gather(void* const* d_peer_gather, int t, int rank, void* x, int T, int H, cudaStream_t s);
 // stream-K partials -> fp32 rows [T,N] in `out` (this rank's symmetric buffer)
 // `signal` != null: the last CTA to finish tells every peer that this rank's buffer is complete
 cudaError_t launch_sk_reduce_f32(const StreamK& sk, float* out, int T, int N, cudaStream_t s, const TpComm::Signal* signal = nullptr);

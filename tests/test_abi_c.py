@@ -52,3 +52,69 @@ def test_header_is_c99_and_a_c_program_links_and_runs(tmp_path):
     tok = os.path.join(ROOT, "tests", "golden", "bpe_llama3_tiny.json")
     r = subprocess.run([str(exe), tok], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout, r.stderr)
+
+
+SRC_GPU = textwrap.dedent(r'''
+    #include <stdio.h>
+    #include <string.h>
+    #include "opsagent_b200.h"
+
+    /* a strict-C99 caller doing real work on the GPU: create an engine, submit a chat completion with the error-buffer variants
+       (what the cgo binding uses), wait with a timeout, print the generated token ids; then cancel a second request */
+    int main(int argc, char** argv) {
+        oa_engine* e = (oa_engine*)0; oa_msg m[2]; oa_chat_req r; oa_chat_resp out; uint64_t t = 0, t2 = 0; char err[256]; int rc, i, spins = 0; char st[2048];
+        if (argc < 2) return 9;
+        rc = oa_engine_create(argv[1], &e);
+        if (rc != 0) { printf("create: %d %s\n", rc, oa_last_error()); return 1; }
+        memset(&r, 0, sizeof r); memset(&out, 0, sizeof out);
+        m[0].role = "system"; m[0].content = "You are a Kubernetes expert."; m[1].role = "user"; m[1].content = "how many namespace in the cluster?";
+        r.model = ""; r.msgs = m; r.n_msgs = 2; r.max_tokens = 16; r.temperature = 0.0f; r.flags = OA_FLAG_IGNORE_EOS;
+        rc = oa_chat_submit_ex(e, &r, &t, err, sizeof err);
+        if (rc != 0) { printf("submit: %d %s\n", rc, err); return 2; }
+        do { rc = oa_chat_wait_ex(e, t, 50, &out, err, sizeof err); ++spins; } while (rc == 408 && spins < 2000);
+        if (rc != 0) { printf("wait: %d %s\n", rc, err); return 3; }
+        printf("ids:");
+        for (i = 0; i < out.completion_tokens; ++i) printf(" %d", (int)out.token_ids[i]);
+        printf("\nprompt_tokens: %d\n", (int)out.prompt_tokens);
+        oa_free_resp(&out);
+        r.max_tokens = 400;
+        if (oa_chat_submit_ex(e, &r, &t2, err, sizeof err) != 0) return 4;
+        if (oa_chat_cancel(e, t2) != 0) return 5;
+        if (oa_chat_wait_ex(e, t2, 10, &out, err, sizeof err) != 400 || !strstr(err, "unknown ticket")) { printf("after cancel: %s\n", err); return 6; }
+        r.model = "not-this-model";
+        if (oa_chat_submit_ex(e, &r, &t2, err, sizeof err) != 400 || !strstr(err, "is not loaded")) { printf("alias: %s\n", err); return 7; }
+        if (oa_engine_stats(e, st, sizeof st) != 0 || !strstr(st, "\"cancelled\": 1")) { printf("stats: %s\n", st); return 8; }
+        oa_engine_destroy(e);
+        printf("ok\n");
+        return 0;
+    }
+''')
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="no C compiler")
+def test_c_program_runs_a_chat_completion_on_the_gpu_and_matches_the_oracle(tmp_path):
+    """the boundary driven from strict C99 with real compute: the ids the C caller gets back equal the oracle's greedy decode"""
+    import json
+    import numpy as np
+    from oracle import oracle as O          # checker only
+    spec = O.PRESETS["tiny-llama"]
+    cfg = spec.engine_json(num_pages=32, max_seq_len=512, max_batch=4, max_step_tokens=256)
+    src = tmp_path / "abi_gpu.c"; src.write_text(SRC_GPU)
+    exe = tmp_path / "abi_gpu"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", LIBDIR, "-lopsagent_b200", f"-Wl,-rpath,{LIBDIR}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), json.dumps(cfg)], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.returncode, r.stdout, r.stderr)
+    got = [int(x) for x in r.stdout.split("ids:")[1].split("\n")[0].split()]
+    ids = O.apply_chat_template(spec, [("system", "You are a Kubernetes expert."), ("user", "how many namespace in the cluster?")])
+    assert int(r.stdout.split("prompt_tokens:")[1].split()[0]) == len(ids)
+    orc = O.Oracle(spec, max_pos=512, mode=1)
+    ref, margins, _ = orc.generate(np.array(ids, np.int32), 16)
+    orc.close()
+    k = 0
+    while k < 16 and got[k] == ref[k]:
+        k += 1
+    assert len(got) == 16 and (k == 16 or margins[k] <= 5e-2), (k, got, list(ref))

@@ -32,6 +32,7 @@ def run_cases(rank: int, world: int, cases=None, tag: str = "0", log=print) -> d
             from opsagent_b200.presets_tiny import TINY_TP      # followers never touch the oracle package
             cfg = dict(TINY_TP[name])
         cfg.update(num_pages=64, max_seq_len=512, max_batch=16, max_step_tokens=256, device=rank, tp=world, tp_rank=rank,
+                   tp_two_shot_rows=160,        # prefill chunks of 200 / 256 rows: two-shot all-reduce; 150 rows: one-shot (both paths covered)
                    tp_shm=f"/oa_tp_{tag}_{name}", tp_nonce=int(tag) if str(tag).isdigit() else 0)
         eng = Engine(cfg)
         if rank > 0:
