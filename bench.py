@@ -134,7 +134,7 @@ def run_tp_block(args, rank, world, nonce, log):
                   "tok_s_per_gpu": round(batch / r["ms_per_step"] * 1e3 / world, 1),
                   "algorithmic_bytes_per_gpu_per_step": gb, "hbm_GBps_per_gpu": round(gb / r["ms_per_step"] / 1e6, 1),
                   "roofline_frac_per_gpu": round(gb / r["ms_per_step"] / 1e6 / peak, 4), "peak_source": peak_src,
-                  "allreduce_us": round(ar_ms / max(ar_n, 1) * 1e3, 2), "allreduce_count_per_step": 2 * info["n_layers"],
+                  "allreduce_us": (round(ar_ms / ar_n * 1e3, 2) if ar_n else None), "allreduce_count_per_step": 2 * info["n_layers"],
                   "allreduce_note": "partial -> symmetric buffer + all-reduce + residual + RMSNorm, in-situ CUDA events on the leader (serialised: upper bound)",
                   "prefill_tokens": batch * (ctx0 - 1), "prefill_ms": round(r["prefill_ms"], 1),
                   "prefill_tok_s": round(batch * (ctx0 - 1) / r["prefill_ms"] * 1e3, 1), "launches_per_step": r["launches_per_step"],
@@ -161,6 +161,9 @@ def router_block(args, rank, world, barrier):
             resource.setrlimit(resource.RLIMIT_NOFILE, (min(hard, 65536) if hard > 0 else 65536, hard))
         except Exception:
             pass
+        # hundreds of Python threads (clients AND the front's handlers live in this process): with the default 5 ms GIL switch interval the
+        # accept loop and the handlers take turns in 5 ms slices and arrivals trickle in over seconds
+        sys.setswitchinterval(2e-4)
         cfg = {"model": MODEL, "kv_gb": args.kv_gb, "max_batch": BATCH, "max_seq_len": 2048, "max_step_tokens": 8192, "seed": 1234, "tokenizer": TOKENIZER,
                "prefix_cache": 0, "max_queue": 4096, **json.loads(args.engine_extra)}
         rt = Router.create(cfg, list(range(world)), max_inflight=2 * BATCH)
@@ -183,9 +186,17 @@ def router_block(args, rank, world, barrier):
             usage[i] = d["usage"] if r.status == 200 else {"error": r.status}
 
         def round_(idx):
-            th = [threading.Thread(target=post, args=(i,)) for i in idx]
+            idx = list(idx)
+            go = threading.Barrier(len(idx) + 1)
+
+            def client(i):
+                go.wait()
+                post(i)
+            th = [threading.Thread(target=client, args=(i,)) for i in idx]
+            [t.start() for t in th]
+            go.wait()                                                  # every client thread exists: they all connect now
             t0 = time.perf_counter()
-            [t.start() for t in th]; [t.join() for t in th]
+            [t.join() for t in th]
             return time.perf_counter() - t0
         round_(range(0, n_req, 16))                                # warm-up: a few requests on every replica
         s0 = rt.stats()
@@ -198,7 +209,10 @@ def router_block(args, rank, world, barrier):
                "requests": n_req, "completed": len(ok), "by_kind": kinds, "seconds": round(dt, 3),
                "e2e_tokens_per_sec": round(comp / dt, 1), "react_steps_per_sec": round(len(ok) / dt, 2), "completion_tokens": comp,
                "prompt_tokens_mean": round(sum(u["prompt_tokens"] for u in ok) / max(1, len(ok)), 1),
-               "routed_per_replica": [b - a for a, b in zip(s0["routed"], s1["routed"])], "rejected_429": s1["rejected_429"] - s0["rejected_429"]}
+               "routed_per_replica": [b - a for a, b in zip(s0["routed"], s1["routed"])], "rejected_429": s1["rejected_429"] - s0["rejected_429"],
+               "engine_forwards": (s1["prefill_steps"] - s0["prefill_steps"]) + (s1["decode_steps"] - s0["decode_steps"]),
+               "engine_busy_ms_max": round(max(b["busy_ms"] - a["busy_ms"] for a, b in zip(s0["per_replica"], s1["per_replica"])), 1),
+               "note": "clients and the Python front share one interpreter (GIL): the gap to `e2e` is host-side HTTP/JSON/thread scheduling, not engine time"}
         srv.shutdown(); rt.close()
     barrier()
     return out
@@ -279,6 +293,15 @@ def run_ours(args, rank, world, local_rank):
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # A rank that merely WAITS (while rank 0 drives every GPU in the router block) must wait on the host: an NCCL barrier is a kernel
+    # spinning on that rank's GPU, taking SMs away from the engine rank 0 runs there (measured: the served round took 8.4 s instead of 3.7 s).
+    cpu_group = dist.new_group(backend="gloo") if dist is not None else None
+
+    def host_barrier():
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=cpu_group)
 
     from opsagent_b200 import dp as DP       # host side of the replica mode: request sharding + max-over-ranks timing (tests/test_dp_gloo.py)
 
@@ -420,12 +443,13 @@ def run_ours(args, rank, world, local_rank):
             line["react"] = rb
     if world >= 2 and not args.no_router:
         try:
-            rb = router_block(args, rank, world, barrier)
+            rb = router_block(args, rank, world, host_barrier)
         except Exception as e:
             rb = {"error": f"{type(e).__name__}: {e}"}
-            barrier()
+            host_barrier()
         if rank == 0:
             line["router"] = rb
+        torch.cuda.set_device(local_rank)          # rank 0 drove engines on every GPU from worker threads; make sure NCCL's device is current again
     hung = False
     if world >= 2 and not args.no_tp:
         tp, hung = tp_block()

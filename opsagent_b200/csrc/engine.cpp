@@ -31,6 +31,13 @@ namespace oa {
 static thread_local std::string g_last_error;
 static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
 
+// selects `dev` on the calling thread for a scope and restores what was current before (the CUDA current device is per thread)
+struct CallerDevice {
+    int prev = -1;
+    explicit CallerDevice(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+    ~CallerDevice() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 enum class SeqState { WAITING, PREFILL, DECODE, DONE };
 
 struct Seq {
@@ -68,7 +75,7 @@ public:
         { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
         cv_work_.notify_all();
         if (worker_.joinable()) worker_.join();
-        if (model_.comm && opt_.tp_rank == 0) { std::lock_guard<std::mutex> step(step_mu_); model_.sync(); model_.comm->shutdown(); }
+        if (model_.comm && opt_.tp_rank == 0) { std::lock_guard<std::mutex> step(step_mu_); CallerDevice on_engine_device(opt_.device); model_.sync(); model_.comm->shutdown(); }
         if (follower_.joinable()) follower_.join();
     }
     bool is_follower() const { return opt_.tp > 1 && opt_.tp_rank > 0; }
@@ -152,6 +159,7 @@ public:
     int debug_prefill_logits(const int32_t* toks, int n, float* logits_out) {
         if (n <= 0 || n > std::min(2048, opt_.max_step_tokens) || n + 1 > opt_.max_seq_len) return fail(OA_ERR_BAD_REQUEST, "debug prefill: 1..min(2048,max_step_tokens) tokens");
         std::lock_guard<std::mutex> step(step_mu_);
+        CallerDevice on_engine_device(opt_.device);      // this helper launches from the CALLER's thread
         try {
             const int V = model_.cfg.vocab;
             std::vector<int32_t> pages;
@@ -177,6 +185,7 @@ public:
         if (batch <= 0 || batch > opt_.max_batch || ctx_len <= 0 || ctx_len + steps + warmup + 1 > opt_.max_seq_len || n_out < 6)
             return fail(OA_ERR_BAD_REQUEST, "bench_decode: batch <= max_batch, ctx_len+steps+warmup < max_seq_len, n_out >= 6");
         std::lock_guard<std::mutex> step(step_mu_);
+        CallerDevice on_engine_device(opt_.device);
         try {
             const int V = model_.cfg.vocab;
             const int total_len = ctx_len + steps + warmup;

@@ -61,7 +61,16 @@ static void rope_table(const ModelConfig& c, int max_pos, std::vector<float>& co
     }
 }
 
+// The CUDA "current device" is per host thread.  Creating or destroying an engine must not leave the CALLER's thread on another device (a
+// router process owns one engine per GPU; torch / NCCL in the same process assume their own device stays current), so both restore it.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c), opt(o) {
+    DeviceGuard guard(opt.device);
     cuda_check(cudaSetDevice(opt.device), "cudaSetDevice");
     cudaDeviceProp prop;
     cuda_check(cudaGetDeviceProperties(&prop, opt.device), "cudaGetDeviceProperties");
@@ -293,7 +302,7 @@ void DeviceModel::load_checkpoint(const std::string& path) {
 }
 
 DeviceModel::~DeviceModel() {
-    cudaSetDevice(opt.device);
+    DeviceGuard guard(opt.device);
     if (stream) cudaStreamSynchronize(stream);
     if (chain_trace_) {      // dev tooling: where the last chained launch spent its cycles (per-CTA clock64 deltas from kernel start)
         std::vector<unsigned long long> t((size_t)sm_count * 32);
@@ -314,6 +323,7 @@ DeviceModel::~DeviceModel() {
     for (void* p : allocs_) cudaFree(p);
     if (h_out_ids) cudaFreeHost(h_out_ids);
     for (int i = 0; i < 2; ++i) { if (h_meta_buf_[i]) cudaFreeHost(h_meta_buf_[i]); if (meta_ev_[i]) cudaEventDestroy(meta_ev_[i]); }
+    comm.reset();                 // peer mappings and symmetric buffers: released while this engine's device is still current
     if (stream) cudaStreamDestroy(stream);
 }
 

@@ -68,6 +68,7 @@ TpComm::TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, i
         if (shm_ == MAP_FAILED) throw std::runtime_error("mmap of the tp shm segment failed");
         shm_->handles_ready.store(0); shm_->peers_opened.store(0); shm_->seq.store(0);
         for (int i = 0; i < TP_MAX; ++i) shm_->ack[i].store(0);
+        for (int i = 0; i < TP_MAX; ++i) shm_->rank_pid[i].store(0);
         shm_->nonce.store(nonce); shm_->leader_pid.store((int64_t)getpid());
         shm_->magic.store(0x4f415450u, std::memory_order_release);
     } else {
@@ -84,6 +85,7 @@ TpComm::TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, i
             shm_ = c; return true; },
                    "follower waiting for the leader's shm segment (same tp_shm name and tp_nonce, live leader)");
     }
+    shm_->rank_pid[rank].store((int64_t)getpid());
     // ---- symmetric device buffers + IPC handle exchange ----
     arg_half_bytes_ = (size_t)max_sample * 8;
     for (int b = 0; b < 3; ++b) { cuda_check(cudaMalloc(&sym_[b], sym_bytes), "cudaMalloc sym"); cuda_check(cudaMemset(sym_[b], 0, sym_bytes), "memset sym"); }
@@ -140,8 +142,14 @@ TpComm::~TpComm() {
 void TpComm::publish(const StepInput& in) {
     // the previous message must have been consumed by every follower before it is overwritten
     const uint64_t cur = shm_->seq.load(std::memory_order_acquire);
-    for (int p = 1; p < t_; ++p)
-        spin_until([&] { return shm_->ack[p].load(std::memory_order_acquire) >= cur; }, "followers acknowledging the previous step", 600.0);
+    for (int p = 1; p < t_; ++p) {
+        uint64_t polls = 0;
+        spin_until([&] {
+            if (shm_->ack[p].load(std::memory_order_acquire) >= cur) return true;
+            if ((++polls & 0x7ff) == 0 && !pid_alive(shm_->rank_pid[p].load()))      // every ~0.4 s
+                throw std::runtime_error("tensor-parallel follower " + std::to_string(p) + " (pid " + std::to_string((long long)shm_->rank_pid[p].load()) + ") is gone");
+            return false; }, "followers acknowledging the previous step", 600.0);
+    }
     int32_t* m = shm_->msg; size_t w = 0;
     auto put = [&](const void* src, size_t words) { if (w + words > TP_MSG_WORDS) throw std::runtime_error("tp step message overflow"); std::memcpy(m + w, src, words * 4); w += words; };
     const int32_t hdr[10] = {(in.decode ? 1 : 0) | (in.n_decode << 1), (int32_t)in.tokens.size(), (int32_t)in.sample_rows.size(), in.n_seqs, (int32_t)in.block_tables.size(),

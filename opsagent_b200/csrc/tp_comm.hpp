@@ -25,7 +25,8 @@ constexpr size_t TP_MSG_WORDS = 2u << 20;     // 8 MB step-message area
 struct TpShm {                                 // lives in POSIX shared memory
     std::atomic<uint32_t> magic;               // set LAST by the leader; cleared first thing when a new leader finds a stale segment
     std::atomic<uint64_t> nonce;               // per-launch id (config "tp_nonce"): followers refuse a segment of another launch
-    std::atomic<int64_t> leader_pid;           // followers refuse a segment whose leader is gone and notice a leader that dies later
+    std::atomic<int64_t> leader_pid;
+    std::atomic<int64_t> rank_pid[TP_MAX];     // every rank's pid (set when it attaches): the leader notices a follower that died instead of waiting out a timeout           // followers refuse a segment whose leader is gone and notice a leader that dies later
     std::atomic<uint32_t> handles_ready;       // ranks that published their IPC handles
     std::atomic<uint32_t> peers_opened;        // ranks that mapped every peer
     cudaIpcMemHandle_t h_sym[TP_MAX][3];       // [rank][buffer]: 0/1 = double-buffered partials, 2 = the gather buffer of the two-shot all-reduce
