@@ -246,7 +246,12 @@ def react_block(args, rank, world, local_rank, barrier, allmax):
     def agent(i, salt):
         q = WL.EXECUTE_QUESTIONS[(rank * n_agents + i) % len(WL.EXECUTE_QUESTIONS)]
         msgs = WL.execute_messages("execute " + q, f"(cluster c{salt}-{rank}-{i})")
-        results[i] = AssistantWithConfig(MODEL, msgs, 2048, True, False, REACT_TOOL_STEPS + 2, CountingClient(eng, i), copilot_tools(1000 * salt + i),
+        tools = copilot_tools(1000 * salt + i)
+        if args.react_tool_ms > 0:                # the reference's tools fork/exec kubectl (~100 ms class): agents drift apart, arrivals stagger
+            import random
+            rr = random.Random(salt * 7919 + i)
+            tools = {k: (lambda inp, f=f: (time.sleep(args.react_tool_ms * (0.5 + rr.random()) / 1e3), f(inp))[1]) for k, f in tools.items()}
+        results[i] = AssistantWithConfig(MODEL, msgs, 2048, True, False, REACT_TOOL_STEPS + 2, CountingClient(eng, i), tools,
                                          count_tokens=eng.count_tokens)
 
     def round_(n, salt):
@@ -271,7 +276,7 @@ def react_block(args, rank, world, local_rank, barrier, allmax):
     return {"workload": f"{n_agents} concurrent ReAct conversations per GPU: verbatim executeSystemPrompt_cn + question, {REACT_TOOL_STEPS} grammar-forced kubectl "
                         "tool steps (seeded synthetic kubectl tables) + final answer; json_mode, prefix cache on",
             "react_steps_per_sec": round(world * n_calls / dt, 2), "chat_calls_per_gpu": n_calls, "seconds": round(dt, 2),
-            "conversations_with_final_answer": ok, "conversations": n_agents,
+            "conversations_with_final_answer": ok, "conversations": n_agents, "tool_latency_ms": args.react_tool_ms,
             "completion_tokens_per_sec": round(world * (s1["decode_tokens"] - s0["decode_tokens"]) / dt, 1),
             "prefill_tokens": pre, "prefix_hit_tokens": hit, "prefix_hit_rate": round(hit / max(1, hit + pre), 4),
             "decode_steps": s1["decode_steps"] - s0["decode_steps"], "prefill_steps": s1["prefill_steps"] - s0["prefill_steps"],
@@ -332,6 +337,11 @@ def run_ours(args, rank, world, local_rank):
         if hung:
             os._exit(3)
         dist.barrier(); dist.destroy_process_group()
+        return
+    if args.react_only:
+        rb = react_block(args, rank, world, local_rank, barrier, allmax)
+        if rank == 0:
+            print(json.dumps({"react": rb}), flush=True)
         return
     K, W = args.steps, max(args.warmup, 3)
     eng = Engine({"model": MODEL, "device": local_rank, "kv_gb": args.kv_gb, "max_batch": BATCH, "max_seq_len": 2048,
@@ -526,6 +536,8 @@ def main():
     ap.add_argument("--no-router", action="store_true", help="N>=2: skip the one-front / N-engines serving block")
     ap.add_argument("--no-react", action="store_true", help="skip the multi-step ReAct block")
     ap.add_argument("--react-agents", type=int, default=128, dest="react_agents")
+    ap.add_argument("--react-tool-ms", type=float, default=0.0, dest="react_tool_ms", help="synthetic tool latency (mean, ms; uniform 0.5x-1.5x): staggers the agents like a real kubectl would")
+    ap.add_argument("--react-only", action="store_true", help="dev: only the react block")
     ap.add_argument("--no-tp", action="store_true", help="N>=2: skip the tensor-parallel block")
     ap.add_argument("--no-tp-parity", action="store_true")
     ap.add_argument("--tp-cases", default="", help="comma-separated tiny presets for the TP parity check (default: by degree)")

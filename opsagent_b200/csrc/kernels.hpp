@@ -84,6 +84,11 @@ cudaError_t launch_gemm_streamk_resid(const CUtensorMap* tmA, const CUtensorMap*
 // launch_gemm_streamk + launch_sk_rope_kv_write
 cudaError_t launch_gemm_streamk_rope(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const StreamK& sk, const SkRopeArgs& rope,
                                      unsigned int* tile_flags, cudaStream_t stream);
+// ---- cluster split-K GEMM for projections with few output tiles (gemm_clusterk.cu): S CTAs of one cluster own one 128-column tile and 1/S
+// of K each, reduce through distributed shared memory and finish the epilogue together (no partial workspace, no consumer launch) ----
+int clusterk_pick(int N, int K, int sms, int min_fill_pct = 80);        // cluster size for this shape (8, 4, 3, 2) or 0 = keep the stream-K path
+cudaError_t launch_gemm_clusterk_resid(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, int S, void* x, int ldx, cudaStream_t stream);
+cudaError_t launch_gemm_clusterk_rope(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, int S, const SkRopeArgs& rope, cudaStream_t stream);
 // xn = rmsnorm(x) * gain with exactly the reduction order of launch_sk_resid_rmsnorm (512 threads per row)
 cudaError_t launch_rmsnorm_wide(const void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s);
 enum SkConsumer : int { SK_CONSUMER_NONE = 0, SK_CONSUMER_RESID_RMSNORM = 1, SK_CONSUMER_SWIGLU = 2, SK_CONSUMER_ROPE_KV = 3 };

@@ -501,6 +501,11 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
         const bool fuse_ok = sk_rows == 128 && sk_G_ <= sm_count && sk_qkv.bn == 128 && sk_o.bn == 128 && sk_dn.bn == 128 &&
                               sk_qkv.n_tiles <= SK_CHAIN_MAX_TILES && sk_o.n_tiles <= SK_CHAIN_MAX_TILES && (D == 64 || D == 128);
         const bool fuse_rope = fuse_ok && (opt.sk_fuse_epi & 1), fuse_o = fuse_ok && !use_tp && (opt.sk_fuse_epi & 2), fuse_dn = fuse_ok && !use_tp && (opt.sk_fuse_epi & 4);
+        // cluster split-K (few-tile projections): cluster size per shape, 0 = keep stream-K.  o / down finish the residual add themselves, so
+        // they are single-GPU only (a tensor-parallel rank must hand its partial to the all-reduce instead)
+        const int ck_qkv = (sk_rows == 128 && (opt.sk_clusterk & 1) && (D == 64 || D == 128)) ? clusterk_pick(qkvd, H, sm_count, opt.sk_clusterk_min_fill) : 0;
+        const int ck_o = (sk_rows == 128 && (opt.sk_clusterk & 2) && !use_tp) ? clusterk_pick(H, qd, sm_count, opt.sk_clusterk_min_fill) : 0;
+        const int ck_dn = (sk_rows == 128 && (opt.sk_clusterk & 4) && !use_tp) ? clusterk_pick(H, F, sm_count, opt.sk_clusterk_min_fill) : 0;
         const bool fuse_swiglu = opt.sk_fuse_swiglu && sk_rows == 128 && sk_gu.bn == 128 && sk_G_ <= sm_count && sk_gu.n_tiles <= SK_CHAIN_MAX_TILES;
         auto qkv_phase = [&](int l, SkChainPhase& P) {
             P.sk = sk_qkv; P.consumer = SK_CONSUMER_ROPE_KV;
@@ -531,7 +536,10 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
                 cuda_check(launch_sk_chain(maps, ch, sk_G_, stream), "chained o/gate_up/down (stream-K)"); MARK(8);
                 continue;
             }
-            if (fuse_rope) {
+            if (ck_qkv) {
+                cuda_check(launch_gemm_clusterk_rope(&tm_xn_, ly.qkv.map(128), T, qkvd, H, ck_qkv, make_sk_rope_args(ly.bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, nh), stream),
+                           "qkv gemm + RoPE + KV write (cluster split-K)"); MARK(2);
+            } else if (fuse_rope) {
                 cuda_check(launch_gemm_streamk_rope(&tm_xn_, ly.qkv.map(128), T, qkvd, H, pf_qkv, make_sk_rope_args(ly.bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, nh),
                                                     chain_flags_ + 0 * SK_CHAIN_MAX_TILES, stream), "qkv gemm + RoPE + KV write (stream-K)"); MARK(2);
             } else {
@@ -539,7 +547,10 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
                 cuda_check(launch_sk_rope_kv_write(sk_qkv, ly.bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, T, nh, stream), "rope (stream-K)"); MARK(3);
             }
             attention(l);
-            if (fuse_o) {
+            if (ck_o) {
+                cuda_check(launch_gemm_clusterk_resid(&tm_attn_, ly.o.map(128), T, H, qd, ck_o, x_, H, stream), "o gemm + residual (cluster split-K)"); MARK(6);
+                cuda_check(launch_rmsnorm_wide(x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "rmsnorm2"); MARK(7);
+            } else if (fuse_o) {
                 cuda_check(launch_gemm_streamk_resid(&tm_attn_, ly.o.map(128), T, H, qd, pf_o, x_, H, chain_flags_ + 1 * SK_CHAIN_MAX_TILES, stream), "o gemm + residual (stream-K)"); MARK(6);
                 cuda_check(launch_rmsnorm_wide(x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "rmsnorm2"); MARK(7);
             } else {
@@ -566,6 +577,11 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
                 cuda_check(launch_sk_swiglu(sk_gu, act_, T, F, stream), "swiglu"); MARK(9);
             }
             const void* next_gain = (l + 1 < L) ? layers[l + 1].ln1 : final_norm;
+            if (ck_dn) {
+                cuda_check(launch_gemm_clusterk_resid(&tm_act_, ly.down.map(128), T, H, F, ck_dn, x_, H, stream), "down gemm + residual (cluster split-K)"); MARK(10);
+                cuda_check(launch_rmsnorm_wide(x_, next_gain, xn_, T, H, cfg.rms_eps, stream), "rmsnorm1"); MARK(7);
+                continue;
+            }
             if (fuse_dn) {
                 cuda_check(launch_gemm_streamk_resid(&tm_act_, ly.down.map(128), T, H, F, pf_dn, x_, H, chain_flags_ + 3 * SK_CHAIN_MAX_TILES, stream), "down gemm + residual (stream-K)"); MARK(10);
                 cuda_check(launch_rmsnorm_wide(x_, next_gain, xn_, T, H, cfg.rms_eps, stream), "rmsnorm1"); MARK(7);
