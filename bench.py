@@ -444,7 +444,7 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "prefill": {"tokens": BATCH * (ctx0 - 1), "ms": round(r["prefill_ms"], 1),
                         "tokens_per_sec": round(BATCH * (ctx0 - 1) / (r["prefill_ms"] / 1e3), 1)}}
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU leg runs on rank 0 at N=1 only
         line["cpu_baseline"] = cpu_baseline(args.cpu_tokens)
     eng.close()
     if not args.no_react:

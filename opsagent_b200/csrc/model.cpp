@@ -340,7 +340,11 @@ int DeviceModel::pick_bn(int M, int N, int override_bn, bool swiglu) const {
     if (override_bn == 32 || override_bn == 64 || override_bn == 128 || override_bn == 256) return override_bn;
     const int m_tiles = (M + 127) / 128;
     const int cands[4] = {256, 128, 64, 32};
-    for (int bn : cands) { if ((long long)((N + bn - 1) / bn) * m_tiles >= sm_count) return bn; }
+    // one or two row tiles (decode-sized batches off the stream-K path, e.g. Qwen2.5-32B TP=4 at B=256): a CTA's k-loop is latency-bound
+    // (~0.3 us per k-block), so wider tiles with fewer, longer-lived CTAs win as long as about half the SMs stream — measured per shape in
+    // profiles/r02e_gemm_shapes_m256.md (gate_up 51 -> 39 us at BN=256, down 36 -> 33 us at BN=128); many row tiles: fill every SM
+    const long long want = m_tiles <= 2 ? sm_count / 2 : sm_count;
+    for (int bn : cands) { if ((long long)((N + bn - 1) / bn) * m_tiles >= want) return bn; }
     (void)swiglu;
     return 32;
 }

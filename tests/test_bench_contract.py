@@ -33,11 +33,22 @@ def check_base(line):
     assert line["cpu_baseline"]["kind"] in ("port", "reference")
 
 
-@pytest.mark.parametrize("name", ["r01h_bench.json", "r01h_bench_dp4.json"])
+@pytest.mark.parametrize("name", ["r01h_bench.json", "r01h_bench_dp4.json", "r02a_bench.json", "r02b_bench_dp4.json", "r02c_bench_dp8.json"])
 def test_our_arm_line(name):
     line = load(name)
-    if name.endswith("dp4.json"):
-        line.setdefault("cpu_baseline", load("r01h_bench.json")["cpu_baseline"])   # the CPU leg runs at N=1 only
+    if "dp" in name:
+        line["cpu_baseline"] = load("r01h_bench.json")["cpu_baseline"]   # the CPU leg runs at N=1 only
+    if name.startswith("r02"):
+        # round 2: the reference's own request shapes, the multi-step loop and (N >= 2) the served mix + tensor parallelism are inside the contract
+        assert "verbatim" in line["e2e"]["prompts"] and set(line["e2e"]["prompt_tokens_by_kind"]) <= {"analyze", "diagnose", "execute"}
+        r = line["react"]
+        assert r["conversations_with_final_answer"] == r["conversations"] and 0 < r["prefix_hit_rate"] < 1 and r["react_steps_per_sec"] > 0
+        if line["n_gpus"] >= 2:
+            assert "configs[2]" in line["config"]["workload"] and set(line["e2e"]["prompt_tokens_by_kind"]) == {"analyze", "diagnose", "execute"}
+            assert line["router"]["completed"] == line["router"]["requests"] == line["n_gpus"] * 128
+            tp = line["tp"]
+            assert tp["parity"]["ok"] is True and tp["parity"]["t"] == line["n_gpus"] and tp["parity"]["max_dlogit"] < 2.5e-2
+            assert tp["t"] == line["n_gpus"] and 0 < tp["roofline_frac_per_gpu"] < 1
     check_base(line)
     assert line["metric"] == "decode_tokens_per_sec" and line["unit"] == "tokens/s" and line["higher_is_better"] is True
     assert line["scaling"] == "weak" and line["dtype"] == "bf16" and line["warmup"] >= 3

@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 
-def launches(src, dst, n_steps=2):
+def launches(src, dst, n_steps=2, cmd=None):
     lines = [l for l in open(src) if not l.startswith("==")]
     agg = collections.OrderedDict()
     for row in csv.DictReader(lines):
@@ -21,7 +21,7 @@ def launches(src, dst, n_steps=2):
     tot = sum(v[1] for v in agg.values())
     with open(dst, "w") as f:
         f.write(f"# ncu launch list — decode steps of BASELINE configs[1] (Llama-3-8B, B=128, ctx~1664), {n_steps} steps\n\n")
-        f.write("`OA_CUDA_PROFILER=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none python tools/profile_step.py --steps 2`\n\n")
+        f.write("`" + (cmd or "OA_CUDA_PROFILER=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none python tools/profile_step.py --steps 2") + "`\n\n")
         f.write(f"Per-launch times are cold-cache and serialised (compare SHARES).  Sum = {tot / n_steps / 1e3:.3f} ms per step.\n\n")
         f.write("| kernel | grid | launches/step | avg us | share |\n|---|---|---:|---:|---:|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -55,6 +55,6 @@ def report(src, dst):
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
-        launches(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 2)
+        launches(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 2, sys.argv[5] if len(sys.argv) > 5 else None)
     else:
         report(sys.argv[2], sys.argv[3])
