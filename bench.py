@@ -138,7 +138,9 @@ def run_tp_block(args, rank, world, nonce, log):
                   "allreduce_note": "partial -> symmetric buffer + all-reduce + residual + RMSNorm, in-situ CUDA events on the leader (serialised: upper bound)",
                   "prefill_tokens": batch * (ctx0 - 1), "prefill_ms": round(r["prefill_ms"], 1),
                   "prefill_tok_s": round(batch * (ctx0 - 1) / r["prefill_ms"] * 1e3, 1), "launches_per_step": r["launches_per_step"],
-                  "collective": "own one-shot all-reduce over NVLink peer memory (tp_comm.cu), rank-ordered sum, fused with residual + RMSNorm; no NCCL on the data path"})
+                  "collective": ("decode: in-switch reduction (multimem.ld_reduce / multimem.st on an NVLS multicast buffer, tp_nvls.cpp) fused with residual + RMSNorm; "
+                                 if info.get("tp_nvls") else "decode: own one-shot all-reduce over NVLink peer memory (bf16 partials, rank-ordered sum) fused with residual + RMSNorm; ") +
+                                "prefill chunks: two-shot reduce-scatter + all-gather over peer memory; no NCCL on the data path", "nvls": bool(info.get("tp_nvls"))})
     eng.close()
     return block
 

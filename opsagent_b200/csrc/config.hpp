@@ -124,6 +124,7 @@ struct EngineOptions {
     int tp = 1, tp_rank = 0;      // tensor parallel degree / this process's rank (one process per GPU)
     std::string tp_shm = "/oa_tp"; // POSIX shm name shared by the ranks of one TP group
     int tp_ar_bf16 = 1;            // decode all-reduce on bf16 partials (half the NVLink bytes; the prefill path always exchanged bf16); 0 = fp32 partials
+    int tp_nvls = 1;               // decode all-reduce inside the NVLink switch (multimem.ld_reduce / multimem.st on a multicast buffer) when every rank can set it up; 0 = peer-memory one-shot
     int tp_two_shot_rows = 1024;   // prefill chunks of at least this many rows use the two-shot all-reduce (reduce-scatter + all-gather: 2(t-1)/t instead of (t-1) partials' bytes per rank); smaller ones the one-shot
     uint64_t tp_nonce = 0;         // per-launch id shared by the ranks (e.g. the rendezvous port + a timestamp): followers ignore segments of other launches (0 = not checked)
 };
@@ -145,7 +146,7 @@ inline void parse_config(const std::string& json, ModelConfig& m, EngineOptions&
     I("device", o.device); o.kv_gb = j.f("kv_gb", o.kv_gb); I("num_pages", o.num_pages); I("max_batch", o.max_batch);
     I("max_seq_len", o.max_seq_len); I("max_step_tokens", o.max_step_tokens); I("max_queue", o.max_queue);
     I("bn_qkv", o.bn_qkv); I("bn_o", o.bn_o); I("bn_gu", o.bn_gu); I("bn_down", o.bn_down); I("bn_lm", o.bn_lm);
-    I("attn_ctas", o.attn_ctas); I("streamk", o.streamk); I("sk_bn", o.sk_bn); I("sk_ctas", o.sk_ctas); I("sk_l2_prefetch_kb", o.sk_l2_prefetch_kb); I("sk_max_rows", o.sk_max_rows); I("sk_chain", o.sk_chain); I("sk_fuse_swiglu", o.sk_fuse_swiglu); I("sk_fuse_epi", o.sk_fuse_epi); I("sk_clusterk", o.sk_clusterk); I("sk_clusterk_min_fill", o.sk_clusterk_min_fill); I("sk_chain_pf_kb", o.sk_chain_pf_kb); I("sk_bn_qkv", o.sk_bn_qkv); I("sk_bn_o", o.sk_bn_o); I("sk_bn_gu", o.sk_bn_gu); I("sk_bn_down", o.sk_bn_down); I("start_thread", o.start_thread); o.weights = j.s("weights", o.weights); o.model_aliases = j.s("model_aliases", o.model_aliases); o.tokenizer = j.s("tokenizer", o.tokenizer); I("prefix_cache", o.prefix_cache); I("json_mode", o.json_mode); I("react_tool_steps", o.react_tool_steps); I("prefill_batch_tokens", o.prefill_batch_tokens); I("mixed_steps", o.mixed_steps); I("prefill_max_wait_ms", o.prefill_max_wait_ms); I("tp", o.tp); I("tp_rank", o.tp_rank); I("tp_ar_bf16", o.tp_ar_bf16); I("tp_two_shot_rows", o.tp_two_shot_rows); o.tp_shm = j.s("tp_shm", o.tp_shm); o.tp_nonce = (uint64_t)j.i("tp_nonce", (int64_t)o.tp_nonce);
+    I("attn_ctas", o.attn_ctas); I("streamk", o.streamk); I("sk_bn", o.sk_bn); I("sk_ctas", o.sk_ctas); I("sk_l2_prefetch_kb", o.sk_l2_prefetch_kb); I("sk_max_rows", o.sk_max_rows); I("sk_chain", o.sk_chain); I("sk_fuse_swiglu", o.sk_fuse_swiglu); I("sk_fuse_epi", o.sk_fuse_epi); I("sk_clusterk", o.sk_clusterk); I("sk_clusterk_min_fill", o.sk_clusterk_min_fill); I("sk_chain_pf_kb", o.sk_chain_pf_kb); I("sk_bn_qkv", o.sk_bn_qkv); I("sk_bn_o", o.sk_bn_o); I("sk_bn_gu", o.sk_bn_gu); I("sk_bn_down", o.sk_bn_down); I("start_thread", o.start_thread); o.weights = j.s("weights", o.weights); o.model_aliases = j.s("model_aliases", o.model_aliases); o.tokenizer = j.s("tokenizer", o.tokenizer); I("prefix_cache", o.prefix_cache); I("json_mode", o.json_mode); I("react_tool_steps", o.react_tool_steps); I("prefill_batch_tokens", o.prefill_batch_tokens); I("mixed_steps", o.mixed_steps); I("prefill_max_wait_ms", o.prefill_max_wait_ms); I("tp", o.tp); I("tp_rank", o.tp_rank); I("tp_ar_bf16", o.tp_ar_bf16); I("tp_nvls", o.tp_nvls); I("tp_two_shot_rows", o.tp_two_shot_rows); o.tp_shm = j.s("tp_shm", o.tp_shm); o.tp_nonce = (uint64_t)j.i("tp_nonce", (int64_t)o.tp_nonce);
     if (m.hidden <= 0 || m.n_layers <= 0 || m.n_heads <= 0 || m.n_kv_heads <= 0 || m.ffn <= 0 || m.vocab <= 0)
         throw std::runtime_error("unknown model '" + name + "' and no explicit dimensions given");
     if (m.head_dim != 64 && m.head_dim != 128) throw std::runtime_error("head_dim must be 64 or 128");

@@ -86,6 +86,7 @@ private:
     uint32_t* mask_table_ = nullptr;               // [mask_slots][mask_words] allowed-token bitsets of grammar states (filled on demand by the scheduler)
     float *part_o_ = nullptr, *part_ml_ = nullptr; int max_part_slots_ = 0;
     float* sk_ws_ = nullptr; int sk_bn_ = 256, sk_G_ = 148;
+    size_t nvls_region_ = 0;                       // bytes of one [128 rows, H] fp32 region of the NVLS multicast buffer (partials 0/1, reduced 0/1)
     unsigned long long* chain_trace_ = nullptr;    // OA_CHAIN_TRACE=1: per-CTA clock stamps of the last chained launch, printed at teardown
     unsigned int* chain_flags_ = nullptr;          // per-tile piece counters of the fused SwiGLU epilogue (self-resetting)
     unsigned long long* chain_bar_ = nullptr;      // grid-barrier counters of the chained decode kernel (self-resetting)

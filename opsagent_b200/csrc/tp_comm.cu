@@ -31,7 +31,7 @@ static void spin_until(const std::function<bool()>& ok, const char* what, double
 
 static bool pid_alive(int64_t pid) { return pid > 0 && (kill((pid_t)pid, 0) == 0 || errno != ESRCH); }
 
-TpComm::TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, int max_sample, uint64_t nonce)
+TpComm::TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, int max_sample, uint64_t nonce, size_t nvls_bytes)
     : t_(t), rank_(rank), shm_name_(shm_name), sym_bytes_(sym_bytes) {
     if (t < 2 || t > TP_MAX || rank < 0 || rank >= t) throw std::runtime_error("tp must be 2..8 and 0 <= tp_rank < tp");
     // ---- shared-memory segment (leader creates, followers attach) ----
@@ -69,6 +69,7 @@ TpComm::TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, i
         shm_->handles_ready.store(0); shm_->peers_opened.store(0); shm_->seq.store(0);
         for (int i = 0; i < TP_MAX; ++i) shm_->ack[i].store(0);
         for (int i = 0; i < TP_MAX; ++i) shm_->rank_pid[i].store(0);
+        shm_->nvls_leader_ready.store(0); shm_->nvls_stage[0].store(0); shm_->nvls_stage[1].store(0); shm_->nvls_fail.store(0);
         shm_->nonce.store(nonce); shm_->leader_pid.store((int64_t)getpid());
         shm_->magic.store(0x4f415450u, std::memory_order_release);
     } else {
@@ -120,9 +121,11 @@ TpComm::TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, i
     cuda_check(cudaMemcpy(d_peer_flags_, peer_flags_, TP_MAX * sizeof(uint32_t*), cudaMemcpyHostToDevice), "ptr table H2D");
     shm_->peers_opened.fetch_add(1, std::memory_order_acq_rel);
     spin_until([&] { return shm_->peers_opened.load(std::memory_order_acquire) >= (uint32_t)t; }, "all ranks mapping their peers");
+    if (nvls_bytes > 0) nvls_setup(nvls_bytes, nonce);          // all ranks or none (tp_nvls.cpp); failure only means the peer-memory path stays
 }
 
 TpComm::~TpComm() {
+    nvls_teardown();
     for (int p = 0; p < t_; ++p) {
         if (p == rank_) continue;
         for (int b = 0; b < 3; ++b) if (peer_sym_[b][p]) cudaIpcCloseMemHandle(peer_sym_[b][p]);
@@ -293,6 +296,70 @@ cudaError_t launch_ar_resid_rmsnorm(void* const* d_peer, int t, void* x, const v
     const TpComm::Signal sg = wait ? *wait : TpComm::Signal{};
     return launch_k(ar_resid_rmsnorm_kernel, dim3(T), dim3(AR_THREADS), 0, s, P, t, reinterpret_cast<uint2*>(x), reinterpret_cast<const uint2*>(gain),
                     reinterpret_cast<uint2*>(xn), H / 4, 1.0f / H, eps, sg, wait ? 1 : 0);
+}
+
+// ---- in-switch all-reduce (NVLS multicast, tp_nvls.cpp) -------------------------------------------------------------------------
+OA_DEVINL float4 multimem_ld_reduce_f4(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+OA_DEVINL void multimem_st_f4(float* mc, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__global__ void __launch_bounds__(AR_THREADS) ar_nvls_resid_rmsnorm_kernel(const float* __restrict__ mc_part, float* __restrict__ mc_red, const float* __restrict__ local_red,
+                                                                           int t, int rank, uint2* __restrict__ x, const uint2* __restrict__ g, uint2* __restrict__ y,
+                                                                           int T, int H4, float inv_h, float eps, const TpComm::Signal sg_in, const TpComm::Signal sg_mid) {
+    griddep_wait();
+    xgpu_wait_peers(sg_in);                                   // every rank's partial is complete in its copy of the buffer
+    {   // reduce-scatter + all-gather through the switch: slice `rank` of the T x H matrix, spread over this rank's CTAs
+        const size_t n4 = (size_t)T * H4, per = (n4 + (size_t)t - 1) / (size_t)t;
+        const size_t lo = (size_t)rank * per < n4 ? (size_t)rank * per : n4, hi = lo + per < n4 ? lo + per : n4;
+        for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
+            const float4 v = multimem_ld_reduce_f4(mc_part + i * 4);
+            multimem_st_f4(mc_red + i * 4, v);
+        }
+        __threadfence_system();
+    }
+    xgpu_signal_when_grid_done(sg_mid, gridDim.x);            // this rank's slice has been broadcast ...
+    xgpu_wait_peers(sg_mid);                                  // ... and so has everybody else's
+    griddep_launch();
+    const int row = blockIdx.x;
+    uint2* xr = x + (size_t)row * H4;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < H4; i += AR_THREADS) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(local_red) + (size_t)row * H4 + i);      // written by remote multicast stores: bypass L1
+        const uint2 xo = xr[i];
+        uint2 xn;
+        xn.x = pack_bf16x2(bf16lo(xo.x) + a.x, bf16hi(xo.x) + a.y); xn.y = pack_bf16x2(bf16lo(xo.y) + a.z, bf16hi(xo.y) + a.w);
+        xr[i] = xn;
+        float q;
+        q = bf16lo(xn.x); ss += q * q; q = bf16hi(xn.x); ss += q * q; q = bf16lo(xn.y); ss += q * q; q = bf16hi(xn.y); ss += q * q;
+    }
+    ss = warp_sum(ss);
+    __shared__ float red[AR_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < AR_THREADS / 32; ++w) tot += red[w];
+    const float r = 1.0f / sqrtf(tot * inv_h + eps);
+    uint2* yr = y + (size_t)row * H4;
+    for (int i = threadIdx.x; i < H4; i += AR_THREADS) {
+        const uint2 v = xr[i], gg = g[i]; uint2 o;
+        o.x = pack_bf16x2(bf16lo(v.x) * r * bf16lo(gg.x), bf16hi(v.x) * r * bf16hi(gg.x));
+        o.y = pack_bf16x2(bf16lo(v.y) * r * bf16lo(gg.y), bf16hi(v.y) * r * bf16hi(gg.y));
+        yr[i] = o;
+    }
+}
+cudaError_t launch_ar_nvls_resid_rmsnorm(const void* mc_base, const void* local_base, size_t part_off, size_t red_off, int t, int rank, void* x, const void* gain, void* xn,
+                                         int T, int H, float eps, cudaStream_t s, const TpComm::Signal& wait, const TpComm::Signal& mid) {
+    if (T <= 0) return cudaSuccess;
+    if (H % 8 != 0 || T > 148) return cudaErrorInvalidValue;            // every CTA waits for every peer: the grid must be co-resident
+    const char* mc = reinterpret_cast<const char*>(mc_base); const char* lc = reinterpret_cast<const char*>(local_base);
+    return launch_k(ar_nvls_resid_rmsnorm_kernel, dim3(T), dim3(AR_THREADS), 0, s, reinterpret_cast<const float*>(mc + part_off),
+                    reinterpret_cast<float*>(const_cast<char*>(mc) + red_off), reinterpret_cast<const float*>(lc + red_off), t, rank, reinterpret_cast<uint2*>(x),
+                    reinterpret_cast<const uint2*>(gain), reinterpret_cast<uint2*>(xn), T, H / 4, 1.0f / H, eps, wait, mid);
 }
 
 // The same collective on bf16 partials: half the NVLink bytes (the one-shot all-reduce of a decode step is bandwidth-bound: every rank

@@ -26,7 +26,10 @@ struct TpShm {                                 // lives in POSIX shared memory
     std::atomic<uint32_t> magic;               // set LAST by the leader; cleared first thing when a new leader finds a stale segment
     std::atomic<uint64_t> nonce;               // per-launch id (config "tp_nonce"): followers refuse a segment of another launch
     std::atomic<int64_t> leader_pid;
-    std::atomic<int64_t> rank_pid[TP_MAX];     // every rank's pid (set when it attaches): the leader notices a follower that died instead of waiting out a timeout           // followers refuse a segment whose leader is gone and notice a leader that dies later
+    std::atomic<int64_t> rank_pid[TP_MAX];
+    std::atomic<uint32_t> nvls_leader_ready;   // multicast setup (tp_nvls.cpp): 0 pending, 1 the leader's fd server is up, 2 the leader could not create the object
+    std::atomic<uint32_t> nvls_stage[2];       // ranks that finished a setup stage
+    std::atomic<uint32_t> nvls_fail;           // ranks that failed at any stage: > 0 -> every rank falls back to the peer-memory all-reduce     // every rank's pid (set when it attaches): the leader notices a follower that died instead of waiting out a timeout           // followers refuse a segment whose leader is gone and notice a leader that dies later
     std::atomic<uint32_t> handles_ready;       // ranks that published their IPC handles
     std::atomic<uint32_t> peers_opened;        // ranks that mapped every peer
     cudaIpcMemHandle_t h_sym[TP_MAX][3];       // [rank][buffer]: 0/1 = double-buffered partials, 2 = the gather buffer of the two-shot all-reduce
@@ -40,7 +43,8 @@ struct TpShm {                                 // lives in POSIX shared memory
 
 class TpComm {
 public:
-    TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, int max_sample, uint64_t nonce = 0);
+    // nvls_bytes > 0: also try to set up an NVLink-switch multicast buffer of that size (in-switch all-reduce); nvls() tells whether every rank succeeded
+    TpComm(int t, int rank, const std::string& shm_name, size_t sym_bytes, int max_sample, uint64_t nonce = 0, size_t nvls_bytes = 0);
     ~TpComm();
     int size() const { return t_; }
     int rank() const { return rank_; }
@@ -49,6 +53,11 @@ public:
     int next_buffer() { return (int)(ar_count_++ & 1); }                // double-buffered symmetric storage
     void* sym(int b) const { return sym_[b]; }                            // this rank's buffer b (0/1: partials, alternating; 2: gather buffer)
     static constexpr int GATHER = 2;
+    // in-switch (NVLS) buffer: this rank's copy at a unicast address, the multicast address spanning every rank's copy
+    bool nvls() const { return nvls_uc_ != nullptr; }
+    void* nvls_local() const { return nvls_uc_; }
+    void* nvls_multicast() const { return nvls_mc_; }
+    size_t nvls_bytes() const { return nvls_bytes_; }
     void* const* d_peer_sym(int b) const { return d_peer_sym_[b]; }       // device array [t] of peer pointers for buffer b
     void* peer_sym_host(int b, int p) const { return peer_sym_[b][p]; }
     size_t sym_bytes() const { return sym_bytes_; }
@@ -67,6 +76,9 @@ public:
     void shutdown();
 
 private:
+    bool nvls_setup(size_t bytes_wanted, uint64_t nonce);      // tp_nvls.cpp
+    void nvls_teardown();
+    void* nvls_uc_ = nullptr; void* nvls_mc_ = nullptr; size_t nvls_bytes_ = 0; unsigned long long nvls_mem_ = 0, nvls_obj_ = 0;
     int t_, rank_; std::string shm_name_; TpShm* shm_ = nullptr; bool owner_ = false;
     void* sym_[3] = {nullptr, nullptr, nullptr}; void* peer_sym_[3][TP_MAX] = {};
     void** d_peer_sym_[3] = {nullptr, nullptr, nullptr};
@@ -79,6 +91,12 @@ private:
 // `wait` != null: every CTA first waits for all peers' signals of that epoch (TpComm::next_signal) instead of a preceding barrier launch
 cudaError_t launch_ar_resid_rmsnorm(void* const* d_peer, int t, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s,
                                     const TpComm::Signal* wait = nullptr);
+// In-switch variant (NVLS): every rank's fp32 partial sits in its copy of the multicast buffer at `part_off`; rank r asks the switch for the SUM of
+// slice r (multimem.ld_reduce) and broadcasts it into every copy at `red_off` (multimem.st); after one cross-GPU handshake each rank finishes
+// residual + RMSNorm from its LOCAL copy.  2/t of a partial crosses a rank's links instead of t-1 partials.  `wait`: peers' partials are written;
+// `mid`: the second handshake (all slices broadcast).  Grid = T CTAs, all co-resident.
+cudaError_t launch_ar_nvls_resid_rmsnorm(const void* mc_base, const void* local_base, size_t part_off, size_t red_off, int t, int rank, void* x, const void* gain, void* xn,
+                                         int T, int H, float eps, cudaStream_t s, const TpComm::Signal& wait, const TpComm::Signal& mid);
 // the same with bf16 partial rows (half the NVLink bytes; engine option tp_ar_bf16)
 cudaError_t launch_ar_resid_rmsnorm_bf16in(void* const* d_peer, int t, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s,
                                            const TpComm::Signal* wait = nullptr);

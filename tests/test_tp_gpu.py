@@ -13,12 +13,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("t", [2, 4, 8])
-def test_tensor_parallel_matches_oracle(t):
+@pytest.mark.parametrize("t,extra", [(2, "{}"), (2, '{"tp_nvls": 0}'), (2, '{"tp_nvls": 0, "tp_ar_bf16": 0}'), (4, "{}"), (8, "{}")])
+def test_tensor_parallel_matches_oracle(t, extra):
+    """default: decode all-reduce inside the NVLink switch (multimem) where the box offers multicast, else bf16 peer-memory one-shot;
+    tp_nvls=0: the peer-memory variants (bf16 and fp32 partials)"""
     if torch.cuda.device_count() < t:
         pytest.skip(f"needs {t} GPUs")
     cmd = [sys.executable, "-u", "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={t}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29600 + t), os.path.join(ROOT, "tests", "tp_worker.py")]
+           "--master-port", str(29600 + t), os.path.join(ROOT, "tests", "tp_worker.py"), extra]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0 and "TP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -18,7 +18,7 @@ LOGIT_TOL = 2.5e-2
 DEFAULT_CASES = {2: ["tiny-llama-tp", "tiny-qwen-tp"], 4: ["tiny-llama-tp", "tiny-qwen-tp4"], 8: ["tiny-llama-tp8"]}
 
 
-def run_cases(rank: int, world: int, cases=None, tag: str = "0", log=print) -> dict:
+def run_cases(rank: int, world: int, cases=None, tag: str = "0", log=print, extra: dict | None = None) -> dict:
     """-> on rank 0: {"t", "cases", "max_dlogit", "tokens_identical", "tokens_compared", "ok"}; on followers: {} (they only serve)."""
     from opsagent_b200 import Engine
     cases = list(cases or DEFAULT_CASES.get(world, ["tiny-llama-tp"]))
@@ -34,7 +34,10 @@ def run_cases(rank: int, world: int, cases=None, tag: str = "0", log=print) -> d
         cfg.update(num_pages=64, max_seq_len=512, max_batch=16, max_step_tokens=256, device=rank, tp=world, tp_rank=rank,
                    tp_two_shot_rows=160,        # prefill chunks of 200 / 256 rows: two-shot all-reduce; 150 rows: one-shot (both paths covered)
                    tp_shm=f"/oa_tp_{tag}_{name}", tp_nonce=int(tag) if str(tag).isdigit() else 0)
+        cfg.update(extra or {})
         eng = Engine(cfg)
+        if rank == 0:
+            out.setdefault("nvls", []).append(int(eng.info.get("tp_nvls", 0)))
         if rank > 0:
             eng.serve(); eng.close()
             continue
@@ -81,7 +84,9 @@ def run_cases(rank: int, world: int, cases=None, tag: str = "0", log=print) -> d
 
 if __name__ == "__main__":
     rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    res = run_cases(rank, world, sys.argv[1:] or None, tag=os.environ.get("MASTER_PORT", "0"), log=lambda m: print(m, flush=True))
+    import json
+    res = run_cases(rank, world, [a for a in sys.argv[1:] if not a.startswith("{")] or None, tag=os.environ.get("MASTER_PORT", "0"), log=lambda m: print(m, flush=True),
+                    extra=next((json.loads(a) for a in sys.argv[1:] if a.startswith("{")), None))
     if rank == 0:
         print(res, flush=True)
         assert res["ok"], res
