@@ -124,7 +124,8 @@ struct EngineOptions {
     int tp = 1, tp_rank = 0;      // tensor parallel degree / this process's rank (one process per GPU)
     std::string tp_shm = "/oa_tp"; // POSIX shm name shared by the ranks of one TP group
     int tp_ar_bf16 = 1;            // decode all-reduce on bf16 partials (half the NVLink bytes; the prefill path always exchanged bf16); 0 = fp32 partials
-    int tp_nvls = 1;               // decode all-reduce inside the NVLink switch (multimem.ld_reduce / multimem.st on a multicast buffer) when every rank can set it up; 0 = peer-memory one-shot
+    int tp_nvls = 0;               // 1: decode all-reduce inside the NVLink switch (multimem.ld_reduce / multimem.st on a multicast buffer, tp_nvls.cpp) when every rank can set it up.  Built, parity-green,
+                                   // measured SLOWER than the peer-memory one-shot at decode sizes (t=2: 38.6-43.2 vs 25.1 us per all-reduce: three dependent cross-GPU latencies instead of one; profiles/r02g_nvls.md): opt-in
     int tp_two_shot_rows = 1024;   // prefill chunks of at least this many rows use the two-shot all-reduce (reduce-scatter + all-gather: 2(t-1)/t instead of (t-1) partials' bytes per rank); smaller ones the one-shot
     uint64_t tp_nonce = 0;         // per-launch id shared by the ranks (e.g. the rendezvous port + a timestamp): followers ignore segments of other launches (0 = not checked)
 };

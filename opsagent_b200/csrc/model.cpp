@@ -225,7 +225,7 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
         const size_t sym_bytes = std::max({(size_t)MR * H * 2, (size_t)256 * H * 4, (size_t)256 * V_l * 4});
         // NVLS buffer: two partial + two reduced regions of 128 rows x H fp32 (decode batches: <= 128 rows on the stream-K path)
         nvls_region_ = (size_t)128 * H * 4;
-        comm.reset(new TpComm(tp, tp_rank, opt.tp_shm, sym_bytes, max_sample_, opt.tp_nonce, opt.tp_nvls ? 4 * nvls_region_ : 0));
+        comm.reset(new TpComm(tp, tp_rank, opt.tp_shm, sym_bytes, max_sample_, opt.tp_nonce, opt.tp_nvls ? 4 * nvls_region_ + 4096 : 0));      // + per-row flags: [2 buffers][128 rows] uint32 epochs
     }
     cuda_check(cudaStreamSynchronize(stream), "init sync");
 }
@@ -565,11 +565,10 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
                 const int b = comm->next_buffer();
                 const TpComm::Signal sg = comm->next_signal();     // "buffer written" handshake rides on the two kernels: no barrier launch
                 if (comm->nvls() && T <= 128) {
-                    const TpComm::Signal sg2 = comm->next_signal();
                     char* loc = reinterpret_cast<char*>(comm->nvls_local());
                     cuda_check(launch_sk_reduce_f32(sk_o, reinterpret_cast<float*>(loc + (size_t)b * nvls_region_), T, H, stream, &sg), "o partial -> multicast buffer");
-                    cuda_check(launch_ar_nvls_resid_rmsnorm(comm->nvls_multicast(), loc, (size_t)b * nvls_region_, (size_t)(2 + b) * nvls_region_, tp, tp_rank, x_, ly.ln2, xn_, T, H,
-                                                            cfg.rms_eps, stream, sg, sg2), "in-switch allreduce+resid+rmsnorm2");
+                    cuda_check(launch_ar_nvls_resid_rmsnorm(comm->nvls_multicast(), loc, (size_t)b * nvls_region_, (size_t)(2 + b) * nvls_region_, 4 * nvls_region_ + (size_t)b * 512, tp, tp_rank,
+                                                            x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream, sg), "in-switch allreduce+resid+rmsnorm2");
                 } else if (opt.tp_ar_bf16) {
                     cuda_check(launch_sk_reduce_bf16(sk_o, comm->sym(b), T, H, stream, &sg), "o partial -> symmetric buffer (bf16)");
                     cuda_check(launch_ar_resid_rmsnorm_bf16in(comm->d_peer_sym(b), tp, x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream, &sg), "allreduce+resid+rmsnorm2");
@@ -604,11 +603,10 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
                 const int b = comm->next_buffer();
                 const TpComm::Signal sg = comm->next_signal();
                 if (comm->nvls() && T <= 128) {
-                    const TpComm::Signal sg2 = comm->next_signal();
                     char* loc = reinterpret_cast<char*>(comm->nvls_local());
                     cuda_check(launch_sk_reduce_f32(sk_dn, reinterpret_cast<float*>(loc + (size_t)b * nvls_region_), T, H, stream, &sg), "down partial -> multicast buffer");
-                    cuda_check(launch_ar_nvls_resid_rmsnorm(comm->nvls_multicast(), loc, (size_t)b * nvls_region_, (size_t)(2 + b) * nvls_region_, tp, tp_rank, x_, next_gain, xn_, T, H,
-                                                            cfg.rms_eps, stream, sg, sg2), "in-switch allreduce+resid+rmsnorm1");
+                    cuda_check(launch_ar_nvls_resid_rmsnorm(comm->nvls_multicast(), loc, (size_t)b * nvls_region_, (size_t)(2 + b) * nvls_region_, 4 * nvls_region_ + (size_t)b * 512, tp, tp_rank,
+                                                            x_, next_gain, xn_, T, H, cfg.rms_eps, stream, sg), "in-switch allreduce+resid+rmsnorm1");
                 } else if (opt.tp_ar_bf16) {
                     cuda_check(launch_sk_reduce_bf16(sk_dn, comm->sym(b), T, H, stream, &sg), "down partial -> symmetric buffer (bf16)");
                     cuda_check(launch_ar_resid_rmsnorm_bf16in(comm->d_peer_sym(b), tp, x_, next_gain, xn_, T, H, cfg.rms_eps, stream, &sg), "allreduce+resid+rmsnorm1");

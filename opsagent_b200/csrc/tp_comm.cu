@@ -307,28 +307,39 @@ OA_DEVINL float4 multimem_ld_reduce_f4(const float* mc) {
 OA_DEVINL void multimem_st_f4(float* mc, const float4& v) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+OA_DEVINL void multimem_st_release_u32(uint32_t* mc, uint32_t v) { asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory"); }
+// One CTA per token row.  Row c is OWNED by rank c % t: the owner's CTA asks the switch for the sum of the row over all ranks and broadcasts it,
+// then broadcasts the row's flag (multimem.st.release after a system fence); every rank's CTA c waits for exactly that one flag in its local copy
+// and finishes residual + RMSNorm from local memory.  No grid-wide barrier and no all-to-all handshake in the middle: the only cross-GPU
+// round trips are the owner's ld_reduce and its two broadcasts.
 __global__ void __launch_bounds__(AR_THREADS) ar_nvls_resid_rmsnorm_kernel(const float* __restrict__ mc_part, float* __restrict__ mc_red, const float* __restrict__ local_red,
+                                                                           uint32_t* __restrict__ mc_flags, const uint32_t* __restrict__ local_flags,
                                                                            int t, int rank, uint2* __restrict__ x, const uint2* __restrict__ g, uint2* __restrict__ y,
-                                                                           int T, int H4, float inv_h, float eps, const TpComm::Signal sg_in, const TpComm::Signal sg_mid) {
+                                                                           int H4, float inv_h, float eps, const TpComm::Signal sg_in, uint32_t epoch) {
     griddep_wait();
-    xgpu_wait_peers(sg_in);                                   // every rank's partial is complete in its copy of the buffer
-    {   // reduce-scatter + all-gather through the switch: slice `rank` of the T x H matrix, spread over this rank's CTAs
-        const size_t n4 = (size_t)T * H4, per = (n4 + (size_t)t - 1) / (size_t)t;
-        const size_t lo = (size_t)rank * per < n4 ? (size_t)rank * per : n4, hi = lo + per < n4 ? lo + per : n4;
-        for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
-            const float4 v = multimem_ld_reduce_f4(mc_part + i * 4);
-            multimem_st_f4(mc_red + i * 4, v);
+    const int row = blockIdx.x;
+    if (row % t == rank) {
+        xgpu_wait_peers(sg_in);                               // every rank's partial is complete in its copy of the buffer
+        for (int i = threadIdx.x; i < H4; i += AR_THREADS) {
+            const float4 v = multimem_ld_reduce_f4(mc_part + ((size_t)row * H4 + i) * 4);
+            multimem_st_f4(mc_red + ((size_t)row * H4 + i) * 4, v);
         }
         __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence_system(); multimem_st_release_u32(mc_flags + row, epoch); }
     }
-    xgpu_signal_when_grid_done(sg_mid, gridDim.x);            // this rank's slice has been broadcast ...
-    xgpu_wait_peers(sg_mid);                                  // ... and so has everybody else's
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(local_flags + row) - epoch) < 0) {
+            if (clock64() - t0 > (long long)3.0e10) __trap();          // ~15 s: the row's owner died
+        }
+    }
+    __syncthreads();
     griddep_launch();
-    const int row = blockIdx.x;
     uint2* xr = x + (size_t)row * H4;
     float ss = 0.f;
     for (int i = threadIdx.x; i < H4; i += AR_THREADS) {
-        const float4 a = __ldcg(reinterpret_cast<const float4*>(local_red) + (size_t)row * H4 + i);      // written by remote multicast stores: bypass L1
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(local_red) + (size_t)row * H4 + i);      // written by a multicast store: bypass L1
         const uint2 xo = xr[i];
         uint2 xn;
         xn.x = pack_bf16x2(bf16lo(xo.x) + a.x, bf16hi(xo.x) + a.y); xn.y = pack_bf16x2(bf16lo(xo.y) + a.z, bf16hi(xo.y) + a.w);
@@ -352,14 +363,14 @@ __global__ void __launch_bounds__(AR_THREADS) ar_nvls_resid_rmsnorm_kernel(const
         yr[i] = o;
     }
 }
-cudaError_t launch_ar_nvls_resid_rmsnorm(const void* mc_base, const void* local_base, size_t part_off, size_t red_off, int t, int rank, void* x, const void* gain, void* xn,
-                                         int T, int H, float eps, cudaStream_t s, const TpComm::Signal& wait, const TpComm::Signal& mid) {
+cudaError_t launch_ar_nvls_resid_rmsnorm(const void* mc_base, const void* local_base, size_t part_off, size_t red_off, size_t flag_off, int t, int rank, void* x,
+                                         const void* gain, void* xn, int T, int H, float eps, cudaStream_t s, const TpComm::Signal& wait) {
     if (T <= 0) return cudaSuccess;
-    if (H % 8 != 0 || T > 148) return cudaErrorInvalidValue;            // every CTA waits for every peer: the grid must be co-resident
-    const char* mc = reinterpret_cast<const char*>(mc_base); const char* lc = reinterpret_cast<const char*>(local_base);
-    return launch_k(ar_nvls_resid_rmsnorm_kernel, dim3(T), dim3(AR_THREADS), 0, s, reinterpret_cast<const float*>(mc + part_off),
-                    reinterpret_cast<float*>(const_cast<char*>(mc) + red_off), reinterpret_cast<const float*>(lc + red_off), t, rank, reinterpret_cast<uint2*>(x),
-                    reinterpret_cast<const uint2*>(gain), reinterpret_cast<uint2*>(xn), T, H / 4, 1.0f / H, eps, wait, mid);
+    if (H % 8 != 0 || T > 148) return cudaErrorInvalidValue;            // CTAs wait for flags set by other ranks' CTAs of the same launch: keep the grid co-resident
+    char* mc = reinterpret_cast<char*>(const_cast<void*>(mc_base)); const char* lc = reinterpret_cast<const char*>(local_base);
+    return launch_k(ar_nvls_resid_rmsnorm_kernel, dim3(T), dim3(AR_THREADS), 0, s, reinterpret_cast<const float*>(mc + part_off), reinterpret_cast<float*>(mc + red_off),
+                    reinterpret_cast<const float*>(lc + red_off), reinterpret_cast<uint32_t*>(mc + flag_off), reinterpret_cast<const uint32_t*>(lc + flag_off), t, rank,
+                    reinterpret_cast<uint2*>(x), reinterpret_cast<const uint2*>(gain), reinterpret_cast<uint2*>(xn), H / 4, 1.0f / H, eps, wait, wait.epoch);
 }
 
 // The same collective on bf16 partials: half the NVLink bytes (the one-shot all-reduce of a decode step is bandwidth-bound: every rank

@@ -91,12 +91,12 @@ private:
 // `wait` != null: every CTA first waits for all peers' signals of that epoch (TpComm::next_signal) instead of a preceding barrier launch
 cudaError_t launch_ar_resid_rmsnorm(void* const* d_peer, int t, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s,
                                     const TpComm::Signal* wait = nullptr);
-// In-switch variant (NVLS): every rank's fp32 partial sits in its copy of the multicast buffer at `part_off`; rank r asks the switch for the SUM of
-// slice r (multimem.ld_reduce) and broadcasts it into every copy at `red_off` (multimem.st); after one cross-GPU handshake each rank finishes
-// residual + RMSNorm from its LOCAL copy.  2/t of a partial crosses a rank's links instead of t-1 partials.  `wait`: peers' partials are written;
-// `mid`: the second handshake (all slices broadcast).  Grid = T CTAs, all co-resident.
-cudaError_t launch_ar_nvls_resid_rmsnorm(const void* mc_base, const void* local_base, size_t part_off, size_t red_off, int t, int rank, void* x, const void* gain, void* xn,
-                                         int T, int H, float eps, cudaStream_t s, const TpComm::Signal& wait, const TpComm::Signal& mid);
+// In-switch variant (NVLS): every rank's fp32 partial sits in its copy of the multicast buffer at `part_off`.  Token row c is owned by rank c % t:
+// the owner asks the switch for the row's SUM over all ranks (multimem.ld_reduce), broadcasts it into every copy at `red_off` (multimem.st) and then
+// broadcasts the row's flag (uint32 epochs at `flag_off`, multimem.st.release); every rank finishes residual + RMSNorm of row c from its LOCAL copy
+// once its local flag shows the epoch.  2/t of a partial crosses a rank's links instead of t-1 partials; `wait` = peers' partials are written.
+cudaError_t launch_ar_nvls_resid_rmsnorm(const void* mc_base, const void* local_base, size_t part_off, size_t red_off, size_t flag_off, int t, int rank, void* x,
+                                         const void* gain, void* xn, int T, int H, float eps, cudaStream_t s, const TpComm::Signal& wait);
 // the same with bf16 partial rows (half the NVLink bytes; engine option tp_ar_bf16)
 cudaError_t launch_ar_resid_rmsnorm_bf16in(void* const* d_peer, int t, void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s,
                                            const TpComm::Signal* wait = nullptr);

@@ -13,10 +13,10 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("t,extra", [(2, "{}"), (2, '{"tp_nvls": 0}'), (2, '{"tp_nvls": 0, "tp_ar_bf16": 0}'), (4, "{}"), (8, "{}")])
+@pytest.mark.parametrize("t,extra", [(2, "{}"), (2, '{"tp_nvls": 1}'), (2, '{"tp_ar_bf16": 0}'), (4, "{}"), (8, "{}")])
 def test_tensor_parallel_matches_oracle(t, extra):
-    """default: decode all-reduce inside the NVLink switch (multimem) where the box offers multicast, else bf16 peer-memory one-shot;
-    tp_nvls=0: the peer-memory variants (bf16 and fp32 partials)"""
+    """default: bf16 peer-memory one-shot all-reduce for decode steps, two-shot for prefill-sized chunks; tp_nvls=1: the in-switch (multimem)
+    decode all-reduce where the box offers multicast; tp_ar_bf16=0: fp32 partials"""
     if torch.cuda.device_count() < t:
         pytest.skip(f"needs {t} GPUs")
     cmd = [sys.executable, "-u", "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={t}", "--master-addr", "127.0.0.1",
