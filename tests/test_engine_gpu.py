@@ -641,3 +641,29 @@ def test_cluster_splitk_projections_match_oracle_and_streamk(name):
                 k += 1
             assert k == 24 or margins[k] <= 2 * LOGIT_TOL, (k, margins[k])
         orc.close()
+
+
+def test_router_keeps_conversations_on_the_replica_that_holds_their_prefix():
+    """opsagent_b200/router.py over REAL engines (two replicas on this GPU): steps of one ReAct conversation — the history is resent every step,
+    simple.go:498-501 — always reach the replica whose prefix cache holds the earlier steps' pages; new conversations spread; results equal a
+    single engine's (greedy, same weights)."""
+    from opsagent_b200.router import Router
+    spec = O.PRESETS["tiny-llama"]
+    cfg = spec.engine_json(num_pages=96, max_seq_len=1024, max_batch=8, max_step_tokens=256, prefix_cache=1)
+    rt = Router.create(cfg, devices=[0, 0], max_inflight=8)
+    solo = Engine(cfg)
+    convs = {c: [("system", "You are a Kubernetes expert. " * 6), ("user", f"question number {c}: why is pod web-{c} crashing? " * 3)] for c in range(4)}
+    home = {}
+    for step in range(3):
+        for c, msgs in convs.items():
+            out = rt.chat_complete(spec.name, msgs, 8, flags=1)
+            ref = solo.chat_complete(spec.name, msgs, 8, flags=1)
+            assert list(out.token_ids) == list(ref.token_ids)
+            r = rt.replica_of(msgs)
+            assert home.setdefault(c, r) == r
+            msgs += [("assistant", bytes(out.content).decode("latin-1")), ("user", "observation: NAME READY STATUS\nweb-0 0/1 CrashLoopBackOff " * 2)]
+    st = rt.stats()
+    assert sorted(st["routed"]) == [6, 6] and st["sticky_hits"] == 8                     # 4 conversations x 3 steps, 2 per replica, steps 2-3 sticky
+    per = st["per_replica"]
+    assert all(p["prefix_hit_tokens"] >= 2 * 2 * 64 for p in per)                          # later steps found their earlier pages on their home replica
+    rt.close(); solo.close()
