@@ -33,7 +33,7 @@ def check_base(line):
     assert line["cpu_baseline"]["kind"] in ("port", "reference")
 
 
-@pytest.mark.parametrize("name", ["r01h_bench.json", "r01h_bench_dp4.json", "r02a_bench.json", "r02b_bench_dp4.json", "r02c_bench_dp8.json"])
+@pytest.mark.parametrize("name", ["r01h_bench.json", "r01h_bench_dp4.json", "r02a_bench.json", "r02h_bench.json", "r02b_bench_dp4.json", "r02f_bench_dp4.json", "r02c_bench_dp8.json"])
 def test_our_arm_line(name):
     line = load(name)
     if "dp" in name:
@@ -66,10 +66,11 @@ def test_our_arm_line(name):
     assert r["traffic"] is None or r["traffic"] >= 0.9 * r["algorithmic_bytes_per_launch"]
 
 
-def test_reference_arm_line():
-    line = load("r01h_bench_reference_arm.json")
+@pytest.mark.parametrize("ref,ours_name", [("r01h_bench_reference_arm.json", "r01h_bench.json"), ("r02h_bench_reference_arm.json", "r02h_bench.json")])
+def test_reference_arm_line(ref, ours_name):
+    line = load(ref)
     check_base(line)
-    ours = load("r01h_bench.json")
+    ours = load(ours_name)
     assert line["impl"] == "reference" and line["gpu_launches"] == 0
     for k in ("metric", "unit", "higher_is_better"):
         assert line[k] == ours[k]
