@@ -145,77 +145,126 @@ def run_tp_block(args, rank, world, nonce, log):
     return block
 
 
-def router_block(args, rank, world, barrier):
+def router_block(args, rank, world, barrier, dist=None, cpu_group=None):
     """BASELINE configs[2] as it would be SERVED: one front process (rank 0) owning one engine per GPU behind the OpenAI-compatible HTTP
-    endpoint (opsagent_b200/router.py + http_front.py; the reference is one process too, pkg/api/router.go:95), world*128 concurrent
-    clients POSTing the 40/30/30 mix with the reference's wire format.  Sticky least-loaded routing, no data-path collective.
-    The other ranks have closed their engines and idle at the barrier."""
+    endpoint (the reference is one process too, pkg/api/router.go:95) — csrc/http_server.cpp, native, routing inside the server (or, with
+    --router-front python, router.py + http_front.py).  world*128 concurrent HTTP clients POST the 40/30/30 mix in the reference's wire
+    format; the clients are spread over ALL ranks' processes (the ranks other than 0 have closed their engines and have nothing else to do),
+    so the load generator's interpreter is not what is measured.  Sticky least-loaded routing, no data-path collective."""
+    import http.client
+    import resource
+    import torch
     barrier()
-    out = None
+    try:
+        soft, hard = resource.getrlimit(resource.RLIMIT_NOFILE)
+        resource.setrlimit(resource.RLIMIT_NOFILE, (min(hard, 65536) if hard > 0 else 65536, hard))
+    except Exception:
+        pass
+    sys.setswitchinterval(2e-4)
+    n_req = world * BATCH
+    setup = [None]
+    front = rt = srv = None
     if rank == 0:
-        import http.client
-        import resource
-        from opsagent_b200 import workloads as WL
-        from opsagent_b200.http_front import serve
-        from opsagent_b200.router import Router
         try:
-            soft, hard = resource.getrlimit(resource.RLIMIT_NOFILE)
-            resource.setrlimit(resource.RLIMIT_NOFILE, (min(hard, 65536) if hard > 0 else 65536, hard))
-        except Exception:
-            pass
-        # hundreds of Python threads (clients AND the front's handlers live in this process): with the default 5 ms GIL switch interval the
-        # accept loop and the handlers take turns in 5 ms slices and arrivals trickle in over seconds
-        sys.setswitchinterval(2e-4)
-        cfg = {"model": MODEL, "kv_gb": args.kv_gb, "max_batch": BATCH, "max_seq_len": 2048, "max_step_tokens": 8192, "seed": 1234, "tokenizer": TOKENIZER,
-               "prefix_cache": 0, "max_queue": 4096, **json.loads(args.engine_extra)}
-        rt = Router.create(cfg, list(range(world)), max_inflight=2 * BATCH)
-        srv, _th = serve(rt, port=0)
-        port = srv.server_address[1]
-        n_req = world * BATCH
-        bodies = []
-        kinds = {}
-        for gi in range(n_req):
-            k, m = WL.mixed_request(gi, rt.count_tokens, p_analyze=PROMPT)
-            kinds[k] = kinds.get(k, 0) + 1
-            bodies.append(json.dumps({"model": MODEL, "max_tokens": GEN, "temperature": 1.401298464324817e-45,
-                                      "messages": [{"role": x.Role, "content": x.Content} for x in m]}).encode("utf-8"))
-        usage = [None] * n_req
+            from opsagent_b200 import workloads as WL
+            from opsagent_b200.router import Router
+            cfg = {"model": MODEL, "kv_gb": args.kv_gb, "max_batch": BATCH, "max_seq_len": 2048, "max_step_tokens": 8192, "seed": 1234, "tokenizer": TOKENIZER,
+                   "prefix_cache": 0, "max_queue": 4096, **json.loads(args.engine_extra)}
+            rt = Router.create(cfg, list(range(world)), max_inflight=2 * BATCH)          # engine creation in parallel; the Router object itself only routes in python mode
+            if args.router_front == "native":
+                from opsagent_b200.native_front import NativeFront
+                front = NativeFront(rt.engines, max_inflight=2 * BATCH)
+                port = front.port
+            else:
+                from opsagent_b200.http_front import serve
+                srv, _th = serve(rt, port=0)
+                port = srv.server_address[1]
+            bodies, kinds = [], {}
+            for gi in range(n_req):
+                k, m = WL.mixed_request(gi, rt.count_tokens, p_analyze=PROMPT)
+                kinds[k] = kinds.get(k, 0) + 1
+                bodies.append(json.dumps({"model": MODEL, "max_tokens": GEN, "temperature": 1.401298464324817e-45,
+                                          "messages": [{"role": x.Role, "content": x.Content} for x in m]}).encode("utf-8"))
+            setup = [{"port": port, "bodies": bodies, "kinds": kinds}]
+        except Exception as e:      # noqa: BLE001
+            setup = [{"error": f"{type(e).__name__}: {e}"}]
+    if dist is not None:
+        dist.broadcast_object_list(setup, src=0, group=cpu_group)
+    cfgd = setup[0]
+    if "error" in cfgd:
+        barrier()
+        return cfgd if rank == 0 else None
+    port, bodies = cfgd["port"], cfgd["bodies"]
+    mine = [i for i in range(n_req) if i % world == rank]
+    usage = {}
 
-        def post(i):
+    def post(i):
+        try:
             c = http.client.HTTPConnection("127.0.0.1", port, timeout=600)
             c.request("POST", "/v1/chat/completions", body=bodies[i], headers={"Content-Type": "application/json", "Authorization": "Bearer sk-local"})
             r = c.getresponse(); d = json.loads(r.read()); c.close()
             usage[i] = d["usage"] if r.status == 200 else {"error": r.status}
+        except Exception as e:      # noqa: BLE001
+            usage[i] = {"error": f"{type(e).__name__}: {e}"}
 
-        def round_(idx):
-            idx = list(idx)
-            go = threading.Barrier(len(idx) + 1)
+    def stats():
+        if front is not None:
+            st = front.stats()
+            return {"routed": st["routed"], "rejected_429": st["rejected_429"], "per_replica": st["engines"]}
+        return rt.stats()
 
-            def client(i):
-                go.wait()
-                post(i)
-            th = [threading.Thread(target=client, args=(i,)) for i in idx]
-            [t.start() for t in th]
-            go.wait()                                                  # every client thread exists: they all connect now
-            t0 = time.perf_counter()
-            [t.join() for t in th]
-            return time.perf_counter() - t0
-        round_(range(0, n_req, 16))                                # warm-up: a few requests on every replica
-        s0 = rt.stats()
-        dt = round_(range(n_req))
-        s1 = rt.stats()
-        ok = [u for u in usage if u and "error" not in u]
+    def round_(idx):
+        idx = list(idx)
+        go = threading.Barrier(len(idx) + 1)
+
+        def client(i):
+            go.wait()
+            post(i)
+        th = [threading.Thread(target=client, args=(i,)) for i in idx]
+        [t.start() for t in th]
+        barrier()                                                  # every rank's client threads exist
+        go.wait()                                                  # they all connect now
+        t0 = time.perf_counter()
+        [t.join() for t in th]
+        dt = time.perf_counter() - t0
+        if dist is not None:                                       # the round ends when the slowest rank's last response is in
+            t = torch.tensor([dt], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=cpu_group)
+            dt = float(t.item())
+        return dt
+    round_(mine[::16])                                             # warm-up: a few requests on every replica
+    s0 = stats() if rank == 0 else None
+    usage.clear()
+    dt = round_(mine)
+    s1 = stats() if rank == 0 else None
+    gathered = [None] * world
+    if dist is not None:
+        dist.all_gather_object(gathered, usage, group=cpu_group)
+    else:
+        gathered = [usage]
+    out = None
+    if rank == 0:
+        allu = {}
+        for g in gathered:
+            allu.update(g)
+        ok = [u for u in allu.values() if u and "error" not in u]
+        errs = sorted({str(u["error"]) for u in allu.values() if u and "error" in u})
         comp = sum(u["completion_tokens"] for u in ok)
-        out = {"workload": f"BASELINE configs[2] served: {n_req} concurrent HTTP clients -> one front (router + OpenAI-compatible endpoint) -> {world} engines; "
-                           "mix 40% analyze (P=1536) / 30% diagnose / 30% execute, verbatim reference prompts, max_tokens 256",
-               "requests": n_req, "completed": len(ok), "by_kind": kinds, "seconds": round(dt, 3),
+        fw = lambda st: sum(p["prefill_steps"] + p["decode_steps"] for p in st["per_replica"])      # noqa: E731
+        out = {"workload": f"BASELINE configs[2] served: {n_req} concurrent HTTP clients (spread over the {world} rank processes) -> one front process ({args.router_front}: "
+                           f"OpenAI-compatible endpoint + sticky least-loaded routing) -> {world} engines; mix 40% analyze (P=1536) / 30% diagnose / 30% execute, "
+                           "verbatim reference prompts, max_tokens 256",
+               "front": args.router_front, "requests": n_req, "completed": len(ok), "errors": errs, "by_kind": cfgd["kinds"], "seconds": round(dt, 3),
                "e2e_tokens_per_sec": round(comp / dt, 1), "react_steps_per_sec": round(len(ok) / dt, 2), "completion_tokens": comp,
                "prompt_tokens_mean": round(sum(u["prompt_tokens"] for u in ok) / max(1, len(ok)), 1),
                "routed_per_replica": [b - a for a, b in zip(s0["routed"], s1["routed"])], "rejected_429": s1["rejected_429"] - s0["rejected_429"],
-               "engine_forwards": (s1["prefill_steps"] - s0["prefill_steps"]) + (s1["decode_steps"] - s0["decode_steps"]),
-               "engine_busy_ms_max": round(max(b["busy_ms"] - a["busy_ms"] for a, b in zip(s0["per_replica"], s1["per_replica"])), 1),
-               "note": "clients and the Python front share one interpreter (GIL): the gap to `e2e` is host-side HTTP/JSON/thread scheduling, not engine time"}
-        srv.shutdown(); rt.close()
+               "engine_forwards": fw(s1) - fw(s0),
+               "engine_busy_ms_max": round(max(b["busy_ms"] - a["busy_ms"] for a, b in zip(s0["per_replica"], s1["per_replica"])), 1)}
+        if front is not None:
+            front.shutdown()
+        if srv is not None:
+            srv.shutdown()
+        rt.close()
     barrier()
     return out
 
@@ -455,7 +504,7 @@ def run_ours(args, rank, world, local_rank):
             line["react"] = rb
     if world >= 2 and not args.no_router:
         try:
-            rb = router_block(args, rank, world, host_barrier)
+            rb = router_block(args, rank, world, host_barrier, dist, cpu_group)
         except Exception as e:
             rb = {"error": f"{type(e).__name__}: {e}"}
             host_barrier()
@@ -535,6 +584,7 @@ def main():
     ap.add_argument("--kv-gb", type=float, default=60.0, dest="kv_gb")
     ap.add_argument("--cpu-tokens", type=int, default=24, dest="cpu_tokens")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--router-front", choices=["native", "python"], default="native", help="the serving block's front: csrc/http_server.cpp (default) or router.py + http_front.py")
     ap.add_argument("--no-router", action="store_true", help="N>=2: skip the one-front / N-engines serving block")
     ap.add_argument("--no-react", action="store_true", help="skip the multi-step ReAct block")
     ap.add_argument("--react-agents", type=int, default=128, dest="react_agents")

@@ -105,6 +105,19 @@ OA_API const char* oa_last_error(void);                      /* thread-local mes
 OA_API int oa_engine_stats(oa_engine*, char* buf, size_t n); /* JSON: steps, tokens, pages, launches, timings */
 OA_API int oa_model_info(oa_engine*, char* buf, size_t n);   /* JSON: resolved architecture */
 
+/* ---- native OpenAI-compatible HTTP front (csrc/http_server.cpp): what the UNMODIFIED reference binary is pointed at (`baseUrl` of POST /api/execute,
+ * pkg/handlers/execute.go:21,205; OPENAI_API_BASE for the swarm flows, pkg/workflows/swarm.go:83).  POST /v1/chat/completions in go-openai's wire
+ * format (openai.go:70-82) incl. `tools` -> grammar-forced `tool_calls`, GET /v1/models, GET /api/perf/stats.  One OS thread per connection; with
+ * n_engines > 1 (data-parallel replicas, BASELINE configs[2]) conversations stick to the replica holding their prefix pages, new ones go to the
+ * least-loaded replica, a replica over `max_inflight` answers 429 (openai.go:91-94 backs off).
+ * options_json (flat): {"host":"127.0.0.1","port":0,"require_key":1,"api_key":"","tool_steps":3,"max_inflight":256,"max_connections":8192} */
+typedef struct oa_http oa_http;
+OA_API int oa_http_start(oa_engine* const* engines, int32_t n_engines, const char* options_json, oa_http** out);
+OA_API int32_t oa_http_port(oa_http*);                        /* the bound port (options "port": 0 picks a free one) */
+OA_API int oa_http_stats(oa_http*, char* buf, size_t n);      /* JSON: requests, routed / in flight per replica, 429s, sticky hits, engine stats */
+OA_API void oa_http_stop(oa_http*);                           /* stops accepting, waits for the connection threads; the engines stay alive */
+OA_API const char* oa_http_last_error(void);
+
 /* ---- measurement + parity hooks (used by bench.py and tests/; not part of the Go seam) ---- */
 /* fresh single-sequence prefill of `tokens`; fp32 logits of every position -> logits_out[n, vocab] */
 OA_API int oa_debug_prefill_logits(oa_engine*, const int32_t* tokens, int32_t n, float* logits_out);
@@ -162,6 +175,7 @@ OA_API int oa_host_grammar_step_ex(int32_t kind, const char* functions, const ui
  * walk the automaton.  key_out receives the canonical cache key of the state (states with equal keys have equal masks). */
 OA_API int oa_host_grammar_token_mask(const char* tokenizer_json_path, int32_t vocab, int32_t kind, const char* functions, const uint8_t* prefix,
                                int32_t n, uint32_t* mask_out, int32_t cap_words, char* key_out, int32_t key_cap);
+OA_API int oa_host_json_roundtrip(const uint8_t* in, size_t n_in, char* out, size_t n_out);   /* the HTTP front's JSON reader + writer, for the CPU tests */
 /* resolved architecture + derived byte counts of a config, no device needed */
 OA_API int oa_host_model_info(const char* config_json, char* buf, size_t n);
 OA_API uint64_t oa_kernel_launches(void);

@@ -34,7 +34,7 @@ SYMBOLS = [
     "oa_tokens_submit", "oa_count_tokens", "oa_apply_chat_template", "oa_last_error", "oa_engine_stats", "oa_model_info",
     "oa_debug_prefill_logits", "oa_bench_decode", "oa_k_rmsnorm", "oa_k_gemm", "oa_k_init_weight", "oa_k_paged_attention",
     "oa_kernel_launches", "oa_version", "oa_host_apply_chat_template", "oa_host_decode_plan", "oa_host_streamk_plan", "oa_host_bpe_encode", "oa_host_bpe_decode", "oa_host_model_info",
-    "oa_k_gemm_streamk", "oa_debug_kernel_times", "oa_engine_serve", "oa_host_grammar_step", "oa_host_grammar_step_ex", "oa_host_grammar_token_mask", "oa_chat_cancel", "oa_chat_submit_ex", "oa_chat_wait_ex",
+    "oa_k_gemm_streamk", "oa_debug_kernel_times", "oa_engine_serve", "oa_host_grammar_step", "oa_host_grammar_step_ex", "oa_host_grammar_token_mask", "oa_http_start", "oa_http_port", "oa_http_stats", "oa_http_stop", "oa_http_last_error", "oa_host_json_roundtrip", "oa_chat_cancel", "oa_chat_submit_ex", "oa_chat_wait_ex",
 ]
 
 _lib = None
@@ -81,6 +81,12 @@ def load() -> C.CDLL:
     L.oa_host_grammar_step.argtypes = [i32, vp, i32, vp, C.POINTER(i32)]; L.oa_host_grammar_step.restype = C.c_int
     L.oa_host_grammar_step_ex.argtypes = [i32, C.c_char_p, vp, i32, vp, C.POINTER(i32)]; L.oa_host_grammar_step_ex.restype = C.c_int
     L.oa_host_grammar_token_mask.argtypes = [C.c_char_p, i32, i32, C.c_char_p, vp, i32, vp, i32, C.c_char_p, i32]; L.oa_host_grammar_token_mask.restype = C.c_int
+    L.oa_http_start.argtypes = [C.POINTER(vp), i32, C.c_char_p, C.POINTER(vp)]; L.oa_http_start.restype = C.c_int
+    L.oa_http_port.argtypes = [vp]; L.oa_http_port.restype = i32
+    L.oa_http_stats.argtypes = [vp, C.c_char_p, C.c_size_t]; L.oa_http_stats.restype = C.c_int
+    L.oa_http_stop.argtypes = [vp]; L.oa_http_stop.restype = None
+    L.oa_http_last_error.restype = C.c_char_p
+    L.oa_host_json_roundtrip.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]; L.oa_host_json_roundtrip.restype = C.c_int
     L.oa_host_model_info.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]; L.oa_host_model_info.restype = C.c_int
     L.oa_kernel_launches.restype = u64
     L.oa_version.restype = C.c_char_p
