@@ -439,7 +439,8 @@ def test_full_size_llama_3_8b_matches_oracle():
     print("llama-3-8b analyze:", res)
 
 
-def test_http_front_function_calling_end_to_end_matches_oracle():
+@pytest.mark.parametrize("front", ["native", "python"])
+def test_http_front_function_calling_end_to_end_matches_oracle(front):
     """the swarm-go wire path (reference pkg/workflows/swarm.go:14-78, analyze.go:47-75): POST /v1/chat/completions with `tools`
     -> grammar-forced tool_calls whose bytes equal the oracle's constrained greedy decode; then a text answer."""
     import json as _json
@@ -447,8 +448,14 @@ def test_http_front_function_calling_end_to_end_matches_oracle():
     from opsagent_b200.http_front import serve
     spec, eng = make_engine("tiny-llama", max_seq_len=2048, num_pages=96)
     orc = O.Oracle(spec, max_pos=1024, mode=1)
-    srv, _ = serve(eng, port=0, tool_steps=1)
-    url = f"http://127.0.0.1:{srv.server_address[1]}/v1/chat/completions"
+    if front == "native":
+        from opsagent_b200.native_front import NativeFront
+        srv = NativeFront([eng], tool_steps=1)
+        port = srv.port
+    else:
+        srv, _ = serve(eng, port=0, tool_steps=1)
+        port = srv.server_address[1]
+    url = f"http://127.0.0.1:{port}/v1/chat/completions"
     tools = [{"type": "function", "function": {"name": "kubectl", "parameters": {"type": "object", "properties": {"command": {"type": "string"}}}}},
              {"type": "function", "function": {"name": "trivy", "parameters": {"type": "object", "properties": {"image": {"type": "string"}}}}}]
     msgs = [{"role": "system", "content": "You are an expert Kubernetes analyst."}, {"role": "user", "content": "analyze pod web-0"}]
@@ -667,3 +674,55 @@ def test_router_keeps_conversations_on_the_replica_that_holds_their_prefix():
     per = st["per_replica"]
     assert all(p["prefix_hit_tokens"] >= 2 * 2 * 64 for p in per)                          # later steps found their earlier pages on their home replica
     rt.close(); solo.close()
+
+
+
+def test_native_front_routes_conversations_like_the_router_and_answers_like_one_engine():
+    """csrc/http_server.cpp over two replicas on this GPU: concurrent HTTP conversations (ReAct: the history is resent every step) stay on their
+    replica, new ones spread, a replica over its in-flight limit answers 429, and every completion equals a single engine's greedy result."""
+    import json as _json
+    import http.client
+    import threading
+    from opsagent_b200.native_front import NativeFront
+    from opsagent_b200.router import Router
+    spec = O.PRESETS["tiny-llama"]
+    cfg = spec.engine_json(num_pages=96, max_seq_len=1024, max_batch=8, max_step_tokens=256, prefix_cache=1)
+    rt = Router.create(cfg, devices=[0, 0])
+    solo = Engine(cfg)
+    front = NativeFront(rt.engines, max_inflight=8)
+
+    def post(msgs, max_tokens=8):
+        c = http.client.HTTPConnection("127.0.0.1", front.port, timeout=120)
+        c.request("POST", "/v1/chat/completions", body=_json.dumps({"model": spec.name, "max_tokens": max_tokens, "messages": [{"role": r, "content": t} for r, t in msgs]}).encode(),
+                  headers={"Authorization": "Bearer sk-local", "Content-Type": "application/json"})
+        r = c.getresponse(); d = _json.loads(r.read()); c.close()
+        return r.status, d
+    convs = {c: [("system", "You are a Kubernetes expert. " * 6), ("user", f"question number {c}: why is pod web-{c} crashing? " * 3)] for c in range(4)}
+    for step in range(3):
+        res = {}
+
+        def run(c):
+            res[c] = post(convs[c])
+        th = [threading.Thread(target=run, args=(c,)) for c in convs]
+        [t.start() for t in th]; [t.join() for t in th]
+        for c, msgs in convs.items():
+            st, d = res[c]
+            assert st == 200, d
+            ref = solo.chat_complete(spec.name, msgs, 8, flags=0)
+            want = bytes(ref.content).decode("utf-8", "replace").rstrip("\n")
+            assert d["choices"][0]["message"]["content"] == want
+            assert d["usage"]["prompt_tokens"] == ref.prompt_tokens and d["usage"]["completion_tokens"] == ref.completion_tokens
+            msgs += [("assistant", want), ("user", "observation: NAME READY STATUS\nweb-0 0/1 CrashLoopBackOff " * 2)]
+    st = front.stats()
+    assert sum(st["routed"]) == 12 and st["sticky_hits"] == 8 and min(st["routed"]) >= 3      # 4 conversations x 3 steps; steps 2-3 sticky; both replicas used
+    assert all(e["prefix_hit_tokens"] >= 64 for e in st["engines"])                          # later steps found their earlier pages on their home replica
+    # admission control: 40 simultaneous long requests of ONE conversation all go to its home replica; more than max_inflight=8 at once -> some 429
+    codes = []
+
+    def flood():
+        codes.append(post(convs[0], max_tokens=200)[0])
+    th = [threading.Thread(target=flood) for _ in range(40)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert set(codes) <= {200, 429} and codes.count(200) >= 8 and codes.count(429) >= 1
+    assert front.stats()["rejected_429"] == codes.count(429)
+    front.shutdown(); rt.close(); solo.close()
