@@ -146,3 +146,27 @@ func (c *LocalCUDAClient) ChatContext(ctx context.Context, model string, maxToke
 	}
 	return "", fmt.Errorf("OpenAI request throttled after retrying %d times", c.Retries)
 }
+
+// ServeLocalCUDA starts the engine library's own OpenAI-compatible HTTP endpoint (csrc/http_server.cpp: POST /v1/chat/completions incl.
+// `tools`, GET /v1/models, GET /api/perf/stats) on the process-wide engine, for the callers that cannot go through the Chat seam: the swarm-go
+// flows build their own OpenAI client from OPENAI_API_BASE (pkg/workflows/swarm.go:80-89).  A maintainer calls it once at start-up
+// (cmd/kube-copilot/main.go) and points OPENAI_API_BASE at the returned URL.  `addr` is "host:port" ("127.0.0.1:0" picks a free port).
+func ServeLocalCUDA(addr string) (string, error) {
+	if _, err := NewLocalCUDAClient("local", "cuda://"); err != nil {
+		return "", err
+	}
+	host, port, ok := strings.Cut(addr, ":")
+	if !ok {
+		return "", fmt.Errorf("ServeLocalCUDA: addr must be host:port")
+	}
+	runtime.LockOSThread() // oa_http_last_error() is thread-local
+	defer runtime.UnlockOSThread()
+	opts := C.CString(fmt.Sprintf(`{"host": %q, "port": %s, "require_key": 1}`, host, port))
+	defer C.free(unsafe.Pointer(opts))
+	var front *C.oa_http
+	engines := []*C.oa_engine{engineInst}
+	if rc := C.oa_http_start(&engines[0], 1, opts, &front); rc != 0 {
+		return "", fmt.Errorf("oa_http_start: %d %s", int(rc), C.GoString(C.oa_http_last_error()))
+	}
+	return fmt.Sprintf("http://%s:%d/v1", host, int(C.oa_http_port(front))), nil
+}

@@ -23,6 +23,8 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <ctime>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -299,6 +301,19 @@ private:
         const char* type = status == 400 ? "invalid_request_error" : status == 401 ? "authentication_error" : status == 429 ? "rate_limit_error" : "server_error";
         return "{\"error\": {\"message\": " + jstr(msg) + ", \"type\": \"" + type + "\", \"code\": " + std::to_string(status) + "}}";
     }
+    // the reference's PerfStats shape (pkg/utils/perf.go:296-320 as marshalled by pkg/handlers/perf.go:12-25): summed durations in ns + call counts
+    // per operation, and the last reset time (RFC 3339, UTC)
+    void perf_record(const char* op, long long ns) { std::lock_guard<std::mutex> lk(perf_mu_); perf_ns_[op] += ns; perf_n_[op] += 1; }
+    std::string perf_json() {
+        std::lock_guard<std::mutex> lk(perf_mu_);
+        std::string t = "\"timers\": {", n = "\"callCounts\": {";
+        bool first = true;
+        for (auto& kv : perf_ns_) { t += (first ? "" : ", ") + jstr(kv.first) + ": " + std::to_string(kv.second); n += (first ? "" : ", ") + jstr(kv.first) + ": " + std::to_string(perf_n_[kv.first]); first = false; }
+        const auto us = std::chrono::duration_cast<std::chrono::microseconds>(perf_reset_.time_since_epoch()).count();
+        const time_t secs = (time_t)(us / 1000000); struct tm tmv; gmtime_r(&secs, &tmv);
+        char ts[64]; std::snprintf(ts, sizeof ts, "%04d-%02d-%02dT%02d:%02d:%02d.%06lldZ", tmv.tm_year + 1900, tmv.tm_mon + 1, tmv.tm_mday, tmv.tm_hour, tmv.tm_min, tmv.tm_sec, (long long)(us % 1000000));
+        return t + "}, " + n + "}, \"lastResetTime\": \"" + ts + "\"";
+    }
     bool authorised(const Request& rq) const {
         if (!require_key_) return true;
         if (rq.auth.rfind("Bearer ", 0) != 0 || rq.auth.size() <= 7) return false;          // the reference always sends its apiKey (openai.go:44)
@@ -321,7 +336,12 @@ private:
         if (rq.method == "GET" && ends("/models")) { body = "{\"object\": \"list\", \"data\": [{\"id\": " + jstr(model_) + ", \"object\": \"model\", \"owned_by\": \"opsagent_b200\"}]}"; return; }
         if (rq.method == "GET" && ends("/perf/stats")) {
             if (!authorised(rq)) { status = 401; body = error_body(401, "missing bearer token"); return; }
-            body = "{\"stats\": {\"front\": " + stats_json() + "}, \"status\": \"success\"}"; return;
+            body = "{\"stats\": {" + perf_json() + ", \"front\": " + stats_json() + "}, \"status\": \"success\"}"; return;
+        }
+        if (rq.method == "POST" && ends("/perf/reset")) {          // pkg/api/router.go:105, pkg/handlers/perf.go:28-39
+            if (!authorised(rq)) { status = 401; body = error_body(401, "missing bearer token"); return; }
+            { std::lock_guard<std::mutex> lk(perf_mu_); perf_ns_.clear(); perf_n_.clear(); perf_reset_ = std::chrono::system_clock::now(); }
+            body = "{\"message\": \"performance statistics reset\", \"status\": \"success\"}"; return;
         }
         if (rq.method != "POST" || !ends("/chat/completions")) { status = 404; body = error_body(404, "not found"); return; }
         if (!authorised(rq)) { status = 401; body = error_body(401, "missing bearer token"); return; }
@@ -391,9 +411,11 @@ private:
         oa_chat_req creq{}; creq.model = model.c_str(); creq.msgs = cm.data(); creq.n_msgs = (int32_t)cm.size(); creq.max_tokens = max_tokens;
         creq.temperature = 1.401298464324817e-45f; creq.flags = flags; creq.functions = (flags & OA_FLAG_JSON_FUNCTION) ? functions.c_str() : nullptr;
         oa_chat_resp out{}; char ebuf[512]; ebuf[0] = 0; uint64_t ticket = 0;
+        const auto t_chat = std::chrono::steady_clock::now();
         int rc = oa_chat_submit_ex(engines_[(size_t)r], &creq, &ticket, ebuf, sizeof ebuf);
         if (rc == 0) rc = oa_chat_wait_ex(engines_[(size_t)r], ticket, -1, &out, ebuf, sizeof ebuf);
         inflight_[(size_t)r].fetch_sub(1);
+        perf_record((flags & OA_FLAG_JSON_FUNCTION) ? "chat_completion_tool_call" : "chat_completion", std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_chat).count());
         if (rc != 0) { status = (rc == 400 || rc == 401 || rc == 429 || rc == 500) ? rc : 500; body = error_body(status, ebuf); return; }
         n_chat_.fetch_add(1);
         const std::string content(out.content ? out.content : "", (size_t)out.content_len);
@@ -423,6 +445,7 @@ private:
     std::vector<oa_engine*> engines_;
     std::vector<std::atomic<int>> inflight_; std::vector<std::atomic<long long>> routed_;
     std::mutex mu_; std::unordered_map<uint64_t, int> home_;
+    std::mutex perf_mu_; std::map<std::string, long long> perf_ns_, perf_n_; std::chrono::system_clock::time_point perf_reset_ = std::chrono::system_clock::now();
     bool require_key_ = true; std::string api_key_, model_; int tool_steps_ = 3, max_inflight_ = 256, max_conn_ = 8192; size_t max_body_ = 64 << 20;
     int lsock_ = -1, port_ = 0; std::thread acceptor_; std::atomic<bool> stop_{false};
     std::atomic<int> n_conn_{0}; std::atomic<long long> n_req_{0}, n_chat_{0}, n_429_{0}, n_sticky_{0};

@@ -53,6 +53,20 @@ def test_paths_auth_and_error_bodies(front):
     assert st == 200 and j["status"] == "success" and j["stats"]["front"]["replicas"] == 0
 
 
+def test_perf_endpoints_have_the_reference_shape(front):
+    """pkg/handlers/perf.go:12-39: {"stats": {"timers", "callCounts", "lastResetTime"}, "status": "success"}; reset answers with a message"""
+    import datetime
+    st, j, _ = _req(front.port, "GET", "/api/perf/stats", key=None)
+    assert st == 401
+    st, j, _ = _req(front.port, "GET", "/api/perf/stats")
+    assert st == 200 and set(j["stats"]) >= {"timers", "callCounts", "lastResetTime", "front"}
+    t0 = datetime.datetime.fromisoformat(j["stats"]["lastResetTime"].replace("Z", "+00:00"))
+    st, j, _ = _req(front.port, "POST", "/api/perf/reset", {})
+    assert st == 200 and j == {"message": "performance statistics reset", "status": "success"}
+    st, j, _ = _req(front.port, "GET", "/api/perf/stats")
+    assert datetime.datetime.fromisoformat(j["stats"]["lastResetTime"].replace("Z", "+00:00")) >= t0 and j["stats"]["timers"] == {}
+
+
 def test_keep_alive_serves_many_requests_on_one_connection(front):
     conn = None
     for i in range(20):
