@@ -17,6 +17,7 @@
 #include <sys/socket.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -314,6 +315,22 @@ private:
         char ts[64]; std::snprintf(ts, sizeof ts, "%04d-%02d-%02dT%02d:%02d:%02d.%06lldZ", tmv.tm_year + 1900, tmv.tm_mon + 1, tmv.tm_mday, tmv.tm_hour, tmv.tm_min, tmv.tm_sec, (long long)(us % 1000000));
         return t + "}, " + n + "}, \"lastResetTime\": \"" + ts + "\"";
     }
+    // oa_engine_stats summed over the replicas (one engine: its own counters) — `stats.engine`, as http_front.py serves it
+    std::string engine_totals_json() {
+        std::vector<std::pair<std::string, double>> tot;
+        for (oa_engine* e : engines_) {
+            char buf[4096]; buf[0] = 0; Json j; std::string err;
+            if (oa_engine_stats(e, buf, sizeof buf) != 0 || !parse_json(buf, j, err) || j.t != Json::Obj) continue;
+            for (auto& kv : j.o) {
+                if (kv.second.t != Json::Num) continue;
+                auto it = std::find_if(tot.begin(), tot.end(), [&](const std::pair<std::string, double>& p) { return p.first == kv.first; });
+                if (it == tot.end()) tot.emplace_back(kv.first, kv.second.n); else it->second += kv.second.n;
+            }
+        }
+        std::string o = "{";
+        for (size_t i = 0; i < tot.size(); ++i) { Json n; n.t = Json::Num; n.n = tot[i].second; o += (i ? ", " : "") + jstr(tot[i].first) + ": "; json_dump(n, o); }
+        return o + "}";
+    }
     bool authorised(const Request& rq) const {
         if (!require_key_) return true;
         if (rq.auth.rfind("Bearer ", 0) != 0 || rq.auth.size() <= 7) return false;          // the reference always sends its apiKey (openai.go:44)
@@ -336,7 +353,7 @@ private:
         if (rq.method == "GET" && ends("/models")) { body = "{\"object\": \"list\", \"data\": [{\"id\": " + jstr(model_) + ", \"object\": \"model\", \"owned_by\": \"opsagent_b200\"}]}"; return; }
         if (rq.method == "GET" && ends("/perf/stats")) {
             if (!authorised(rq)) { status = 401; body = error_body(401, "missing bearer token"); return; }
-            body = "{\"stats\": {" + perf_json() + ", \"front\": " + stats_json() + "}, \"status\": \"success\"}"; return;
+            body = "{\"stats\": {" + perf_json() + ", \"engine\": " + engine_totals_json() + ", \"front\": " + stats_json() + "}, \"status\": \"success\"}"; return;
         }
         if (rq.method == "POST" && ends("/perf/reset")) {          // pkg/api/router.go:105, pkg/handlers/perf.go:28-39
             if (!authorised(rq)) { status = 401; body = error_body(401, "missing bearer token"); return; }
