@@ -232,11 +232,16 @@ def router_block(args, rank, world, barrier, dist=None, cpu_group=None):
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=cpu_group)
             dt = float(t.item())
         return dt
+    def safe_stats():          # rank-0-only code must not raise between collectives: the other ranks would wait at the next one forever
+        try:
+            return stats() if rank == 0 else None
+        except Exception as e:      # noqa: BLE001
+            return {"error": f"{type(e).__name__}: {e}"}
     round_(mine[::16])                                             # warm-up: a few requests on every replica
-    s0 = stats() if rank == 0 else None
+    s0 = safe_stats()
     usage.clear()
     dt = round_(mine)
-    s1 = stats() if rank == 0 else None
+    s1 = safe_stats()
     gathered = [None] * world
     if dist is not None:
         dist.all_gather_object(gathered, usage, group=cpu_group)
@@ -244,27 +249,31 @@ def router_block(args, rank, world, barrier, dist=None, cpu_group=None):
         gathered = [usage]
     out = None
     if rank == 0:
-        allu = {}
-        for g in gathered:
-            allu.update(g)
-        ok = [u for u in allu.values() if u and "error" not in u]
-        errs = sorted({str(u["error"]) for u in allu.values() if u and "error" in u})
-        comp = sum(u["completion_tokens"] for u in ok)
-        fw = lambda st: sum(p["prefill_steps"] + p["decode_steps"] for p in st["per_replica"])      # noqa: E731
-        out = {"workload": f"BASELINE configs[2] served: {n_req} concurrent HTTP clients (spread over the {world} rank processes) -> one front process ({args.router_front}: "
-                           f"OpenAI-compatible endpoint + sticky least-loaded routing) -> {world} engines; mix 40% analyze (P=1536) / 30% diagnose / 30% execute, "
-                           "verbatim reference prompts, max_tokens 256",
-               "front": args.router_front, "requests": n_req, "completed": len(ok), "errors": errs, "by_kind": cfgd["kinds"], "seconds": round(dt, 3),
-               "e2e_tokens_per_sec": round(comp / dt, 1), "react_steps_per_sec": round(len(ok) / dt, 2), "completion_tokens": comp,
-               "prompt_tokens_mean": round(sum(u["prompt_tokens"] for u in ok) / max(1, len(ok)), 1),
-               "routed_per_replica": [b - a for a, b in zip(s0["routed"], s1["routed"])], "rejected_429": s1["rejected_429"] - s0["rejected_429"],
-               "engine_forwards": fw(s1) - fw(s0),
-               "engine_busy_ms_max": round(max(b["busy_ms"] - a["busy_ms"] for a, b in zip(s0["per_replica"], s1["per_replica"])), 1)}
-        if front is not None:
-            front.shutdown()
-        if srv is not None:
-            srv.shutdown()
-        rt.close()
+        try:
+            allu = {}
+            for g in gathered:
+                allu.update(g)
+            ok = [u for u in allu.values() if u and "error" not in u]
+            errs = sorted({str(u["error"]) for u in allu.values() if u and "error" in u})
+            comp = sum(u["completion_tokens"] for u in ok)
+            fw = lambda st: sum(p["prefill_steps"] + p["decode_steps"] for p in st["per_replica"])      # noqa: E731
+            out = {"workload": f"BASELINE configs[2] served: {n_req} concurrent HTTP clients (spread over the {world} rank processes) -> one front process ({args.router_front}: "
+                               f"OpenAI-compatible endpoint + sticky least-loaded routing) -> {world} engines; mix 40% analyze (P=1536) / 30% diagnose / 30% execute, "
+                               "verbatim reference prompts, max_tokens 256",
+                   "front": args.router_front, "requests": n_req, "completed": len(ok), "errors": errs, "by_kind": cfgd["kinds"], "seconds": round(dt, 3),
+                   "e2e_tokens_per_sec": round(comp / dt, 1), "react_steps_per_sec": round(len(ok) / dt, 2), "completion_tokens": comp,
+                   "prompt_tokens_mean": round(sum(u["prompt_tokens"] for u in ok) / max(1, len(ok)), 1),
+                   "routed_per_replica": [b - a for a, b in zip(s0["routed"], s1["routed"])], "rejected_429": s1["rejected_429"] - s0["rejected_429"],
+                   "engine_forwards": fw(s1) - fw(s0),
+                   "engine_busy_ms_max": round(max(b["busy_ms"] - a["busy_ms"] for a, b in zip(s0["per_replica"], s1["per_replica"])), 1)}
+        except Exception as e:      # noqa: BLE001
+            out = {"error": f"{type(e).__name__}: {e}"}
+        for closer in ((front.shutdown if front is not None else None), (srv.shutdown if srv is not None else None), rt.close):
+            try:
+                if closer:
+                    closer()
+            except Exception:      # noqa: BLE001
+                pass
     barrier()
     return out
 
