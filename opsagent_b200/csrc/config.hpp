@@ -105,9 +105,6 @@ struct EngineOptions {
                                   // Bit-identical to the consumers; default set from the measured sweep (profiles/r02_*): few tiles cut into 4-5 pieces each make the finishers a serial tail
     int sk_clusterk = 0;          // bitmask — 1: qkv, 2: o, 4: down as a cluster split-K GEMM with DSMEM reduction and the epilogue (RoPE + KV write / residual) inside (gemm_clusterk.cu), where the shape fills >= 80 % of the SMs
     int sk_clusterk_min_fill = 80; // ... and only where n_tiles x cluster size covers at least this percentage of the SMs (tests: 0)
-    int sk_chain = 0;             // decode (tp == 1): 0 = one kernel per projection/consumer (default: measured fastest, 8.19 vs 8.41 ms); 1 = o -> gate_up -> down chained in one persistent kernel;
-                                  // 2 = also the next layer's qkv projection + RoPE/KV write
-    int sk_chain_pf_kb = 0;       // chained kernel: weight KB of the next projection each CTA prefetches into L2 at a phase boundary
     int sk_l2_prefetch_kb = 0;    // per-CTA weight KB prefetched into L2 ahead of the dependency wait (measured: hurts, 8.75 -> 9.3 ms; off)
     int sk_bn_qkv = 0, sk_bn_o = 0, sk_bn_gu = 0, sk_bn_down = 0;   // per-projection overrides (0 = sk_bn)
     int start_thread = 1;
@@ -147,7 +144,7 @@ inline void parse_config(const std::string& json, ModelConfig& m, EngineOptions&
     I("device", o.device); o.kv_gb = j.f("kv_gb", o.kv_gb); I("num_pages", o.num_pages); I("max_batch", o.max_batch);
     I("max_seq_len", o.max_seq_len); I("max_step_tokens", o.max_step_tokens); I("max_queue", o.max_queue);
     I("bn_qkv", o.bn_qkv); I("bn_o", o.bn_o); I("bn_gu", o.bn_gu); I("bn_down", o.bn_down); I("bn_lm", o.bn_lm);
-    I("attn_ctas", o.attn_ctas); I("streamk", o.streamk); I("sk_bn", o.sk_bn); I("sk_ctas", o.sk_ctas); I("sk_l2_prefetch_kb", o.sk_l2_prefetch_kb); I("sk_max_rows", o.sk_max_rows); I("sk_chain", o.sk_chain); I("sk_fuse_swiglu", o.sk_fuse_swiglu); I("sk_fuse_epi", o.sk_fuse_epi); I("sk_clusterk", o.sk_clusterk); I("sk_clusterk_min_fill", o.sk_clusterk_min_fill); I("sk_chain_pf_kb", o.sk_chain_pf_kb); I("sk_bn_qkv", o.sk_bn_qkv); I("sk_bn_o", o.sk_bn_o); I("sk_bn_gu", o.sk_bn_gu); I("sk_bn_down", o.sk_bn_down); I("start_thread", o.start_thread); o.weights = j.s("weights", o.weights); o.model_aliases = j.s("model_aliases", o.model_aliases); o.tokenizer = j.s("tokenizer", o.tokenizer); I("prefix_cache", o.prefix_cache); I("json_mode", o.json_mode); I("react_tool_steps", o.react_tool_steps); I("prefill_batch_tokens", o.prefill_batch_tokens); I("mixed_steps", o.mixed_steps); I("prefill_max_wait_ms", o.prefill_max_wait_ms); I("tp", o.tp); I("tp_rank", o.tp_rank); I("tp_ar_bf16", o.tp_ar_bf16); I("tp_nvls", o.tp_nvls); I("tp_two_shot_rows", o.tp_two_shot_rows); o.tp_shm = j.s("tp_shm", o.tp_shm); o.tp_nonce = (uint64_t)j.i("tp_nonce", (int64_t)o.tp_nonce);
+    I("attn_ctas", o.attn_ctas); I("streamk", o.streamk); I("sk_bn", o.sk_bn); I("sk_ctas", o.sk_ctas); I("sk_l2_prefetch_kb", o.sk_l2_prefetch_kb); I("sk_max_rows", o.sk_max_rows); I("sk_fuse_swiglu", o.sk_fuse_swiglu); I("sk_fuse_epi", o.sk_fuse_epi); I("sk_clusterk", o.sk_clusterk); I("sk_clusterk_min_fill", o.sk_clusterk_min_fill); I("sk_bn_qkv", o.sk_bn_qkv); I("sk_bn_o", o.sk_bn_o); I("sk_bn_gu", o.sk_bn_gu); I("sk_bn_down", o.sk_bn_down); I("start_thread", o.start_thread); o.weights = j.s("weights", o.weights); o.model_aliases = j.s("model_aliases", o.model_aliases); o.tokenizer = j.s("tokenizer", o.tokenizer); I("prefix_cache", o.prefix_cache); I("json_mode", o.json_mode); I("react_tool_steps", o.react_tool_steps); I("prefill_batch_tokens", o.prefill_batch_tokens); I("mixed_steps", o.mixed_steps); I("prefill_max_wait_ms", o.prefill_max_wait_ms); I("tp", o.tp); I("tp_rank", o.tp_rank); I("tp_ar_bf16", o.tp_ar_bf16); I("tp_nvls", o.tp_nvls); I("tp_two_shot_rows", o.tp_two_shot_rows); o.tp_shm = j.s("tp_shm", o.tp_shm); o.tp_nonce = (uint64_t)j.i("tp_nonce", (int64_t)o.tp_nonce);
     if (m.hidden <= 0 || m.n_layers <= 0 || m.n_heads <= 0 || m.n_kv_heads <= 0 || m.ffn <= 0 || m.vocab <= 0)
         throw std::runtime_error("unknown model '" + name + "' and no explicit dimensions given");
     if (m.head_dim != 64 && m.head_dim != 128) throw std::runtime_error("head_dim must be 64 or 128");

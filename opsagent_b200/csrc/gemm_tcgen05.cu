@@ -914,310 +914,6 @@ cudaError_t launch_gemm_streamk(const CUtensorMap* tmA, const CUtensorMap* tmB, 
     return cudaErrorInvalidValue;
 }
 
-// =============================================================================================
-// chained decode kernel: several stream-K GEMMs and their consumers in one persistent launch
-// =============================================================================================
-// Why: at decode sizes every projection streams its weights in 15-50 us, and each kernel boundary (drain, launch, pipeline
-// refill) plus each stand-alone consumer launch costs about as much again.  Here the CTAs stay resident: the TMA producer
-// runs ahead into the NEXT projection's weight tiles (they depend on nothing) while the epilogue warps publish partials,
-// meet at a grid-wide counter barrier and run the consumer (residual+RMSNorm / SwiGLU / RoPE+KV write) on 12 warps.
-//   warp 0: TMA producer   warp 1: tcgen05.mma issuer   warps 2-5: TMEM -> partial workspace   warps 2-17: consumers
-// The gate/up projection needs no consumer at all: its tiles are split over at most a few CTAs, so the CTA holding a tile's
-// FIRST k-block (its last segment, finished at the end of the phase) adds the other pieces to its accumulator in CTA order
-// and writes silu(gate)*up straight from TMEM (the other CTAs publish their piece and bump a per-tile flag).
-// Grid barriers on two monotonically increasing counters (all CTAs are co-resident: grid <= SM count, one CTA per SM):
-//   B1_p: bar[0] == (p+1)*G: every partial of GEMM p is in L2            -> consumers may read them
-//   B2_p: bar[1] == (p+1)*G: every consumer output of phase p is written -> GEMM p+1 may TMA-load it as its A operand
-// (two counters: a CTA without units in phase p+1 arrives at B1_{p+1} before B2_p has completed)
-constexpr int CHAIN_EPI_WARPS = 4, CHAIN_HELPER_WARPS = 12;
-constexpr int CHAIN_THREADS = 64 + 32 * (CHAIN_EPI_WARPS + CHAIN_HELPER_WARPS);     // 576
-constexpr int CHAIN_CONSUMER_THREADS = 32 * (CHAIN_EPI_WARPS + CHAIN_HELPER_WARPS); // 512
-static_assert(CHAIN_CONSUMER_THREADS == SK_RESID_THREADS, "the residual consumer runs on all consumer threads");
-
-OA_DEVINL void chain_stamp(const SkChain& ch, int c, int slot) { if (ch.trace) ch.trace[(size_t)c * 32 + slot] = (unsigned long long)clock64(); }
-
-OA_DEVINL void sk_chain_consume(const SkChainPhase& P, int M, int c, int nG, int ctid, float* red) {
-    if (P.consumer == SK_CONSUMER_RESID_RMSNORM) {
-        const int H8 = P.H >> 3;
-        const float inv_h = 1.0f / (float)P.H;
-        auto X = reinterpret_cast<uint4*>(P.x); auto G = reinterpret_cast<const uint4*>(P.gain); auto Y = reinterpret_cast<uint4*>(P.xn);
-        for (int row = c; row < M; row += nG) {
-            if (H8 <= SK_RESID_THREADS) sk_resid_rmsnorm_row<1>(P.sk, row, ctid, red, 4, X, G, Y, H8, inv_h, P.eps);
-            else sk_resid_rmsnorm_row<2>(P.sk, row, ctid, red, 4, X, G, Y, H8, inv_h, P.eps);
-            named_bar_sync(4, SK_RESID_THREADS);       // `red` is reused by the next row
-        }
-    } else if (P.consumer == SK_CONSUMER_ROPE_KV) {
-        const int items = sk_rope_items_per_row(P.rope), total = M * items;
-        for (int idx = c * CHAIN_CONSUMER_THREADS + ctid; idx < total; idx += nG * CHAIN_CONSUMER_THREADS) {
-            const int t = idx / items;
-            sk_rope_item(P.sk, P.rope, t, idx - t * items);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(CHAIN_THREADS, 1) gemm_sk_chain_kernel(const __grid_constant__ SkChainMaps maps, const __grid_constant__ SkChain ch) {
-    constexpr int BN = 128;
-    using Cfg = SkCfg<BN, 1, 1>;
-    constexpr int STAGES = Cfg::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* epi_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + 4 * Cfg::EPI_WARP_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* acc_full = empty_bar + STAGES;      // [2]
-    uint64_t* acc_empty = acc_full + 2;           // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float* red = reinterpret_cast<float*>(tmem_slot + 4);     // [8]
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = blockIdx.x, nG = gridDim.x, NP = ch.n_phases;
-    // units [u0, u1) of phase p owned by this CTA (phases with fewer units than CTAs leave the high CTAs idle)
-    auto range = [&](const StreamK& sk, long long& u0, long long& u1) {
-        if (c < sk.G) { u0 = (long long)c * sk.total / sk.G; u1 = (long long)(c + 1) * sk.total / sk.G; } else { u0 = 0; u1 = 0; }
-    };
-
-    if (warp == 0 && lane == 0) {
-        for (int p = 0; p < NP; ++p) { tma_prefetch_desc(&maps.a[p]); tma_prefetch_desc(&maps.b[p]); }
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], CHAIN_EPI_WARPS); }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    griddep_launch();
-    if (threadIdx.x == 64) chain_stamp(ch, c, 0);
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int p = 0; p < NP; ++p) {
-                const StreamK& sk = ch.ph[p].sk;
-                const CUtensorMap* tA = &maps.a[p]; const CUtensorMap* tB = &maps.b[p];
-                long long u0, u1; range(sk, u0, u1);
-                const int pre = (u1 - u0) < STAGES ? (int)(u1 - u0) : STAGES;
-                // weights first: they depend on nothing, so the HBM stream continues while phase p-1 is reduced and consumed
-                { int sp = s; uint32_t pp = ph;
-                  for (int i = 0; i < pre; ++i) {
-                      const long long u = u0 + i;
-                      const int tile = (int)(u / sk.kb), kblk = (int)(u - (long long)tile * sk.kb);
-                      mbar_wait(&empty_bar[sp], pp ^ 1);
-                      mbar_expect_tx(&full_bar[sp], Cfg::STAGE_BYTES);
-                      tma_load_2d(smem + sp * Cfg::STAGE_BYTES + Cfg::A_BYTES, tB, &full_bar[sp], kblk * BLOCK_K, tile * BN, kEvictFirst);
-                      if (++sp == STAGES) { sp = 0; pp ^= 1; }
-                  } }
-                // the A operand is the predecessor kernel's output (phase 0) or the previous phase's consumer output
-                if (p == 0) griddep_wait();
-                else if (u1 > u0) {
-                    // ... and, while the barrier is pending, pull the following weight tiles into L2 (nothing else uses HBM now)
-                    const long long pf_end = (u0 + pre + ch.l2_prefetch_units) < u1 ? (u0 + pre + ch.l2_prefetch_units) : u1;
-                    for (long long u = u0 + pre; u < pf_end; ++u) {
-                        const int tile = (int)(u / sk.kb), kblk = (int)(u - (long long)tile * sk.kb);
-                        tma_prefetch_l2_2d(tB, kblk * BLOCK_K, tile * BN);
-                    }
-                    grid_counter_wait(ch.bar + 1, (unsigned long long)p * (unsigned long long)nG); fence_proxy_async_all();
-                }
-                chain_stamp(ch, c, 1 + 5 * p + 3);
-                for (int i = 0; i < pre; ++i) {
-                    const long long u = u0 + i;
-                    const int tile = (int)(u / sk.kb), kblk = (int)(u - (long long)tile * sk.kb);
-                    tma_load_2d(smem + s * Cfg::STAGE_BYTES, tA, &full_bar[s], kblk * BLOCK_K, 0, kEvictLast);
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
-                }
-                for (long long u = u0 + pre; u < u1; ++u) {
-                    const int tile = (int)(u / sk.kb), kblk = (int)(u - (long long)tile * sk.kb);
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                    tma_load_2d(a_dst, tA, &full_bar[s], kblk * BLOCK_K, 0, kEvictLast);
-                    tma_load_2d(a_dst + Cfg::A_BYTES, tB, &full_bar[s], kblk * BLOCK_K, tile * BN, kEvictFirst);
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
-            int s = 0; uint32_t ph = 0; int seg = 0;
-            for (int p = 0; p < NP; ++p) {
-                const StreamK& sk = ch.ph[p].sk;
-                long long u0, u1; range(sk, u0, u1);
-                for (long long u = u0; u < u1; ++seg) {
-                    const int tile = (int)(u / sk.kb);
-                    const long long uend = min(u1, (long long)(tile + 1) * sk.kb);
-                    const int as = seg & 1;
-                    mbar_wait(&acc_empty[as], (((uint32_t)seg >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
-                    tcgen05_fence_after();
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-                    for (long long uu = u; uu < uend; ++uu) {
-                        mbar_wait(&full_bar[s], ph);
-                        tcgen05_fence_after();
-                        const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                        const uint64_t a_desc = umma_desc_sw128(a_addr), b_desc = umma_desc_sw128(a_addr + Cfg::A_BYTES);
-#pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                            umma_bf16(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (uu > u || k > 0) ? 1u : 0u);
-                        umma_commit(&empty_bar[s]);
-                        if (++s == STAGES) { s = 0; ph ^= 1; }
-                    }
-                    umma_commit(&acc_full[as]);
-                    u = uend;
-                }
-            }
-        }
-    } else {
-        const bool is_epi = warp < 2 + CHAIN_EPI_WARPS;
-        const int ctid = (int)threadIdx.x - 64;
-        const int q = warp & 3;
-        int seg = 0;
-        unsigned long long n_b1 = 0;                  // grid barriers of kind B1 so far (fused phases have none)
-        if (is_epi) griddep_wait();                   // the predecessor may still be reading the partial workspace
-        for (int p = 0; p < NP; ++p) {
-            const SkChainPhase& P = ch.ph[p];
-            const bool fused = P.consumer == SK_CONSUMER_SWIGLU;      // finished in the epilogue by the tile's first CTA
-            if (!fused) ++n_b1;
-            if (is_epi) {
-                const StreamK& sk = P.sk;
-                long long u0, u1; range(sk, u0, u1);
-                float* stage = epi_smem + (warp - 2) * (Cfg::EPI_WARP_BYTES / 4);
-                const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
-                for (long long u = u0; u < u1; ++seg) {
-                    const int tile = (int)(u / sk.kb);
-                    const long long uend = min(u1, (long long)(tile + 1) * sk.kb);
-                    const int as = seg & 1;
-                    // CTAs c_first..c_last hold pieces of this tile (same arithmetic as sk_sum8)
-                    uint32_t cf, cl;
-                    sk_tile_ctas(sk, (uint32_t)tile, cf, cl);
-                    const int c_first = (int)cf, c_last = (int)cl;
-                    const bool finish = fused && c == c_first;
-                    unsigned int* flag = ch.tile_flags + p * SK_CHAIN_MAX_TILES + tile;
-                    mbar_wait(&acc_full[as], ((uint32_t)seg >> 1) & 1);
-                    tcgen05_fence_after();
-                    if (threadIdx.x == 64 && u == u0) chain_stamp(ch, c, 1 + 5 * p + 4);
-                    if (finish) {
-                        const int n_other = c_last - c_first;
-                        if (n_other > 0) {            // the other pieces were computed FIRST by their CTAs: normally long done
-                            if (threadIdx.x == 64) { grid_counter_wait32(flag, (unsigned int)n_other); *flag = 0u; }
-                            named_bar_sync(1, 32 * CHAIN_EPI_WARPS);
-                        }
-                        const int row = q * 32 + lane;
-                        const float* other = sk.ws + ((size_t)(c_first + 1 + tile) * BLOCK_M + row) * BN;
-                        uint16_t* act_row = reinterpret_cast<uint16_t*>(P.act) + (size_t)row * P.F;
-#pragma unroll 1
-                        for (int mc = 0; mc < BN; mc += 32) {
-                            uint32_t v[32];
-                            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + mc), v);
-                            tmem_ld_wait();
-                            float acc[32];
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) acc[j] = 0.f + __uint_as_float(v[j]);      // "0 +" as in sk_sum8: bit-identical sums
-                            for (int o = 0; o < n_other; ++o) {
-                                const float4* pp = reinterpret_cast<const float4*>(other + (size_t)o * BLOCK_M * BN + mc);
-#pragma unroll
-                                for (int h = 0; h < 8; h += 4) {
-                                    float4 t4[4];
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) t4[j] = __ldcg(pp + h + j);
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) { acc[4 * (h + j)] += t4[j].x; acc[4 * (h + j) + 1] += t4[j].y; acc[4 * (h + j) + 2] += t4[j].z; acc[4 * (h + j) + 3] += t4[j].w; }
-                                }
-                            }
-                            const int f0 = (tile * BN + mc) >> 1;          // 32 physical columns = 16 gate + 16 up -> 16 outputs
-                            if (row < ch.M && f0 < P.F) {
-                                float f[16];
-#pragma unroll
-                                for (int k = 0; k < 16; ++k) f[k] = __fdividef(acc[k], 1.0f + __expf(-acc[k])) * acc[16 + k];
-                                uint4 o0, o1;
-                                o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]); o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
-                                o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]); o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-                                *reinterpret_cast<uint4*>(act_row + f0) = o0;
-                                *reinterpret_cast<uint4*>(act_row + f0 + 8) = o1;
-                            }
-                        }
-                    } else {
-                        float* dst = sk.ws + ((size_t)(c + tile) * BLOCK_M + q * 32) * BN;
-#pragma unroll 1
-                        for (int mc = 0; mc < BN; mc += 32) {
-                            uint32_t v[32];
-                            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + mc), v);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(stage + lane * Cfg::EPI_ROW_FLOATS + j) =
-                                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                            __syncwarp();
-#pragma unroll
-                            for (int it = 0; it < 8; ++it) {
-                                const int r = it * 4 + r_sub;
-                                const float4 val = *reinterpret_cast<const float4*>(stage + r * Cfg::EPI_ROW_FLOATS + c4);
-                                if (q * 32 + r < ch.M) *reinterpret_cast<float4*>(dst + (size_t)r * BN + mc + c4) = val;
-                            }
-                            __syncwarp();
-                        }
-                        if (fused) {                  // publish this piece to the tile's first CTA
-                            __threadfence();
-                            named_bar_sync(1, 32 * CHAIN_EPI_WARPS);
-                            if (threadIdx.x == 64) atomicAdd(flag, 1u);
-                        }
-                    }
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[as]);
-                    u = uend;
-                }
-                if (!fused) {
-                    // B1_p: this CTA's partials are globally visible; wait until everybody's are
-                    __threadfence();
-                    named_bar_sync(1, 32 * CHAIN_EPI_WARPS);
-                    if (threadIdx.x == 64) {
-                        chain_stamp(ch, c, 1 + 5 * p + 0);
-                        atomicAdd(ch.bar, 1ULL);
-                        grid_counter_wait(ch.bar, n_b1 * (unsigned long long)nG);
-                        chain_stamp(ch, c, 1 + 5 * p + 1);
-                    }
-                }
-            }
-            named_bar_sync(2, CHAIN_CONSUMER_THREADS);
-            if (!fused) sk_chain_consume(P, ch.M, c, nG, ctid, red);
-            if (p + 1 < NP) {
-                // B2_p: consumer outputs are read next through TMA (async proxy) by every CTA
-                __threadfence();
-                fence_proxy_async_all();
-                named_bar_sync(3, CHAIN_CONSUMER_THREADS);
-                if (threadIdx.x == 64) { chain_stamp(ch, c, 1 + 5 * p + 2); atomicAdd(ch.bar + 1, 1ULL); }
-            } else {
-                named_bar_sync(3, CHAIN_CONSUMER_THREADS);
-                if (threadIdx.x == 64) {
-                    // every CTA has passed the last barrier once it gets here: the last one re-arms the counters for the next launch
-                    chain_stamp(ch, c, 1 + 5 * p + 2);
-                    if (atomicAdd(ch.bar + 2, 1ULL) == (unsigned long long)(nG - 1)) { ch.bar[0] = 0ULL; ch.bar[1] = 0ULL; ch.bar[2] = 0ULL; __threadfence(); }
-                }
-            }
-        }
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 1) { tcgen05_fence_after(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
-}
-
-cudaError_t launch_sk_chain(const SkChainMaps& maps, const SkChain& chain, int grid, cudaStream_t stream) {
-    if (chain.n_phases < 1 || chain.n_phases > SK_CHAIN_MAX_PHASES || chain.M <= 0 || chain.M > BLOCK_M || !chain.bar) return cudaErrorInvalidValue;
-    if (grid < 1 || grid > sm_count_cached()) return cudaErrorInvalidValue;      // the grid barrier needs every CTA resident
-    for (int p = 0; p < chain.n_phases; ++p) {
-        const SkChainPhase& P = chain.ph[p];
-        if (P.sk.bn != 128 || P.sk.rows != 128 || P.sk.G < 1 || P.sk.G > grid || !P.sk.ws) return cudaErrorInvalidValue;
-        if (P.consumer == SK_CONSUMER_RESID_RMSNORM && (P.H % 8 != 0 || P.H > 8192)) return cudaErrorInvalidValue;
-        if (P.consumer == SK_CONSUMER_SWIGLU && (P.F % 16 != 0 || !chain.tile_flags || P.sk.n_tiles > SK_CHAIN_MAX_TILES)) return cudaErrorInvalidValue;
-        if (P.consumer == SK_CONSUMER_ROPE_KV && P.rope.D % 16 != 0) return cudaErrorInvalidValue;
-    }
-    constexpr int SMEM = SkCfg<128, 1, 1>::SMEM_BYTES + 64;
-    static bool attr_done[16] = {};
-    { cudaError_t e = ensure_dynamic_smem(gemm_sk_chain_kernel, SMEM, attr_done); if (e != cudaSuccess) return e; }
-    return launch_k(gemm_sk_chain_kernel, dim3(grid), dim3(CHAIN_THREADS), SMEM, stream, maps, chain);
-}
-
 // ---------------------------------------------------------------------------------------------
 __global__ void argmax_reduce_kernel(const float* __restrict__ val, const int* __restrict__ idx, int M, int n_tiles,
                                      int32_t* __restrict__ out_ids, float* __restrict__ out_val) {

@@ -91,22 +91,7 @@ cudaError_t launch_gemm_clusterk_resid(const CUtensorMap* tmA, const CUtensorMap
 cudaError_t launch_gemm_clusterk_rope(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, int S, const SkRopeArgs& rope, cudaStream_t stream);
 // xn = rmsnorm(x) * gain with exactly the reduction order of launch_sk_resid_rmsnorm (512 threads per row)
 cudaError_t launch_rmsnorm_wide(const void* x, const void* gain, void* xn, int T, int H, float eps, cudaStream_t s);
-enum SkConsumer : int { SK_CONSUMER_NONE = 0, SK_CONSUMER_RESID_RMSNORM = 1, SK_CONSUMER_SWIGLU = 2, SK_CONSUMER_ROPE_KV = 3 };
-struct SkChainPhase {
-    StreamK sk; int consumer;
-    void* x; const void* gain; void* xn; int H; float eps;     // SK_CONSUMER_RESID_RMSNORM
-    void* act; int F;                                          // SK_CONSUMER_SWIGLU
-    SkRopeArgs rope;                                           // SK_CONSUMER_ROPE_KV
-};
-constexpr int SK_CHAIN_MAX_PHASES = 4, SK_CHAIN_MAX_TILES = 1024;
-struct SkChain {
-    int n_phases, M; unsigned long long* bar; SkChainPhase ph[SK_CHAIN_MAX_PHASES];
-    unsigned int* tile_flags;       // [SK_CHAIN_MAX_PHASES][SK_CHAIN_MAX_TILES], zero between launches: pieces of a fused-SwiGLU tile published so far
-    int l2_prefetch_units;          // weight tiles of the next phase each CTA pulls into L2 while it waits at a phase boundary
-    unsigned long long* trace;      // null, or [grid][32] clock64 stamps of the phase boundaries (OA_CHAIN_TRACE=1, dev tooling)
-};   // bar: 3 counters, zero between launches (the kernel resets them)
-struct SkChainMaps { CUtensorMap a[SK_CHAIN_MAX_PHASES], b[SK_CHAIN_MAX_PHASES]; };
-cudaError_t launch_sk_chain(const SkChainMaps& maps, const SkChain& chain, int grid, cudaStream_t stream);
+constexpr int SK_MAX_FLAG_TILES = 1024;      // per-projection capacity of the per-tile piece counters the fused stream-K epilogues use
 
 // reduce EPI_LOGITS partials: out_ids[M] = argmax over n_tiles (ties -> lowest column index)
 cudaError_t launch_argmax_reduce(const float* amax_val, const int* amax_idx, int M, int n_tiles, int32_t* out_ids,

@@ -205,14 +205,8 @@ DeviceModel::DeviceModel(const ModelConfig& c, const EngineOptions& o) : cfg(c),
         size_t wsb = 0;
         for (int n : {qkvd, H, 2 * F}) { wsb = std::max(wsb, streamk_ws_bytes(n, 256, sk_G_, 128)); wsb = std::max(wsb, streamk_ws_bytes(n, 128, sk_G_, 256)); wsb = std::max(wsb, streamk_ws_bytes(n, 64, sk_G_, 128)); }
         sk_ws_ = reinterpret_cast<float*>(dmalloc(wsb));
-        chain_bar_ = reinterpret_cast<unsigned long long*>(dmalloc(64));
-        cuda_check(cudaMemset(chain_bar_, 0, 64), "chain barrier memset");
-        chain_flags_ = reinterpret_cast<unsigned int*>(dmalloc((size_t)SK_CHAIN_MAX_PHASES * SK_CHAIN_MAX_TILES * 4));
-        cuda_check(cudaMemset(chain_flags_, 0, (size_t)SK_CHAIN_MAX_PHASES * SK_CHAIN_MAX_TILES * 4), "chain flags memset");
-        if (const char* e = std::getenv("OA_CHAIN_TRACE")) if (e[0] == '1') {
-            chain_trace_ = reinterpret_cast<unsigned long long*>(dmalloc((size_t)sm_count * 32 * 8));
-            cuda_check(cudaMemset(chain_trace_, 0, (size_t)sm_count * 32 * 8), "chain trace memset");
-        }
+        tile_flags_ = reinterpret_cast<unsigned int*>(dmalloc((size_t)4 * SK_MAX_FLAG_TILES * 4));
+        cuda_check(cudaMemset(tile_flags_, 0, (size_t)4 * SK_MAX_FLAG_TILES * 4), "stream-K tile flags memset");
         // 32-bit index arithmetic in the consumers: (units of the largest shape + kb) * G must stay below 2^32
         const double worst = ((double)((2 * F + sk_bn_ - 1) / sk_bn_) * ((std::max(H, F) + 63) / 64) + (std::max(H, F) + 63) / 64) * sk_G_;
         if (worst >= 4.0e9) throw std::runtime_error("stream-K index range exceeds 32 bits for this model");
@@ -306,21 +300,6 @@ void DeviceModel::load_checkpoint(const std::string& path) {
 DeviceModel::~DeviceModel() {
     DeviceGuard guard(opt.device);
     if (stream) cudaStreamSynchronize(stream);
-    if (chain_trace_) {      // dev tooling: where the last chained launch spent its cycles (per-CTA clock64 deltas from kernel start)
-        std::vector<unsigned long long> t((size_t)sm_count * 32);
-        cudaMemcpy(t.data(), chain_trace_, t.size() * 8, cudaMemcpyDeviceToHost);
-        static const char* nm[5] = {"partials stored", "B1 passed", "consumer done", "A dependency met (producer)", "first accumulator ready"};
-        std::fprintf(stderr, "[chain trace] cycles since kernel start, mean/min/max over CTAs\n");
-        for (int slot = 1; slot < 1 + 5 * SK_CHAIN_MAX_PHASES; ++slot) {
-            double sum = 0; long long mn = 1LL << 60, mx = 0; int n = 0;
-            for (int c = 0; c < sm_count; ++c) {
-                const unsigned long long t0 = t[(size_t)c * 32], v = t[(size_t)c * 32 + slot];
-                if (!v || !t0) continue;
-                const long long d = (long long)(v - t0); sum += d; mn = std::min(mn, d); mx = std::max(mx, d); ++n;
-            }
-            if (n) std::fprintf(stderr, "  phase %d %-28s %9.0f %9lld %9lld  (%d CTAs)\n", (slot - 1) / 5, nm[(slot - 1) % 5], sum / n, mn, mx, n);
-        }
-    }
     for (auto& e : ev) cudaEventDestroy(e);
     for (void* p : allocs_) cudaFree(p);
     if (h_out_ids) cudaFreeHost(h_out_ids);
@@ -499,55 +478,24 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
         const StreamK sk_gu = make_streamk(sk_ws_, 2 * F, H, bn_of(opt.sk_bn_gu), sk_G_, sk_rows), sk_dn = make_streamk(sk_ws_, H, F, bn_of(opt.sk_bn_down), sk_G_, sk_rows);
         cuda_check(launch_rmsnorm(x_, layers[0].ln1, xn_, T, H, cfg.rms_eps, stream), "rmsnorm1"); MARK(1);
         const StreamK pf_qkv = with_pf(sk_qkv), pf_o = with_pf(sk_o), pf_gu = with_pf(sk_gu), pf_dn = with_pf(sk_dn);
-        // tp == 1, one row tile, BN=128 everywhere: o -> resid+norm -> gate_up -> SwiGLU -> down -> resid+norm (and, with
-        // sk_chain=2, the next layer's qkv -> RoPE/KV write) run as ONE persistent kernel with grid barriers between the phases
-        const int chain_mode = (!use_tp && sk_rows == 128 && sk_G_ <= sm_count && sk_gu.n_tiles <= SK_CHAIN_MAX_TILES && sk_qkv.bn == 128 && sk_o.bn == 128 && sk_gu.bn == 128 && sk_dn.bn == 128)
-                                   ? opt.sk_chain : 0;
         // qkv / o / down epilogues finished inside the GEMM (same conditions as the fused SwiGLU; every projection at BN = 128, tile counts within the flag arrays)
         const bool fuse_ok = sk_rows == 128 && sk_G_ <= sm_count && sk_qkv.bn == 128 && sk_o.bn == 128 && sk_dn.bn == 128 &&
-                              sk_qkv.n_tiles <= SK_CHAIN_MAX_TILES && sk_o.n_tiles <= SK_CHAIN_MAX_TILES && (D == 64 || D == 128);
+                              sk_qkv.n_tiles <= SK_MAX_FLAG_TILES && sk_o.n_tiles <= SK_MAX_FLAG_TILES && (D == 64 || D == 128);
         const bool fuse_rope = fuse_ok && (opt.sk_fuse_epi & 1), fuse_o = fuse_ok && !use_tp && (opt.sk_fuse_epi & 2), fuse_dn = fuse_ok && !use_tp && (opt.sk_fuse_epi & 4);
         // cluster split-K (few-tile projections): cluster size per shape, 0 = keep stream-K.  o / down finish the residual add themselves, so
         // they are single-GPU only (a tensor-parallel rank must hand its partial to the all-reduce instead)
         const int ck_qkv = (sk_rows == 128 && (opt.sk_clusterk & 1) && (D == 64 || D == 128)) ? clusterk_pick(qkvd, H, sm_count, opt.sk_clusterk_min_fill) : 0;
         const int ck_o = (sk_rows == 128 && (opt.sk_clusterk & 2) && !use_tp) ? clusterk_pick(H, qd, sm_count, opt.sk_clusterk_min_fill) : 0;
         const int ck_dn = (sk_rows == 128 && (opt.sk_clusterk & 4) && !use_tp) ? clusterk_pick(H, F, sm_count, opt.sk_clusterk_min_fill) : 0;
-        const bool fuse_swiglu = opt.sk_fuse_swiglu && sk_rows == 128 && sk_gu.bn == 128 && sk_G_ <= sm_count && sk_gu.n_tiles <= SK_CHAIN_MAX_TILES;
-        auto qkv_phase = [&](int l, SkChainPhase& P) {
-            P.sk = sk_qkv; P.consumer = SK_CONSUMER_ROPE_KV;
-            P.rope = make_sk_rope_args(layers[l].bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, nh);
-        };
+        const bool fuse_swiglu = opt.sk_fuse_swiglu && sk_rows == 128 && sk_gu.bn == 128 && sk_G_ <= sm_count && sk_gu.n_tiles <= SK_MAX_FLAG_TILES;
         for (int l = 0; l < L; ++l) {
             const Layer& ly = layers[l];
-            if (chain_mode) {
-                if (chain_mode < 2 || l == 0) {
-                    cuda_check(launch_gemm_streamk(&tm_xn_, ly.qkv.map(128), T, qkvd, H, pf_qkv, stream), "qkv gemm (stream-K)"); MARK(2);
-                    cuda_check(launch_sk_rope_kv_write(sk_qkv, ly.bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, T, nh, stream), "rope (stream-K)"); MARK(3);
-                }
-                attention(l);
-                SkChainMaps maps; SkChain ch{}; ch.M = T; ch.bar = chain_bar_; ch.trace = chain_trace_; ch.tile_flags = chain_flags_;
-                ch.l2_prefetch_units = std::max(0, opt.sk_chain_pf_kb * 1024 / (128 * 128));
-                maps.a[0] = tm_attn_; maps.b[0] = *ly.o.map(128);
-                ch.ph[0].sk = sk_o; ch.ph[0].consumer = SK_CONSUMER_RESID_RMSNORM; ch.ph[0].x = x_; ch.ph[0].gain = ly.ln2; ch.ph[0].xn = xn_; ch.ph[0].H = H; ch.ph[0].eps = cfg.rms_eps;
-                maps.a[1] = tm_xn_; maps.b[1] = *ly.gu.map(128);
-                ch.ph[1].sk = sk_gu; ch.ph[1].consumer = SK_CONSUMER_SWIGLU; ch.ph[1].act = act_; ch.ph[1].F = F;
-                maps.a[2] = tm_act_; maps.b[2] = *ly.down.map(128);
-                ch.ph[2].sk = sk_dn; ch.ph[2].consumer = SK_CONSUMER_RESID_RMSNORM; ch.ph[2].x = x_; ch.ph[2].gain = (l + 1 < L) ? layers[l + 1].ln1 : final_norm;
-                ch.ph[2].xn = xn_; ch.ph[2].H = H; ch.ph[2].eps = cfg.rms_eps;
-                ch.n_phases = 3;
-                if (chain_mode >= 2 && l + 1 < L) {
-                    maps.a[3] = tm_xn_; maps.b[3] = *layers[l + 1].qkv.map(128);
-                    qkv_phase(l + 1, ch.ph[3]); ch.n_phases = 4;
-                } else { maps.a[3] = tm_xn_; maps.b[3] = maps.b[2]; }
-                cuda_check(launch_sk_chain(maps, ch, sk_G_, stream), "chained o/gate_up/down (stream-K)"); MARK(8);
-                continue;
-            }
             if (ck_qkv) {
                 cuda_check(launch_gemm_clusterk_rope(&tm_xn_, ly.qkv.map(128), T, qkvd, H, ck_qkv, make_sk_rope_args(ly.bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, nh), stream),
                            "qkv gemm + RoPE + KV write (cluster split-K)"); MARK(2);
             } else if (fuse_rope) {
                 cuda_check(launch_gemm_streamk_rope(&tm_xn_, ly.qkv.map(128), T, qkvd, H, pf_qkv, make_sk_rope_args(ly.bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, nh),
-                                                    chain_flags_ + 0 * SK_CHAIN_MAX_TILES, stream), "qkv gemm + RoPE + KV write (stream-K)"); MARK(2);
+                                                    tile_flags_ + 0 * SK_MAX_FLAG_TILES, stream), "qkv gemm + RoPE + KV write (stream-K)"); MARK(2);
             } else {
                 cuda_check(launch_gemm_streamk(&tm_xn_, ly.qkv.map(sk_qkv.bn), T, qkvd, H, pf_qkv, stream), "qkv gemm (stream-K)"); MARK(2);
                 cuda_check(launch_sk_rope_kv_write(sk_qkv, ly.bqkv, d_pos, d_slot, rope_cos, rope_sin, q_, kv, l, T, nh, stream), "rope (stream-K)"); MARK(3);
@@ -557,7 +505,7 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
                 cuda_check(launch_gemm_clusterk_resid(&tm_attn_, ly.o.map(128), T, H, qd, ck_o, x_, H, stream), "o gemm + residual (cluster split-K)"); MARK(6);
                 cuda_check(launch_rmsnorm_wide(x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "rmsnorm2"); MARK(7);
             } else if (fuse_o) {
-                cuda_check(launch_gemm_streamk_resid(&tm_attn_, ly.o.map(128), T, H, qd, pf_o, x_, H, chain_flags_ + 1 * SK_CHAIN_MAX_TILES, stream), "o gemm + residual (stream-K)"); MARK(6);
+                cuda_check(launch_gemm_streamk_resid(&tm_attn_, ly.o.map(128), T, H, qd, pf_o, x_, H, tile_flags_ + 1 * SK_MAX_FLAG_TILES, stream), "o gemm + residual (stream-K)"); MARK(6);
                 cuda_check(launch_rmsnorm_wide(x_, ly.ln2, xn_, T, H, cfg.rms_eps, stream), "rmsnorm2"); MARK(7);
             } else {
             cuda_check(launch_gemm_streamk(&tm_attn_, ly.o.map(sk_o.bn), T, H, qd, pf_o, stream), "o gemm (stream-K)"); MARK(6);
@@ -582,7 +530,7 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
             MARK(7);
             }
             if (fuse_swiglu) {
-                cuda_check(launch_gemm_streamk_swiglu(&tm_xn_, ly.gu.map(128), T, F, H, pf_gu, act_, chain_flags_ + 2 * SK_CHAIN_MAX_TILES, stream), "gate_up gemm + SwiGLU (stream-K)"); MARK(8);
+                cuda_check(launch_gemm_streamk_swiglu(&tm_xn_, ly.gu.map(128), T, F, H, pf_gu, act_, tile_flags_ + 2 * SK_MAX_FLAG_TILES, stream), "gate_up gemm + SwiGLU (stream-K)"); MARK(8);
             } else {
                 cuda_check(launch_gemm_streamk(&tm_xn_, ly.gu.map(sk_gu.bn), T, 2 * F, H, pf_gu, stream), "gate_up gemm (stream-K)"); MARK(8);
                 cuda_check(launch_sk_swiglu(sk_gu, act_, T, F, stream), "swiglu"); MARK(9);
@@ -594,7 +542,7 @@ void DeviceModel::forward(const StepInput& in, float* logits_out) {
                 continue;
             }
             if (fuse_dn) {
-                cuda_check(launch_gemm_streamk_resid(&tm_act_, ly.down.map(128), T, H, F, pf_dn, x_, H, chain_flags_ + 3 * SK_CHAIN_MAX_TILES, stream), "down gemm + residual (stream-K)"); MARK(10);
+                cuda_check(launch_gemm_streamk_resid(&tm_act_, ly.down.map(128), T, H, F, pf_dn, x_, H, tile_flags_ + 3 * SK_MAX_FLAG_TILES, stream), "down gemm + residual (stream-K)"); MARK(10);
                 cuda_check(launch_rmsnorm_wide(x_, next_gain, xn_, T, H, cfg.rms_eps, stream), "rmsnorm1"); MARK(7);
                 continue;
             }

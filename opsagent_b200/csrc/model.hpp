@@ -87,9 +87,7 @@ private:
     float *part_o_ = nullptr, *part_ml_ = nullptr; int max_part_slots_ = 0;
     float* sk_ws_ = nullptr; int sk_bn_ = 256, sk_G_ = 148;
     size_t nvls_region_ = 0;                       // bytes of one [128 rows, H] fp32 region of the NVLS multicast buffer (partials 0/1, reduced 0/1)
-    unsigned long long* chain_trace_ = nullptr;    // OA_CHAIN_TRACE=1: per-CTA clock stamps of the last chained launch, printed at teardown
-    unsigned int* chain_flags_ = nullptr;          // per-tile piece counters of the fused SwiGLU epilogue (self-resetting)
-    unsigned long long* chain_bar_ = nullptr;      // grid-barrier counters of the chained decode kernel (self-resetting)
+    unsigned int* tile_flags_ = nullptr;           // per-tile piece counters of the fused stream-K epilogues, [4 projections][SK_MAX_FLAG_TILES] (self-resetting)
     // pinned staging is double-buffered and fenced by events: the host may run ahead of the stream by a whole forward
     int32_t* h_meta_buf_[2] = {nullptr, nullptr}; cudaEvent_t meta_ev_[2] = {nullptr, nullptr}; int meta_idx_ = 0;
     int32_t *h_meta_ = nullptr, *d_meta_ = nullptr; size_t meta_cap_words_ = 0;

@@ -1,6 +1,6 @@
 // sk_consumers.cuh — the consumers of stream-K partials as device functions: each adds a tile's fp32 partials in CTA
 // order (deterministic) and finishes the op.  Shared by the stand-alone consumer kernels (elementwise.cu) and by the
-// chained decode kernel (gemm_tcgen05.cu: gemm_sk_chain_kernel), so both paths produce bit-identical results.
+// GEMM epilogues that finish an op themselves (gemm_tcgen05.cu FUSE=2/3, gemm_clusterk.cu), so every path produces bit-identical results.
 #pragma once
 #include "common.cuh"
 #include "kernels.hpp"

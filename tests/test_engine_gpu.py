@@ -78,20 +78,18 @@ def test_two_row_tile_streamk_path_matches_oracle():
 
 @pytest.mark.parametrize("name", CASES + ["llama-3.2-1b"])
 def test_fused_decode_epilogues_are_bit_identical_to_separate_kernels(name):
-    """Baseline: one kernel per projection and per consumer (sk_fuse_swiglu=0, sk_fuse_epi=0, sk_chain=0).  Variants: the qkv projection
+    """Baseline: one kernel per projection and per consumer (sk_fuse_swiglu=0, sk_fuse_epi=0).  Variants: the qkv projection
     finishing bias + RoPE + the paged-KV write and the o / down projections finishing the residual add in their own epilogues
     (sk_fuse_epi bitmask 1 / 2 / 4; o and down are followed by a norm-only kernel with the consumer's reduction order); the gate/up projection finishing
-    SwiGLU in its own epilogue (the CTA holding a tile's first k-block adds the other CTAs' pieces in CTA order); and the opt-in chained
-    kernel (sk_chain=1/2: o -> resid+norm -> gate_up+SwiGLU -> down -> resid+norm (-> next qkv -> RoPE/KV) in ONE persistent launch with
-    grid barriers).  Reduction order and consumer code are shared, so logits and generated ids must be EQUAL, not close.
+    SwiGLU in its own epilogue (the CTA holding a tile's first k-block adds the other CTAs' pieces in CTA order).  Reduction order and consumer code are shared, so logits and generated ids must be EQUAL, not close.
     llama-3.2-1b exercises real multi-CTA tile splits on all 148 SMs."""
     full = name == "llama-3.2-1b"
     rng = np.random.default_rng(77)
     spec = O.PRESETS[name]
     prompts = [rng.integers(0, spec.vocab if not full else 256, size=n).astype(np.int32) for n in ((1, 33, 128) if not full else (7, 128))]
     gen_prompts = [rng.integers(0, 256, size=n).astype(np.int32).tolist() for n in (3, 19, 40, 64, 90)]
-    variants = [dict(sk_fuse_swiglu=0, sk_fuse_epi=0, sk_chain=0), dict(sk_fuse_swiglu=1, sk_fuse_epi=0, sk_chain=0), dict(sk_fuse_swiglu=0, sk_fuse_epi=7, sk_chain=0),
-                dict(sk_fuse_swiglu=1, sk_fuse_epi=1, sk_chain=0), dict(sk_fuse_swiglu=1, sk_fuse_epi=6, sk_chain=0), dict(sk_chain=1), dict(sk_chain=2)]
+    variants = [dict(sk_fuse_swiglu=0, sk_fuse_epi=0), dict(sk_fuse_swiglu=1, sk_fuse_epi=0), dict(sk_fuse_swiglu=0, sk_fuse_epi=7),
+                dict(sk_fuse_swiglu=1, sk_fuse_epi=1), dict(sk_fuse_swiglu=1, sk_fuse_epi=6)]
     results = []
     for kw in variants:
         if full:
@@ -100,7 +98,7 @@ def test_fused_decode_epilogues_are_bit_identical_to_separate_kernels(name):
             _, eng = make_engine(name, **kw)
         logits = [eng.debug_prefill_logits(t) for t in prompts]
         # one request at a time keeps the batch composition (and with it the attention work plan) identical across variants;
-        # twice: the barrier counters and tile flags must re-arm between launches
+        # twice: the tile flags must re-arm between launches
         outs = []
         for _ in range(2):
             outs.append([list(eng.generate(pt, 12 if full else 30, flags=1).token_ids) for pt in gen_prompts])
