@@ -163,3 +163,14 @@ def test_json_writer_replaces_ill_formed_utf8_like_python():
         rc, out = _roundtrip(b'"' + raw + b'"')
         assert rc == 0
         assert json.loads(out.decode("utf-8")) == raw.decode("utf-8", "replace"), raw
+
+
+def test_serve_cli_fails_loudly_without_a_gpu_and_never_falls_back():
+    """python -m opsagent_b200.serve on a box without CUDA: a non-zero exit naming the reason, not a CPU path"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the GPU-less container")
+    r = subprocess.run([sys.executable, "-m", "opsagent_b200.serve", "--model", "llama-3.2-1b", "--port", "0"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
