@@ -118,9 +118,11 @@ struct JsonParser {
         else if (e - p >= 4 && !std::strncmp(p, "null", 4)) { j.t = Json::Null; p += 4; }
         else {
             const char* b = p;
-            while (p < e && (std::strchr("+-.eE", *p) || (*p >= '0' && *p <= '9'))) ++p;
-            if (p == b) { err = "unexpected character"; ok = false; }
-            else { j.t = Json::Num; j.n = std::strtod(std::string(b, p).c_str(), nullptr); }
+            while (p < e && *p != 0 && (std::strchr("+-.eE", *p) || (*p >= '0' && *p <= '9'))) ++p;
+            const std::string tok(b, p); char* endp = nullptr;
+            if (!tok.empty()) j.n = std::strtod(tok.c_str(), &endp);
+            if (tok.empty() || tok[0] == '+' || tok[0] == '.' || endp != tok.c_str() + tok.size() || !std::isfinite(j.n)) { err = "unexpected character"; ok = false; }
+            else j.t = Json::Num;
         }
         --depth; return ok;
     }

@@ -145,14 +145,14 @@ def test_json_reader_and_writer_agree_with_python(value, ascii_escapes):
 
 
 def test_json_reader_rejects_what_python_rejects():
-    for bad in [b"", b"{", b"[1,]", b'{"a" 1}', b'{"a":1,}', b"tru", b'"unterminated', b'"bad \\x escape"', b"01", b"1 2", b'{"a":1} x', b"[" * 100, b'"\\ud800"x']:
+    for bad in [b"", b"{", b"[1,]", b'{"a" 1}', b'{"a":1,}', b"tru", b'"unterminated', b'"bad \\x escape"', b"01", b"1 2", b'{"a":1} x', b"[" * 100, b'"\\ud800"x', b"1-2", b"1e", b"--1", b"+1", b".5", b"[1\x00]", b"1e999"]:
         rc, out = _roundtrip(bad)
         ok = True
         try:
             json.loads(bad)
         except Exception:
             ok = False
-        assert (rc == 0) == ok or bad in (b"01",), (bad, rc, out)      # leading zeros: accepted by strtod-style readers, harmless
+        assert (rc == 0) == ok or bad in (b"01", b"1e999"), (bad, rc, out)      # leading zeros: accepted by strtod-style readers, harmless; an overflowing number is refused (Python reads inf)
     rc, out = _roundtrip(b'"\\ud83d\\ude00 \\u00e9 \\u4e2d"')
     assert rc == 0 and json.loads(out.decode()) == "\U0001F600 é 中"
 
