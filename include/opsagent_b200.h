@@ -110,7 +110,7 @@ OA_API int oa_model_info(oa_engine*, char* buf, size_t n);   /* JSON: resolved a
  * format (openai.go:70-82) incl. `tools` -> grammar-forced `tool_calls`, GET /v1/models, GET /api/perf/stats.  One OS thread per connection; with
  * n_engines > 1 (data-parallel replicas, BASELINE configs[2]) conversations stick to the replica holding their prefix pages, new ones go to the
  * least-loaded replica, a replica over `max_inflight` answers 429 (openai.go:91-94 backs off).
- * options_json (flat): {"host":"127.0.0.1","port":0,"require_key":1,"api_key":"","tool_steps":3,"max_inflight":256,"max_connections":8192} */
+ * options_json (flat): {"host":"127.0.0.1","port":0,"require_key":1,"api_key":"","tool_steps":3,"max_inflight":256,"max_connections":8192,"max_body_bytes":67108864,"idle_timeout_s":120} */
 typedef struct oa_http oa_http;
 OA_API int oa_http_start(oa_engine* const* engines, int32_t n_engines, const char* options_json, oa_http** out);
 OA_API int32_t oa_http_port(oa_http*);                        /* the bound port (options "port": 0 picks a free one) */

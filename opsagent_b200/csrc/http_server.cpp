@@ -191,6 +191,7 @@ public:
     HttpFront(std::vector<oa_engine*> engines, const JsonFlat& opt) : engines_(std::move(engines)), inflight_(engines_.size()), routed_(engines_.size()) {
         require_key_ = opt.i("require_key", 1) != 0; api_key_ = opt.s("api_key", ""); tool_steps_ = (int)opt.i("tool_steps", 3);
         max_inflight_ = (int)opt.i("max_inflight", 256); max_conn_ = (int)opt.i("max_connections", 8192); max_body_ = (size_t)opt.i("max_body_bytes", 64 << 20);
+        idle_timeout_ms_ = (int)std::max<long long>(200, opt.i("idle_timeout_s", 120) * 1000);
         for (auto& a : inflight_) a.store(0);
         for (auto& a : routed_) a.store(0);
         const std::string host = opt.s("host", "127.0.0.1");
@@ -209,8 +210,9 @@ public:
     // false: a connection thread is still inside the engine — the caller must not free this object
     bool stop() {
         if (!stop_.exchange(true)) {
-            shutdown(lsock_, SHUT_RDWR); close(lsock_);
+            shutdown(lsock_, SHUT_RDWR);                       // wakes the acceptor's poll; the descriptor is closed only after the thread is gone
             if (acceptor_.joinable()) acceptor_.join();
+            close(lsock_);
         }
         const auto t0 = std::chrono::steady_clock::now();
         while (n_conn_.load() > 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < 30.0) std::this_thread::sleep_for(std::chrono::milliseconds(5));
@@ -239,7 +241,8 @@ private:
             if (n_conn_.load() >= max_conn_) { respond(c, 429, error_body(429, "too many connections"), false); close(c); continue; }
             int one = 1; setsockopt(c, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
             n_conn_.fetch_add(1);
-            std::thread([this, c] { serve_connection(c); close(c); n_conn_.fetch_sub(1); }).detach();
+            try { std::thread([this, c] { serve_connection(c); close(c); n_conn_.fetch_sub(1); }).detach(); }
+            catch (const std::exception&) { n_conn_.fetch_sub(1); respond(c, 429, error_body(429, "cannot start a connection thread"), false); close(c); }
         }
     }
     // read one request; false = connection closed / malformed (a reply has been sent where one was possible)
@@ -280,11 +283,12 @@ private:
         return true;
     }
     bool fill(int c, std::string& buf) {
+        int idle_ms = 0;
         while (!stop_.load()) {
             pollfd p{c, POLLIN, 0};
             const int r = poll(&p, 1, 200);
             if (r < 0) return false;
-            if (r == 0) continue;
+            if (r == 0) { if ((idle_ms += 200) >= idle_timeout_ms_) return false; continue; }      // silent for too long (idle keep-alive or a stalled sender): drop it
             char tmp[16384];
             const ssize_t n = recv(c, tmp, sizeof tmp, 0);
             if (n <= 0) return false;
@@ -345,7 +349,8 @@ private:
             if (!read_request(c, buf, rq)) return;
             n_req_.fetch_add(1);
             int status = 200; std::string body;
-            handle(rq, status, body);
+            try { handle(rq, status, body); }
+            catch (const std::exception& e) { status = 500; body = error_body(500, std::string("internal error: ") + e.what()); }
             respond(c, status, body, rq.keep_alive);
             if (!rq.keep_alive) return;
         }
@@ -465,7 +470,7 @@ private:
     std::vector<std::atomic<int>> inflight_; std::vector<std::atomic<long long>> routed_;
     std::mutex mu_; std::unordered_map<uint64_t, int> home_;
     std::mutex perf_mu_; std::map<std::string, long long> perf_ns_, perf_n_; std::chrono::system_clock::time_point perf_reset_ = std::chrono::system_clock::now();
-    bool require_key_ = true; std::string api_key_, model_; int tool_steps_ = 3, max_inflight_ = 256, max_conn_ = 8192; size_t max_body_ = 64 << 20;
+    bool require_key_ = true; std::string api_key_, model_; int tool_steps_ = 3, max_inflight_ = 256, max_conn_ = 8192, idle_timeout_ms_ = 120000; size_t max_body_ = 64 << 20;
     int lsock_ = -1, port_ = 0; std::thread acceptor_; std::atomic<bool> stop_{false};
     std::atomic<int> n_conn_{0}; std::atomic<long long> n_req_{0}, n_chat_{0}, n_429_{0}, n_sticky_{0};
 };

@@ -12,11 +12,12 @@ from .engine import EngineError
 
 class NativeFront:
     def __init__(self, engines, host: str = "127.0.0.1", port: int = 0, require_key: bool = True, api_key: str = "", tool_steps: int = 3,
-                 max_inflight: int = 256):
+                 max_inflight: int = 256, **options):
         self._L = _lib.load()
         self.engines = list(engines)               # keep them alive as long as the front runs
         arr = (C.c_void_p * max(1, len(self.engines)))(*[e._h for e in self.engines])
-        opts = json.dumps({"host": host, "port": port, "require_key": int(require_key), "api_key": api_key, "tool_steps": tool_steps, "max_inflight": max_inflight})
+        opts = json.dumps({"host": host, "port": port, "require_key": int(require_key), "api_key": api_key, "tool_steps": tool_steps, "max_inflight": max_inflight,
+                           **options})          # further flat options of oa_http_start: max_connections, max_body_bytes, idle_timeout_s
         h = C.c_void_p()
         rc = self._L.oa_http_start(arr, len(self.engines), opts.encode(), C.byref(h))
         if rc != 0:

@@ -96,6 +96,21 @@ def test_hostile_clients_do_not_take_the_server_down(front):
     assert st == 200
 
 
+def test_silent_connections_are_dropped_after_the_idle_timeout():
+    import time
+    f = NativeFront([], idle_timeout_s=1)
+    try:
+        s = socket.create_connection(("127.0.0.1", f.port)); s.settimeout(10)
+        s.sendall(b"POST /v1/chat/completions HTTP/1.1\r\nContent-Length: 10\r\n\r\nabc")        # stalls mid-body
+        t0 = time.time()
+        assert s.recv(100) == b"" and 0.5 < time.time() - t0 < 5         # closed by the server, no reply owed
+        s.close()
+        st, j, _ = _req(f.port, "GET", "/v1/models")
+        assert st == 200
+    finally:
+        f.shutdown()
+
+
 def test_no_key_required_when_disabled():
     f = NativeFront([], require_key=False)
     try:
