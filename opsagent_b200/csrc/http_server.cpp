@@ -10,6 +10,9 @@
 //     resends its history, pkg/assistants/simple.go:498-501); new conversations go to the replica with the fewest requests in flight; a
 //     replica over `max_inflight` answers 429, which the caller's retry loop backs off on (openai.go:91-94)  [opsagent_b200/router.py];
 //   * status codes are the ones Chat switches on: 400 fail fast, 401, 429 / 500 retry (openai.go:85-101); errors use the OpenAI error body.
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE      // POLLRDHUP
+#endif
 #include <arpa/inet.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
@@ -221,7 +224,7 @@ public:
     int port() const { return port_; }
     std::string stats_json() {
         std::string s = "{\"replicas\": " + std::to_string(engines_.size()) + ", \"requests\": " + std::to_string(n_req_.load()) + ", \"chat_completions\": " + std::to_string(n_chat_.load()) +
-                        ", \"rejected_429\": " + std::to_string(n_429_.load()) + ", \"sticky_hits\": " + std::to_string(n_sticky_.load()) + ", \"connections\": " + std::to_string(n_conn_.load()) + ", \"routed\": [";
+                        ", \"rejected_429\": " + std::to_string(n_429_.load()) + ", \"sticky_hits\": " + std::to_string(n_sticky_.load()) + ", \"cancelled\": " + std::to_string(n_cancelled_.load()) + ", \"connections\": " + std::to_string(n_conn_.load()) + ", \"routed\": [";
         for (size_t i = 0; i < routed_.size(); ++i) s += (i ? ", " : "") + std::to_string(routed_[i].load());
         s += "], \"inflight\": [";
         for (size_t i = 0; i < inflight_.size(); ++i) s += (i ? ", " : "") + std::to_string(inflight_[i].load());
@@ -231,7 +234,7 @@ public:
     }
 
 private:
-    struct Request { std::string method, path, auth, body; bool keep_alive = true; };
+    struct Request { std::string method, path, auth, body; bool keep_alive = true; int fd = -1; };
     void accept_loop() {
         while (!stop_.load()) {
             pollfd p{lsock_, POLLIN, 0};
@@ -345,12 +348,13 @@ private:
     void serve_connection(int c) {
         std::string buf;
         while (!stop_.load()) {
-            Request rq;
+            Request rq; rq.fd = c;
             if (!read_request(c, buf, rq)) return;
             n_req_.fetch_add(1);
             int status = 200; std::string body;
             try { handle(rq, status, body); }
             catch (const std::exception& e) { status = 500; body = error_body(500, std::string("internal error: ") + e.what()); }
+            if (status == 499) return;                      // the client hung up while its completion was running: nobody to answer
             respond(c, status, body, rq.keep_alive);
             if (!rq.keep_alive) return;
         }
@@ -429,6 +433,7 @@ private:
         if (engines_.empty()) { status = 500; body = error_body(500, "no engine behind this front"); return; }
         const int r = acquire(msgs);
         if (r < 0) { status = 429; body = error_body(429, "replica over its in-flight limit"); return; }
+        struct Release { std::atomic<int>& n; bool done = false; void now() { if (!done) { n.fetch_sub(1); done = true; } } ~Release() { now(); } } release{inflight_[(size_t)r]};
         const std::string model = req.str("model");
         std::vector<oa_msg> cm(msgs.size());
         for (size_t i = 0; i < msgs.size(); ++i) { cm[i].role = msgs[i].first.c_str(); cm[i].content = msgs[i].second.c_str(); }
@@ -437,8 +442,21 @@ private:
         oa_chat_resp out{}; char ebuf[512]; ebuf[0] = 0; uint64_t ticket = 0;
         const auto t_chat = std::chrono::steady_clock::now();
         int rc = oa_chat_submit_ex(engines_[(size_t)r], &creq, &ticket, ebuf, sizeof ebuf);
-        if (rc == 0) rc = oa_chat_wait_ex(engines_[(size_t)r], ticket, -1, &out, ebuf, sizeof ebuf);
-        inflight_[(size_t)r].fetch_sub(1);
+        // wait in slices: a caller that hangs up (the reference's HTTP client timing out, a cancelled context) or a front that is shutting down gives
+        // its KV pages and decode slot back instead of generating for nobody
+        while (rc == 0) {
+            rc = oa_chat_wait_ex(engines_[(size_t)r], ticket, 250, &out, ebuf, sizeof ebuf);
+            if (rc != OA_ERR_TIMEOUT) break;
+            rc = 0;
+            pollfd p{rq.fd, POLLRDHUP, 0};
+            const bool gone = rq.fd >= 0 && poll(&p, 1, 0) > 0 && (p.revents & (POLLRDHUP | POLLHUP | POLLERR));
+            if (gone || stop_.load()) {
+                oa_chat_cancel(engines_[(size_t)r], ticket); n_cancelled_.fetch_add(1);
+                if (gone) { status = 499; return; }
+                status = 500; body = error_body(500, "the front is shutting down"); return;
+            }
+        }
+        release.now();
         perf_record((flags & OA_FLAG_JSON_FUNCTION) ? "chat_completion_tool_call" : "chat_completion", std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_chat).count());
         if (rc != 0) { status = (rc == 400 || rc == 401 || rc == 429 || rc == 500) ? rc : 500; body = error_body(status, ebuf); return; }
         n_chat_.fetch_add(1);
@@ -472,7 +490,7 @@ private:
     std::mutex perf_mu_; std::map<std::string, long long> perf_ns_, perf_n_; std::chrono::system_clock::time_point perf_reset_ = std::chrono::system_clock::now();
     bool require_key_ = true; std::string api_key_, model_; int tool_steps_ = 3, max_inflight_ = 256, max_conn_ = 8192, idle_timeout_ms_ = 120000; size_t max_body_ = 64 << 20;
     int lsock_ = -1, port_ = 0; std::thread acceptor_; std::atomic<bool> stop_{false};
-    std::atomic<int> n_conn_{0}; std::atomic<long long> n_req_{0}, n_chat_{0}, n_429_{0}, n_sticky_{0};
+    std::atomic<int> n_conn_{0}; std::atomic<long long> n_req_{0}, n_chat_{0}, n_429_{0}, n_sticky_{0}, n_cancelled_{0};
 };
 
 }  // namespace oa

@@ -29,7 +29,7 @@ struct oa_engine {
     int id = 0;
     std::mutex mu; std::condition_variable cv_work, cv_done;
     std::deque<Job> queue; std::unordered_map<uint64_t, Job> done;
-    uint64_t next = 1; bool stop = false; long served = 0;
+    uint64_t next = 1; bool stop = false; long served = 0, cancelled = 0; std::unordered_map<uint64_t, bool> cancel_req;
     std::thread worker;
     void run() {
         std::mt19937 rng(1234u + (unsigned)id);
@@ -42,6 +42,14 @@ struct oa_engine {
                 j = std::move(queue.front()); queue.pop_front();
             }
             std::this_thread::sleep_for(std::chrono::microseconds(rng() % 1500));
+            if (j.text == "slow please") {          // a long completion: runs until it is cancelled (or 3 s)
+                bool dropped = false;
+                for (int k = 0; k < 60 && !dropped; ++k) {
+                    std::this_thread::sleep_for(std::chrono::milliseconds(50));
+                    std::lock_guard<std::mutex> lk(mu); dropped = cancel_req.count(j.ticket) != 0;
+                }
+                if (dropped) { std::lock_guard<std::mutex> lk(mu); cancel_req.erase(j.ticket); ++cancelled; continue; }
+            }
             if (j.flags & OA_FLAG_JSON_FUNCTION) {
                 const std::string f = j.functions.substr(0, j.functions.find(','));
                 const size_t c = f.find(':');
@@ -63,9 +71,11 @@ int oa_chat_submit_ex(oa_engine* e, const oa_chat_req* r, uint64_t* ticket, char
     e->cv_work.notify_one();
     return 0;
 }
-int oa_chat_wait_ex(oa_engine* e, uint64_t ticket, int32_t, oa_chat_resp* out, char*, size_t) {
+int oa_chat_cancel(oa_engine* e, uint64_t ticket) { std::lock_guard<std::mutex> lk(e->mu); e->cancel_req[ticket] = true; return 0; }
+int oa_chat_wait_ex(oa_engine* e, uint64_t ticket, int32_t timeout_ms, oa_chat_resp* out, char*, size_t) {
     std::unique_lock<std::mutex> lk(e->mu);
-    e->cv_done.wait(lk, [&] { return e->done.count(ticket) != 0; });
+    if (timeout_ms < 0) e->cv_done.wait(lk, [&] { return e->done.count(ticket) != 0; });
+    else if (!e->cv_done.wait_for(lk, std::chrono::milliseconds(timeout_ms), [&] { return e->done.count(ticket) != 0; })) return OA_ERR_TIMEOUT;
     Job j = std::move(e->done[ticket]); e->done.erase(ticket);
     out->content = (char*)std::malloc(j.text.size() + 1); std::memcpy(out->content, j.text.c_str(), j.text.size() + 1);
     out->content_len = (int32_t)j.text.size(); out->prompt_tokens = j.prompt_tokens; out->completion_tokens = 7; out->finish_reason = 0; out->token_ids = nullptr;
@@ -142,11 +152,26 @@ int main() {
         }
         if (s >= 0 && c % 2 == 0) close(s);          // odd clients leave their keep-alive connection open: stop() has to deal with it
     });
+    clients.emplace_back([&] {          // abandons three long completions: the front must notice the hang-up and cancel them in the engine
+        for (int k = 0; k < 3; ++k) {
+            const int s = dial(port);
+            const std::string body = "{\"messages\": [{\"role\": \"system\", \"content\": \"abandoner " + std::to_string(k) + "\"}, {\"role\": \"user\", \"content\": \"slow please\"}]}";
+            const std::string rq = "POST /v1/chat/completions HTTP/1.1\r\nAuthorization: Bearer k\r\nContent-Length: " + std::to_string(body.size()) + "\r\n\r\n" + body;
+            send(s, rq.data(), rq.size(), MSG_NOSIGNAL);
+            std::this_thread::sleep_for(std::chrono::milliseconds(300));
+            close(s);
+        }
+    });
     for (auto& t : clients) t.join();
+    std::this_thread::sleep_for(std::chrono::milliseconds(800));          // one wait slice + one stub poll tick
     char buf[1 << 14];
     CHECK(oa_http_stats(front, buf, sizeof buf) == 0);
     std::string st(buf);
     CHECK(st.find("\"replicas\": 3") != std::string::npos);
+    long cancelled = 0;
+    for (auto* e : engines) { std::lock_guard<std::mutex> lk(e->mu); cancelled += e->cancelled; }
+    CHECK(cancelled >= 1);                              // (a request rejected with 429 never reached an engine)
+    CHECK(st.find("\"cancelled\": 0") == std::string::npos);
     long served = 0;
     for (auto* e : engines) { std::lock_guard<std::mutex> lk(e->mu); served += e->served; }
     CHECK(served == n200.load());

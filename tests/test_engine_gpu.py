@@ -724,3 +724,35 @@ def test_native_front_routes_conversations_like_the_router_and_answers_like_one_
     assert set(codes) <= {200, 429} and codes.count(200) >= 8 and codes.count(429) >= 1
     assert front.stats()["rejected_429"] == codes.count(429)
     front.shutdown(); rt.close(); solo.close()
+
+
+def test_native_front_cancels_completions_of_clients_that_hang_up():
+    """a caller that gives up (the reference's HTTP client timing out, a cancelled context) must not keep a decode slot and KV pages: the front notices
+    the hang-up within one wait slice and calls oa_chat_cancel; the engine's own counter agrees and the pages come back"""
+    import json as _json
+    import socket
+    import time
+    from opsagent_b200.native_front import NativeFront
+    spec, eng = make_engine("tiny-llama", max_seq_len=8192, num_pages=800, max_batch=8)
+    front = NativeFront([eng])
+    socks = []
+    for k in range(6):          # six long completions (greedy on random weights mostly loops without ever emitting EOS; one that does simply finishes)
+        body = _json.dumps({"model": spec.name, "max_tokens": 7000, "messages": [{"role": "user", "content": f"prompt number {k}: " + "describe the cluster " * (k + 1)}]}).encode()
+        s = socket.create_connection(("127.0.0.1", front.port))
+        s.sendall(b"POST /v1/chat/completions HTTP/1.1\r\nAuthorization: Bearer x\r\nContent-Length: " + str(len(body)).encode() + b"\r\n\r\n" + body)
+        socks.append(s)
+    time.sleep(0.2)
+    for s in socks:
+        s.close()
+    t0 = time.time()
+    while time.time() - t0 < 10 and front.stats()["connections"] > 0:
+        time.sleep(0.05)
+    st = front.stats()
+    assert st["connections"] == 0 and st["cancelled"] >= 1, st
+    assert st["engines"][0]["cancelled"] == st["cancelled"]
+    assert time.time() - t0 < 3.0          # well before 7000 tokens would have been generated
+    out = eng.chat_complete(spec.name, [("user", "still alive?")], 8, flags=1)      # the engine carries on, pages are back
+    assert out.completion_tokens == 8
+    es = eng.stats()
+    assert es["running"] == 0 and es["waiting"] == 0 and es["pages_free"] >= es["pages_total"] - 16      # only prefix-cache pages of short prompts stay held
+    front.shutdown(); eng.close()
