@@ -118,3 +118,67 @@ def test_c_program_runs_a_chat_completion_on_the_gpu_and_matches_the_oracle(tmp_
     while k < 16 and got[k] == ref[k]:
         k += 1
     assert len(got) == 16 and (k == 16 or margins[k] <= 5e-2), (k, got, list(ref))
+
+
+def _build_server(tmp_path):
+    exe = tmp_path / "opsagent_serve"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "integration", "c", "opsagent_serve.c"),
+           "-o", str(exe), "-L", LIBDIR, "-lopsagent_b200", f"-Wl,-rpath,{LIBDIR}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="no C compiler")
+def test_standalone_c_server_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """integration/c/opsagent_serve.c: strict C99 on the C ABI only.  Without CUDA it must say so and exit 1 — never serve from a CPU path."""
+    import torch
+    exe = _build_server(tmp_path)
+    r = subprocess.run([str(exe), "--bogus"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "usage:" in r.stderr
+    r = subprocess.run([str(exe), "--engine", "[]"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2
+    if torch.cuda.is_available():
+        pytest.skip("the no-GPU half of this check is for the GPU-less container")
+    r = subprocess.run([str(exe), "--engine", '{"model": "llama-3.2-1b"}', "--port", "0"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="no C compiler")
+def test_standalone_c_server_serves_chat_completions_on_the_gpu(tmp_path):
+    """the C server with two replicas of a tiny model on this GPU: the wire answer equals the engine's own greedy completion; SIGTERM exits 0"""
+    import http.client
+    import json
+    import signal
+    from oracle import oracle as O          # presets only
+    from opsagent_b200 import Engine
+    spec = O.PRESETS["tiny-llama"]
+    cfg = spec.engine_json(num_pages=64, max_seq_len=512, max_batch=4, max_step_tokens=256)
+    exe = _build_server(tmp_path)
+    p = subprocess.Popen([str(exe), "--engine", json.dumps(cfg), "--devices", "0,0", "--port", "0", "--api-key", "k"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    try:
+        line = json.loads(p.stdout.readline())
+        assert line["replicas"] == 2
+        port = int(line["listening"].rsplit(":", 1)[1].split("/")[0])
+        msgs = [("system", "You are a Kubernetes expert."), ("user", "how many namespace in the cluster?")]
+        c = http.client.HTTPConnection("127.0.0.1", port, timeout=120)
+        c.request("POST", "/v1/chat/completions", body=json.dumps({"model": "gpt-4", "max_tokens": 12, "messages": [{"role": r, "content": t} for r, t in msgs]}),
+                  headers={"Authorization": "Bearer k"})
+        r = c.getresponse(); d = json.loads(r.read())
+        assert r.status == 200, d                     # "gpt-4": the server answers to any model name (execute.go:168-171 sends it when currentModel is empty)
+        c.request("POST", "/v1/chat/completions", body="{}", headers={"Authorization": "Bearer wrong"})
+        r = c.getresponse(); r.read()
+        assert r.status == 401
+        eng = Engine(cfg)
+        ref = eng.chat_complete(spec.name, msgs, 12)
+        eng.close()
+        assert d["choices"][0]["message"]["content"] == bytes(ref.content).decode("utf-8", "replace").rstrip("\n")
+        assert d["usage"]["completion_tokens"] == ref.completion_tokens
+    finally:
+        p.send_signal(signal.SIGTERM)
+        try:
+            rc = p.wait(timeout=60)
+        except subprocess.TimeoutExpired:
+            p.kill(); rc = -9
+    assert rc == 0, p.stderr.read()[-500:]
