@@ -417,7 +417,7 @@ private:
         if (const Json* st = req.get("stream")) if (st->t == Json::Bool && st->b) { status = 400; body = error_body(400, "streaming is not implemented (the reference does not request it)"); return; }
         if (const Json* tj = req.get("temperature")) if (tj->t == Json::Num && tj->n > 1e-3) { status = 400; body = error_body(400, "only greedy decoding is implemented"); return; }
         int max_tokens = 1024;
-        for (const char* k : {"max_tokens", "max_completion_tokens"}) if (const Json* mt = req.get(k)) if (mt->t == Json::Num && mt->n >= 1) { max_tokens = (int)mt->n; break; }
+        for (const char* k : {"max_tokens", "max_completion_tokens"}) if (const Json* mt = req.get(k)) if (mt->t == Json::Num && mt->n >= 1) { max_tokens = (int)std::min(mt->n, 1048576.0); break; }      // the engine clips to max_seq_len; the clamp keeps the double -> int conversion defined
         // OpenAI function calling (swarm-go flows, pkg/workflows/swarm.go:14-78): a grammar-forced call of one offered function while fewer than
         // `tool_steps` tool results are in the history, afterwards one line of text
         uint32_t flags = 0; std::string functions;
