@@ -75,6 +75,7 @@ int main(int argc, char** argv) {
         }
     }
     if (n == 0) { fprintf(stderr, "no devices given\n"); return 2; }
+    if (strpbrk(host, "\"\\") || strpbrk(api_key, "\"\\")) { fprintf(stderr, "--host / --api-key must not contain quotes or backslashes\n"); while (n > 0) oa_engine_destroy(engines[--n]); return 2; }
     snprintf(opts, sizeof opts, "{\"host\": \"%s\", \"port\": %d, \"require_key\": 1, \"api_key\": \"%s\", \"tool_steps\": %d, \"max_inflight\": %d}", host, port, api_key, tool_steps, max_inflight);
     if (oa_http_start(engines, n, opts, &front) != OA_OK) {
         fprintf(stderr, "front: %s\n", oa_http_last_error());
