@@ -33,7 +33,7 @@ def check_base(line):
     assert line["cpu_baseline"]["kind"] in ("port", "reference")
 
 
-@pytest.mark.parametrize("name", ["r01h_bench.json", "r01h_bench_dp4.json", "r02a_bench.json", "r02h_bench.json", "r02b_bench_dp4.json", "r02f_bench_dp4.json", "r02c_bench_dp8.json"])
+@pytest.mark.parametrize("name", ["r01h_bench.json", "r01h_bench_dp4.json", "r02a_bench.json", "r02h_bench.json", "r02b_bench_dp4.json", "r02f_bench_dp4.json", "r02c_bench_dp8.json", "r02j_bench_dp2.json", "r02k_bench.json"])
 def test_our_arm_line(name):
     line = load(name)
     if "dp" in name:
@@ -46,6 +46,8 @@ def test_our_arm_line(name):
         if line["n_gpus"] >= 2:
             assert "configs[2]" in line["config"]["workload"] and set(line["e2e"]["prompt_tokens_by_kind"]) == {"analyze", "diagnose", "execute"}
             assert line["router"]["completed"] == line["router"]["requests"] == line["n_gpus"] * 128
+            if name >= "r02i":          # the serving block goes through the native front from r02i on
+                assert line["router"]["front"] == "native" and line["router"]["errors"] == [] and line["router"]["rejected_429"] == 0
             tp = line["tp"]
             assert tp["parity"]["ok"] is True and tp["parity"]["t"] == line["n_gpus"] and tp["parity"]["max_dlogit"] < 2.5e-2
             assert tp["t"] == line["n_gpus"] and 0 < tp["roofline_frac_per_gpu"] < 1

@@ -189,3 +189,17 @@ def test_serve_cli_fails_loudly_without_a_gpu_and_never_falls_back():
         pytest.skip("this check is for the GPU-less container")
     r = subprocess.run([sys.executable, "-m", "opsagent_b200.serve", "--model", "llama-3.2-1b", "--port", "0"], capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
+def test_documented_front_options_are_the_ones_the_server_reads():
+    """include/opsagent_b200.h documents oa_http_start's options_json; csrc/http_server.cpp reads them with opt.i("…") / opt.s("…") — same set"""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "opsagent_b200.h")).read()
+    doc = hdr[hdr.index("options_json (flat):"):]
+    doc = doc[:doc.index("*/")]
+    documented = set(re.findall(r'"([a-z_]+)":', doc))
+    src = open(os.path.join(root, "opsagent_b200", "csrc", "http_server.cpp")).read()
+    parsed = set(re.findall(r'opt\.[is]\("([a-z_]+)"', src))
+    assert documented == parsed, (documented ^ parsed)
