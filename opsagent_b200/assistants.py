@@ -16,7 +16,7 @@ import json
 from dataclasses import dataclass, field
 from .perf import GetPerfStats
 
-from .llms import ChatCompletionMessage, ChatMessageRoleAssistant, ChatMessageRoleUser, ConstrictPrompt
+from .llms import ChatCompletionMessage, ChatMessageRoleAssistant, ChatMessageRoleUser, ConstrictPrompt, TrimSpace
 
 defaultMaxIterations = 5                                     # simple.go:22
 _TEMPLATE_PATTERNS = ["<最终答案", "<final_answer", "<Final answer", "<最终回答", "<回答", "<答案", "使用 Markdown 格式", "使用Markdown格式",
@@ -91,6 +91,10 @@ def go_json_string(s: str) -> str:
             out.append("\\r")
         elif ch == "\t":
             out.append("\\t")
+        elif ch == "\b":
+            out.append("\\b")            # Go >= 1.22 writes \b and \f in short form (the reference builds with go 1.24: go.mod:3, Dockerfile:2)
+        elif ch == "\f":
+            out.append("\\f")
         elif o < 0x20 or ch in "<>&" or o in (0x2028, 0x2029):
             out.append("\\u%04x" % o)
         elif 0xD800 <= o <= 0xDFFF:
@@ -148,7 +152,7 @@ def _assistant_loop(perf, model, prompts, maxTokens, maxIterations, client, tool
             if fn is not None:
                 perf.StartTimer("assistant_tool_" + tp.action["name"])                        # simple.go:440-475
                 try:
-                    observation = fn(tp.action["input"]).strip()
+                    observation = TrimSpace(fn(tp.action["input"]))                             # strings.TrimSpace (simple.go:444)
                 except Exception as e:
                     observation = f"Tool {tp.action['name']} failed with error {e}. Considering refine the inputs for the tool."
                 finally:

@@ -1,0 +1,200 @@
+// assistants.hpp — C++ host-side mirror of the CALLER of the Chat seam: the reference's ReAct loop
+//     func AssistantWithConfig(model, prompts, maxTokens, countTokens, verbose, maxIterations, apiKey, baseUrl) (string, []ChatCompletionMessage, error)
+//                                                                                             reference pkg/assistants/simple.go:292-616
+// with the pieces it needs from its neighbours:
+//     type ToolPrompt struct{ Question, Thought, Action{Name, Input}, Observation, FinalAnswer }          reference pkg/tools/tool.go:29-38
+//     json.Marshal / json.Unmarshal of it (encoding/json of go 1.24: go.mod:3)                            simple.go:366, 497, 541
+//     isTemplateValue                                                                                     simple.go:624-657
+//     llms.NumTokensFromMessages / llms.ConstrictPrompt                                                   reference pkg/llms/tokens.go:60, 128-144
+// The reference is Go (no toolchain in this image), so — like localcuda_client.hpp for the seam itself — the host side above the C ABI is written in
+// C++ with the same names, argument meaning and error behaviour.  The LLM call and the tools are injected (`ChatFn`, `Tool`): the reference's
+// pkg/tools shell out to kubectl / trivy (out of scope) and its client is built from apiKey/baseUrl on every call (simple.go:316),
+// which here is LocalCUDAClient::Chat bound to the process-wide engine.  opsagent_b200/assistants.py is the same loop in Python;
+// tests/test_host_cpp.py runs both on the same scripted scenarios and demands identical results and histories.
+#pragma once
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../csrc/json_dom.hpp"
+#include "localcuda_client.hpp"
+
+namespace opsagent {
+
+constexpr int defaultMaxIterations = 5;                                   // simple.go:22
+
+// encoding/json's string encoder with escapeHTML = true (the json.Marshal default), go >= 1.22: '<' '>' '&' become backslash-u 003c / 003e / 0026,
+// U+2028 / U+2029 become backslash-u 2028 / 2029, \b \f \n \r \t use the short forms, other control bytes backslash-u 00XX, every invalid UTF-8
+// byte becomes backslash-u fffd, everything else stays raw
+inline std::string GoJSONString(const std::string& s) {
+    std::string o = "\"";
+    for (size_t i = 0; i < s.size();) {
+        const unsigned char c = (unsigned char)s[i];
+        if (c < 0x80) {
+            switch (c) {
+                case '"': o += "\\\""; break; case '\\': o += "\\\\"; break; case '\n': o += "\\n"; break; case '\r': o += "\\r"; break; case '\t': o += "\\t"; break;
+                case '\b': o += "\\b"; break; case '\f': o += "\\f"; break;
+                default:
+                    if (c < 0x20 || c == '<' || c == '>' || c == '&') { char b[8]; std::snprintf(b, sizeof b, "\\u%04x", c); o += b; } else o += (char)c;
+            }
+            ++i; continue;
+        }
+        int bad; const int n = oa::utf8_seq(s, i, &bad);
+        if (!n) { o += "\\ufffd"; i += 1; continue; }                     // Go replaces every invalid byte on its own
+        if (n == 3 && c == 0xE2 && (unsigned char)s[i + 1] == 0x80 && ((unsigned char)s[i + 2] == 0xA8 || (unsigned char)s[i + 2] == 0xA9)) o += (unsigned char)s[i + 2] == 0xA8 ? "\\u2028" : "\\u2029";
+        else o.append(s, i, (size_t)n);
+        i += (size_t)n;
+    }
+    return o + "\"";
+}
+
+struct ToolAction { std::string Name, Input; };
+struct ToolPrompt {                                                       // tool.go:29-38, JSON keys question / thought / action{name,input} / observation / final_answer
+    std::string Question, Thought; ToolAction Action; std::string Observation, FinalAnswer;
+
+    // json.Marshal(toolPrompt), byte for byte: struct field order, no spaces (simple.go:497 sends this string as the next user message)
+    std::string Marshal() const {
+        return "{\"question\":" + GoJSONString(Question) + ",\"thought\":" + GoJSONString(Thought) + ",\"action\":{\"name\":" + GoJSONString(Action.Name) + ",\"input\":" +
+               GoJSONString(Action.Input) + "},\"observation\":" + GoJSONString(Observation) + ",\"final_answer\":" + GoJSONString(FinalAnswer) + "}";
+    }
+    // json.Unmarshal([]byte(text), &toolPrompt): the whole text must be valid JSON and an object; unknown keys are ignored, missing keys and JSON null
+    // leave the zero value, a key matches exactly or else case-insensitively, any other non-string value for a string field (or a non-object
+    // `action`) is an UnmarshalTypeError — the caller's "not JSON, assume final answer" / "Summarize…" branches, not a coercion
+    static bool Unmarshal(const std::string& text, ToolPrompt* out, std::string* err) {
+        oa::Json d; std::string perr;
+        if (!oa::parse_json(text, d, perr)) { *err = "invalid character: " + perr; return false; }
+        if (d.t != oa::Json::Obj) { *err = "json: cannot unmarshal non-object into Go value of type tools.ToolPrompt"; return false; }
+        ToolPrompt tp;
+        auto lower = [](std::string s) { for (auto& ch : s) if (ch >= 'A' && ch <= 'Z') ch = (char)(ch - 'A' + 'a'); return s; };
+        auto find = [&](const oa::Json& obj, const char* key) -> const oa::Json* {
+            const oa::Json* hit = nullptr;
+            for (auto& kv : obj.o) if (kv.first == key) hit = &kv.second;                  // the last duplicate wins
+            if (hit) return hit;
+            for (auto& kv : obj.o) if (lower(kv.first) == key) { hit = &kv.second; break; }
+            return hit;
+        };
+        auto str_field = [&](const oa::Json& obj, const char* key, std::string* dst) {
+            const oa::Json* v = find(obj, key);
+            if (!v || v->t == oa::Json::Null) return true;
+            if (v->t != oa::Json::Str) { *err = std::string("json: cannot unmarshal a non-string into Go struct field ToolPrompt.") + key + " of type string"; return false; }
+            *dst = v->s; return true;
+        };
+        if (!str_field(d, "question", &tp.Question) || !str_field(d, "thought", &tp.Thought) || !str_field(d, "observation", &tp.Observation) || !str_field(d, "final_answer", &tp.FinalAnswer)) return false;
+        if (const oa::Json* a = find(d, "action")) if (a->t != oa::Json::Null) {
+            if (a->t != oa::Json::Obj) { *err = "json: cannot unmarshal non-object into Go struct field ToolPrompt.action"; return false; }
+            if (!str_field(*a, "name", &tp.Action.Name) || !str_field(*a, "input", &tp.Action.Input)) return false;
+        }
+        *out = tp; return true;
+    }
+};
+
+// simple.go:624-657: a final_answer that is still the prompt's placeholder text does not count as an answer
+inline bool isTemplateValue(const std::string& value) {
+    if (value.size() < 10) return true;                                   // len() of a Go string is bytes
+    static const char* patterns[] = {"<最终答案", "<final_answer", "<Final answer", "<最终回答", "<回答", "<答案", "使用 Markdown 格式", "使用Markdown格式", "换行符用 \\n 表示", "换行符用\\n表示"};
+    for (const char* p : patterns) if (value.find(p) != std::string::npos) return true;
+    return value.find('<') != std::string::npos && value.find('>') != std::string::npos;
+}
+
+// `count` = tokens of a message list under the ENGINE's tokenizer + chat template (oa_count_tokens).  The reference counts with tiktoken for OpenAI
+// model names and returns 0 for anything else (tokens.go:61-66), which silently disables truncation for local models; an empty `count` keeps that.
+using CountTokensFn = std::function<int(const std::vector<ChatCompletionMessage>&)>;
+inline int NumTokensFromMessages(const std::vector<ChatCompletionMessage>& messages, const std::string& /*model*/, const CountTokensFn& count) { return count ? count(messages) : 0; }
+
+inline std::string TrimSpace(const std::string& s);
+// tokens.go:128-144: while the prompt does not fit, drop its first ceil(n/3) lines
+inline std::string ConstrictPrompt(std::string prompt, const std::string& model, int tokenLimits, const CountTokensFn& count) {
+    for (;;) {
+        if (NumTokensFromMessages({ChatCompletionMessage{"", prompt}}, model, count) < tokenLimits) return prompt;
+        std::vector<std::string> lines;
+        size_t b = 0;
+        for (;;) { const size_t e = prompt.find('\n', b); if (e == std::string::npos) { lines.push_back(prompt.substr(b)); break; } lines.push_back(prompt.substr(b, e - b)); b = e + 1; }
+        const size_t drop = (lines.size() + 2) / 3;
+        std::string next;
+        for (size_t i = drop; i < lines.size(); ++i) { if (i > drop) next += '\n'; next += lines[i]; }
+        prompt = next;
+        if (TrimSpace(prompt).empty()) return "";
+    }
+}
+
+// strings.TrimSpace: strips unicode.IsSpace code points — \t \n \v \f \r ' ' U+0085 U+00A0 and the Z category (U+1680, U+2000-200A, U+2028, U+2029,
+// U+202F, U+205F, U+3000) — from both ends of a UTF-8 string
+inline size_t go_space_at(const std::string& s, size_t i) {               // bytes of the white-space code point starting at i, 0 = not white space
+    const unsigned char c = (unsigned char)s[i];
+    if (c == ' ' || (c >= '\t' && c <= '\r')) return 1;
+    auto at = [&](size_t k) { return i + k < s.size() ? (unsigned char)s[i + k] : 0u; };
+    if (c == 0xC2 && (at(1) == 0x85 || at(1) == 0xA0)) return 2;
+    if (c == 0xE1 && at(1) == 0x9A && at(2) == 0x80) return 3;                                            // U+1680
+    if (c == 0xE2 && at(1) == 0x80 && ((at(2) >= 0x80 && at(2) <= 0x8A) || at(2) == 0xA8 || at(2) == 0xA9 || at(2) == 0xAF)) return 3;      // U+2000-200A, 2028, 2029, 202F
+    if (c == 0xE2 && at(1) == 0x81 && at(2) == 0x9F) return 3;                                            // U+205F
+    if (c == 0xE3 && at(1) == 0x80 && at(2) == 0x80) return 3;                                            // U+3000
+    return 0;
+}
+inline std::string TrimSpace(const std::string& s) {
+    size_t b = 0, e = s.size();
+    while (b < e) { const size_t n = go_space_at(s, b); if (!n) break; b += n; }
+    while (e > b) {
+        size_t k = e - 1;
+        while (k > b && ((unsigned char)s[k] & 0xC0) == 0x80) --k;        // start of the last code point
+        const size_t n = go_space_at(s, k);
+        if (!n || k + n != e) break;
+        e = k;
+    }
+    return s.substr(b, e - b);
+}
+
+using ChatFn = std::function<std::string(const std::string& model, int maxTokens, const std::vector<ChatCompletionMessage>& prompts, Error* err)>;
+using Tool = std::function<std::string(const std::string& input, std::string* err)>;      // *err non-empty = the tool failed (Go: (string, error))
+
+struct AssistantResult { std::string Result; std::vector<ChatCompletionMessage> ChatHistory; Error Err; };
+
+// -> (result, chatHistory, error).  Control flow and strings of simple.go:292-616:
+//   first Chat -> Unmarshal into ToolPrompt; a reply that is not JSON is returned verbatim                                       (343-382)
+//   loop (<= maxIterations, default 5): final_answer set, not a placeholder, and an observation present -> return it            (391-419)
+//     action.name set -> run the tool; errors / unknown tools become the observation text                                       (421-481)
+//     observation = ConstrictPrompt(observation, model, 1024); the whole ToolPrompt marshalled as a USER message                 (495-501)
+//     Chat again; reply with final_answer -> return it; unparsable reply -> "Summarize all the chat history…" Chat              (515-600)
+inline AssistantResult AssistantWithConfig(const std::string& model, const std::vector<ChatCompletionMessage>& prompts, int maxTokens, bool /*countTokens*/, bool /*verbose*/,
+                                           int maxIterations, const ChatFn& chat, const std::map<std::string, Tool>& tools, const CountTokensFn& count = nullptr) {
+    AssistantResult R;
+    if (prompts.empty()) { R.Err = Error{0, "prompts cannot be empty"}; return R; }                                              // simple.go:312
+    R.ChatHistory = prompts;
+    auto timed_chat = [&](std::string* resp) {
+        Error e; *resp = chat(model, maxTokens, R.ChatHistory, &e);
+        if (!e.ok()) { R.Err = Error{e.HTTPStatusCode, "chat completion error: " + e.Message}; return false; }
+        return true;
+    };
+    std::string resp;
+    if (!timed_chat(&resp)) return R;                                                                                              // simple.go:341-346
+    R.ChatHistory.push_back({"assistant", resp});
+    ToolPrompt tp; std::string perr;
+    if (!ToolPrompt::Unmarshal(resp, &tp, &perr)) { R.Result = resp; return R; }                                                   // not JSON: assume final answer
+    if (maxIterations <= 0) maxIterations = defaultMaxIterations;
+    for (int iterations = 1;; ++iterations) {
+        if (iterations > maxIterations) { R.Result = tp.FinalAnswer; return R; }
+        if (!tp.FinalAnswer.empty() && !isTemplateValue(tp.FinalAnswer) && !tp.Observation.empty()) { R.Result = tp.FinalAnswer; return R; }
+        if (tp.Action.Name.empty()) continue;                                    // nothing to run: the iteration budget ends the loop (simple.go:421)
+        std::string observation;
+        auto it = tools.find(tp.Action.Name);
+        if (it != tools.end()) {
+            std::string terr; const std::string out = it->second(tp.Action.Input, &terr);
+            observation = terr.empty() ? TrimSpace(out) : "Tool " + tp.Action.Name + " failed with error " + terr + ". Considering refine the inputs for the tool.";
+        } else observation = "Tool " + tp.Action.Name + " is not available. Considering switch to other supported tools.";
+        tp.Observation = ConstrictPrompt(observation, model, 1024, count);
+        R.ChatHistory.push_back({"user", tp.Marshal()});
+        if (!timed_chat(&resp)) return R;                                                                                          // simple.go:513-518
+        R.ChatHistory.push_back({"assistant", resp});
+        ToolPrompt next;
+        if (!ToolPrompt::Unmarshal(resp, &next, &perr)) {
+            R.ChatHistory.push_back({"user", "Summarize all the chat history and respond to original question with final answer"});
+            if (!timed_chat(&resp)) return R;                                                                                      // simple.go:564-569
+            R.Result = resp; return R;
+        }
+        tp = next;
+        if (!tp.FinalAnswer.empty()) { R.Result = tp.FinalAnswer; return R; }
+    }
+}
+
+}  // namespace opsagent

@@ -65,6 +65,15 @@ class LocalCUDAClient:
         raise RuntimeError(f"OpenAI request throttled after retrying {self.Retries} times")
 
 
+# unicode.IsSpace, the set strings.TrimSpace strips: Python's str.strip() also strips \x1c-\x1f, which Go keeps
+GO_SPACE = "\t\n\v\f\r \x85\xa0\u1680\u2000\u2001\u2002\u2003\u2004\u2005\u2006\u2007\u2008\u2009\u200a\u2028\u2029\u202f\u205f\u3000"
+
+
+def TrimSpace(s: str) -> str:
+    """strings.TrimSpace"""
+    return s.strip(GO_SPACE)
+
+
 def NumTokensFromMessages(messages, model, count_tokens=None) -> int:
     """Mirror of pkg/llms/tokens.go:60.  For OpenAI names the reference counts with tiktoken; for local models it logs an error and
     returns 0 (tokens.go:61-66), which silently disables truncation.  Here the count comes from the engine's own tokenizer + chat
@@ -83,7 +92,7 @@ def ConstrictPrompt(prompt: str, model: str, tokenLimits: int, count_tokens=None
         lines = prompt.split("\n")
         lines = lines[int(math.ceil(len(lines) / 3)):]
         prompt = "\n".join(lines)
-        if prompt.strip() == "":
+        if TrimSpace(prompt) == "":
             return ""
 
 

@@ -96,3 +96,111 @@ def test_cpp_client_semantics(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     sys.stdout.write(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+# ---- the C++ twin of the ReAct loop (host/assistants.hpp) against the Python mirror (assistants.py) on scripted scenarios ----------------
+def _scenarios(n, seed):
+    import json
+    import random
+    r = random.Random(seed)
+    words = ["pods", "<none>", "a&b", "中文 节点", "CrashLoopBackOff", "tab\there", "quote\"q", "back\\slash", "bell\b\f", " sep", "emoji 😀", "x" * 40, "", "line1\nline2"]
+
+    def text(k=3):
+        return " ".join(r.choice(words) for _ in range(r.randrange(1, k + 1)))
+
+    def reply():
+        kind = r.randrange(12)
+        if kind == 0:
+            return "plain text, not JSON at all " + text()
+        if kind == 1:
+            return "!ERR:backend said no"
+        if kind == 2:
+            return json.dumps({"question": 5})                                # wrong type -> Unmarshal error
+        if kind == 3:
+            return json.dumps([1, 2])
+        tp = {"question": text(), "thought": text(), "action": {"name": r.choice(["kubectl", "trivy", "nosuchtool", "", "failing"]), "input": text()},
+              "observation": r.choice(["", text()]), "final_answer": r.choice(["", "", "<final_answer placeholder>", "short", "The deployment has " + text(4)])}
+        if kind == 4:
+            tp["action"] = None
+        if kind == 5:
+            tp = {("Question" if k == "question" else k.upper() if k == "thought" else k): v for k, v in tp.items()}      # case-insensitive keys
+        if kind == 6:
+            tp["extra"] = {"nested": [1, 2, {"a": None}]}; del tp["thought"]
+        if kind == 7:
+            tp["action"] = "kubectl"                                          # non-object action -> error
+        if kind == 8:
+            tp["final_answer"] = None
+        return json.dumps(tp, ensure_ascii=r.random() < 0.5)
+    out = []
+    for _ in range(n):
+        long_table = "\n".join(f"pod-{i} 1/1 Running {text(2)}" for i in range(r.randrange(1, 400)))
+        out.append({"prompts": [["system", "You are " + text()], ["user", text()]] if r.random() < 0.95 else [],
+                    "replies": [reply() for _ in range(r.randrange(0, 9))],
+                    "tools": {"kubectl": {"outputs": ["  " + long_table + " \n", text(), ""]}, "trivy": {"outputs": [text()]}, "failing": {"error": "exit status 1: " + text()}},
+                    "maxIterations": r.choice([0, 1, 2, 5, 7]), "count_div": r.choice([0, 1, 3, 4])})
+    return out
+
+
+def _python_mirror(sc):
+    from opsagent_b200.assistants import AssistantWithConfig
+    from opsagent_b200.llms import ChatCompletionMessage
+
+    class Client:
+        def __init__(self):
+            self.i, self.calls = 0, 0
+
+        def Chat(self, model, maxTokens, prompts):
+            self.calls += 1
+            if self.i >= len(sc["replies"]):
+                raise RuntimeError("no more replies")
+            rep = sc["replies"][self.i]; self.i += 1
+            if rep.startswith("!ERR:"):
+                raise RuntimeError(rep[5:])
+            return rep
+    cursor = {}
+
+    def tool(name, spec):
+        def run(inp):
+            if "error" in spec:
+                raise RuntimeError(spec["error"])
+            k = cursor.get(name, 0); cursor[name] = k + 1
+            return spec["outputs"][k % len(spec["outputs"])]
+        return run
+    tools = {k: tool(k, v) for k, v in sc["tools"].items()}
+    div = sc["count_div"]
+    count = (lambda ms: sum(4 + len(c.encode("utf-8")) // div for _, c in ms)) if div else None
+    cl = Client()
+    try:
+        res, hist = AssistantWithConfig("m", [ChatCompletionMessage(r_, c) for r_, c in sc["prompts"]], 256, False, False, sc["maxIterations"], cl, tools, count_tokens=count)
+        return {"result": res, "error": "", "chat_calls": cl.calls, "history": [[m.Role, m.Content] for m in hist]}
+    except Exception as e:      # noqa: BLE001
+        return {"result": "", "error": str(e), "chat_calls": cl.calls, "history": None}
+
+
+def test_cpp_react_loop_equals_the_python_mirror_on_scripted_scenarios(tmp_path):
+    """host/assistants.hpp (AssistantWithConfig, ToolPrompt Marshal / Unmarshal, isTemplateValue, ConstrictPrompt) against assistants.py / llms.py on
+    400 seeded scenarios: same result, same error, same number of Chat calls and a byte-identical chat history (the history IS the next prompt)."""
+    import json
+    exe = tmp_path / "assistants_driver"
+    b = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-I", ROOT, os.path.join(ROOT, "tests", "host", "assistants_driver.cpp"), "-o", str(exe),
+                        "-L", os.path.join(ROOT, "opsagent_b200", "lib"), "-lopsagent_b200", f"-Wl,-rpath,{os.path.join(ROOT, 'opsagent_b200', 'lib')}"], capture_output=True, text=True, timeout=600)
+    assert b.returncode == 0, b.stderr[-2000:]
+    scs = _scenarios(400, seed=20260921)
+    path = tmp_path / "scenarios.json"
+    path.write_text(json.dumps(scs, ensure_ascii=False), encoding="utf-8")
+    r = subprocess.run([str(exe), str(path)], capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.decode("utf-8").rstrip("\n").split("\n")          # not splitlines(): U+2028 inside a JSON string is not a line end
+    assert len(lines) == len(scs)
+    kinds = set()
+    for sc, line in zip(scs, lines):
+        got, want = json.loads(line), _python_mirror(sc)
+        assert got["chat_calls"] == want["chat_calls"], (sc, got, want)
+        if want["error"]:
+            assert got["error"].endswith(want["error"].split("chat completion error: ")[-1]) and got["result"] == "", (got, want)
+            kinds.add("error")
+            continue
+        assert got["error"] == "" and got["result"] == want["result"], (sc["replies"], got["result"], want["result"])
+        assert got["history"] == want["history"]
+        kinds.add("loop" if want["chat_calls"] > 1 else "first")
+    assert kinds == {"error", "loop", "first"}

@@ -516,12 +516,14 @@ def test_prompt_fixtures_are_the_reference_constants_verbatim():
 
 
 def test_toolprompt_marshal_is_go_json_marshal_byte_for_byte():
+    from opsagent_b200.assistants import go_json_string
     """json.Marshal escapes <, >, & and U+2028/9 (simple.go:497 sends this string as the next user message)"""
     tp = ToolPrompt("q", "t", {"name": "kubectl", "input": "get pods | grep <none> && echo 'a&b'"}, "NODE  <none>\t中 \x01\"\\", "")
     want = ('{"question":"q","thought":"t","action":{"name":"kubectl","input":"get pods | grep \\u003cnone\\u003e \\u0026\\u0026 echo \'a\\u0026b\'"},'
             '"observation":"NODE  \\u003cnone\\u003e\\t中\\u2028\\u0001\\"\\\\","final_answer":""}')
     assert tp.marshal() == want
     assert ToolPrompt.unmarshal(tp.marshal()) == tp
+    assert go_json_string("a\b\f\x0b\x7f") == '"a\\b\\f\\u000b\x7f"'          # go 1.22+: \b \f short forms, other controls \u00XX, DEL raw
     # Unmarshal: wrong types are errors (Go: UnmarshalTypeError), null / missing / unknown keys are not, keys match case-insensitively
     for bad in ('{"question": 5}', '{"action": "kubectl"}', '{"action": {"name": 1}}', '[1]', '"x"'):
         with pytest.raises(ValueError):
@@ -676,3 +678,11 @@ def test_router_is_sticky_balanced_and_rejects_overload():
     st = rt.stats()
     assert st["sticky_hits"] == 24 and st["routed"] == [8, 8, 8, 8] and st["decode_tokens"] == 32 and st["replicas"] == 4
     assert rt.replica_of(conv(3, 7)) == home[3] and rt.replica_of(conv(12345, 0)) is None
+
+
+def test_trimspace_is_gos_unicode_isspace_set_not_pythons():
+    """strings.TrimSpace (simple.go:444, tokens.go:140) strips unicode.IsSpace; Python's str.strip() would also strip \x1c-\x1f, which Go keeps"""
+    from opsagent_b200.llms import TrimSpace
+    assert TrimSpace(" \t\n\u2028\u3000\xa0\x85 x y \u200a\r") == "x y"
+    assert TrimSpace("\x1c x \x1f") == "\x1c x \x1f"
+    assert TrimSpace("\u200b x") == "\u200b x"          # ZERO WIDTH SPACE is not white space in Go
