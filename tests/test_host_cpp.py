@@ -204,3 +204,67 @@ def test_cpp_react_loop_equals_the_python_mirror_on_scripted_scenarios(tmp_path)
         assert got["history"] == want["history"]
         kinds.add("loop" if want["chat_calls"] > 1 else "first")
     assert kinds == {"error", "loop", "first"}
+
+
+SRC_REACT_GPU = r'''
+#include <cstdio>
+#include "opsagent_b200/host/assistants.hpp"
+using namespace opsagent;
+int main(int argc, char** argv) {
+    oa_engine* eng = nullptr;
+    if (argc < 2 || oa_engine_create(argv[1], &eng) != 0) { std::printf("create failed: %s\n", oa_last_error()); return 1; }
+    LocalCUDAClient c; if (!LocalCUDAClient::New("sk-local", eng, &c).ok()) return 2;
+    ChatFn chat = [&](const std::string& model, int maxTokens, const std::vector<ChatCompletionMessage>& prompts, Error* err) { return c.Chat(model, maxTokens, prompts, err); };
+    int calls = 0;
+    std::map<std::string, Tool> tools;
+    for (const char* name : {"kubectl", "python", "trivy", "jq", "search"})
+        tools[name] = [&calls, name](const std::string& input, std::string*) { ++calls; return std::string("  NAME READY STATUS <none>\nweb-0 0/1 CrashLoopBackOff  # ") + name + " " + input + " \n"; };
+    CountTokensFn count = [&](const std::vector<ChatCompletionMessage>& ms) {
+        std::vector<oa_msg> m(ms.size()); for (size_t i = 0; i < ms.size(); ++i) { m[i].role = ms[i].Role.c_str(); m[i].content = ms[i].Content.c_str(); }
+        int32_t n = 0; oa_count_tokens(eng, m.data(), (int32_t)m.size(), &n); return (int)n;
+    };
+    AssistantResult R = AssistantWithConfig("", {{"system", "You are a Kubernetes expert. Answer in JSON."}, {"user", "why is pod web-0 crashing?"}}, 600, false, false, 5, chat, tools, count);
+    if (!R.Err.ok()) { std::printf("error: %s\n", R.Err.Message.c_str()); return 3; }
+    std::string line = "{\"result\": " + oa::jstr(R.Result) + ", \"tool_calls\": " + std::to_string(calls) + ", \"history\": [";
+    for (size_t i = 0; i < R.ChatHistory.size(); ++i) line += (i ? ", [" : "[") + oa::jstr(R.ChatHistory[i].Role) + ", " + oa::jstr(R.ChatHistory[i].Content) + "]";
+    std::printf("%s]}\n", line.c_str());
+    oa_engine_destroy(eng);
+    return 0;
+}
+'''
+
+
+@pytest.mark.gpu
+def test_cpp_react_loop_drives_the_engine_like_the_python_mirror(tmp_path):
+    """the compiled host side end to end: host/assistants.hpp + host/localcuda_client.hpp over the C ABI run a multi-step ReAct conversation on the GPU
+    (json_mode: two grammar-forced tool calls, then a final answer); the Python mirror over the same engine configuration produces the same history"""
+    import json
+    from oracle import oracle as O          # presets only
+    from opsagent_b200 import Engine, LocalCUDAClient
+    from opsagent_b200.assistants import AssistantWithConfig
+    from opsagent_b200.llms import ChatCompletionMessage
+    spec = O.PRESETS["tiny-llama"]
+    cfg = spec.engine_json(num_pages=160, max_seq_len=4096, max_batch=4, max_step_tokens=512, json_mode=1, react_tool_steps=2, prefix_cache=1)
+    src = tmp_path / "react.cpp"; src.write_text(SRC_REACT_GPU)
+    exe = tmp_path / "react"
+    lib = os.path.join(ROOT, "opsagent_b200", "lib")
+    subprocess.run(["g++", "-std=c++17", "-O1", f"-I{ROOT}", str(src), "-o", str(exe), f"-L{lib}", "-lopsagent_b200", f"-Wl,-rpath,{lib}", "-Wl,-rpath,/usr/local/cuda/lib64", "-lpthread"], check=True)
+    r = subprocess.run([str(exe), json.dumps(cfg)], capture_output=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-600:] + r.stderr[-600:]
+    got = json.loads(r.stdout.decode("utf-8").strip().split("\n")[-1])
+    eng = Engine(cfg)
+    calls = [0]
+
+    def tool(name):
+        def run(inp):
+            calls[0] += 1
+            return f"  NAME READY STATUS <none>\nweb-0 0/1 CrashLoopBackOff  # {name} {inp} \n"
+        return run
+    tools = {n: tool(n) for n in ("kubectl", "python", "trivy", "jq", "search")}
+    res, hist = AssistantWithConfig("", [ChatCompletionMessage("system", "You are a Kubernetes expert. Answer in JSON."), ChatCompletionMessage("user", "why is pod web-0 crashing?")],
+                                    600, False, False, 5, LocalCUDAClient(eng), tools, count_tokens=eng.count_tokens)
+    eng.close()
+    assert got["tool_calls"] == calls[0] == 2                      # react_tool_steps grammar-forced tool calls, then the final answer
+    assert got["result"] == res and len(res.encode()) >= 10
+    assert got["history"] == [[m.Role, m.Content] for m in hist]
+    assert "\\u003cnone\\u003e" in got["history"][3][1]            # the observation went back Go-marshalled
