@@ -20,6 +20,7 @@
 
 #include "../csrc/json_dom.hpp"
 #include "localcuda_client.hpp"
+#include "perf.hpp"
 
 namespace opsagent {
 
@@ -159,18 +160,25 @@ struct AssistantResult { std::string Result; std::vector<ChatCompletionMessage> 
 inline AssistantResult AssistantWithConfig(const std::string& model, const std::vector<ChatCompletionMessage>& prompts, int maxTokens, bool /*countTokens*/, bool /*verbose*/,
                                            int maxIterations, const ChatFn& chat, const std::map<std::string, Tool>& tools, const CountTokensFn& count = nullptr) {
     AssistantResult R;
+    PerfStats& perf = GetPerfStats();
+    struct Total { std::function<void()> done; ~Total() { done(); } } total{perf.TraceFunc("assistant_total")};                    // simple.go:296
     if (prompts.empty()) { R.Err = Error{0, "prompts cannot be empty"}; return R; }                                              // simple.go:312
     R.ChatHistory = prompts;
-    auto timed_chat = [&](std::string* resp) {
+    auto timed_chat = [&](const char* op, std::string* resp) {
+        perf.StartTimer(op);
         Error e; *resp = chat(model, maxTokens, R.ChatHistory, &e);
+        perf.StopTimer(op);
         if (!e.ok()) { R.Err = Error{e.HTTPStatusCode, "chat completion error: " + e.Message}; return false; }
         return true;
     };
     std::string resp;
-    if (!timed_chat(&resp)) return R;                                                                                              // simple.go:341-346
+    if (!timed_chat("assistant_first_chat", &resp)) return R;                                                                      // simple.go:341-346
     R.ChatHistory.push_back({"assistant", resp});
     ToolPrompt tp; std::string perr;
-    if (!ToolPrompt::Unmarshal(resp, &tp, &perr)) { R.Result = resp; return R; }                                                   // not JSON: assume final answer
+    perf.StartTimer("assistant_parse_tool_prompt");                                                                                // simple.go:364-385
+    const bool parsed = ToolPrompt::Unmarshal(resp, &tp, &perr);
+    perf.StopTimer("assistant_parse_tool_prompt");
+    if (!parsed) { R.Result = resp; return R; }                                                                                    // not JSON: assume final answer
     if (maxIterations <= 0) maxIterations = defaultMaxIterations;
     for (int iterations = 1;; ++iterations) {
         if (iterations > maxIterations) { R.Result = tp.FinalAnswer; return R; }
@@ -179,17 +187,24 @@ inline AssistantResult AssistantWithConfig(const std::string& model, const std::
         std::string observation;
         auto it = tools.find(tp.Action.Name);
         if (it != tools.end()) {
+            perf.StartTimer("assistant_tool_" + tp.Action.Name);                                                                   // simple.go:440-475
             std::string terr; const std::string out = it->second(tp.Action.Input, &terr);
+            perf.StopTimer("assistant_tool_" + tp.Action.Name);
             observation = terr.empty() ? TrimSpace(out) : "Tool " + tp.Action.Name + " failed with error " + terr + ". Considering refine the inputs for the tool.";
         } else observation = "Tool " + tp.Action.Name + " is not available. Considering switch to other supported tools.";
+        perf.StartTimer("assistant_construct_message");                                                                            // simple.go:491-507
         tp.Observation = ConstrictPrompt(observation, model, 1024, count);
         R.ChatHistory.push_back({"user", tp.Marshal()});
-        if (!timed_chat(&resp)) return R;                                                                                          // simple.go:513-518
+        perf.StopTimer("assistant_construct_message");
+        if (!timed_chat("assistant_intermediate_chat", &resp)) return R;                                                           // simple.go:513-518
         R.ChatHistory.push_back({"assistant", resp});
         ToolPrompt next;
-        if (!ToolPrompt::Unmarshal(resp, &next, &perr)) {
+        perf.StartTimer("assistant_parse_intermediate");                                                                           // simple.go:541-603
+        const bool ok = ToolPrompt::Unmarshal(resp, &next, &perr);
+        perf.StopTimer("assistant_parse_intermediate");
+        if (!ok) {
             R.ChatHistory.push_back({"user", "Summarize all the chat history and respond to original question with final answer"});
-            if (!timed_chat(&resp)) return R;                                                                                      // simple.go:564-569
+            if (!timed_chat("assistant_summarize", &resp)) return R;                                                               // simple.go:564-569
             R.Result = resp; return R;
         }
         tp = next;

@@ -42,8 +42,11 @@ int main(int argc, char** argv) {
         const int div = (int)(sc.get("count_div") ? sc.get("count_div")->n : 0);
         CountTokensFn count;
         if (div > 0) count = [div](const std::vector<ChatCompletionMessage>& ms) { int n = 0; for (auto& m : ms) n += 4 + (int)m.Content.size() / div; return n; };
+        GetPerfStats().Reset();
         const AssistantResult R = AssistantWithConfig("m", prompts, 256, false, false, (int)sc.get("maxIterations")->n, chat, tools, count);
-        std::string line = "{\"result\": " + oa::jstr(R.Result) + ", \"error\": " + oa::jstr(R.Err.Message) + ", \"chat_calls\": " + std::to_string(calls) + ", \"history\": [";
+        std::string line = "{\"result\": " + oa::jstr(R.Result) + ", \"error\": " + oa::jstr(R.Err.Message) + ", \"chat_calls\": " + std::to_string(calls) + ", \"callCounts\": {";
+        { bool first = true; for (auto& kv : GetPerfStats().GetStats().callCounts) { line += (first ? "" : ", ") + oa::jstr(kv.first) + ": " + std::to_string(kv.second); first = false; } }
+        line += "}, \"history\": [";
         for (size_t i = 0; i < R.ChatHistory.size(); ++i) line += (i ? ", [" : "[") + oa::jstr(R.ChatHistory[i].Role) + ", " + oa::jstr(R.ChatHistory[i].Content) + "]";
         std::printf("%s]}\n", line.c_str());
     }

@@ -170,11 +170,13 @@ def _python_mirror(sc):
     div = sc["count_div"]
     count = (lambda ms: sum(4 + len(c.encode("utf-8")) // div for _, c in ms)) if div else None
     cl = Client()
+    from opsagent_b200.perf import GetPerfStats
+    GetPerfStats().Reset()
     try:
         res, hist = AssistantWithConfig("m", [ChatCompletionMessage(r_, c) for r_, c in sc["prompts"]], 256, False, False, sc["maxIterations"], cl, tools, count_tokens=count)
-        return {"result": res, "error": "", "chat_calls": cl.calls, "history": [[m.Role, m.Content] for m in hist]}
+        return {"result": res, "error": "", "chat_calls": cl.calls, "history": [[m.Role, m.Content] for m in hist], "callCounts": GetPerfStats().GetStats()["callCounts"]}
     except Exception as e:      # noqa: BLE001
-        return {"result": "", "error": str(e), "chat_calls": cl.calls, "history": None}
+        return {"result": "", "error": str(e), "chat_calls": cl.calls, "history": None, "callCounts": GetPerfStats().GetStats()["callCounts"]}
 
 
 def test_cpp_react_loop_equals_the_python_mirror_on_scripted_scenarios(tmp_path):
@@ -196,6 +198,7 @@ def test_cpp_react_loop_equals_the_python_mirror_on_scripted_scenarios(tmp_path)
     for sc, line in zip(scs, lines):
         got, want = json.loads(line), _python_mirror(sc)
         assert got["chat_calls"] == want["chat_calls"], (sc, got, want)
+        assert got["callCounts"] == want["callCounts"], (got["callCounts"], want["callCounts"])      # the reference's operation names (simple.go:296-569), same counts
         if want["error"]:
             assert got["error"].endswith(want["error"].split("chat completion error: ")[-1]) and got["result"] == "", (got, want)
             kinds.add("error")
