@@ -104,6 +104,32 @@ inline bool isTemplateValue(const std::string& value) {
 using CountTokensFn = std::function<int(const std::vector<ChatCompletionMessage>&)>;
 inline int NumTokensFromMessages(const std::vector<ChatCompletionMessage>& messages, const std::string& /*model*/, const CountTokensFn& count) { return count ? count(messages) : 0; }
 
+// tokens.go:26-56: context windows by OpenAI model name (the reference's lookup data; lower-cased key, 4096 when unknown).  `engine_limit` (the local
+// engine's max_seq_len) wins when given: the engine answers to any model name, and what bounds a request is ITS window
+inline int GetTokenLimits(std::string model, int engine_limit = 0) {
+    if (engine_limit > 0) return engine_limit;
+    static const std::map<std::string, int> tokenLimitsPerModel = {
+        {"code-davinci-002", 4096}, {"gpt-3.5-turbo-0301", 4096}, {"gpt-3.5-turbo-0613", 4096}, {"gpt-3.5-turbo-1106", 16385}, {"gpt-3.5-turbo-16k-0613", 16385}, {"gpt-3.5-turbo-16k", 16385},
+        {"gpt-3.5-turbo-instruct", 4096}, {"gpt-3.5-turbo", 4096}, {"gpt-4-0314", 8192}, {"gpt-4-0613", 8192}, {"gpt-4-1106-preview", 128000}, {"gpt-4-32k-0314", 32768},
+        {"gpt-4-32k-0613", 32768}, {"gpt-4-32k", 32768}, {"gpt-4-vision-preview", 128000}, {"gpt-4", 8192}, {"text-davinci-002", 4096}, {"text-davinci-003", 4096}, {"qwen-plus", 4096}};
+    for (auto& ch : model) if (ch >= 'A' && ch <= 'Z') ch = (char)(ch - 'A' + 'a');
+    auto it = tokenLimitsPerModel.find(model);
+    return it == tokenLimitsPerModel.end() ? 4096 : it->second;
+}
+// tokens.go:110-125: nil (*ok = true, empty result, *none = true) when maxTokens alone exceeds the window; otherwise drop the oldest message after the
+// first until prompt + maxTokens fit.  A single message that does not fit panics in the reference (messages[2:] out of range): *ok = false here.
+inline std::vector<ChatCompletionMessage> ConstrictMessages(std::vector<ChatCompletionMessage> messages, const std::string& model, int maxTokens, const CountTokensFn& count,
+                                                            bool* ok, bool* none = nullptr, int engine_limit = 0) {
+    *ok = true; if (none) *none = false;
+    const int tokenLimits = GetTokenLimits(model, engine_limit);
+    if (maxTokens >= tokenLimits) { if (none) *none = true; return {}; }
+    for (;;) {
+        if (NumTokensFromMessages(messages, model, count) + maxTokens < tokenLimits) return messages;
+        if (messages.size() < 2) { *ok = false; return {}; }
+        messages.erase(messages.begin() + 1);
+    }
+}
+
 inline std::string TrimSpace(const std::string& s);
 // tokens.go:128-144: while the prompt does not fit, drop its first ceil(n/3) lines
 inline std::string ConstrictPrompt(std::string prompt, const std::string& model, int tokenLimits, const CountTokensFn& count) {

@@ -96,6 +96,38 @@ def ConstrictPrompt(prompt: str, model: str, tokenLimits: int, count_tokens=None
             return ""
 
 
+# pkg/llms/tokens.go:26-46: context windows by OpenAI model name (the reference's lookup data; lower-cased key, 4096 when unknown: tokens.go:49-56)
+tokenLimitsPerModel = {"code-davinci-002": 4096, "gpt-3.5-turbo-0301": 4096, "gpt-3.5-turbo-0613": 4096, "gpt-3.5-turbo-1106": 16385, "gpt-3.5-turbo-16k-0613": 16385,
+                       "gpt-3.5-turbo-16k": 16385, "gpt-3.5-turbo-instruct": 4096, "gpt-3.5-turbo": 4096, "gpt-4-0314": 8192, "gpt-4-0613": 8192, "gpt-4-1106-preview": 128000,
+                       "gpt-4-32k-0314": 32768, "gpt-4-32k-0613": 32768, "gpt-4-32k": 32768, "gpt-4-vision-preview": 128000, "gpt-4": 8192, "text-davinci-002": 4096,
+                       "text-davinci-003": 4096, "qwen-plus": 4096}
+
+
+def GetTokenLimits(model: str, engine_limit: int | None = None) -> int:
+    """Mirror of pkg/llms/tokens.go:49-56.  `engine_limit` (the local engine's max_seq_len, Engine.info["max_seq_len"]) wins when given: the engine
+    answers to any model name (model_aliases "*"), and what bounds a request is ITS context window, not the window of the name the caller sent."""
+    if engine_limit:
+        return int(engine_limit)
+    return tokenLimitsPerModel.get(model.lower(), 4096)
+
+
+def ConstrictMessages(messages, model: str, maxTokens: int, count_tokens=None, engine_limit: int | None = None):
+    """Mirror of pkg/llms/tokens.go:110-125: None when maxTokens alone exceeds the window; otherwise drop the oldest message after the first (the
+    system prompt) until prompt + maxTokens fit.  The reference slices messages[2:] unconditionally, so a single message that does not fit panics
+    there (slice bounds out of range); here that case raises IndexError with the same meaning.  (No caller in the reference uses it today —
+    AssistantWithConfig truncates observations with ConstrictPrompt instead — it is mirrored because it is part of the pkg/llms surface.)"""
+    tokenLimits = GetTokenLimits(model, engine_limit)
+    if maxTokens >= tokenLimits:
+        return None
+    messages = list(messages)
+    while True:
+        if NumTokensFromMessages(messages, model, count_tokens) + maxTokens < tokenLimits:
+            return messages
+        if len(messages) < 2:
+            raise IndexError("slice bounds out of range [2:%d]" % len(messages))
+        messages = messages[:1] + messages[2:]
+
+
 _ENGINES: dict = {}
 
 

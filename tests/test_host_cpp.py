@@ -271,3 +271,15 @@ def test_cpp_react_loop_drives_the_engine_like_the_python_mirror(tmp_path):
     assert got["result"] == res and len(res.encode()) >= 10
     assert got["history"] == [[m.Role, m.Content] for m in hist]
     assert "\\u003cnone\\u003e" in got["history"][3][1]            # the observation went back Go-marshalled
+
+
+def test_cpp_llms_helpers_on_the_reference_cases(tmp_path):
+    """tests/host/llms_check.cpp: GetTokenLimits (reference-held cases, tokens_test.go:20-51), ConstrictMessages, ConstrictPrompt, TrimSpace, GoJSONString and
+    isTemplateValue of host/assistants.hpp on the cases the Python mirrors are tested with, under ASAN + UBSAN"""
+    exe = tmp_path / "llms_check"
+    lib = os.path.join(ROOT, "opsagent_b200", "lib")
+    b = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-I", ROOT, os.path.join(ROOT, "tests", "host", "llms_check.cpp"), "-o", str(exe),
+                        "-L", lib, "-lopsagent_b200", f"-Wl,-rpath,{lib}"], capture_output=True, text=True, timeout=600)
+    assert b.returncode == 0, b.stderr[-2000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", (r.stdout, r.stderr[-1500:])

@@ -686,3 +686,18 @@ def test_trimspace_is_gos_unicode_isspace_set_not_pythons():
     assert TrimSpace(" \t\n\u2028\u3000\xa0\x85 x y \u200a\r") == "x y"
     assert TrimSpace("\x1c x \x1f") == "\x1c x \x1f"
     assert TrimSpace("\u200b x") == "\u200b x"          # ZERO WIDTH SPACE is not white space in Go
+
+
+def test_get_token_limits_and_constrict_messages_follow_the_reference():
+    """pkg/llms/tokens_test.go:20-51 holds two GetTokenLimits cases; ConstrictMessages (tokens.go:110-125) keeps the first message and drops the oldest after it"""
+    from opsagent_b200.llms import ChatCompletionMessage as M, ConstrictMessages, GetTokenLimits
+    assert GetTokenLimits("gpt-3.5-turbo-0613") == 4096 and GetTokenLimits("gpt-4") == 8192            # the reference's own golden cases
+    assert GetTokenLimits("GPT-4-32K") == 32768 and GetTokenLimits("llama-3-8b") == 4096 and GetTokenLimits("gpt-4", engine_limit=16384) == 16384
+    count = lambda ms: sum(3 + len(c) for _, c in ms) + 3          # noqa: E731
+    msgs = [M("system", "s" * 100), M("user", "a" * 300), M("assistant", "b" * 300), M("user", "c" * 300)]
+    assert ConstrictMessages(msgs, "m", 5000, count) is None                                               # maxTokens >= the 4096 window
+    assert ConstrictMessages(msgs, "m", 100, count, engine_limit=2000) == msgs                             # fits: untouched
+    got = ConstrictMessages(msgs, "m", 100, count, engine_limit=600)
+    assert [m.Content[0] for m in got] == ["s", "c"]                                                       # system prompt + the newest that fit
+    with pytest.raises(IndexError):
+        ConstrictMessages([M("system", "s" * 1000)], "m", 100, count, engine_limit=600)                   # the reference panics here
