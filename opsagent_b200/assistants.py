@@ -41,30 +41,49 @@ class ToolPrompt:                                            # reference pkg/too
 
     @classmethod
     def unmarshal(cls, text: str) -> "ToolPrompt":
-        """json.Unmarshal([]byte(text), &toolPrompt) (simple.go:366): unknown keys are ignored, missing keys stay "", JSON null leaves the
-        field at its zero value, and any other non-string value for a string field is an UnmarshalTypeError (-> the caller's
-        'not JSON, assume final answer' / 'Summarize…' branches), not a silent coercion."""
-        d = json.loads(text)
-        if not isinstance(d, dict):
+        """json.Unmarshal([]byte(text), &toolPrompt) (simple.go:366) as encoding/json does it: the document's keys are visited IN ORDER, each one
+        matched to a field exactly or else case-insensitively (so duplicates and differently-cased duplicates overwrite each other, the last one in the
+        document wins); unknown keys are ignored; JSON null leaves the field as it is; any other non-string value for a string field, or a non-object
+        `action`, is an UnmarshalTypeError — decoding goes on, but Unmarshal returns that error, which sends the caller into its 'not JSON, assume final
+        answer' / 'Summarize…' branches.  Nothing is coerced."""
+        class Obj(list):
+            pass
+        d = json.loads(text, object_pairs_hook=Obj)
+        if not isinstance(d, Obj):
             raise ValueError("json: cannot unmarshal non-object into Go value of type tools.ToolPrompt")
+        tp = cls()
+        errors = []
 
-        def field_(obj, key):
-            v = obj.get(key)
-            if key not in obj:                       # encoding/json prefers an exact key match and falls back to a case-insensitive one
-                v = next((x for k, x in obj.items() if k.lower() == key), None)
+        def fold(k: str) -> str:                     # encoding/json's foldName (simple case folding): U+017F folds to 's', U+212A (Kelvin) to 'k' — str.lower() does the latter
+            return k.replace("\u017f", "s").lower()
+
+        def set_string(target, attr, v, path):
             if v is None:
-                return ""
+                return
             if not isinstance(v, str):
-                raise ValueError(f"json: cannot unmarshal {type(v).__name__} into Go struct field ToolPrompt.{key} of type string")
-            return v
-
-        a = d.get("action") if "action" in d else next((x for k, x in d.items() if k.lower() == "action"), None)
-        if a is None:
-            a = {}
-        if not isinstance(a, dict):
-            raise ValueError("json: cannot unmarshal non-object into Go struct field ToolPrompt.action")
-        return cls(field_(d, "question"), field_(d, "thought"), {"name": field_(a, "name"), "input": field_(a, "input")},
-                   field_(d, "observation"), field_(d, "final_answer"))
+                errors.append(f"json: cannot unmarshal {type(v).__name__} into Go struct field ToolPrompt.{path} of type string")
+                return
+            if isinstance(target, dict):
+                target[attr] = v
+            else:
+                setattr(target, attr, v)
+        for k, v in d:
+            f = fold(k)
+            if f in ("question", "thought", "observation", "final_answer"):
+                set_string(tp, f, v, f)
+            elif f == "action":
+                if v is None:
+                    continue
+                if not isinstance(v, Obj):
+                    errors.append("json: cannot unmarshal non-object into Go struct field ToolPrompt.action")
+                    continue
+                for k2, v2 in v:
+                    f2 = fold(k2)
+                    if f2 in ("name", "input"):
+                        set_string(tp.action, f2, v2, "action." + f2)
+        if errors:
+            raise ValueError(errors[0])
+        return tp
 
     def marshal(self) -> str:
         r"""json.Marshal(toolPrompt) (simple.go:497), byte for byte: struct field order, no spaces, and Go's default HTML-safe string

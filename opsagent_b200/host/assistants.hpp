@@ -60,33 +60,48 @@ struct ToolPrompt {                                                       // too
         return "{\"question\":" + GoJSONString(Question) + ",\"thought\":" + GoJSONString(Thought) + ",\"action\":{\"name\":" + GoJSONString(Action.Name) + ",\"input\":" +
                GoJSONString(Action.Input) + "},\"observation\":" + GoJSONString(Observation) + ",\"final_answer\":" + GoJSONString(FinalAnswer) + "}";
     }
-    // json.Unmarshal([]byte(text), &toolPrompt): the whole text must be valid JSON and an object; unknown keys are ignored, missing keys and JSON null
-    // leave the zero value, a key matches exactly or else case-insensitively, any other non-string value for a string field (or a non-object
-    // `action`) is an UnmarshalTypeError — the caller's "not JSON, assume final answer" / "Summarize…" branches, not a coercion
+    // json.Unmarshal([]byte(text), &toolPrompt) as encoding/json does it: the whole text must be valid JSON and an object; its keys are visited IN ORDER,
+    // each matched to a field exactly or else case-insensitively (duplicates and differently-cased duplicates overwrite each other, the last one in
+    // the document wins); unknown keys are ignored; JSON null leaves the field as it is; any other non-string value for a string field, or a non-object
+    // `action`, is an UnmarshalTypeError — decoding goes on but Unmarshal returns that error: the caller's "not JSON, assume final answer" /
+    // "Summarize…" branches.  Nothing is coerced.
     static bool Unmarshal(const std::string& text, ToolPrompt* out, std::string* err) {
         oa::Json d; std::string perr;
         if (!oa::parse_json(text, d, perr)) { *err = "invalid character: " + perr; return false; }
         if (d.t != oa::Json::Obj) { *err = "json: cannot unmarshal non-object into Go value of type tools.ToolPrompt"; return false; }
-        ToolPrompt tp;
-        auto lower = [](std::string s) { for (auto& ch : s) if (ch >= 'A' && ch <= 'Z') ch = (char)(ch - 'A' + 'a'); return s; };
-        auto find = [&](const oa::Json& obj, const char* key) -> const oa::Json* {
-            const oa::Json* hit = nullptr;
-            for (auto& kv : obj.o) if (kv.first == key) hit = &kv.second;                  // the last duplicate wins
-            if (hit) return hit;
-            for (auto& kv : obj.o) if (lower(kv.first) == key) { hit = &kv.second; break; }
-            return hit;
+        ToolPrompt tp; std::string first_error;
+        auto fold = [](const std::string& k) {          // encoding/json's foldName: simple case folding; U+017F and U+212A are the only non-ASCII runes that fold onto ASCII letters
+            std::string o;
+            for (size_t i = 0; i < k.size(); ++i) {
+                const unsigned char c = (unsigned char)k[i];
+                if (c == 0xC5 && i + 1 < k.size() && (unsigned char)k[i + 1] == 0xBF) { o += 's'; ++i; }
+                else if (c == 0xE2 && i + 2 < k.size() && (unsigned char)k[i + 1] == 0x84 && (unsigned char)k[i + 2] == 0xAA) { o += 'k'; i += 2; }
+                else o += (c >= 'A' && c <= 'Z') ? (char)(c - 'A' + 'a') : (char)c;
+            }
+            return o;
         };
-        auto str_field = [&](const oa::Json& obj, const char* key, std::string* dst) {
-            const oa::Json* v = find(obj, key);
-            if (!v || v->t == oa::Json::Null) return true;
-            if (v->t != oa::Json::Str) { *err = std::string("json: cannot unmarshal a non-string into Go struct field ToolPrompt.") + key + " of type string"; return false; }
-            *dst = v->s; return true;
+        auto set_string = [&](std::string* dst, const oa::Json& v, const std::string& path) {
+            if (v.t == oa::Json::Null) return;
+            if (v.t != oa::Json::Str) { if (first_error.empty()) first_error = "json: cannot unmarshal a non-string into Go struct field ToolPrompt." + path + " of type string"; return; }
+            *dst = v.s;
         };
-        if (!str_field(d, "question", &tp.Question) || !str_field(d, "thought", &tp.Thought) || !str_field(d, "observation", &tp.Observation) || !str_field(d, "final_answer", &tp.FinalAnswer)) return false;
-        if (const oa::Json* a = find(d, "action")) if (a->t != oa::Json::Null) {
-            if (a->t != oa::Json::Obj) { *err = "json: cannot unmarshal non-object into Go struct field ToolPrompt.action"; return false; }
-            if (!str_field(*a, "name", &tp.Action.Name) || !str_field(*a, "input", &tp.Action.Input)) return false;
+        for (auto& kv : d.o) {
+            const std::string f = fold(kv.first);
+            if (f == "question") set_string(&tp.Question, kv.second, f);
+            else if (f == "thought") set_string(&tp.Thought, kv.second, f);
+            else if (f == "observation") set_string(&tp.Observation, kv.second, f);
+            else if (f == "final_answer") set_string(&tp.FinalAnswer, kv.second, f);
+            else if (f == "action") {
+                if (kv.second.t == oa::Json::Null) continue;
+                if (kv.second.t != oa::Json::Obj) { if (first_error.empty()) first_error = "json: cannot unmarshal non-object into Go struct field ToolPrompt.action"; continue; }
+                for (auto& kv2 : kv.second.o) {
+                    const std::string f2 = fold(kv2.first);
+                    if (f2 == "name") set_string(&tp.Action.Name, kv2.second, "action.name");
+                    else if (f2 == "input") set_string(&tp.Action.Input, kv2.second, "action.input");
+                }
+            }
         }
+        if (!first_error.empty()) { *err = first_error; return false; }
         *out = tp; return true;
     }
 };

@@ -17,6 +17,15 @@ int main(int argc, char** argv) {
     oa::Json root; std::string err;
     if (!oa::parse_json(ss.str(), root, err) || root.t != oa::Json::Arr) { std::fprintf(stderr, "bad scenario file: %s\n", err.c_str()); return 2; }
     for (const oa::Json& sc : root.a) {
+        if (const oa::Json* texts = sc.get("unmarshal")) {          // {"unmarshal": [text, ...]} -> one line: [marshal(unmarshal(text)) or null, ...]
+            std::string line = "[";
+            for (size_t i = 0; i < texts->a.size(); ++i) {
+                ToolPrompt tp; std::string e;
+                line += (i ? ", " : "") + (ToolPrompt::Unmarshal(texts->a[i].s, &tp, &e) ? oa::jstr(tp.Marshal()) : std::string("null"));
+            }
+            std::printf("%s]\n", line.c_str());
+            continue;
+        }
         std::vector<ChatCompletionMessage> prompts;
         for (const oa::Json& m : sc.get("prompts")->a) prompts.push_back({m.a[0].s, m.a[1].s});
         std::vector<std::string> replies;

@@ -29,6 +29,13 @@ int main() {
     const std::string cut = ConstrictPrompt(table, "m", 30, c4);
     CHECK(!cut.empty() && cut.size() / 4 < 30 && table.size() >= cut.size() && table.compare(table.size() - cut.size(), cut.size(), cut) == 0);      // a suffix of the input
     CHECK(ConstrictPrompt("  \n \n", "m", 0, c4) == "");
+    {   // Unmarshal visits keys in document order like encoding/json: folded matches overwrite each other, null keeps, a wrong type anywhere is an error
+        ToolPrompt tp; std::string e;
+        CHECK(ToolPrompt::Unmarshal("{\"que\xc5\xbftion\":\"a\",\"THOUGHT\":\"t\",\"thought\":null,\"action\":{\"Name\":\"x\"},\"ACTION\":{\"input\":\"y\"}}", &tp, &e));
+        CHECK(tp.Question == "a" && tp.Thought == "t" && tp.Action.Name == "x" && tp.Action.Input == "y");
+        CHECK(ToolPrompt::Unmarshal("{\"thought\":\"b\",\"Thought\":\"a\"}", &tp, &e) && tp.Thought == "a");
+        CHECK(!ToolPrompt::Unmarshal("{\"Thought\": 7, \"Thought\": \"ok\"}", &tp, &e) && !ToolPrompt::Unmarshal("{\"action\": \"kubectl\"}", &tp, &e) && !ToolPrompt::Unmarshal("[1]", &tp, &e));
+    }
     std::printf("ok\n");
     return 0;
 }

@@ -283,3 +283,61 @@ def test_cpp_llms_helpers_on_the_reference_cases(tmp_path):
     assert b.returncode == 0, b.stderr[-2000:]
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == "ok", (r.stdout, r.stderr[-1500:])
+
+
+def test_cpp_toolprompt_unmarshal_equals_the_python_mirror_on_random_json(tmp_path):
+    """ToolPrompt::Unmarshal + Marshal (host/assistants.hpp) against ToolPrompt.unmarshal / marshal (assistants.py) on 3000 seeded random documents: keys in
+    random case, duplicate keys, null / number / list / object values where strings are expected, nested junk, broken JSON"""
+    import json
+    import random
+    from opsagent_b200.assistants import ToolPrompt
+    exe = tmp_path / "assistants_driver"
+    lib = os.path.join(ROOT, "opsagent_b200", "lib")
+    b = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-I", ROOT, os.path.join(ROOT, "tests", "host", "assistants_driver.cpp"), "-o", str(exe), "-L", lib, "-lopsagent_b200", f"-Wl,-rpath,{lib}"],
+                       capture_output=True, text=True, timeout=600)
+    assert b.returncode == 0, b.stderr[-2000:]
+    r = random.Random(7)
+    names = ["question", "thought", "action", "observation", "final_answer", "name", "input", "extra"]
+
+    def key(k):
+        return r.choice([k, k, k, k.upper(), k.capitalize(), k[:-1]])
+
+    def val(depth=0):
+        c = r.randrange(10)
+        if c < 5:
+            return r.choice(["", "x", "<none> &  ", "中文", "a\"b\\c", "tab\t\b\f", "😀"])
+        if c == 5:
+            return None
+        if c == 6:
+            return r.randrange(100)
+        if c == 7:
+            return [1, "a"]
+        if c == 8 and depth < 2:
+            return {key(n): val(depth + 1) for n in r.sample(names, r.randrange(0, 4))}
+        return True
+
+    texts = []
+    for _ in range(3000):
+        pairs = [(key(n), val()) for n in r.sample(names, r.randrange(0, 7))]
+        if r.random() < 0.3:
+            pairs += [(key("action"), {key("name"): val(1), key("input"): val(1)})]
+        if r.random() < 0.2 and pairs:
+            pairs.append((pairs[0][0], val()))                       # duplicate key: the last one wins
+        body = "{" + ", ".join(json.dumps(k) + ": " + json.dumps(v, ensure_ascii=r.random() < 0.5) for k, v in pairs) + "}"
+        if r.random() < 0.05:
+            body = body[:r.randrange(len(body))]                      # broken JSON
+        texts.append(body)
+    path = tmp_path / "u.json"
+    path.write_text(json.dumps([{"unmarshal": texts}], ensure_ascii=False), encoding="utf-8")
+    out = subprocess.run([str(exe), str(path)], capture_output=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-1500:]
+    got = json.loads(out.stdout.decode("utf-8").rstrip("\n").split("\n")[0])
+    n_ok = 0
+    for text, g in zip(texts, got):
+        try:
+            want = ToolPrompt.unmarshal(text).marshal()
+            n_ok += 1
+        except Exception:      # noqa: BLE001
+            want = None
+        assert g == want, (text, g, want)
+    assert 300 < n_ok < 2900          # both outcomes are well represented

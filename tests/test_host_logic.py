@@ -528,6 +528,12 @@ def test_toolprompt_marshal_is_go_json_marshal_byte_for_byte():
     for bad in ('{"question": 5}', '{"action": "kubectl"}', '{"action": {"name": 1}}', '[1]', '"x"'):
         with pytest.raises(ValueError):
             ToolPrompt.unmarshal(bad)
+    # keys are visited in document order (encoding/json): folded duplicates overwrite each other, null keeps the value, a wrong type anywhere is an error
+    got = ToolPrompt.unmarshal('{"que\u017ftion":"a","THOUGHT":"t","thought":null,"action":{"Name":"x"},"ACTION":{"input":"y"}}')
+    assert (got.question, got.thought, got.action) == ("a", "t", {"name": "x", "input": "y"})
+    assert ToolPrompt.unmarshal('{"thought":"b","Thought":"a"}').thought == "a"
+    with pytest.raises(ValueError):
+        ToolPrompt.unmarshal('{"Thought": 7, "Thought": "ok"}')
     got = ToolPrompt.unmarshal('{"Question": "Q", "thought": null, "action": {"NAME": "jq"}, "extra": [1]}')
     assert (got.question, got.thought, got.action) == ("Q", "", {"name": "jq", "input": ""})
 
